@@ -1,0 +1,58 @@
+"""Builds libbvcf.so (and the synthetic-workload helper library) in-tree with nvcc for sm_100a.
+
+nvcc cross-compiles without a GPU, so this runs on the CPU-only build box; the .so travels to the
+GPU box with the repo snapshot.  Usage: python -m bystro_vcf_b200.build [--force]
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+ROOT = os.path.dirname(HERE)
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "128",
+]
+
+TARGETS = {
+    "libbvcf.so": ["bvcf_api.cu"],
+    "libbvcfsynth.so": ["bvcf_synth.cu"],
+}
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def _stale(out: str, srcs) -> bool:
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "bvcf.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> None:
+    os.makedirs(LIBDIR, exist_ok=True)
+    for lib, srcs in TARGETS.items():
+        srcs = [os.path.join(CSRC, s) for s in srcs]
+        if not all(os.path.exists(s) for s in srcs):
+            continue
+        out = os.path.join(LIBDIR, lib)
+        if not force and not _stale(out, srcs):
+            continue
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
+        print("[build]", " ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -1,0 +1,730 @@
+// bvcf_api.cu -- host side of libbvcf: contexts, staging slots, the kernel pipeline and the C ABI.
+//
+// Pipeline per sub-chunk (all launches on one stream, no host synchronisation in between):
+//   bvcf_scan_genotype_kernel      index + genotype events                    (north-star kernels 1+3)
+//   bvcf_prefix_* (mode 0)         per-range record counts -> bases
+//   bvcf_compact_lines_kernel      input-ordered line table
+//   bvcf_rows_kernel<SIZE>         FILTER + getAlleles + row sizes            (north-star kernels 2+4a)
+//   bvcf_prefix_* (mode 1)         row offsets, advances the run's output cursor
+//   bvcf_rows_kernel<EMIT>         scatter-write of the rows                  (north-star kernel 4b)
+#include "../../include/bvcf.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvcf_common.cuh"
+#include "bvcf_prefix.cuh"
+#include "bvcf_rows.cuh"
+#include "bvcf_scan.cuh"
+
+using namespace bvcf;
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Scratch {
+  // geometry
+  uint64_t sub_bytes = 0;     // sub-chunk size (multiple of range_bytes)
+  uint32_t range_bytes = 0, n_ranges = 0, slots = 0, evcap_words = 0;
+  uint64_t max_records = 0;
+  DevBuf recs, range_nrec, range_nlines, rec_base, line_base, events, dense, line_bytes, line_rows, line_off,
+      row_off, partial;
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  DevBuf d_in, d_out, d_dosage, d_loci, d_diags;
+  Scratch sc;
+  RunCounters *d_ctr = nullptr;
+  RunCounters *h_ctr = nullptr;  // pinned
+  uint8_t *h_out = nullptr;      // pinned
+  size_t h_out_cap = 0;
+  int8_t *h_dosage = nullptr;    // pinned
+  size_t h_dosage_cap = 0;
+  std::vector<uint8_t> h_loci;
+  std::vector<uint64_t> h_loci_off;
+  std::vector<uint8_t> h_loci_raw;
+  std::vector<bvcf_diag> h_diags;
+  std::vector<uint32_t> h_diag_raw;
+  bool busy = false;
+  uint64_t seq = 0;
+  const uint8_t *h_src = nullptr;
+  size_t len = 0;
+  uint32_t retries = 0;
+};
+
+constexpr uint32_t LOCI_STRIDE = 64;
+constexpr uint32_t DIAG_CAP = 1u << 16;
+
+}  // namespace
+
+struct bvcf_ctx {
+  int device = 0;
+  bvcf_config cfg{};
+  std::string empty_field, field_delim;
+  std::vector<std::string> allow, exclude;
+  bool header_set = false;
+  DevCfg dcfg{};
+  DevBuf d_filt_blob, d_filt_off, d_names, d_name_off;
+  std::vector<Slot> slots;
+  // resident path
+  DevBuf r_in, r_out, r_dosage, r_loci;
+  size_t r_in_bytes = 0;
+  Scratch r_sc;
+  cudaStream_t r_stream = nullptr;
+  RunCounters *r_d_ctr = nullptr, *r_h_ctr = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  double ev_factor = 0.5;  // event slice bytes per range byte
+  uint64_t launches = 0;
+  std::string last_error;
+  uint64_t r_last_records = 0;
+  uint64_t r_last_len = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);               \
+      return BVCF_E_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+int dev_reserve(bvcf_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  if (bytes == 0) bytes = 256;
+  CK(cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  return 0;
+}
+void dev_free(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
+
+// choose the range size for `total` bytes: enough ranges to fill 148 SMs x 32 warps a few times over,
+// large enough that re-reading one line per range boundary stays cheap
+uint32_t choose_range_bytes(uint64_t total) {
+  uint64_t r = total / (148ull * 32 * 3);
+  r = round_up(std::max<uint64_t>(r, 1), 512);
+  r = std::min<uint64_t>(std::max<uint64_t>(r, 16 * 1024), 256 * 1024);
+  return (uint32_t)r;
+}
+
+int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t sub_limit) {
+  const int H = ctx->dcfg.H;
+  sc.range_bytes = choose_range_bytes(total_bytes);
+  uint64_t sub = std::min<uint64_t>(round_up(total_bytes + 512, sc.range_bytes), round_up(sub_limit, sc.range_bytes));
+  sc.sub_bytes = sub;
+  sc.n_ranges = (uint32_t)(sub / sc.range_bytes);
+  sc.slots = sc.range_bytes / (uint32_t)std::max(H, 16) + 2;
+  uint64_t evb = (uint64_t)(sc.range_bytes * ctx->ev_factor) + 16 * 1024;
+  if (ctx->dcfg.n_samples == 0) evb = 64;
+  sc.evcap_words = (uint32_t)(evb / 4);
+  while ((uint64_t)sc.n_ranges * sc.evcap_words >= (1ull << 32)) {  // event indices are 32-bit
+    sc.n_ranges /= 2;
+    sc.sub_bytes = (uint64_t)sc.n_ranges * sc.range_bytes;
+  }
+  sc.max_records = (uint64_t)sc.n_ranges * sc.slots;
+  int rc;
+  if ((rc = dev_reserve(ctx, sc.recs, sc.max_records * sizeof(LineRec)))) return rc;
+  if ((rc = dev_reserve(ctx, sc.dense, sc.max_records * sizeof(LineRec)))) return rc;
+  if ((rc = dev_reserve(ctx, sc.range_nrec, (size_t)sc.n_ranges * 4))) return rc;
+  if ((rc = dev_reserve(ctx, sc.range_nlines, (size_t)sc.n_ranges * 4))) return rc;
+  if ((rc = dev_reserve(ctx, sc.rec_base, (size_t)sc.n_ranges * 8))) return rc;
+  if ((rc = dev_reserve(ctx, sc.line_base, (size_t)sc.n_ranges * 8))) return rc;
+  if ((rc = dev_reserve(ctx, sc.events, (size_t)sc.n_ranges * sc.evcap_words * 4))) return rc;
+  if ((rc = dev_reserve(ctx, sc.line_bytes, sc.max_records * 4))) return rc;
+  if ((rc = dev_reserve(ctx, sc.line_rows, sc.max_records * 4))) return rc;
+  if ((rc = dev_reserve(ctx, sc.line_off, sc.max_records * 8))) return rc;
+  if ((rc = dev_reserve(ctx, sc.row_off, sc.max_records * 8))) return rc;
+  if ((rc = dev_reserve(ctx, sc.partial, 2 * PFX_BLOCKS * 8))) return rc;
+  return 0;
+}
+void scratch_free(Scratch &sc) {
+  for (DevBuf *b : {&sc.recs, &sc.range_nrec, &sc.range_nlines, &sc.rec_base, &sc.line_base, &sc.events, &sc.dense,
+                    &sc.line_bytes, &sc.line_rows, &sc.line_off, &sc.row_off, &sc.partial})
+    dev_free(*b);
+}
+
+struct StageEvents {  // optional per-stage timing of one sub-chunk
+  cudaEvent_t e[5];
+};
+
+// Enqueue the whole pipeline for data lines in [0, len) of d_in.  Never synchronises.
+int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t *d_in, uint64_t len, uint64_t buf_len,
+                     uint8_t *d_out, uint64_t out_cap, RunCounters *d_ctr, int8_t *d_dosage, uint64_t dosage_cap_rows,
+                     uint8_t *d_loci, uint32_t *d_diags, std::vector<StageEvents> *timing) {
+  const DevCfg &dc = ctx->dcfg;
+  const uint64_t total_ranges = (len + sc.range_bytes - 1) / sc.range_bytes;
+  static bool attr_set = false;
+  const int smem = SCAN_WARPS * RING;
+  if (!attr_set) {
+    cudaFuncSetAttribute(bvcf_scan_genotype_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(bvcf_scan_genotype_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+  for (uint64_t r0 = 0; r0 < total_ranges; r0 += sc.n_ranges) {
+    const uint32_t nr = (uint32_t)std::min<uint64_t>(sc.n_ranges, total_ranges - r0);
+    StageEvents *se = nullptr;
+    if (timing) {
+      timing->emplace_back();
+      se = &timing->back();
+      for (int i = 0; i < 5; i++) {
+        if (ctx->ev_pool.empty()) {
+          cudaEvent_t e;
+          CK(cudaEventCreate(&e));
+          se->e[i] = e;
+        } else {
+          se->e[i] = ctx->ev_pool.back();
+          ctx->ev_pool.pop_back();
+        }
+      }
+      CK(cudaEventRecord(se->e[0], st));
+    }
+    // 1. scan: index + genotype events
+    ScanParams sp{};
+    sp.in = d_in; sp.begin = 0; sp.end = len; sp.buf_len = buf_len; sp.a0 = 0;
+    sp.range_bytes = sc.range_bytes; sp.r0 = (uint32_t)r0; sp.n_ranges = nr;
+    sp.slots_per_range = sc.slots; sp.evcap_words = sc.evcap_words;
+    sp.recs = (LineRec *)sc.recs.p; sp.range_nrec = (uint32_t *)sc.range_nrec.p;
+    sp.range_nlines = (uint32_t *)sc.range_nlines.p; sp.events = (uint32_t *)sc.events.p;
+    sp.ctr = d_ctr; sp.H = dc.H; sp.eol_width = dc.eol_width;
+    const unsigned grid = (nr + SCAN_WARPS - 1) / SCAN_WARPS;
+    if (dc.n_samples > 0)
+      bvcf_scan_genotype_kernel<true><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);
+    else
+      bvcf_scan_genotype_kernel<false><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);
+    ctx->launches++;
+    if (se) CK(cudaEventRecord(se->e[1], st));
+    // 2. per-range counts -> bases
+    PrefixParams pp{};
+    pp.a = sp.range_nrec; pp.b = sp.range_nlines;
+    pp.out_a = (uint64_t *)sc.rec_base.p; pp.out_b = (uint64_t *)sc.line_base.p;
+    pp.partial = (unsigned long long *)sc.partial.p;
+    pp.n_ptr = nullptr; pp.n_imm = nr; pp.ctr = d_ctr; pp.mode = 0; pp.out_cap = 0;
+    bvcf_prefix_reduce_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pp);
+    bvcf_prefix_spine_kernel<<<1, 1024, 0, st>>>(pp);
+    bvcf_prefix_scan_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pp);
+    // 3. compaction
+    CompactParams cp{};
+    cp.recs = sp.recs; cp.range_nrec = sp.range_nrec; cp.rec_base = pp.out_a; cp.line_base = pp.out_b;
+    cp.dense = (LineRec *)sc.dense.p; cp.n_ranges = nr; cp.slots_per_range = sc.slots; cp.evcap_words = sc.evcap_words;
+    bvcf_compact_lines_kernel<<<(nr + 7) / 8, 256, 0, st>>>(cp);
+    ctx->launches += 4;
+    if (se) CK(cudaEventRecord(se->e[2], st));
+    // 4. size pass
+    RowsParams rp{};
+    rp.in = d_in; rp.cfg = dc; rp.lines = cp.dense; rp.events = sp.events;
+    rp.line_bytes = (uint32_t *)sc.line_bytes.p; rp.line_rows = (uint32_t *)sc.line_rows.p;
+    rp.line_off = (uint64_t *)sc.line_off.p; rp.row_off = (uint64_t *)sc.row_off.p;
+    rp.out = d_out; rp.out_cap = out_cap; rp.ctr = d_ctr;
+    rp.dosage = d_dosage; rp.dosage_cap_rows = dosage_cap_rows; rp.loci = d_loci; rp.loci_stride = LOCI_STRIDE;
+    rp.diags = d_diags; rp.diag_cap = DIAG_CAP;
+    const unsigned rgrid = (unsigned)n_sm * 8;
+    bvcf_rows_kernel<false><<<rgrid, ROWS_WARPS * 32, 0, st>>>(rp);
+    // 5. row offsets
+    PrefixParams pq{};
+    pq.a = rp.line_bytes; pq.b = rp.line_rows; pq.out_a = (uint64_t *)sc.line_off.p; pq.out_b = (uint64_t *)sc.row_off.p;
+    pq.partial = (unsigned long long *)sc.partial.p;
+    pq.n_ptr = &d_ctr->chunk_records; pq.n_imm = 0; pq.ctr = d_ctr; pq.mode = 1; pq.out_cap = out_cap;
+    bvcf_prefix_reduce_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pq);
+    bvcf_prefix_spine_kernel<<<1, 1024, 0, st>>>(pq);
+    bvcf_prefix_scan_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pq);
+    ctx->launches += 4;
+    if (se) CK(cudaEventRecord(se->e[3], st));
+    // 6. emit pass
+    bvcf_rows_kernel<true><<<rgrid, ROWS_WARPS * 32, 0, st>>>(rp);
+    ctx->launches++;
+    if (se) CK(cudaEventRecord(se->e[4], st));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+void fill_dcfg(bvcf_ctx *ctx) {
+  DevCfg &d = ctx->dcfg;
+  const bvcf_config &c = ctx->cfg;
+  d.eol_width = c.eol_width == 2 ? 2 : 1;
+  d.keep_id = c.keep_id != 0; d.keep_info = c.keep_info != 0; d.keep_pos = c.keep_pos != 0;
+  d.want_tsv = c.want_tsv != 0; d.want_dosage = c.want_dosage != 0;
+  d.allow_all = c.n_allow < 0;
+  d.n_allow = c.n_allow < 0 ? 0 : (int)ctx->allow.size();
+  d.n_excl = (int)ctx->exclude.size();
+  d.empty_len = (int)ctx->empty_field.size();
+  memcpy(d.empty, ctx->empty_field.data(), ctx->empty_field.size());
+  d.delim_len = (int)ctx->field_delim.size();
+  memcpy(d.delim, ctx->field_delim.data(), ctx->field_delim.size());
+}
+
+Slot *find_slot(bvcf_ctx *ctx, uint64_t seq) {
+  for (auto &s : ctx->slots)
+    if (s.busy && s.seq == seq) return &s;
+  return nullptr;
+}
+
+int slot_enqueue(bvcf_ctx *ctx, Slot &s, bool upload) {
+  const uint64_t len = s.len;
+  const uint64_t buf_len = round_up(len, 512) + 1024;
+  int rc;
+  if ((rc = dev_reserve(ctx, s.d_in, buf_len))) return rc;
+  if ((rc = scratch_reserve(ctx, s.sc, len, ctx->cfg.resident_subchunk_bytes))) return rc;
+  if (s.d_out.cap == 0) {
+    if ((rc = dev_reserve(ctx, s.d_out, std::max<size_t>(len / 2, 1 << 20)))) return rc;
+  }
+  const DevCfg &dc = ctx->dcfg;
+  uint64_t dos_rows = 0;
+  if (dc.want_dosage && dc.n_samples > 0) {
+    dos_rows = s.d_dosage.cap / (uint64_t)dc.n_samples;
+    if (dos_rows == 0) {
+      const uint64_t est = std::max<uint64_t>(len / std::max(1, dc.H) * 2, 1024);
+      if ((rc = dev_reserve(ctx, s.d_dosage, est * dc.n_samples))) return rc;
+      if ((rc = dev_reserve(ctx, s.d_loci, est * LOCI_STRIDE))) return rc;
+      dos_rows = est;
+    }
+  }
+  if ((rc = dev_reserve(ctx, s.d_diags, (size_t)DIAG_CAP * 16))) return rc;
+  if (upload) CK(cudaMemcpyAsync(s.d_in.p, s.h_src, len, cudaMemcpyHostToDevice, s.stream));
+  CK(cudaMemsetAsync((uint8_t *)s.d_in.p + len, '\n', buf_len - len, s.stream));
+  CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(RunCounters), s.stream));
+  rc = enqueue_pipeline(ctx, s.sc, s.stream, (const uint8_t *)s.d_in.p, len, buf_len, (uint8_t *)s.d_out.p, s.d_out.cap,
+                        s.d_ctr, (int8_t *)s.d_dosage.p, dos_rows, (uint8_t *)s.d_loci.p, (uint32_t *)s.d_diags.p,
+                        nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(RunCounters), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaEventRecord(s.done, s.stream));
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int bvcf_abi_version(void) { return BVCF_ABI_VERSION; }
+
+const char *bvcf_strerror(int rc) {
+  switch (rc) {
+    case BVCF_OK: return "ok";
+    case BVCF_E_ARG: return "bad argument";
+    case BVCF_E_CUDA: return "CUDA error (see bvcf_last_error)";
+    case BVCF_E_STATE: return "bad call order or no free slot";
+    case BVCF_E_NOT_ALIGNED: return "chunk does not end with a newline";
+    case BVCF_E_TOO_LARGE: return "input exceeds a library limit";
+    case BVCF_E_NOMEM: return "out of host memory";
+    default: return "unknown error";
+  }
+}
+
+const char *bvcf_last_error(const bvcf_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t bvcf_launch_count(const bvcf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int bvcf_header_line(const bvcf_config *cfg, char *buf, size_t cap) {
+  // parse.Header + optional columns (main.go:219-239)
+  std::string h =
+      "chrom\tpos\ttype\tref\talt\ttrTv\theterozygotes\theterozygosity\thomozygotes\thomozygosity\tmissingGenos\t"
+      "missingness\tac\tan\tsampleMaf";
+  if (cfg && cfg->keep_pos) h += "\tvcfPos";
+  if (cfg && cfg->keep_id) h += "\tid";
+  if (cfg && cfg->keep_info) h += "\talleleIdx\tinfo";
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, h.size());
+    memcpy(buf, h.data(), n);
+    buf[n] = 0;
+  }
+  return (int)h.size();
+}
+
+int bvcf_create(bvcf_ctx **out, int cuda_device, const bvcf_config *cfg) {
+  if (!out || !cfg) return BVCF_E_ARG;
+  *out = nullptr;
+  bvcf_ctx *ctx = new (std::nothrow) bvcf_ctx();
+  if (!ctx) return BVCF_E_NOMEM;
+  ctx->device = cuda_device;
+  ctx->cfg = *cfg;
+  ctx->empty_field = cfg->empty_field ? cfg->empty_field : "!";
+  ctx->field_delim = cfg->field_delim ? cfg->field_delim : ";";
+  if (ctx->empty_field.size() > 63 || ctx->field_delim.size() > 63) { delete ctx; return BVCF_E_TOO_LARGE; }
+  for (int i = 0; i < cfg->n_allow; i++) ctx->allow.push_back(cfg->allow[i] ? cfg->allow[i] : "");
+  for (int i = 0; i < cfg->n_exclude; i++) ctx->exclude.push_back(cfg->exclude[i] ? cfg->exclude[i] : "");
+  if (ctx->allow.size() + ctx->exclude.size() > 64) { delete ctx; return BVCF_E_TOO_LARGE; }
+  if (ctx->cfg.n_slots <= 0) ctx->cfg.n_slots = 3;
+  if (ctx->cfg.max_chunk_bytes == 0) ctx->cfg.max_chunk_bytes = 256ull << 20;
+  if (ctx->cfg.resident_subchunk_bytes == 0) ctx->cfg.resident_subchunk_bytes = 4ull << 30;
+  ctx->cfg.allow = nullptr; ctx->cfg.exclude = nullptr; ctx->cfg.empty_field = nullptr; ctx->cfg.field_delim = nullptr;
+
+  auto fail = [&](int rc) { *out = ctx; bvcf_destroy(ctx); *out = nullptr; return rc; };
+  // no CPU fallback: a missing device is an error
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || cuda_device < 0 || cuda_device >= n_dev) {
+    fprintf(stderr, "libbvcf: no usable CUDA device %d (%s)\n", cuda_device,
+            e != cudaSuccess ? cudaGetErrorString(e) : "index out of range");
+    delete ctx;
+    return BVCF_E_CUDA;
+  }
+  if (cudaSetDevice(cuda_device) != cudaSuccess) { delete ctx; return BVCF_E_CUDA; }
+
+  // FILTER table
+  std::vector<uint8_t> blob;
+  std::vector<uint32_t> off{0};
+  for (auto &s : ctx->allow) { blob.insert(blob.end(), s.begin(), s.end()); off.push_back((uint32_t)blob.size()); }
+  for (auto &s : ctx->exclude) { blob.insert(blob.end(), s.begin(), s.end()); off.push_back((uint32_t)blob.size()); }
+  if (blob.size() > FILT_SMEM) return fail(BVCF_E_TOO_LARGE);
+  if (dev_reserve(ctx, ctx->d_filt_blob, blob.size() + 16)) return fail(BVCF_E_CUDA);
+  if (dev_reserve(ctx, ctx->d_filt_off, off.size() * 4)) return fail(BVCF_E_CUDA);
+  if (!blob.empty()) cudaMemcpy(ctx->d_filt_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(ctx->d_filt_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice);
+  ctx->dcfg.filt_blob = (const uint8_t *)ctx->d_filt_blob.p;
+  ctx->dcfg.filt_off = (const uint32_t *)ctx->d_filt_off.p;
+  ctx->dcfg.filt_bytes = (int)blob.size();
+  fill_dcfg(ctx);
+
+  ctx->slots.resize(ctx->cfg.n_slots);
+  for (auto &s : ctx->slots) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return fail(BVCF_E_CUDA);
+    if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) return fail(BVCF_E_CUDA);
+    if (cudaMalloc(&s.d_ctr, sizeof(RunCounters)) != cudaSuccess) return fail(BVCF_E_CUDA);
+    if (cudaMallocHost(&s.h_ctr, sizeof(RunCounters)) != cudaSuccess) return fail(BVCF_E_CUDA);
+  }
+  if (cudaStreamCreateWithFlags(&ctx->r_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(BVCF_E_CUDA);
+  if (cudaMalloc(&ctx->r_d_ctr, sizeof(RunCounters)) != cudaSuccess) return fail(BVCF_E_CUDA);
+  if (cudaMallocHost(&ctx->r_h_ctr, sizeof(RunCounters)) != cudaSuccess) return fail(BVCF_E_CUDA);
+  *out = ctx;
+  return BVCF_OK;
+}
+
+void bvcf_destroy(bvcf_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto &s : ctx->slots) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+    for (DevBuf *b : {&s.d_in, &s.d_out, &s.d_dosage, &s.d_loci, &s.d_diags}) dev_free(*b);
+    scratch_free(s.sc);
+    if (s.d_ctr) cudaFree(s.d_ctr);
+    if (s.h_ctr) cudaFreeHost(s.h_ctr);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.h_dosage) cudaFreeHost(s.h_dosage);
+  }
+  for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->r_in, &ctx->r_out,
+                    &ctx->r_dosage, &ctx->r_loci})
+    dev_free(*b);
+  scratch_free(ctx->r_sc);
+  if (ctx->r_stream) cudaStreamDestroy(ctx->r_stream);
+  if (ctx->r_d_ctr) cudaFree(ctx->r_d_ctr);
+  if (ctx->r_h_ctr) cudaFreeHost(ctx->r_h_ctr);
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  delete ctx;
+}
+
+int bvcf_set_header(bvcf_ctx *ctx, const char *chrom_line, size_t len) {
+  if (!ctx || !chrom_line) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  while (len && (chrom_line[len - 1] == '\n' || chrom_line[len - 1] == '\r')) len--;  // chomp (main.go:281)
+  std::vector<std::string> f;
+  size_t s = 0;
+  for (size_t i = 0; i <= len; i++) {
+    if (i == len || chrom_line[i] == '\t') { f.emplace_back(chrom_line + s, i - s); s = i + 1; }
+  }
+  const int H = (int)f.size();
+  if (H < 8) return BVCF_E_ARG;  // the reference would panic indexing FILTER/INFO
+  const int ns = H > 9 ? H - 9 : 0;  // main.go:505-509
+  if ((uint32_t)ns > MAX_SAMPLES) return BVCF_E_TOO_LARGE;
+  std::vector<uint8_t> blob;
+  std::vector<uint32_t> off{0};
+  int fixed_w = -1;
+  for (int i = 0; i < ns; i++) {
+    std::string nm = f[9 + i];
+    if (ctx->cfg.normalize_dots)
+      for (auto &c : nm) if (c == '.') c = '_';  // parse.NormalizeHeader (main.go:296)
+    blob.insert(blob.end(), nm.begin(), nm.end());
+    off.push_back((uint32_t)blob.size());
+    if (i == 0) fixed_w = (int)nm.size();
+    else if (fixed_w != (int)nm.size()) fixed_w = 0;
+  }
+  if (fixed_w < 0) fixed_w = 0;
+  int rc;
+  if ((rc = dev_reserve(ctx, ctx->d_names, blob.size() + 16))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_name_off, off.size() * 4))) return rc;
+  if (!blob.empty()) CK(cudaMemcpy(ctx->d_names.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_name_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  ctx->dcfg.H = H;
+  ctx->dcfg.n_samples = ns;
+  ctx->dcfg.names = (const uint8_t *)ctx->d_names.p;
+  ctx->dcfg.name_off = (const uint32_t *)ctx->d_name_off.p;
+  ctx->dcfg.name_fixed_w = fixed_w;
+  ctx->header_set = true;
+  return BVCF_OK;
+}
+
+int bvcf_host_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return BVCF_E_ARG;
+  return cudaMallocHost(ptr, bytes ? bytes : 1) == cudaSuccess ? BVCF_OK : BVCF_E_CUDA;
+}
+void bvcf_host_free(void *ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+int bvcf_submit(bvcf_ctx *ctx, uint64_t seq, const uint8_t *chunk, size_t len) {
+  if (!ctx || (!chunk && len)) return BVCF_E_ARG;
+  if (!ctx->header_set) return BVCF_E_STATE;
+  if (len > ctx->cfg.max_chunk_bytes || len >= (1ull << 31)) return BVCF_E_TOO_LARGE;
+  if (len && chunk[len - 1] != '\n') return BVCF_E_NOT_ALIGNED;
+  if (find_slot(ctx, seq)) return BVCF_E_STATE;
+  Slot *s = nullptr;
+  for (auto &x : ctx->slots)
+    if (!x.busy) { s = &x; break; }
+  if (!s) return BVCF_E_STATE;
+  cudaSetDevice(ctx->device);
+  s->busy = true; s->seq = seq; s->h_src = chunk; s->len = len; s->retries = 0;
+  const int rc = slot_enqueue(ctx, *s, true);
+  if (rc) s->busy = false;
+  return rc;
+}
+
+int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_len, bvcf_dosage_batch *dosage,
+                 const bvcf_diag **diags, size_t *n_diags, bvcf_chunk_stats *stats) {
+  if (!ctx) return BVCF_E_ARG;
+  Slot *s = find_slot(ctx, seq);
+  if (!s) return BVCF_E_STATE;
+  cudaSetDevice(ctx->device);
+  const DevCfg &dc = ctx->dcfg;
+  for (;;) {
+    CK(cudaEventSynchronize(s->done));
+    const RunCounters &c = *s->h_ctr;
+    bool again = false;
+    if (c.ev_overflow) { ctx->ev_factor *= 4; again = true; }           // dense genotype block: more event slots
+    if (c.slot_overflow) return BVCF_E_TOO_LARGE;                       // cannot happen: slots cover the minimum line
+    if (c.out_overflow) {
+      int rc = dev_reserve(ctx, s->d_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096));
+      if (rc) return rc;
+      again = true;
+    }
+    if (dc.want_dosage && dc.n_samples > 0 && c.row_cursor * (uint64_t)dc.n_samples > s->d_dosage.cap) {
+      int rc = dev_reserve(ctx, s->d_dosage, (size_t)(c.row_cursor + 64) * dc.n_samples);
+      if (rc) return rc;
+      if ((rc = dev_reserve(ctx, s->d_loci, (size_t)(c.row_cursor + 64) * LOCI_STRIDE))) return rc;
+      again = true;
+    }
+    if (!again) break;
+    s->retries++;
+    if (s->retries > 8) return BVCF_E_TOO_LARGE;
+    const int rc = slot_enqueue(ctx, *s, false);  // input is still on the device
+    if (rc) return rc;
+  }
+  const RunCounters c = *s->h_ctr;
+  // rows back to pinned host memory
+  if (c.out_cursor > s->h_out_cap) {
+    if (s->h_out) cudaFreeHost(s->h_out);
+    s->h_out = nullptr;
+    s->h_out_cap = 0;
+    const size_t cap = (size_t)(c.out_cursor + c.out_cursor / 4 + 4096);
+    CK(cudaMallocHost(&s->h_out, cap));
+    s->h_out_cap = cap;
+  }
+  if (c.out_cursor) CK(cudaMemcpyAsync(s->h_out, s->d_out.p, c.out_cursor, cudaMemcpyDeviceToHost, s->stream));
+  const bool dos = dc.want_dosage && dc.n_samples > 0;
+  if (dos && c.row_cursor) {
+    const size_t nb = (size_t)c.row_cursor * dc.n_samples;
+    if (nb > s->h_dosage_cap) {
+      if (s->h_dosage) cudaFreeHost(s->h_dosage);
+      s->h_dosage = nullptr;
+      CK(cudaMallocHost(&s->h_dosage, nb + nb / 4));
+      s->h_dosage_cap = nb + nb / 4;
+    }
+    CK(cudaMemcpyAsync(s->h_dosage, s->d_dosage.p, nb, cudaMemcpyDeviceToHost, s->stream));
+    s->h_loci_raw.resize((size_t)c.row_cursor * LOCI_STRIDE);
+    CK(cudaMemcpyAsync(s->h_loci_raw.data(), s->d_loci.p, s->h_loci_raw.size(), cudaMemcpyDeviceToHost, s->stream));
+  }
+  const uint32_t nd = std::min<uint32_t>(c.n_diags, DIAG_CAP);
+  if (nd) {
+    s->h_diag_raw.resize((size_t)nd * 4);
+    CK(cudaMemcpyAsync(s->h_diag_raw.data(), s->d_diags.p, (size_t)nd * 16, cudaMemcpyDeviceToHost, s->stream));
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  if (tsv) *tsv = s->h_out;
+  if (tsv_len) *tsv_len = (size_t)c.out_cursor;
+  if (dosage) {
+    memset(dosage, 0, sizeof(*dosage));
+    dosage->n_samples = (uint32_t)dc.n_samples;
+    if (dos && c.row_cursor) {
+      s->h_loci.clear();
+      s->h_loci_off.assign(1, 0);
+      for (uint64_t r = 0; r < c.row_cursor; r++) {
+        const char *p = (const char *)s->h_loci_raw.data() + r * LOCI_STRIDE;
+        const size_t n = strnlen(p, LOCI_STRIDE);
+        s->h_loci.insert(s->h_loci.end(), p, p + n);
+        s->h_loci_off.push_back(s->h_loci.size());
+      }
+      dosage->n_rows = c.row_cursor;
+      dosage->dosage = s->h_dosage;
+      dosage->loci = s->h_loci.data();
+      dosage->loci_off = s->h_loci_off.data();
+    }
+  }
+  s->h_diags.clear();
+  for (uint32_t i = 0; i < nd; i++) {
+    bvcf_diag d;
+    d.line_no = (uint64_t)s->h_diag_raw[4 * i] | ((uint64_t)s->h_diag_raw[4 * i + 1] << 32);
+    d.alt_no = (int32_t)s->h_diag_raw[4 * i + 2];
+    d.code = (int32_t)s->h_diag_raw[4 * i + 3];
+    s->h_diags.push_back(d);
+  }
+  std::sort(s->h_diags.begin(), s->h_diags.end(), [](const bvcf_diag &a, const bvcf_diag &b) {
+    return a.line_no != b.line_no ? a.line_no < b.line_no : a.alt_no < b.alt_no;
+  });
+  if (diags) *diags = s->h_diags.data();
+  if (n_diags) *n_diags = s->h_diags.size();
+  if (stats) {
+    stats->n_lines = c.n_lines; stats->n_records = c.n_records; stats->n_rows = c.row_cursor;
+    stats->in_bytes = s->len; stats->out_bytes = c.out_cursor; stats->retries = s->retries;
+  }
+  return BVCF_OK;
+}
+
+int bvcf_release(bvcf_ctx *ctx, uint64_t seq) {
+  if (!ctx) return BVCF_E_ARG;
+  Slot *s = find_slot(ctx, seq);
+  if (!s) return BVCF_E_STATE;
+  s->busy = false;
+  s->h_src = nullptr;
+  return BVCF_OK;
+}
+
+// ---- resident path ----------------------------------------------------------------------------
+
+int bvcf_resident_alloc(bvcf_ctx *ctx, size_t in_bytes, size_t out_capacity, void **d_in, void **d_out) {
+  if (!ctx) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  const uint64_t buf_len = round_up(in_bytes, 512) + 1024;
+  int rc;
+  if ((rc = dev_reserve(ctx, ctx->r_in, buf_len))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->r_out, std::max<size_t>(out_capacity, 4096)))) return rc;
+  CK(cudaMemset((uint8_t *)ctx->r_in.p + in_bytes, '\n', ctx->r_in.cap - in_bytes));
+  ctx->r_in_bytes = in_bytes;
+  if (d_in) *d_in = ctx->r_in.p;
+  if (d_out) *d_out = ctx->r_out.p;
+  return BVCF_OK;
+}
+
+int bvcf_resident_upload(bvcf_ctx *ctx, size_t offset, const void *host, size_t len) {
+  if (!ctx || !host) return BVCF_E_ARG;
+  if (offset + len > ctx->r_in_bytes) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaMemcpy((uint8_t *)ctx->r_in.p + offset, host, len, cudaMemcpyHostToDevice));
+  return BVCF_OK;
+}
+
+int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_kernel_times *times) {
+  if (!ctx) return BVCF_E_ARG;
+  if (!ctx->header_set) return BVCF_E_STATE;
+  if (len > ctx->r_in_bytes) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  const DevCfg &dc = ctx->dcfg;
+  uint32_t retries = 0;
+  std::vector<StageEvents> timing;
+  for (;;) {
+    int rc;
+    if ((rc = scratch_reserve(ctx, ctx->r_sc, len, ctx->cfg.resident_subchunk_bytes))) return rc;
+    // the bytes after `len` must not look like data: pad (idempotent)
+    const uint64_t buf_len = std::min<uint64_t>(ctx->r_in.cap / 512 * 512, round_up(len, 512) + 1024);
+    CK(cudaMemsetAsync(ctx->r_d_ctr, 0, sizeof(RunCounters), ctx->r_stream));
+    uint64_t dos_rows = 0;
+    if (dc.want_dosage && dc.n_samples > 0) dos_rows = ctx->r_dosage.cap / (uint64_t)dc.n_samples;
+    for (auto &t : timing)
+      for (auto e : t.e) ctx->ev_pool.push_back(e);
+    timing.clear();
+    rc = enqueue_pipeline(ctx, ctx->r_sc, ctx->r_stream, (const uint8_t *)ctx->r_in.p, len, buf_len,
+                          (uint8_t *)ctx->r_out.p, ctx->r_out.cap, ctx->r_d_ctr, (int8_t *)ctx->r_dosage.p, dos_rows,
+                          (uint8_t *)ctx->r_loci.p, nullptr, times ? &timing : nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->r_h_ctr, ctx->r_d_ctr, sizeof(RunCounters), cudaMemcpyDeviceToHost, ctx->r_stream));
+    CK(cudaStreamSynchronize(ctx->r_stream));
+    const RunCounters &c = *ctx->r_h_ctr;
+    bool again = false;
+    if (c.ev_overflow) { ctx->ev_factor *= 4; again = true; }
+    if (c.slot_overflow) return BVCF_E_TOO_LARGE;
+    if (c.out_overflow) {
+      if ((rc = dev_reserve(ctx, ctx->r_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096)))) return rc;
+      again = true;
+    }
+    if (dc.want_dosage && dc.n_samples > 0 && c.row_cursor * (uint64_t)dc.n_samples > ctx->r_dosage.cap) {
+      if ((rc = dev_reserve(ctx, ctx->r_dosage, (size_t)(c.row_cursor + 64) * dc.n_samples))) return rc;
+      if ((rc = dev_reserve(ctx, ctx->r_loci, (size_t)(c.row_cursor + 64) * LOCI_STRIDE))) return rc;
+      again = true;
+    }
+    if (!again) break;
+    if (++retries > 8) return BVCF_E_TOO_LARGE;
+  }
+  const RunCounters &c = *ctx->r_h_ctr;
+  ctx->r_last_records = c.n_records;
+  ctx->r_last_len = len;
+  if (stats) {
+    stats->n_lines = c.n_lines; stats->n_records = c.n_records; stats->n_rows = c.row_cursor;
+    stats->in_bytes = len; stats->out_bytes = c.out_cursor; stats->retries = retries;
+  }
+  if (times) {
+    memset(times, 0, sizeof(*times));
+    for (auto &t : timing) {
+      float ms;
+      cudaEventElapsedTime(&ms, t.e[0], t.e[1]); times->scan_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[1], t.e[2]); times->compact_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[2], t.e[3]); times->size_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->emit_ms += ms;
+      times->launches += 10;
+    }
+    if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[4]);
+    for (auto &t : timing)
+      for (auto e : t.e) ctx->ev_pool.push_back(e);
+  }
+  return BVCF_OK;
+}
+
+int bvcf_resident_download(bvcf_ctx *ctx, size_t offset, void *host, size_t len) {
+  if (!ctx || !host) return BVCF_E_ARG;
+  if (offset + len > ctx->r_out.cap) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaMemcpy(host, (uint8_t *)ctx->r_out.p + offset, len, cudaMemcpyDeviceToHost));
+  return BVCF_OK;
+}
+
+int bvcf_resident_line_index(bvcf_ctx *ctx, uint64_t *starts, uint32_t *lens, uint32_t *an, size_t cap,
+                             size_t *n_records) {
+  if (!ctx) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  // valid for single-sub-chunk runs: the dense table of the last sub-chunk
+  const size_t n = (size_t)std::min<uint64_t>(ctx->r_h_ctr->chunk_records, cap);
+  if (n_records) *n_records = ctx->r_h_ctr->chunk_records;
+  if (n == 0) return BVCF_OK;
+  std::vector<LineRec> tmp(n);
+  CK(cudaMemcpy(tmp.data(), ctx->r_sc.dense.p, n * sizeof(LineRec), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; i++) {
+    if (starts) starts[i] = tmp[i].start;
+    if (lens) lens[i] = tmp[i].len;
+    if (an) an[i] = tmp[i].an;
+  }
+  return BVCF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// bvcf_common.cuh -- shared device-side types and warp helpers for libbvcf (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bvcf {
+
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+// ---- line table -------------------------------------------------------------------------------
+// One record per data line that has the header's field count (main.go:449).  Written by the scan
+// kernel into per-range slots, then compacted into input order.
+struct __align__(16) LineRec {
+  uint64_t start;     // byte offset of the line in the input region
+  uint32_t len;       // length including the EOL
+  uint32_t an;        // non-missing allele count of the fast-classified samples (main.go:1067,1169)
+  uint32_t ev_start;  // first event word of this line
+  uint32_t ev_count;  // event words of this line
+  uint32_t ord;       // ordinal of this line among ALL lines that start in its range
+  uint32_t pad;
+};
+
+// ---- genotype events ----------------------------------------------------------------------------
+// The scan kernel emits one 32-bit event per sample whose GT is not plain reference:
+//   bits  0..19  sample index (header order)
+//   bits 20..24  c1, bits 25..29  c2 : allele codes; 0 = ref/other token, 1..9 = that allele number,
+//                30 = absent (haploid), 31 = '.' (sample missing)
+//   bit  30      complex: GT needs the general grammar (polyploid, allele >= 10, mixed separators);
+//                the NEXT word is (1u<<31 | byte offset of the field from the line start)
+//   bit  31      set only on the offset word that follows a complex event
+constexpr uint32_t EV_SAMPLE_MASK = 0xFFFFFu;
+constexpr uint32_t EV_COMPLEX = 1u << 30;
+constexpr uint32_t EV_OFFSET_TAG = 1u << 31;
+constexpr uint32_t EV_CODE_ABSENT = 30, EV_CODE_MISSING = 31;
+constexpr uint32_t MAX_SAMPLES = 1u << 20;
+
+__device__ __forceinline__ uint32_t ev_make(uint32_t sample, uint32_t c1, uint32_t c2) {
+  return sample | (c1 << 20) | (c2 << 25);
+}
+
+// ---- flags written by kernels, read by the host after the run -----------------------------------
+struct RunCounters {
+  unsigned long long out_cursor;   // bytes of TSV written so far (device-side running offset)
+  unsigned long long row_cursor;   // rows written so far
+  unsigned long long n_lines;      // all newline-terminated lines
+  unsigned long long n_records;    // lines with the right field count
+  unsigned int ev_overflow;        // a range ran out of event slots
+  unsigned int slot_overflow;      // a range ran out of line slots
+  unsigned int out_overflow;       // output region too small
+  unsigned int n_diags;
+  unsigned long long chunk_out_base;  // out_cursor before this sub-chunk (set by the scan-finalize kernel)
+  unsigned long long chunk_row_base;
+  unsigned long long chunk_line_base; // n_lines before this sub-chunk (diagnostic line numbers)
+  unsigned int chunk_records;      // records in the current sub-chunk (device-side n for grid-stride kernels)
+  unsigned int pad;
+};
+
+// ---- configuration as the kernels see it ---------------------------------------------------------
+struct DevCfg {
+  int H;           // header field count (main.go:449)
+  int n_samples;   // max(H-9,0)
+  int eol_width;   // numChars
+  int keep_id, keep_info, keep_pos, want_tsv, want_dosage;
+  int allow_all;   // allowedFilters == nil
+  int n_allow, n_excl;
+  const uint8_t *filt_blob;   // allow strings then exclude strings, back to back
+  const uint32_t *filt_off;   // n_allow + n_excl + 1 offsets
+  int filt_bytes;
+  uint8_t empty[64];
+  int empty_len;
+  uint8_t delim[64];
+  int delim_len;
+  const uint8_t *names;       // sample names back to back
+  const uint32_t *name_off;   // n_samples + 1
+  int name_fixed_w;           // > 0 when every sample name has this length
+};
+
+// ---- warp helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+// 4-bit mask of the bytes of w equal to the byte replicated in pat (exact, no false positives)
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t pat) {
+  uint32_t t = w ^ pat;
+  uint32_t y = (t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+  y = ~(y | t | 0x7F7F7F7Fu);               // 0x80 in every zero byte of t
+  return ((y >> 7) * 0x00204081u >> 21) & 0xFu;
+}
+__device__ __forceinline__ uint32_t eq_mask16(const uint4 &v, uint32_t pat) {
+  return eq_mask4(v.x, pat) | (eq_mask4(v.y, pat) << 4) | (eq_mask4(v.z, pat) << 8) | (eq_mask4(v.w, pat) << 12);
+}
+
+}  // namespace bvcf

@@ -1,0 +1,348 @@
+// bvcf_scan.cuh -- north-star kernels (1)+(3) fused: newline/tab index + per-sample genotype classify.
+//
+// One warp streams one byte range of the input exactly once (cp.async 16-byte loads into a per-warp
+// shared-memory ring, 512 B per step), finds line boundaries and tab counts with SWAR byte compares +
+// __ballot_sync/__popc + warp prefix sums, and classifies every sample's GT token on the fly.  It owns the
+// lines that START in its range (it reads past the range end to finish the last one).  Products:
+//   * LineRec per record with the header's field count (main.go:449 len(record)==len(header)),
+//   * `an` of the fast-classified samples (main.go:1067-1169 totalGtCount),
+//   * one 32-bit event per non-reference sample, in header order (main.go:1057 loop order), which the
+//     rows kernel turns into the het/hom/missing lists and ac for each output allele.
+// Replaces: strings.Split (main.go:535) + the sample loop of makeHetHomozygotes (main.go:1057-1191).
+//
+// Three tiers per 512-byte window, chosen warp-uniformly:
+//   T1  all 128 fields are "0|0\t" (or "0/0\t")  -> 4 compares + vote, nothing else
+//   T2  all 128 fields are "x|y\t" / "x/y\t", x,y in [0-9.] -> classify in registers, ballot-compact events
+//   T3  anything else (line start/end, fixed fields, FORMAT suffixes, odd widths): general path
+#pragma once
+#include "bvcf_common.cuh"
+
+namespace bvcf {
+
+constexpr int WIN = 512;                 // bytes per warp step
+constexpr int STAGES = 8;                // ring stages per warp
+constexpr int RING = WIN * STAGES;       // 4 KiB per warp
+constexpr int PF = 6;                    // prefetch distance (windows in flight)
+constexpr int SCAN_WARPS = 8;            // warps per CTA
+constexpr uint64_t FS_NONE = ~0ull;
+
+struct ScanParams {
+  const uint8_t *in;        // region base (>= 16-byte aligned)
+  uint64_t begin, end;      // data lines live in [begin, end); in[end-1] == '\n'
+  uint64_t buf_len;         // readable bytes from `in`: multiple of 512 and >= round_up(end,512)+512
+  uint64_t a0;              // begin & ~511: ranges tile [a0, ...)
+  uint32_t range_bytes;     // multiple of 512
+  uint32_t r0, n_ranges;    // this launch handles global ranges [r0, r0+n_ranges)
+  uint32_t slots_per_range, evcap_words;
+  LineRec *recs;            // n_ranges * slots_per_range
+  uint32_t *range_nrec;     // records per range
+  uint32_t *range_nlines;   // all newline-terminated lines that start in the range
+  uint32_t *events;         // n_ranges * evcap_words
+  RunCounters *ctr;
+  int H, eol_width;
+};
+
+struct WarpState {
+  uint64_t line_start;
+  uint64_t fs;              // absolute offset of the first unprocessed field start, or FS_NONE (inside a field)
+  uint32_t col;             // field index of the field at fs == tabs of this line before fs
+  uint32_t an_lane, an_uni; // non-missing allele count: per-lane part and warp-uniform part
+  uint32_t ev_w, line_ev_start;  // event write cursor (words, relative to this range's slice)
+  uint32_t nrec, nlines;
+  uint32_t refpat;          // "0|0\t" or "0/0\t", adapted to the data
+  int mode;                 // 0 seeking the first line start, 1 inside an owned line, 2 done
+};
+
+__device__ __forceinline__ uint32_t bits_range16(int lo, int hi) {  // bits [lo, hi) clipped to [0,16)
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > 16 ? 16 : hi;
+  return hi <= lo ? 0u : (((1u << hi) - 1u) & ~((1u << lo) - 1u));
+}
+
+__device__ __forceinline__ uint32_t tok_code(uint32_t c) {  // single-character allele token
+  uint32_t d = c - '0';
+  return c == '.' ? EV_CODE_MISSING : (d <= 9 ? d : 0u);
+}
+
+// ---- T3: the general window ------------------------------------------------------------------------
+template <bool HAS_SAMPLES>
+__device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpState &st, const uint8_t *ring,
+                                                 uint32_t stage_off, const uint4 &v, uint64_t pos, uint64_t rend,
+                                                 int lane, LineRec *my_recs, uint32_t *my_events) {
+  const bool eol2 = p.eol_width == 2;
+  uint32_t tm = eq_mask16(v, 0x09090909u);
+  const uint32_t nm = eq_mask16(v, 0x0A0A0A0Au);
+
+  int seg_lo = 0;
+  if (st.mode == 1 && st.fs != FS_NONE && st.fs > pos) seg_lo = (int)(st.fs - pos);  // bytes before fs are consumed
+
+  while (seg_lo < WIN) {
+    // first newline at or after seg_lo
+    const int lo_l = seg_lo - lane * 16;
+    const uint32_t nm_l = nm & bits_range16(lo_l, 16);
+    const uint32_t ball = __ballot_sync(FULL, nm_l != 0);
+    int nl = WIN;
+    if (ball) {
+      const int l = __ffs(ball) - 1;
+      const uint32_t m = __shfl_sync(FULL, nm_l, l);
+      nl = l * 16 + __ffs(m) - 1;
+    }
+    if (st.mode == 0) {  // seeking the first owned line start
+      if (nl == WIN) return;
+      const uint64_t start = pos + nl + 1;
+      if (start >= rend) { st.mode = 2; return; }
+      st.mode = 1;
+      st.line_start = start; st.fs = start; st.col = 0;
+      st.an_lane = 0; st.an_uni = 0; st.line_ev_start = st.ev_w;
+      seg_lo = nl + 1;
+      continue;
+    }
+    // tabs of this segment: bytes [seg_lo, nl)
+    int tab_hi = nl;
+    if (eol2 && nl < WIN && nl > 0) tab_hi = nl - 1;  // row[:len-2] strips the byte before '\n' (main.go:535)
+    const uint32_t tm_l = tm & bits_range16(lo_l, tab_hi - lane * 16);
+    const uint32_t cnt = __popc(tm_l);
+    const uint32_t incl = warp_incl_scan(cnt, lane);
+    const uint32_t excl = incl - cnt;
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+
+    int last_end = -1;   // window-relative index of the '\t' that ends this lane's last field, if known
+    uint32_t fm_all = 0;
+    if (HAS_SAMPLES) {
+      // field starts owned by this lane: byte after a tab, or the carried-in start st.fs
+      const uint32_t prev_hi = __shfl_up_sync(FULL, tm_l >> 15, 1);
+      uint32_t fm = ((tm_l << 1) | (lane > 0 ? (prev_hi & 1u) : 0u)) & 0xFFFFu;
+      if (st.fs == pos + (uint64_t)seg_lo) {
+        const int sl = seg_lo - lane * 16;
+        if (sl >= 0 && sl < 16) fm |= 1u << sl;
+      }
+      fm_all = fm;
+      uint32_t evbuf[16];
+      int nev = 0;
+      while (fm) {
+        const int sl = __ffs(fm) - 1;
+        fm &= fm - 1;
+        const uint32_t fidx = st.col + excl + __popc(tm_l & ((1u << sl) - 1u));
+        last_end = -1;
+        if (fidx < 9) continue;
+        const uint32_t samp = fidx - 9;
+        const int s = lane * 16 + sl;
+        // 5 bytes at s from the ring (s+4 may reach into the next window: already loaded)
+        const uint32_t a = stage_off + (uint32_t)s;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(ring + ((a & ~3u) & (RING - 1)));
+        const uint32_t w1 = *reinterpret_cast<const uint32_t *>(ring + (((a & ~3u) + 4u) & (RING - 1)));
+        const uint32_t sh = (a & 3u) * 8u;
+        const uint32_t lo = __funnelshift_r(w0, w1, sh);
+        const uint32_t b0 = lo & 0xFF, b1 = (lo >> 8) & 0xFF, b2 = (lo >> 16) & 0xFF, b3 = lo >> 24;
+        const uint32_t b4 = (w1 >> sh) & 0xFF;
+        auto is_end = [&](uint32_t c, uint32_t nx) { return c == '\t' || c == '\n' || c == ':' || (eol2 && nx == '\n'); };
+        auto is_sep = [](uint32_t c) { return c == '|' || c == '/'; };
+        const bool e0 = is_end(b0, b1), e1 = is_end(b1, b2), e2 = is_end(b2, b3), e3 = is_end(b3, b4);
+        if (e0) {  // empty GT: one token "" (main.go:1143,1166)
+          st.an_lane += 1;
+          if (b0 == '\t') last_end = s;
+        } else if (!is_sep(b0) && e1) {  // haploid, one single-character token
+          const uint32_t c = tok_code(b0);
+          if (c == EV_CODE_MISSING) {
+            evbuf[nev++] = ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
+          } else {
+            st.an_lane += 1;
+            if (c) evbuf[nev++] = ev_make(samp, c, EV_CODE_ABSENT);
+          }
+          if (b1 == '\t') last_end = s + 1;
+        } else if (!is_sep(b0) && is_sep(b1) && !e2 && !is_sep(b2) && e3) {  // diploid x|y or x/y
+          const uint32_t c1 = tok_code(b0), c2 = tok_code(b2);
+          if (c1 == EV_CODE_MISSING || c2 == EV_CODE_MISSING) {
+            evbuf[nev++] = ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
+          } else {
+            st.an_lane += 2;
+            if (c1 | c2) evbuf[nev++] = ev_make(samp, c1, c2);
+          }
+          if (b3 == '\t') last_end = s + 3;
+        } else {  // general grammar: resolved exactly by the rows kernel
+          evbuf[nev++] = samp | EV_COMPLEX;
+          evbuf[nev++] = EV_OFFSET_TAG | (uint32_t)(pos + (uint64_t)s - st.line_start);
+        }
+      }
+      // ordered compaction of this segment's events
+      const uint32_t eincl = warp_incl_scan((uint32_t)nev, lane);
+      const uint32_t etot = __shfl_sync(FULL, eincl, 31);
+      if (etot) {
+        if (st.ev_w + etot <= p.evcap_words) {
+          uint32_t *dst = my_events + st.ev_w + (eincl - nev);
+          for (int k = 0; k < nev; k++) dst[k] = evbuf[k];
+        } else if (lane == 0) {
+          p.ctr->ev_overflow = 1;
+        }
+        st.ev_w += etot;
+      }
+    }
+    st.col += total;
+
+    if (nl < WIN) {  // the line ends inside this window
+      st.nlines++;
+      const uint32_t an = warp_sum(st.an_lane) + st.an_uni;
+      if (st.col == (uint32_t)(p.H - 1)) {
+        if (st.nrec < p.slots_per_range) {
+          if (lane == 0) {
+            LineRec r;
+            r.start = st.line_start;
+            r.len = (uint32_t)(pos + nl + 1 - st.line_start);
+            r.an = an;
+            r.ev_start = st.line_ev_start;
+            r.ev_count = st.ev_w - st.line_ev_start;
+            r.ord = st.nlines - 1;
+            r.pad = 0;
+            my_recs[st.nrec] = r;
+          }
+        } else if (lane == 0) {
+          p.ctr->slot_overflow = 1;
+        }
+        st.nrec++;
+      } else {
+        st.ev_w = st.line_ev_start;  // wrong field count: the line yields nothing (main.go:449)
+      }
+      const uint64_t start = pos + nl + 1;
+      if (start >= rend) { st.mode = 2; return; }
+      st.line_start = start; st.fs = start; st.col = 0;
+      st.an_lane = 0; st.an_uni = 0; st.line_ev_start = st.ev_w;
+      seg_lo = nl + 1;
+      continue;
+    }
+
+    // segment runs to the window end: hand the field phase over to the next window
+    uint64_t nfs = FS_NONE;
+    if (HAS_SAMPLES) {
+      const uint32_t last_tab = __shfl_sync(FULL, tm_l >> 15, 31) & 1u;
+      if (last_tab) {
+        nfs = pos + WIN;
+      } else {
+        const uint32_t have = __ballot_sync(FULL, fm_all != 0);
+        if (have) {
+          const int l = 31 - __clz(have);
+          const int le = __shfl_sync(FULL, last_end, l);
+          if (le >= WIN) { nfs = pos + (uint64_t)le + 1; st.col += 1; }  // pre-count that tab
+        }
+      }
+    }
+    st.fs = nfs;
+    return;
+  }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+template <bool HAS_SAMPLES>
+__global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(const ScanParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rl = blockIdx.x * SCAN_WARPS + warp;  // range index within this launch
+  if (rl >= p.n_ranges) return;
+  const uint64_t rstart = p.a0 + (uint64_t)(p.r0 + rl) * p.range_bytes;  // 512-aligned
+  uint64_t rend = rstart + p.range_bytes;
+  if (rend > p.end) rend = p.end;
+  LineRec *my_recs = p.recs + (size_t)rl * p.slots_per_range;
+  uint32_t *my_events = p.events + (size_t)rl * p.evcap_words;
+
+  WarpState st;
+  st.nrec = 0; st.nlines = 0; st.ev_w = 0; st.line_ev_start = 0;
+  st.an_lane = 0; st.an_uni = 0; st.col = 0;
+  st.refpat = 0x09307C30u;  // "0|0\t"
+  st.fs = FS_NONE; st.line_start = 0;
+  st.mode = 0;
+  if (rstart >= p.end) {
+    st.mode = 2;
+  } else if (rstart <= p.begin) {  // first range: the region starts with a line
+    st.mode = 1; st.line_start = p.begin; st.fs = p.begin;
+  } else if (p.in[rstart - 1] == '\n') {
+    st.mode = 1; st.line_start = rstart; st.fs = rstart;
+  }
+
+  uint8_t *ring = smem + warp * RING;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  auto issue = [&](uint32_t it) {
+    const uint64_t a = rstart + (uint64_t)it * WIN;
+    if (a + WIN <= p.buf_len) {
+      const uint32_t dst = ring_s + ((it & (STAGES - 1)) * WIN) + lane * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(p.in + a + lane * 16));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  if (st.mode != 2) {
+#pragma unroll
+    for (int k = 0; k < PF; k++) issue(k);
+    for (uint32_t it = 0;; ++it) {
+      issue(it + PF);
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(PF - 1));
+      __syncwarp();
+      const uint64_t pos = rstart + (uint64_t)it * WIN;
+      if (pos + 2 * WIN > p.buf_len) break;  // safety: never run off the padded buffer
+      if (st.mode == 0 && pos >= rend) break;  // no line starts in this range
+      const uint32_t stage_off = (it & (STAGES - 1)) * WIN;
+      const uint4 v = *reinterpret_cast<const uint4 *>(ring + stage_off + lane * 16);
+      bool handled = false;
+      if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (st.fs - pos) < 4ull) {
+        const uint32_t w4 = *reinterpret_cast<const uint32_t *>(ring + ((stage_off + lane * 16 + 16) & (RING - 1)));
+        const uint32_t sh = (uint32_t)(st.fs - pos) * 8u;
+        const uint32_t W0 = __funnelshift_r(v.x, v.y, sh), W1 = __funnelshift_r(v.y, v.z, sh);
+        const uint32_t W2 = __funnelshift_r(v.z, v.w, sh), W3 = __funnelshift_r(v.w, w4, sh);
+        const uint32_t rp = st.refpat;
+        // T1: every field of the window is the reference genotype
+        if (__all_sync(FULL, ((W0 ^ rp) | (W1 ^ rp) | (W2 ^ rp) | (W3 ^ rp)) == 0)) {
+          st.an_uni += 256; st.col += 128; st.fs += WIN;
+          handled = true;
+        } else {
+          // T2: every field is x|y\t or x/y\t with single-character alleles
+          const uint32_t Ws[4] = {W0, W1, W2, W3};
+          bool ok = true;
+          uint32_t ev[4];
+          uint32_t nev = 0, miss = 0;
+          const uint32_t samp0 = st.col - 9 + lane * 4;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t W = Ws[j];
+            const uint32_t stc = W & 0xFF00FF00u;
+            const uint32_t x = W & 0xFF, y = (W >> 16) & 0xFF;
+            const uint32_t dx = x - '0', dy = y - '0';
+            const bool mx = x == '.', my = y == '.';
+            ok = ok && (stc == 0x09007C00u || stc == 0x09002F00u) && (dx <= 9 || mx) && (dy <= 9 || my);
+            uint32_t e = 0;
+            if (mx || my) { e = ev_make(samp0 + j, EV_CODE_MISSING, EV_CODE_MISSING); miss++; }
+            else if (dx | dy) e = ev_make(samp0 + j, dx, dy);
+            ev[j] = e;
+            nev += e != 0;
+          }
+          if (__all_sync(FULL, ok)) {
+            const uint32_t eincl = warp_incl_scan(nev, lane);
+            const uint32_t etot = __shfl_sync(FULL, eincl, 31);
+            if (st.ev_w + etot <= p.evcap_words) {
+              uint32_t *dst = my_events + st.ev_w + (eincl - nev);
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+                if (ev[j]) *dst++ = ev[j];
+            } else if (lane == 0) {
+              p.ctr->ev_overflow = 1;
+            }
+            st.ev_w += etot;
+            st.an_uni += 256; st.an_lane -= 2 * miss;
+            st.col += 128; st.fs += WIN;
+            st.refpat = 0x09300030u | (__shfl_sync(FULL, W0, 0) & 0xFF00u);  // follow the data's separator
+            handled = true;
+          }
+        }
+      }
+      if (!handled) {
+        scan_window_general<HAS_SAMPLES>(p, st, ring, stage_off, v, pos, rend, lane, my_recs, my_events);
+        if (st.mode == 2) break;
+      }
+      __syncwarp();  // everyone is done with this stage before it is refilled
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  if (lane == 0) {
+    p.range_nrec[rl] = st.nrec < p.slots_per_range ? st.nrec : p.slots_per_range;  // overflow is flagged
+    p.range_nlines[rl] = st.nlines;
+  }
+}
+
+}  // namespace bvcf

@@ -1,0 +1,450 @@
+"""Host side of the B200 transform, mirroring the reference's own interface for this path.
+
+Reference (Go, /root/reference/main.go)      ->  here
+  type Config            main.go:63-80       ->  Config
+  setup(args)            main.go:82-126      ->  setup(args)
+  header / stringHeader  main.go:219-239     ->  header(config) / string_header(config)
+  readVcf(cfg, r, w)     main.go:241-396     ->  read_vcf(config, reader, writer)
+  processLines(...)      main.go:476-721     ->  Transformer (libbvcf: CUDA kernels behind the C ABI)
+
+The per-line work never runs on the CPU: Transformer raises if libbvcf.so or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from dataclasses import dataclass, field
+from typing import BinaryIO, Dict, List, Optional, Sequence
+
+from . import _lib
+from ._lib import BvcfError, CChunkStats, CConfig, CDiag, CDosageBatch, CKernelTimes, check
+
+# message table main.go:41-51, indexed by BVCF_DIAG_* code
+DIAG_TEXT = {
+    1: "REF == ALT",
+    2: "ALT not ACTG",
+    3: "1st base REF != ALT",
+    4: "Invalid POS",
+    5: "1st base ALT != REF",
+    6: "Mixed indel/snp sites not supported",
+}
+
+# parse.Header of github.com/bystrogenomics/bystro-utils (pinned by main_test.go:79-80)
+PARSE_HEADER = ["chrom", "pos", "type", "ref", "alt", "trTv", "heterozygotes", "heterozygosity", "homozygotes",
+                "homozygosity", "missingGenos", "missingness", "ac", "an", "sampleMaf"]
+
+
+class NotAVcfError(ValueError):
+    """log.Fatal("Not a VCF file") main.go:263 / log.Fatal("No header found") main.go:293"""
+
+
+@dataclass
+class Config:
+    """main.go:63-80.  Field names follow the reference's flags."""
+
+    inPath: str = ""
+    outPath: str = ""
+    noOut: bool = False
+    dosageMatrixOutPath: str = ""
+    sampleListPath: str = ""
+    famPath: str = ""
+    errPath: str = ""
+    emptyField: str = "!"
+    fieldDelimiter: str = ";"
+    keepID: bool = False
+    keepInfo: bool = False
+    keepQual: bool = False
+    keepPos: bool = False
+    cpuProfile: str = ""
+    allowedFilters: Optional[Dict[str, bool]] = None   # None == nil map: every FILTER allowed
+    excludedFilters: Optional[Dict[str, bool]] = None  # None == nil map: nothing excluded
+    # not in the reference: which GPU, chunking
+    device: int = 0
+    chunkBytes: int = 64 << 20
+    normalizeHeader: bool = True
+
+
+_STRING_FLAGS = {"in": "inPath", "fam": "famPath", "err": "errPath", "out": "outPath", "dosageOutput": "dosageMatrixOutPath",
+                 "sample": "sampleListPath", "emptyField": "emptyField", "fieldDelimiter": "fieldDelimiter",
+                 "cpuProfile": "cpuProfile", "allowFilter": None, "excludeFilter": None}
+_BOOL_FLAGS = {"noOut": "noOut", "keepId": "keepID", "keepQual": "keepQual", "keepPos": "keepPos", "keepInfo": "keepInfo"}
+
+
+def setup(args: Optional[Sequence[str]] = None) -> Config:
+    """main.go:82-126 with Go `flag` syntax: -x/--x, --x=v / --x v, bool flags --x / --x=true|false,
+    parsing stops at the first non-flag argument or after "--"."""
+    import sys
+
+    a = list(sys.argv[1:] if args is None else args)
+    cfg = Config()
+    allow, exclude = "PASS,.", ""
+    i = 0
+    while i < len(a):
+        s = a[i]
+        if len(s) < 2 or s[0] != "-":
+            break
+        if s == "--":
+            break
+        name = s[2:] if s.startswith("--") else s[1:]
+        if not name or name[0] in "-=":
+            raise ValueError(f"bad flag syntax: {s}")
+        val = None
+        if "=" in name:
+            name, val = name.split("=", 1)
+        if name in _BOOL_FLAGS:
+            if val is None:
+                b = True
+            else:
+                lv = val
+                if lv in ("1", "t", "T", "true", "TRUE", "True"):
+                    b = True
+                elif lv in ("0", "f", "F", "false", "FALSE", "False"):
+                    b = False
+                else:
+                    raise ValueError(f"invalid boolean value {val!r} for -{name}")
+            setattr(cfg, _BOOL_FLAGS[name], b)
+        elif name in _STRING_FLAGS:
+            if val is None:
+                i += 1
+                if i >= len(a):
+                    raise ValueError(f"flag needs an argument: -{name}")
+                val = a[i]
+            if name == "allowFilter":
+                allow = val
+            elif name == "excludeFilter":
+                exclude = val
+            else:
+                setattr(cfg, _STRING_FLAGS[name], val)
+        else:
+            raise ValueError(f"flag provided but not defined: -{name}")
+        i += 1
+    if allow != "" and allow != "*":  # main.go:108-114
+        cfg.allowedFilters = {v.strip(): True for v in allow.split(",")}
+    if exclude != "":  # main.go:117-123
+        cfg.excludedFilters = {v.strip(): True for v in exclude.split(",")}
+    return cfg
+
+
+def header(config: Config) -> List[str]:
+    """main.go:223-239"""
+    h = list(PARSE_HEADER)
+    if config.keepPos:
+        h.append("vcfPos")
+    if config.keepID:
+        h.append("id")
+    if config.keepInfo:
+        h += ["alleleIdx", "info"]
+    return h
+
+
+def string_header(config: Config) -> str:
+    """main.go:219-221"""
+    return "\t".join(header(config))
+
+
+@dataclass
+class ChunkResult:
+    tsv: bytes
+    n_lines: int
+    n_records: int
+    n_rows: int
+    diags: List[tuple] = field(default_factory=list)
+    loci: List[bytes] = field(default_factory=list)
+    dosage: Optional[object] = None  # numpy int8 [rows, samples]
+    retries: int = 0
+
+
+class Transformer:
+    """One GPU's processLines: owns a bvcf_ctx.  Not thread-safe (one host thread per GPU)."""
+
+    def __init__(self, config: Config, eol_width: int = 1, n_slots: int = 3, max_chunk_bytes: int = 0,
+                 resident_subchunk_bytes: int = 0):
+        L = _lib.lib()
+        self._L = L
+        self._keep = []
+        c = CConfig()
+        c.empty_field = config.emptyField.encode()
+        c.field_delim = config.fieldDelimiter.encode()
+        c.keep_id, c.keep_info, c.keep_pos = int(config.keepID), int(config.keepInfo), int(config.keepPos)
+        c.want_tsv = int(not config.noOut)
+        c.want_dosage = int(config.dosageMatrixOutPath != "")
+        if config.allowedFilters is None:
+            c.n_allow, c.allow = -1, None
+        else:
+            vals = [k.encode() for k, v in config.allowedFilters.items() if v]
+            arr = (C.c_char_p * max(1, len(vals)))(*vals)
+            self._keep.append(arr)
+            c.allow, c.n_allow = arr, len(vals)
+        if not config.excludedFilters:
+            c.n_exclude, c.exclude = 0, None
+        else:
+            vals = [k.encode() for k, v in config.excludedFilters.items() if v]
+            arr = (C.c_char_p * max(1, len(vals)))(*vals)
+            self._keep.append(arr)
+            c.exclude, c.n_exclude = arr, len(vals)
+        c.eol_width = eol_width
+        c.normalize_dots = int(config.normalizeHeader)
+        c.n_slots = n_slots
+        c.max_chunk_bytes = max_chunk_bytes
+        c.resident_subchunk_bytes = resident_subchunk_bytes
+        self._cconfig = c
+        self.config = config
+        self.n_slots = n_slots
+        ctx = C.c_void_p()
+        rc = L.bvcf_create(C.byref(ctx), config.device, C.byref(c))
+        if rc != 0:
+            raise BvcfError(f"bvcf_create failed ({rc}): {L.bvcf_strerror(rc).decode()} -- a CUDA device is required, "
+                            "there is no CPU fallback")
+        self._ctx = ctx
+        self.n_samples = 0
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.bvcf_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- header ---------------------------------------------------------------------------------
+    def set_header(self, chrom_line: bytes) -> None:
+        check(self._L.bvcf_set_header(self._ctx, chrom_line, len(chrom_line)), self._ctx, "bvcf_set_header")
+        n = len(chrom_line.rstrip(b"\r\n").split(b"\t"))
+        self.n_samples = max(n - 9, 0)
+
+    # -- streaming path ---------------------------------------------------------------------------
+    def submit(self, seq: int, chunk) -> None:
+        """chunk: bytes-like or (address, length).  It must stay alive until collect(seq)."""
+        if isinstance(chunk, tuple):
+            addr, n = chunk
+        else:
+            n = len(chunk)
+            if isinstance(chunk, bytes):
+                addr = C.cast(C.c_char_p(chunk), C.c_void_p).value
+            else:
+                addr = C.addressof((C.c_char * n).from_buffer(chunk)) if n else 0
+            self._keep_chunk = getattr(self, "_keep_chunk", {})
+            self._keep_chunk[seq] = chunk
+        check(self._L.bvcf_submit(self._ctx, seq, addr, n), self._ctx, "bvcf_submit")
+
+    def collect(self, seq: int, copy: bool = True) -> ChunkResult:
+        import numpy as np
+
+        tsv = C.c_void_p()
+        n = C.c_size_t()
+        dos = CDosageBatch()
+        dg = C.POINTER(CDiag)()
+        nd = C.c_size_t()
+        st = CChunkStats()
+        check(self._L.bvcf_collect(self._ctx, seq, C.byref(tsv), C.byref(n), C.byref(dos), C.byref(dg), C.byref(nd),
+                                   C.byref(st)), self._ctx, "bvcf_collect")
+        out = ChunkResult(tsv=C.string_at(tsv, n.value) if n.value else b"", n_lines=st.n_lines,
+                          n_records=st.n_records, n_rows=st.n_rows, retries=st.retries)
+        out.diags = [(dg[i].line_no, dg[i].alt_no, dg[i].code) for i in range(nd.value)]
+        if dos.n_rows:
+            nr, ns = dos.n_rows, dos.n_samples
+            out.dosage = np.frombuffer(C.string_at(dos.dosage, nr * ns), dtype=np.int8).reshape(nr, ns).copy()
+            offs = [dos.loci_off[i] for i in range(nr + 1)]
+            blob = C.string_at(dos.loci, offs[-1])
+            out.loci = [blob[offs[i]:offs[i + 1]] for i in range(nr)]
+        check(self._L.bvcf_release(self._ctx, seq), self._ctx, "bvcf_release")
+        if hasattr(self, "_keep_chunk"):
+            self._keep_chunk.pop(seq, None)
+        return out
+
+    def process(self, block: bytes) -> ChunkResult:
+        """One newline-aligned block of data lines in, rows out (blocking convenience)."""
+        self.submit(0, block)
+        return self.collect(0)
+
+    # -- device-resident path -----------------------------------------------------------------------
+    def resident_alloc(self, in_bytes: int, out_capacity: int):
+        d_in, d_out = C.c_void_p(), C.c_void_p()
+        check(self._L.bvcf_resident_alloc(self._ctx, in_bytes, out_capacity, C.byref(d_in), C.byref(d_out)), self._ctx,
+              "bvcf_resident_alloc")
+        return d_in.value, d_out.value
+
+    def resident_upload(self, offset: int, data) -> None:
+        if isinstance(data, tuple):
+            addr, n = data
+        else:
+            n = len(data)
+            addr = C.cast(C.c_char_p(bytes(data)), C.c_void_p).value if not isinstance(data, bytes) else \
+                C.cast(C.c_char_p(data), C.c_void_p).value
+        check(self._L.bvcf_resident_upload(self._ctx, offset, addr, n), self._ctx, "bvcf_resident_upload")
+
+    def resident_run(self, length: int, want_times: bool = True):
+        st, kt = CChunkStats(), CKernelTimes()
+        check(self._L.bvcf_resident_run(self._ctx, length, C.byref(st), C.byref(kt) if want_times else None), self._ctx,
+              "bvcf_resident_run")
+        stats = {k: getattr(st, k) for k, _ in CChunkStats._fields_}
+        times = {k: getattr(kt, k) for k, _ in CKernelTimes._fields_}
+        return stats, times
+
+    def resident_download(self, offset: int, length: int) -> bytes:
+        buf = C.create_string_buffer(max(length, 1))
+        check(self._L.bvcf_resident_download(self._ctx, offset, buf, length), self._ctx, "bvcf_resident_download")
+        return buf.raw[:length]
+
+    def resident_line_index(self, cap: int):
+        import numpy as np
+
+        starts = np.zeros(cap, dtype=np.uint64)
+        lens = np.zeros(cap, dtype=np.uint32)
+        an = np.zeros(cap, dtype=np.uint32)
+        n = C.c_size_t()
+        check(self._L.bvcf_resident_line_index(
+            self._ctx, starts.ctypes.data_as(C.POINTER(C.c_uint64)), lens.ctypes.data_as(C.POINTER(C.c_uint32)),
+            an.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(n)), self._ctx, "bvcf_resident_line_index")
+        k = min(cap, n.value)
+        return starts[:k], lens[:k], an[:k], n.value
+
+    @property
+    def launches(self) -> int:
+        return self._L.bvcf_launch_count(self._ctx)
+
+
+# ---- stream driver ------------------------------------------------------------------------------------
+
+def find_end_of_line(first: bytes):
+    """parse.FindEndOfLine (main.go:250): (eol byte, numChars, first line without EOL, bytes consumed)."""
+    m = re.search(rb"[\r\n]", first)
+    if not m:
+        return None
+    i = m.start()
+    if first[i:i + 1] == b"\r":
+        if first[i + 1:i + 2] == b"\n":
+            return b"\n", 2, first[:i], i + 2
+        return b"\r", 1, first[:i], i + 1
+    return b"\n", 1, first[:i], i + 1
+
+
+def parse_preamble(data: bytes):
+    """main.go:250-294: version-line check, locate the #CHROM line.
+    Returns (eol_width, chrom_line_without_eol, offset_of_first_data_line) or raises NotAVcfError.
+    `data` only has to hold the meta lines + header."""
+    r = find_end_of_line(data)
+    if r is None:
+        raise NotAVcfError("Not a VCF file")
+    eol, width, version, p = r
+    if b"##fileformat=VCFv4" not in version:  # regexp.MatchString main.go:256
+        raise NotAVcfError("Not a VCF file")
+    if eol != b"\n":
+        raise NotAVcfError("bare-CR line endings are not supported by the GPU path")
+    while True:
+        e = data.find(eol, p)
+        if e < 0:
+            raise NotAVcfError("No header found")
+        row = data[p:e + 1]
+        content = row[:len(row) - width] if len(row) >= width else b""
+        if content.split(b"\t")[0] == b"#CHROM":
+            return width, content, e + 1
+        p = e + 1
+
+
+def write_sample_list(config: Config, chrom_line: bytes, normalize: bool = True) -> None:
+    """writeSampleListIfWanted / makeSampleList main.go:398-445"""
+    if not config.sampleListPath:
+        return
+    f = chrom_line.split(b"\t")
+    with open(config.sampleListPath, "wb") as fh:
+        if len(f) >= 10:
+            for s in f[9:]:
+                fh.write((s.replace(b".", b"_") if normalize else s) + b"\n")
+
+
+def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], transformer: Optional[Transformer] = None,
+             diag_sink=None) -> dict:
+    """readVcf (main.go:241-396) on the GPU: header discovery on the host, every data line on the device.
+
+    reader/writer are binary file objects (the reference's *bufio.Reader / *bufio.Writer).  Rows are
+    written in input order.  The TSV header line is NOT written here (main() does that, main.go:199)."""
+    chunk_bytes = max(int(config.chunkBytes), 1 << 16)
+    head = reader.read(1 << 20)
+    while True:  # make sure the whole preamble (meta lines + #CHROM line) is in `head`
+        try:
+            width, chrom_line, off = parse_preamble(head)
+            break
+        except NotAVcfError as e:
+            first_line_done = re.search(rb"[\r\n]", head) is not None
+            if str(e) == "Not a VCF file" and first_line_done:
+                raise
+            more = reader.read(1 << 20)
+            if not more:
+                raise
+            head += more
+    own = transformer is None
+    tr = transformer or Transformer(config, eol_width=width, max_chunk_bytes=2 * chunk_bytes + (64 << 20))
+    totals = {"n_lines": 0, "n_records": 0, "n_rows": 0, "out_bytes": 0, "in_bytes": 0}
+    arrow = None
+    try:
+        tr.set_header(chrom_line)
+        if not config.noOut:
+            write_sample_list(config, chrom_line, config.normalizeHeader)
+        if config.dosageMatrixOutPath:
+            from .dosage import DosageWriter  # Arrow IPC framing
+
+            names = [s.replace(b".", b"_") if config.normalizeHeader else s for s in chrom_line.split(b"\t")[9:]]
+            arrow = DosageWriter(config.dosageMatrixOutPath, names)
+        carry = head[off:]
+        seq_in = seq_out = 0
+        pending = {}
+
+        def drain(upto: int):
+            nonlocal seq_out
+            while seq_out < upto:
+                res = tr.collect(seq_out)
+                pending.pop(seq_out, None)
+                if writer is not None and not config.noOut:
+                    writer.write(res.tsv)
+                if arrow is not None and res.dosage is not None:
+                    arrow.write(res.loci, res.dosage)
+                if diag_sink is not None:
+                    for d in res.diags:
+                        diag_sink(totals["n_lines"] + d[0], d[1], d[2])
+                totals["n_lines"] += res.n_lines
+                totals["n_records"] += res.n_records
+                totals["n_rows"] += res.n_rows
+                totals["out_bytes"] += len(res.tsv)
+                seq_out += 1
+
+        eof = False
+        while not eof:
+            data = reader.read(chunk_bytes)
+            if not data:
+                eof = True
+                block = carry
+                carry = b""
+                cut = block.rfind(b"\n")
+                block = block[:cut + 1]  # an unterminated last line is dropped (main.go:354-357)
+            else:
+                block = carry + data if carry else data
+                cut = block.rfind(b"\n")
+                if cut < 0:
+                    carry = block
+                    continue
+                carry = block[cut + 1:]
+                block = block[:cut + 1]
+            if block:
+                if seq_in - seq_out >= tr.n_slots:
+                    drain(seq_out + 1)
+                pending[seq_in] = block
+                tr.submit(seq_in, block)
+                totals["in_bytes"] += len(block)
+                seq_in += 1
+        drain(seq_in)
+    finally:
+        if arrow is not None:
+            arrow.close()
+        if own:
+            tr.close()
+    return totals
