@@ -75,7 +75,7 @@ class CKernelTimes(C.Structure):
 SYMBOLS = [
     "bvcf_create", "bvcf_destroy", "bvcf_header_line", "bvcf_set_header", "bvcf_host_alloc", "bvcf_host_free",
     "bvcf_submit", "bvcf_collect", "bvcf_release", "bvcf_resident_alloc", "bvcf_resident_upload",
-    "bvcf_resident_run", "bvcf_resident_download", "bvcf_resident_line_index", "bvcf_strerror",
+    "bvcf_resident_run", "bvcf_resident_download", "bvcf_resident_peek", "bvcf_resident_line_index", "bvcf_strerror",
     "bvcf_last_error", "bvcf_abi_version", "bvcf_launch_count",
 ]
 
@@ -120,6 +120,8 @@ def lib():
     L.bvcf_resident_run.argtypes = [vp, sz, C.POINTER(CChunkStats), C.POINTER(CKernelTimes)]
     L.bvcf_resident_download.restype = C.c_int
     L.bvcf_resident_download.argtypes = [vp, sz, vp, sz]
+    L.bvcf_resident_peek.restype = C.c_int
+    L.bvcf_resident_peek.argtypes = [vp, sz, vp, sz]
     L.bvcf_resident_line_index.restype = C.c_int
     L.bvcf_resident_line_index.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), sz,
                                            C.POINTER(sz)]

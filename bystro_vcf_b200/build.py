@@ -20,8 +20,9 @@ NVCC_FLAGS = [
 ]
 
 TARGETS = {
-    "libbvcf.so": ["bvcf_api.cu"],
-    "libbvcfsynth.so": ["bvcf_synth.cu"],
+    "libbvcf.so": (["bvcf_api.cu"], []),
+    # host and device must produce the same bytes: no FMA contraction in the generator
+    "libbvcfsynth.so": (["bvcf_synth.cu"], ["-fmad=false"]),
 }
 
 
@@ -42,14 +43,14 @@ def _stale(out: str, srcs) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> None:
     os.makedirs(LIBDIR, exist_ok=True)
-    for lib, srcs in TARGETS.items():
+    for lib, (srcs, extra) in TARGETS.items():
         srcs = [os.path.join(CSRC, s) for s in srcs]
         if not all(os.path.exists(s) for s in srcs):
             continue
         out = os.path.join(LIBDIR, lib)
         if not force and not _stale(out, srcs):
             continue
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + extra + ["-o", out] + srcs
         print("[build]", " ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
 

@@ -174,13 +174,9 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
                      uint8_t *d_loci, uint32_t *d_diags, std::vector<StageEvents> *timing) {
   const DevCfg &dc = ctx->dcfg;
   const uint64_t total_ranges = (len + sc.range_bytes - 1) / sc.range_bytes;
-  static bool attr_set = false;
   const int smem = SCAN_WARPS * RING;
-  if (!attr_set) {
-    cudaFuncSetAttribute(bvcf_scan_genotype_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(bvcf_scan_genotype_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(bvcf_scan_genotype_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(bvcf_scan_genotype_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
   for (uint64_t r0 = 0; r0 < total_ranges; r0 += sc.n_ranges) {
@@ -706,6 +702,14 @@ int bvcf_resident_download(bvcf_ctx *ctx, size_t offset, void *host, size_t len)
   if (offset + len > ctx->r_out.cap) return BVCF_E_ARG;
   cudaSetDevice(ctx->device);
   CK(cudaMemcpy(host, (uint8_t *)ctx->r_out.p + offset, len, cudaMemcpyDeviceToHost));
+  return BVCF_OK;
+}
+
+int bvcf_resident_peek(bvcf_ctx *ctx, size_t offset, void *host, size_t len) {
+  if (!ctx || !host) return BVCF_E_ARG;
+  if (offset + len > ctx->r_in.cap) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaMemcpy(host, (uint8_t *)ctx->r_in.p + offset, len, cudaMemcpyDeviceToHost));
   return BVCF_OK;
 }
 

@@ -295,6 +295,15 @@ class Transformer:
         check(self._L.bvcf_resident_download(self._ctx, offset, buf, length), self._ctx, "bvcf_resident_download")
         return buf.raw[:length]
 
+    def resident_peek(self, offset: int, length: int, addr: int = 0) -> bytes:
+        """bytes of the resident INPUT region (device-generated workloads); into `addr` when given."""
+        if addr:
+            check(self._L.bvcf_resident_peek(self._ctx, offset, addr, length), self._ctx, "bvcf_resident_peek")
+            return b""
+        buf = C.create_string_buffer(max(length, 1))
+        check(self._L.bvcf_resident_peek(self._ctx, offset, buf, length), self._ctx, "bvcf_resident_peek")
+        return buf.raw[:length]
+
     def resident_line_index(self, cap: int):
         import numpy as np
 

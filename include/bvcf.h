@@ -147,6 +147,8 @@ int bvcf_resident_upload(bvcf_ctx *ctx, size_t offset, const void *host, size_t 
 int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_kernel_times *times);
 /* Copy `len` output bytes starting at `offset` back to the host. */
 int bvcf_resident_download(bvcf_ctx *ctx, size_t offset, void *host, size_t len);
+/* Copy `len` bytes of the resident INPUT region back to the host (device-generated workloads). */
+int bvcf_resident_peek(bvcf_ctx *ctx, size_t offset, void *host, size_t len);
 
 /* ---- introspection ----------------------------------------------------------------------- */
 
