@@ -35,8 +35,9 @@ struct Scratch {
   uint64_t sub_bytes = 0;     // sub-chunk size (multiple of range_bytes)
   uint32_t range_bytes = 0, n_ranges = 0, slots = 0, evcap_words = 0;
   uint64_t max_records = 0;
+  uint64_t row_cap = 0;       // RowDesc slots (rows one sub-chunk may emit)
   DevBuf recs, range_nrec, range_nlines, rec_base, line_base, events, dense, line_bytes, line_rows, line_off,
-      row_off, partial;
+      row_off, partial, stats1, row_desc;
 };
 
 struct Slot {
@@ -156,16 +157,22 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
   if ((rc = dev_reserve(ctx, sc.line_off, sc.max_records * 8))) return rc;
   if ((rc = dev_reserve(ctx, sc.row_off, sc.max_records * 8))) return rc;
   if ((rc = dev_reserve(ctx, sc.partial, 2 * PFX_BLOCKS * 8))) return rc;
+  if (ctx->dcfg.n_samples > 0) {
+    sc.row_cap = std::max<uint64_t>(sc.row_cap, sc.max_records + sc.max_records / 4 + 1024);
+    if ((rc = dev_reserve(ctx, sc.stats1, sc.max_records * sizeof(GtStats)))) return rc;
+    if ((rc = dev_reserve(ctx, sc.row_desc, sc.row_cap * sizeof(RowDesc)))) return rc;
+  }
   return 0;
 }
 void scratch_free(Scratch &sc) {
   for (DevBuf *b : {&sc.recs, &sc.range_nrec, &sc.range_nlines, &sc.rec_base, &sc.line_base, &sc.events, &sc.dense,
-                    &sc.line_bytes, &sc.line_rows, &sc.line_off, &sc.row_off, &sc.partial})
+                    &sc.line_bytes, &sc.line_rows, &sc.line_off, &sc.row_off, &sc.partial, &sc.stats1, &sc.row_desc})
     dev_free(*b);
 }
 
+constexpr int N_STAGE_EV = 7;
 struct StageEvents {  // optional per-stage timing of one sub-chunk
-  cudaEvent_t e[5];
+  cudaEvent_t e[N_STAGE_EV];
 };
 
 // Enqueue the whole pipeline for data lines in [0, len) of d_in.  Never synchronises.
@@ -185,7 +192,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     if (timing) {
       timing->emplace_back();
       se = &timing->back();
-      for (int i = 0; i < 5; i++) {
+      for (int i = 0; i < N_STAGE_EV; i++) {
         if (ctx->ev_pool.empty()) {
           cudaEvent_t e;
           CK(cudaEventCreate(&e));
@@ -228,30 +235,50 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     bvcf_compact_lines_kernel<<<(nr + 7) / 8, 256, 0, st>>>(cp);
     ctx->launches += 4;
     if (se) CK(cudaEventRecord(se->e[2], st));
-    // 4. size pass
+    const unsigned wgrid = (unsigned)n_sm * 8;
+    // 3b. ALT #1 genotype summary per record (warp per record)
+    if (dc.n_samples > 0) {
+      StatsParams tp{};
+      tp.in = d_in; tp.cfg = dc; tp.lines = cp.dense; tp.events = sp.events; tp.stats1 = (GtStats *)sc.stats1.p; tp.ctr = d_ctr;
+      bvcf_line_stats_kernel<<<wgrid, 256, 0, st>>>(tp);
+      ctx->launches++;
+    }
+    if (se) CK(cudaEventRecord(se->e[3], st));
+    // 4. size pass (thread per record)
     RowsParams rp{};
-    rp.in = d_in; rp.cfg = dc; rp.lines = cp.dense; rp.events = sp.events;
+    rp.in = d_in; rp.cfg = dc; rp.lines = cp.dense; rp.events = sp.events; rp.stats1 = (const GtStats *)sc.stats1.p;
     rp.line_bytes = (uint32_t *)sc.line_bytes.p; rp.line_rows = (uint32_t *)sc.line_rows.p;
     rp.line_off = (uint64_t *)sc.line_off.p; rp.row_off = (uint64_t *)sc.row_off.p;
     rp.out = d_out; rp.out_cap = out_cap; rp.ctr = d_ctr;
-    rp.dosage = d_dosage; rp.dosage_cap_rows = dosage_cap_rows; rp.loci = d_loci; rp.loci_stride = LOCI_STRIDE;
+    rp.row_desc = (RowDesc *)sc.row_desc.p; rp.row_desc_cap = dc.n_samples > 0 ? sc.row_cap : 0;
+    rp.dosage_cap_rows = dosage_cap_rows; rp.loci = d_loci; rp.loci_stride = LOCI_STRIDE;
     rp.diags = d_diags; rp.diag_cap = DIAG_CAP;
-    const unsigned rgrid = (unsigned)n_sm * 8;
-    bvcf_rows_kernel<false><<<rgrid, ROWS_WARPS * 32, 0, st>>>(rp);
+    const unsigned rgrid = (unsigned)n_sm * 16;
+    bvcf_rows_kernel<false><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
     // 5. row offsets
     PrefixParams pq{};
     pq.a = rp.line_bytes; pq.b = rp.line_rows; pq.out_a = (uint64_t *)sc.line_off.p; pq.out_b = (uint64_t *)sc.row_off.p;
     pq.partial = (unsigned long long *)sc.partial.p;
     pq.n_ptr = &d_ctr->chunk_records; pq.n_imm = 0; pq.ctr = d_ctr; pq.mode = 1; pq.out_cap = out_cap;
+    pq.row_cap = dc.n_samples > 0 ? sc.row_cap : ~0ull;
     bvcf_prefix_reduce_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pq);
     bvcf_prefix_spine_kernel<<<1, 1024, 0, st>>>(pq);
     bvcf_prefix_scan_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pq);
     ctx->launches += 4;
-    if (se) CK(cudaEventRecord(se->e[3], st));
-    // 6. emit pass
-    bvcf_rows_kernel<true><<<rgrid, ROWS_WARPS * 32, 0, st>>>(rp);
-    ctx->launches++;
     if (se) CK(cudaEventRecord(se->e[4], st));
+    // 6. emit pass: every non-list byte + one RowDesc per row
+    bvcf_rows_kernel<true><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
+    ctx->launches++;
+    if (se) CK(cudaEventRecord(se->e[5], st));
+    // 7. sample-name lists + dosage rows (warp per row)
+    if (dc.n_samples > 0) {
+      NamesParams np{};
+      np.in = d_in; np.cfg = dc; np.lines = cp.dense; np.events = sp.events; np.row_desc = (const RowDesc *)sc.row_desc.p;
+      np.row_desc_cap = sc.row_cap; np.out = d_out; np.ctr = d_ctr; np.dosage = d_dosage; np.dosage_cap_rows = dosage_cap_rows;
+      bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
+      ctx->launches++;
+    }
+    if (se) CK(cudaEventRecord(se->e[6], st));
   }
   CK(cudaGetLastError());
   return 0;
@@ -512,6 +539,7 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
     bool again = false;
     if (c.ev_overflow) { ctx->ev_factor *= 4; again = true; }           // dense genotype block: more event slots
     if (c.slot_overflow) return BVCF_E_TOO_LARGE;                       // cannot happen: slots cover the minimum line
+    if (c.row_overflow) { s->sc.row_cap = s->sc.row_cap * 4 + c.row_cursor; again = true; }  // MNP/multi-ALT heavy block
     if (c.out_overflow) {
       int rc = dev_reserve(ctx, s->d_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096));
       if (rc) return rc;
@@ -661,6 +689,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
     bool again = false;
     if (c.ev_overflow) { ctx->ev_factor *= 4; again = true; }
     if (c.slot_overflow) return BVCF_E_TOO_LARGE;
+    if (c.row_overflow) { ctx->r_sc.row_cap = ctx->r_sc.row_cap * 4 + c.row_cursor; again = true; }
     if (c.out_overflow) {
       if ((rc = dev_reserve(ctx, ctx->r_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096)))) return rc;
       again = true;
@@ -686,11 +715,13 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       float ms;
       cudaEventElapsedTime(&ms, t.e[0], t.e[1]); times->scan_ms += ms;
       cudaEventElapsedTime(&ms, t.e[1], t.e[2]); times->compact_ms += ms;
-      cudaEventElapsedTime(&ms, t.e[2], t.e[3]); times->size_ms += ms;
-      cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->emit_ms += ms;
-      times->launches += 10;
+      cudaEventElapsedTime(&ms, t.e[2], t.e[3]); times->stats_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->size_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[4], t.e[5]); times->emit_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[5], t.e[6]); times->names_ms += ms;
+      times->launches += ctx->dcfg.n_samples > 0 ? 12 : 10;
     }
-    if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[4]);
+    if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[N_STAGE_EV - 1]);
     for (auto &t : timing)
       for (auto e : t.e) ctx->ev_pool.push_back(e);
   }

@@ -17,8 +17,11 @@ struct __align__(16) LineRec {
   uint32_t ev_start;  // first event word of this line
   uint32_t ev_count;  // event words of this line
   uint32_t ord;       // ordinal of this line among ALL lines that start in its range
-  uint32_t pad;
+  uint16_t tab[9];    // offsets of the first nine tabs from `start` (0xFFFF: beyond 64 KiB, rescan); only
+                      // the first min(H-1, 9) entries are meaningful
+  uint16_t pad;
 };
+static_assert(sizeof(LineRec) == 48, "LineRec layout");
 
 // ---- genotype events ----------------------------------------------------------------------------
 // The scan kernel emits one 32-bit event per sample whose GT is not plain reference:
@@ -48,6 +51,8 @@ struct RunCounters {
   unsigned int slot_overflow;      // a range ran out of line slots
   unsigned int out_overflow;       // output region too small
   unsigned int n_diags;
+  unsigned int row_overflow;       // a sub-chunk emitted more rows than RowDesc slots
+  unsigned int pad0;
   unsigned long long chunk_out_base;  // out_cursor before this sub-chunk (set by the scan-finalize kernel)
   unsigned long long chunk_row_base;
   unsigned long long chunk_line_base; // n_lines before this sub-chunk (diagnostic line numbers)

@@ -21,6 +21,7 @@ struct PrefixParams {
   RunCounters *ctr;
   int mode;                     // 0: range counts (a=records, b=lines)   1: row sizes (a=bytes, b=rows)
   unsigned long long out_cap;   // mode 1: capacity of the output region
+  unsigned long long row_cap;   // mode 1: RowDesc slots per sub-chunk
 };
 
 __device__ __forceinline__ uint32_t pfx_n(const PrefixParams &p) { return p.n_ptr ? *p.n_ptr : p.n_imm; }
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(1024) bvcf_prefix_spine_kernel(const PrefixPar
       c->out_cursor += sa[t];
       c->row_cursor += sb[t];
       if (c->out_cursor > p.out_cap) c->out_overflow = 1;
+      if (sb[t] > p.row_cap) c->row_overflow = 1;
     }
   }
 }

@@ -1,30 +1,48 @@
 // bvcf_rows.cuh -- north-star kernels (2)+(4): per-line fixed-field kernel + two-pass row emitter.
 //
-// One warp per record.  The same code runs twice: SIZE pass (counts the bytes and rows each record will
-// emit) and, after an exclusive scan of the sizes, EMIT pass (scatter-writes the rows into one contiguous
-// output buffer, in input order).  Per record it
-//   * finds the first nine tabs with __ballot_sync/__fns,
-//   * applies linePasses' FILTER allow/exclude test against a shared-memory table   (main.go:447-454),
-//   * walks getAlleles' decision tree: ACTG QC, multiallelic split, MNP decomposition, indel padding
-//     trim + left-normalisation, site type, transition/transversion                 (main.go:723-1038, 602-606),
-//   * for each distinct ALT index reduces the scan kernel's genotype events to het/hom/missing counts,
-//     ac, an with ballot/popc                                                        (main.go:1042-1194),
-//   * formats the 15 (+4) TSV columns incl. Go 'G'-format floats                    (main.go:586-695).
+//   bvcf_line_stats_kernel   warp per record: reduce the scan kernel's genotype events for ALT #1 to
+//                            het/hom/missing counts, ac, an with __ballot_sync/__popc   (main.go:1042-1194)
+//   bvcf_rows_kernel<SIZE>   thread per record: FILTER allow/exclude against a shared-memory table
+//                            (main.go:447-454), getAlleles' decision tree -- ACTG QC, multiallelic split, MNP
+//                            decomposition, padding trim + left-normalisation, site type, trTv
+//                            (main.go:723-1038, 602-606) -- and the exact size of every row it will emit
+//   (exclusive scan of the sizes: bvcf_prefix.cuh)
+//   bvcf_rows_kernel<EMIT>   same code, now writing every non-list byte of its rows at the scanned offsets
+//                            (main.go:586-695) and one RowDesc per row
+//   bvcf_names_kernel        warp per row: scatter-writes the heterozygote / homozygote / missing sample-name
+//                            lists (main.go:617,639,653 strings.Join) and the int8 dosage row (main.go:576-584)
+//
+// Rows of ALT #1 (99 % of real data) use the warp-reduced stats; other ALT numbers are reduced by the
+// record's own thread straight from the event list.
 #pragma once
 #include "bvcf_common.cuh"
 #include "bvcf_text.cuh"
 
 namespace bvcf {
 
-constexpr int ROWS_WARPS = 8;
-constexpr int STAGE_BYTES = 256;     // per-warp shared staging for the scalar parts of a row
+constexpr int ROWS_THREADS = 128;
+constexpr int NAMES_WARPS = 8;
 constexpr int FILT_SMEM = 1024;      // FILTER table bytes kept in shared memory
+
+// genotype summary of one (record, ALT number)
+struct GtStats {
+  uint32_t n_het, n_hom, n_miss, ac, an;
+  uint32_t het_bytes, hom_bytes, miss_bytes;  // sum of the sample-name lengths per class
+};
+
+// one emitted row, for the names kernel
+struct __align__(16) RowDesc {
+  uint32_t line;        // record index in the dense line table
+  uint32_t allele;      // ALT number (altIdx + 1)
+  unsigned long long het_dst, hom_dst, miss_dst;  // absolute byte offsets of the three lists in the output
+};
 
 struct RowsParams {
   const uint8_t *in;
   DevCfg cfg;
   const LineRec *lines;      // dense, input order
   const uint32_t *events;    // sub-chunk event buffer
+  const GtStats *stats1;     // per record, ALT #1 (null when there are no samples)
   uint32_t *line_bytes;      // SIZE out
   uint32_t *line_rows;       // SIZE out
   const uint64_t *line_off;  // EMIT in: exclusive prefix of line_bytes
@@ -32,8 +50,9 @@ struct RowsParams {
   uint8_t *out;
   unsigned long long out_cap;
   RunCounters *ctr;
+  RowDesc *row_desc;         // EMIT out, indexed by the row number within the sub-chunk
+  unsigned long long row_desc_cap;
   // dosage matrix (main.go:576-584)
-  int8_t *dosage;            // rows x n_samples
   unsigned long long dosage_cap_rows;
   uint8_t *loci;             // rows x loci_stride, NUL padded
   uint32_t loci_stride;
@@ -55,65 +74,6 @@ __device__ __forceinline__ uint8_t trtv_char(uint8_t r, uint8_t a) {
   return tr ? '1' : '2';
 }
 
-// ---- row writer: counts in the SIZE pass, stages + scatter-writes in the EMIT pass -----------------
-template <bool WRITE>
-struct RowWriter {
-  uint8_t *sbuf;  // per-warp shared staging
-  uint8_t *g;     // global cursor
-  int n;          // bytes staged
-  unsigned long long count;
-  int lane;
-
-  __device__ __forceinline__ void flush() {
-    if (WRITE) {
-      __syncwarp();
-      for (int i = lane; i < n; i += 32) g[i] = sbuf[i];
-      g += n;
-      n = 0;
-      __syncwarp();
-    }
-  }
-  __device__ __forceinline__ void byte(uint8_t c) {
-    if (WRITE) {
-      if (lane == 0) sbuf[n] = c;
-      if (++n == STAGE_BYTES) flush();
-    } else {
-      count++;
-    }
-  }
-  // any span of global/constant memory
-  __device__ __forceinline__ void span(const uint8_t *p, int len) {
-    if (!WRITE) { count += len; return; }
-    if (len <= 24) {
-      for (int i = 0; i < len; i++) byte(p[i]);
-    } else {
-      flush();
-      for (int i = lane; i < len; i += 32) g[i] = p[i];
-      g += len;
-    }
-  }
-  __device__ __forceinline__ void packed(uint64_t chars, int len) {
-    if (!WRITE) { count += len; return; }
-    for (int i = 0; i < len; i++) byte((uint8_t)(chars >> (8 * i)));
-  }
-  __device__ __forceinline__ void dec(long long v) {
-    uint8_t buf[24];
-    const int len = itoa_dec(v, buf);
-    if (!WRITE) { count += len; return; }
-    for (int i = 0; i < len; i++) byte(buf[i]);
-  }
-  // leave room for bytes that were written directly (name lists)
-  __device__ __forceinline__ void skip(unsigned long long len) {
-    if (WRITE) { flush(); g += len; } else { count += len; }
-  }
-};
-
-// per (record, ALT index) genotype summary
-struct GtStats {
-  uint32_t n_het, n_hom, n_miss, ac, an;
-  unsigned long long het_bytes, hom_bytes, miss_bytes;  // sum of name lengths per class
-};
-
 __device__ __forceinline__ uint32_t name_len(const DevCfg &c, uint32_t s) {
   return c.name_fixed_w > 0 ? (uint32_t)c.name_fixed_w : c.name_off[s + 1] - c.name_off[s];
 }
@@ -122,7 +82,7 @@ __device__ __forceinline__ const uint8_t *name_ptr(const DevCfg &c, uint32_t s) 
 }
 
 // classify one event word for allele number a; returns class 0..3 (none/het/hom/missing) and gt/alt.
-// ev points at the word; complex events read the next word and re-parse the field.
+// Complex events read the next word and re-parse the field with the general GT grammar.
 __device__ __forceinline__ int classify_event(const uint32_t *ev, uint32_t k, uint32_t n, const uint8_t *L,
                                               uint32_t content_len, uint32_t a, uint32_t &samp, uint32_t &gt_extra,
                                               uint32_t &alt) {
@@ -145,11 +105,19 @@ __device__ __forceinline__ int classify_event(const uint32_t *ev, uint32_t k, ui
   return alt == 0 ? 0 : (alt == gt ? 2 : 1);
 }
 
-// reduce the record's events for allele number a (makeHetHomozygotes, main.go:1042-1194)
-__device__ __noinline__ GtStats count_events(const DevCfg &cfg, const LineRec &rec, const uint32_t *ev,
-                                                const uint8_t *L, uint32_t content_len, uint32_t a, int lane) {
-  uint32_t n_het = 0, n_hom = 0, n_miss = 0, ac = 0, an_x = 0;
-  unsigned long long hb = 0, mb = 0, ob = 0;
+// ---- warp per record: ALT #1 summary ---------------------------------------------------------------
+struct StatsParams {
+  const uint8_t *in;
+  DevCfg cfg;
+  const LineRec *lines;
+  const uint32_t *events;
+  GtStats *stats1;
+  RunCounters *ctr;
+};
+
+__device__ __forceinline__ GtStats reduce_events_warp(const DevCfg &cfg, const LineRec &rec, const uint32_t *ev,
+                                                      const uint8_t *L, uint32_t content_len, uint32_t a, int lane) {
+  uint32_t n_het = 0, n_hom = 0, n_miss = 0, ac = 0, an_x = 0, hb = 0, mb = 0, ob = 0;
   const bool fixed = cfg.name_fixed_w > 0;
   for (uint32_t base = 0; base < rec.ev_count; base += 32) {
     uint32_t samp, gtx, alt;
@@ -169,61 +137,65 @@ __device__ __noinline__ GtStats count_events(const DevCfg &cfg, const LineRec &r
   s.ac = warp_sum(ac);
   s.an = rec.an + warp_sum(an_x);
   if (fixed) {
-    s.het_bytes = (unsigned long long)n_het * cfg.name_fixed_w;
-    s.hom_bytes = (unsigned long long)n_hom * cfg.name_fixed_w;
-    s.miss_bytes = (unsigned long long)n_miss * cfg.name_fixed_w;
+    s.het_bytes = n_het * cfg.name_fixed_w; s.hom_bytes = n_hom * cfg.name_fixed_w; s.miss_bytes = n_miss * cfg.name_fixed_w;
   } else {
-    s.het_bytes = warp_sum64(hb); s.hom_bytes = warp_sum64(ob); s.miss_bytes = warp_sum64(mb);
+    s.het_bytes = warp_sum(hb); s.hom_bytes = warp_sum(ob); s.miss_bytes = warp_sum(mb);
   }
   return s;
 }
 
-// scatter-write the three name lists of one row (main.go:617,639,653 strings.Join)
-__device__ __noinline__ void write_name_lists(const DevCfg &cfg, const LineRec &rec, const uint32_t *ev,
-                                                 const uint8_t *L, uint32_t content_len, uint32_t a, int lane,
-                                                 uint8_t *het_dst, uint8_t *hom_dst, uint8_t *miss_dst) {
-  const uint32_t dl = (uint32_t)cfg.delim_len;
-  const bool fixed = cfg.name_fixed_w > 0;
-  uint32_t run_n[3] = {0, 0, 0};
-  unsigned long long run_b[3] = {0, 0, 0};
-  uint8_t *dsts[3] = {het_dst, hom_dst, miss_dst};
-  const uint32_t lt = (1u << lane) - 1u;
-  for (uint32_t base = 0; base < rec.ev_count; base += 32) {
-    uint32_t samp, gtx, alt;
-    const int cls = classify_event(ev, base + lane, rec.ev_count, L, content_len, a, samp, gtx, alt);
-    const uint32_t nl = cls ? name_len(cfg, samp) : 0;
-    unsigned long long my_off = 0;
-    uint32_t my_idx = 0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const uint32_t bal = __ballot_sync(FULL, cls == c + 1);
-      if (bal == 0) continue;
-      const uint32_t rank = __popc(bal & lt);
-      const uint32_t cnt = __popc(bal);
-      if (fixed) {
-        if (cls == c + 1) { my_idx = run_n[c] + rank; my_off = (unsigned long long)my_idx * (cfg.name_fixed_w + dl); }
-        run_n[c] += cnt;
-      } else {
-        const uint32_t v = cls == c + 1 ? nl + dl : 0;
-        const uint32_t incl = warp_incl_scan(v, lane);
-        if (cls == c + 1) { my_idx = run_n[c] + rank; my_off = run_b[c] + incl - v; }
-        run_n[c] += cnt;
-        run_b[c] += __shfl_sync(FULL, incl, 31);
-      }
-    }
-    if (cls) {
-      // item i occupies [delim if i>0] + name; my_off counts a delimiter per earlier item
-      uint8_t *d = dsts[cls - 1] + my_off;
-      if (my_idx > 0) {
-        d -= dl;
-        for (uint32_t i = 0; i < dl; i++) d[i] = cfg.delim[i];
-        d += dl;
-      }
-      const uint8_t *src = name_ptr(cfg, samp);
-      for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
-    }
+__global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams p) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_rec = p.ctr->chunk_records;
+  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); li < n_rec; li += total_warps) {
+    const LineRec rec = p.lines[li];
+    const uint32_t n = rec.len >= (uint32_t)p.cfg.eol_width ? rec.len - (uint32_t)p.cfg.eol_width : 0;
+    const GtStats s = reduce_events_warp(p.cfg, rec, p.events + rec.ev_start, p.in + rec.start, n, 1, lane);
+    if (lane == 0) p.stats1[li] = s;
   }
 }
+
+// the record's own thread reduces the events for an ALT number other than 1
+__device__ __noinline__ GtStats reduce_events_thread(const DevCfg &cfg, const LineRec &rec, const uint32_t *ev,
+                                                     const uint8_t *L, uint32_t content_len, uint32_t a) {
+  GtStats s;
+  s.n_het = s.n_hom = s.n_miss = s.ac = 0; s.an = rec.an;
+  s.het_bytes = s.hom_bytes = s.miss_bytes = 0;
+  for (uint32_t k = 0; k < rec.ev_count; k++) {
+    uint32_t samp, gtx, alt;
+    const int cls = classify_event(ev, k, rec.ev_count, L, content_len, a, samp, gtx, alt);
+    s.ac += alt;
+    s.an += gtx;
+    if (cls) {
+      const uint32_t nl = name_len(cfg, samp);
+      if (cls == 1) { s.n_het++; s.het_bytes += nl; }
+      else if (cls == 2) { s.n_hom++; s.hom_bytes += nl; }
+      else { s.n_miss++; s.miss_bytes += nl; }
+    }
+  }
+  return s;
+}
+
+// ---- row writer: counts in the SIZE pass, byte stores in the EMIT pass --------------------------------
+template <bool WRITE>
+struct RowWriter {
+  uint8_t *g;                // global cursor (EMIT)
+  unsigned long long count;  // bytes (SIZE)
+  __device__ __forceinline__ void byte(uint8_t c) { if (WRITE) *g++ = c; else count++; }
+  __device__ __forceinline__ void span(const uint8_t *p, int len) {
+    if (WRITE) { for (int i = 0; i < len; i++) g[i] = p[i]; g += len; } else count += len;
+  }
+  __device__ __forceinline__ void packed(uint64_t chars, int len) {
+    if (WRITE) { for (int i = 0; i < len; i++) g[i] = (uint8_t)(chars >> (8 * i)); g += len; } else count += len;
+  }
+  __device__ __forceinline__ void dec(long long v) {
+    uint8_t buf[24];
+    const int len = itoa_dec(v, buf);
+    if (WRITE) { for (int i = 0; i < len; i++) g[i] = buf[i]; g += len; } else count += len;
+  }
+  __device__ __forceinline__ void skip(unsigned long long len) { if (WRITE) g += len; else count += len; }
+};
 
 // ---- one output allele of getAlleles ------------------------------------------------------------
 struct OutAllele {
@@ -244,126 +216,107 @@ struct LineCtx {
   int chrom_n, pos_n, id_n, info_n;
   int site_type;
   bool multi;
+  uint32_t li;
 };
 
 template <bool WRITE>
 __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, const LineCtx &lc, const OutAllele &oa,
-                                         GtStats &gs, int &gs_idx, RowWriter<WRITE> &w, uint32_t &n_rows,
-                                         unsigned long long row_base, int lane) {
+                                      GtStats &gs, int &gs_idx, RowWriter<WRITE> &w, uint32_t &n_rows,
+                                      unsigned long long row_base) {
   const DevCfg &cfg = p.cfg;
-  const uint32_t *ev = p.events + rec.ev_start;
   const uint32_t a = (uint32_t)oa.alt_idx + 1;
   if (cfg.n_samples > 0) {
     if (gs_idx != oa.alt_idx) {  // MNP bases share their ALT index: reduce once (main.go:865-868)
-      gs = count_events(cfg, rec, ev, lc.L, lc.content_len, a, lane);
+      if (a == 1) gs = p.stats1[lc.li];
+      else gs = reduce_events_thread(cfg, rec, p.events + rec.ev_start, lc.L, lc.content_len, a);
       gs_idx = oa.alt_idx;
     }
     if (gs.ac == 0) return;  // main.go:558
   }
   const uint32_t row_id = n_rows++;
+  const unsigned long long r = row_base + row_id;  // row number within the sub-chunk
 
-  if (cfg.want_dosage && cfg.n_samples > 0 && WRITE) {  // main.go:576-584
-    const unsigned long long r = row_base + row_id;
-    if (r < p.dosage_cap_rows) {
-      int8_t *drow = p.dosage + r * (unsigned long long)cfg.n_samples;
-      for (int i = lane; i < cfg.n_samples; i += 32) drow[i] = 0;
-      __syncwarp();
-      for (uint32_t base = 0; base < rec.ev_count; base += 32) {
-        uint32_t samp, gtx, alt;
-        const uint32_t k = base + lane;
-        const int cls = classify_event(ev, k, rec.ev_count, lc.L, lc.content_len, a, samp, gtx, alt);
-        const bool is_ev = k < rec.ev_count && !(ev[k] & EV_OFFSET_TAG);
-        if (is_ev) drow[samp] = cls == 3 ? (int8_t)-1 : (int8_t)(alt > 127 ? 127 : alt);  // main.go:1172-1178
-      }
-      // locus "chrom:pos:ref:alt"
-      if (lane == 0) {
-        uint8_t *lo = p.loci + r * (unsigned long long)p.loci_stride;
-        uint32_t n = 0;
-        const uint32_t cap = p.loci_stride - 1;
-        auto put = [&](uint8_t c) { if (n < cap) lo[n] = c; n++; };
-        if (lc.chrom_n < 4 || lc.chrom[0] != 'c') { put('c'); put('h'); put('r'); }
-        for (int i = 0; i < lc.chrom_n; i++) put(lc.chrom[i]);
-        put(':');
-        if (oa.pos_verbatim) { for (int i = 0; i < lc.pos_n; i++) put(lc.pos[i]); }
-        else { uint8_t b[24]; const int l = itoa_dec(oa.pos_val, b); for (int i = 0; i < l; i++) put(b[i]); }
-        put(':'); put(oa.ref); put(':');
-        if (oa.kind == 0) put(oa.alt_c);
-        else if (oa.kind == 1) { put('+'); for (int i = 0; i < oa.ins_n; i++) put(oa.ins_p[i]); }
-        else { uint8_t b[24]; const int l = itoa_dec(oa.del_n, b); for (int i = 0; i < l; i++) put(b[i]); }
-        lo[n < cap ? n : cap] = 0;
-      }
+  if (WRITE && cfg.want_dosage && cfg.n_samples > 0) {  // locus "chrom:pos:ref:alt" main.go:577
+    const unsigned long long gr = p.ctr->chunk_row_base + r;
+    if (gr < p.dosage_cap_rows) {
+      uint8_t *lo = p.loci + gr * (unsigned long long)p.loci_stride;
+      uint32_t n = 0;
+      const uint32_t cap = p.loci_stride - 1;
+      auto put = [&](uint8_t c) { if (n < cap) lo[n] = c; n++; };
+      if (lc.chrom_n < 4 || lc.chrom[0] != 'c') { put('c'); put('h'); put('r'); }
+      for (int i = 0; i < lc.chrom_n; i++) put(lc.chrom[i]);
+      put(':');
+      if (oa.pos_verbatim) { for (int i = 0; i < lc.pos_n; i++) put(lc.pos[i]); }
+      else { uint8_t b[24]; const int l = itoa_dec(oa.pos_val, b); for (int i = 0; i < l; i++) put(b[i]); }
+      put(':'); put(oa.ref); put(':');
+      if (oa.kind == 0) put(oa.alt_c);
+      else if (oa.kind == 1) { put('+'); for (int i = 0; i < oa.ins_n; i++) put(oa.ins_p[i]); }
+      else { uint8_t b[24]; const int l = itoa_dec(oa.del_n, b); for (int i = 0; i < l; i++) put(b[i]); }
+      lo[n < cap ? n : cap] = 0;
     }
   }
-  if (!cfg.want_tsv) return;
+  RowDesc rd;
+  rd.line = lc.li; rd.allele = a;
+  rd.het_dst = rd.hom_dst = rd.miss_dst = ~0ull;
 
-  // chrom (main.go:570-574)
-  if (lc.chrom_n < 4 || lc.chrom[0] != 'c') { w.byte('c'); w.byte('h'); w.byte('r'); }
-  w.span(lc.chrom, lc.chrom_n);
-  w.byte('\t');
-  if (oa.pos_verbatim) w.span(lc.pos, lc.pos_n); else w.dec(oa.pos_val);
-  w.byte('\t');
-  w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
-  w.byte('\t');
-  w.byte(oa.ref);
-  w.byte('\t');
-  if (oa.kind == 0) w.byte(oa.alt_c);
-  else if (oa.kind == 1) { w.byte('+'); w.span(oa.ins_p, oa.ins_n); }
-  else w.dec(oa.del_n);
-  w.byte('\t');
-  w.byte(lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0'));  // main.go:602-606
-  w.byte('\t');
+  if (cfg.want_tsv) {
+    // chrom (main.go:570-574)
+    if (lc.chrom_n < 4 || lc.chrom[0] != 'c') { w.byte('c'); w.byte('h'); w.byte('r'); }
+    w.span(lc.chrom, lc.chrom_n);
+    w.byte('\t');
+    if (oa.pos_verbatim) w.span(lc.pos, lc.pos_n); else w.dec(oa.pos_val);
+    w.byte('\t');
+    w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
+    w.byte('\t');
+    w.byte(oa.ref);
+    w.byte('\t');
+    if (oa.kind == 0) w.byte(oa.alt_c);
+    else if (oa.kind == 1) { w.byte('+'); w.span(oa.ins_p, oa.ins_n); }
+    else w.dec(oa.del_n);
+    w.byte('\t');
+    w.byte(lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0'));  // main.go:602-606
+    w.byte('\t');
 
-  if (cfg.n_samples == 0) {  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0"
-    for (int k = 0; k < 3; k++) { w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0'); w.byte('\t'); }
-    w.byte('0'); w.byte('\t'); w.byte('0'); w.byte('\t'); w.byte('0');
-  } else {
-    // four ratios formatted by four lanes in parallel
-    const uint32_t eff = (uint32_t)cfg.n_samples - gs.n_miss;  // main.go:563
-    uint32_t fk = 1, fn = 1;
-    if (lane == 0) { fk = gs.n_het; fn = eff; }
-    else if (lane == 1) { fk = gs.n_hom; fn = eff; }
-    else if (lane == 2) { fk = gs.n_miss; fn = (uint32_t)cfg.n_samples; }
-    else if (lane == 3) { fk = gs.ac; fn = gs.an; }
-    if (fk == 0 || fn == 0) { fk = 1; fn = 1; }
-    int fl;
-    const uint64_t ft = format_ratio_g3(fk, fn, fl);
-    const uint32_t dl = (uint32_t)cfg.delim_len;
-    const uint32_t cnts[3] = {gs.n_het, gs.n_hom, gs.n_miss};
-    const unsigned long long nb[3] = {gs.het_bytes, gs.hom_bytes, gs.miss_bytes};
-    unsigned long long list_len[3];
-    for (int k = 0; k < 3; k++) list_len[k] = cnts[k] ? nb[k] + (unsigned long long)(cnts[k] - 1) * dl : 0;
-    uint8_t *list_dst[3] = {nullptr, nullptr, nullptr};
-    for (int k = 0; k < 3; k++) {
-      const uint64_t t = __shfl_sync(FULL, ft, k);
-      const int tl = __shfl_sync(FULL, fl, k);
-      if (cnts[k] == 0) {
-        w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0');
-      } else {
-        if (WRITE) { w.flush(); list_dst[k] = w.g; }
-        w.skip(list_len[k]);
+    if (cfg.n_samples == 0) {  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0"
+      for (int k = 0; k < 3; k++) { w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0'); w.byte('\t'); }
+      w.byte('0'); w.byte('\t'); w.byte('0'); w.byte('\t'); w.byte('0');
+    } else {
+      const uint32_t eff = (uint32_t)cfg.n_samples - gs.n_miss;  // main.go:563
+      const uint32_t dl = (uint32_t)cfg.delim_len;
+      const uint32_t cnts[3] = {gs.n_het, gs.n_hom, gs.n_miss};
+      const uint32_t nb[3] = {gs.het_bytes, gs.hom_bytes, gs.miss_bytes};
+      const uint32_t den[3] = {eff, eff, (uint32_t)cfg.n_samples};
+      unsigned long long dsts[3] = {~0ull, ~0ull, ~0ull};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (cnts[k] == 0) {
+          w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0');
+        } else {
+          if (WRITE) dsts[k] = (unsigned long long)(w.g - p.out);
+          w.skip((unsigned long long)nb[k] + (unsigned long long)(cnts[k] - 1) * dl);  // filled by the names kernel
+          w.byte('\t');
+          int fl;
+          const uint64_t ft = format_ratio_g3(cnts[k], den[k], fl);
+          w.packed(ft, fl);
+        }
         w.byte('\t');
-        w.packed(t, tl);
       }
-      w.byte('\t');
+      rd.het_dst = dsts[0]; rd.hom_dst = dsts[1]; rd.miss_dst = dsts[2];
+      w.dec(gs.ac); w.byte('\t');
+      w.dec(gs.an); w.byte('\t');
+      if (gs.ac == 0) w.byte('0');
+      else { int fl; const uint64_t ft = format_ratio_g3(gs.ac, gs.an, fl); w.packed(ft, fl); }
     }
-    if (WRITE && (gs.n_het | gs.n_hom | gs.n_miss))
-      write_name_lists(cfg, rec, ev, lc.L, lc.content_len, a, lane, list_dst[0], list_dst[1], list_dst[2]);
-    w.dec(gs.ac); w.byte('\t');
-    w.dec(gs.an); w.byte('\t');
-    {
-      const uint64_t t = __shfl_sync(FULL, ft, 3);
-      const int tl = __shfl_sync(FULL, fl, 3);
-      if (gs.ac == 0) w.byte('0'); else w.packed(t, tl);
-    }
+    if (cfg.keep_pos) { w.byte('\t'); w.span(lc.pos, lc.pos_n); }
+    if (cfg.keep_id) { w.byte('\t'); w.span(lc.id, lc.id_n); }
+    if (cfg.keep_info) { w.byte('\t'); w.dec(oa.alt_idx); w.byte('\t'); w.span(lc.info, lc.info_n); }
+    w.byte('\n');
   }
-  if (cfg.keep_pos) { w.byte('\t'); w.span(lc.pos, lc.pos_n); }
-  if (cfg.keep_id) { w.byte('\t'); w.span(lc.id, lc.id_n); }
-  if (cfg.keep_info) { w.byte('\t'); w.dec(oa.alt_idx); w.byte('\t'); w.span(lc.info, lc.info_n); }
-  w.byte('\n');
+  if (WRITE && cfg.n_samples > 0 && r < p.row_desc_cap) p.row_desc[r] = rd;
 }
 
-__device__ __forceinline__ void push_diag(const RowsParams &p, unsigned long long line_no, int alt_no, int code, int lane) {
-  if (!p.diags || lane != 0) return;
+__device__ __forceinline__ void push_diag(const RowsParams &p, unsigned long long line_no, int alt_no, int code) {
+  if (!p.diags) return;
   const uint32_t i = atomicAdd(&p.ctr->n_diags, 1u);
   if (i < p.diag_cap) {
     p.diags[4 * i] = (uint32_t)line_no;
@@ -373,14 +326,12 @@ __device__ __forceinline__ void push_diag(const RowsParams &p, unsigned long lon
   }
 }
 
-// ---- the kernel: one warp per record, grid-stride, record count read from device memory -------------
+// ---- thread per record, grid-stride, record count read from device memory ----------------------------
 template <bool WRITE>
-__global__ void __launch_bounds__(ROWS_WARPS * 32) bvcf_rows_kernel(const RowsParams p) {
-  __shared__ uint8_t s_stage[ROWS_WARPS][STAGE_BYTES];
+__global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_kernel(const RowsParams p) {
   __shared__ uint8_t s_filt[FILT_SMEM];
   __shared__ uint32_t s_filt_off[65];
   const DevCfg &cfg = p.cfg;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // FILTER allow/exclude table -> shared memory
   const int n_filt = cfg.n_allow + cfg.n_excl;
   for (int i = threadIdx.x; i < cfg.filt_bytes && i < FILT_SMEM; i += blockDim.x) s_filt[i] = cfg.filt_blob[i];
@@ -388,48 +339,47 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) bvcf_rows_kernel(const RowsPa
   __syncthreads();
   if (WRITE && p.ctr->out_overflow) return;
   const uint32_t n_rec = p.ctr->chunk_records;
-  const unsigned long long out_base = p.ctr->chunk_out_base, row_base0 = p.ctr->chunk_row_base;
-  const uint32_t total_warps = gridDim.x * ROWS_WARPS;
+  const unsigned long long out_base = p.ctr->chunk_out_base;
+  const uint32_t total_threads = gridDim.x * blockDim.x;
 
-  for (uint32_t li = blockIdx.x * ROWS_WARPS + warp; li < n_rec; li += total_warps) {
+  for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_rec; li += total_threads) {
     const LineRec rec = p.lines[li];
     const uint8_t *L = p.in + rec.start;
     const uint32_t n = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;  // main.go:535
 
     RowWriter<WRITE> w;
-    w.sbuf = s_stage[warp]; w.n = 0; w.count = 0; w.lane = lane;
+    w.count = 0;
     w.g = WRITE ? p.out + out_base + p.line_off[li] : nullptr;
     uint32_t n_rows = 0;
-    const unsigned long long row_base = WRITE ? row_base0 + p.row_off[li] : 0;
+    const unsigned long long row_base = WRITE ? p.row_off[li] : 0;  // row number within the sub-chunk
 
     // ---- first eight/nine tabs (strings.Split, main.go:535) ----
     const int need = cfg.H - 1 < 9 ? cfg.H - 1 : 9;
-    uint32_t my_tab = n;  // lane j holds the offset of tab j
-    int found = 0;
-    for (uint32_t base = 0; base < n && found < need; base += 32) {
-      const uint32_t i = base + lane;
-      const uint32_t bal = __ballot_sync(FULL, i < n && L[i] == '\t');
-      const int c = __popc(bal);
-      if (lane >= found && lane < found + c) my_tab = base + __fns(bal, 0, lane - found + 1);
-      found += c;
+    uint32_t t[9];
+    int found = need;
+    bool far = false;  // a tab beyond 64 KiB from the line start: the scan kernel could not record it
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      t[k] = rec.tab[k];
+      far = far || (k < need && t[k] == 0xFFFFu);
     }
-    auto tab = [&](int j) -> uint32_t { return __shfl_sync(FULL, my_tab, j); };  // j < need, else n
-    auto fstart = [&](int k) -> uint32_t { return k == 0 ? 0u : tab(k - 1) + 1; };
-    auto fend = [&](int k) -> uint32_t { return k < need ? tab(k) : n; };
-
+    if (far) {
+      found = 0;
+      for (uint32_t i = 0; i < n && found < need; i++)
+        if (L[i] == '\t') t[found++] = i;
+    }
     bool pass = found >= need;  // always true for scan-kernel records; defensive
+    for (int k = found; k < 9; k++) t[k] = n;
     LineCtx lc;
-    lc.L = L; lc.content_len = n;
-    const uint32_t t0 = fend(0), t1 = fend(1), t2 = fend(2), t3 = fend(3), t4 = fend(4), t5 = fend(5), t6 = fend(6);
-    const uint32_t t7 = fend(7);
-    lc.chrom = L; lc.chrom_n = (int)t0;
-    lc.pos = L + t0 + 1; lc.pos_n = (int)(t1 - t0 - 1);
-    lc.id = L + t1 + 1; lc.id_n = (int)(t2 - t1 - 1);
-    const uint8_t *ref = L + t2 + 1; const int ref_n = (int)(t3 - t2 - 1);
-    const uint8_t *alt = L + t3 + 1; const int alt_n = (int)(t4 - t3 - 1);
-    const uint8_t *filt = L + t5 + 1; const int filt_n = (int)(t6 - t5 - 1);
-    lc.info = L + t6 + 1; lc.info_n = (int)(t7 - t6 - 1);
-    (void)fstart;
+    lc.L = L; lc.content_len = n; lc.li = li;
+    lc.chrom = L; lc.chrom_n = (int)t[0];
+    lc.pos = L + t[0] + 1; lc.pos_n = (int)(t[1] - t[0] - 1);
+    lc.id = L + t[1] + 1; lc.id_n = (int)(t[2] - t[1] - 1);
+    const uint8_t *ref = L + t[2] + 1; const int ref_n = (int)(t[3] - t[2] - 1);
+    const uint8_t *alt = L + t[3] + 1; const int alt_n = (int)(t[4] - t[3] - 1);
+    const uint8_t *filt = L + t[5] + 1; const int filt_n = (int)(t[6] - t[5] - 1);
+    lc.info = L + t[6] + 1; lc.info_n = (int)(t[7] - t[6] - 1);
+    lc.multi = false; lc.site_type = T_SNP;
 
     // ---- linePasses (main.go:447-454): exact whole-field match against the shared-memory table ----
     if (pass && (!cfg.allow_all || cfg.n_excl > 0)) {
@@ -456,24 +406,23 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) bvcf_rows_kernel(const RowsPa
       bool same = alt_n == ref_n;
       for (int i = 0; same && i < alt_n; i++) same = alt[i] == ref[i];
       if (same) {                                                       // :729
-        if (!WRITE) push_diag(p, line_no, 0, 1, lane);
+        if (!WRITE) push_diag(p, line_no, 0, 1);
       } else if (alt_n == 1) {                                          // :735
-        lc.multi = false;
         if (!is_acgt(alt[0])) {
-          if (!WRITE) push_diag(p, line_no, 1, 2, lane);
+          if (!WRITE) push_diag(p, line_no, 1, 2);
         } else if (ref_n == 1) {                                        // :742 SNP, POS text verbatim
           lc.site_type = T_SNP;
           oa.kind = 0; oa.ref = ref[0]; oa.alt_c = alt[0]; oa.alt_idx = 0; oa.pos_verbatim = true;
-          emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base, lane);
+          emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
         } else if (alt[0] != ref[0]) {                                  // :747
-          if (!WRITE) push_diag(p, line_no, 1, 3, lane);
+          if (!WRITE) push_diag(p, line_no, 1, 3);
         } else if (!pos_ok) {                                           // :752
-          if (!WRITE) push_diag(p, line_no, 1, 4, lane);
+          if (!WRITE) push_diag(p, line_no, 1, 4);
         } else {                                                        // :764 simple deletion
           lc.site_type = T_DEL;
           oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n; oa.alt_idx = 0;
           oa.pos_verbatim = false; oa.pos_val = ipos + 1;
-          emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base, lane);
+          emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
         }
       } else {
         // multi == the ALT field holds a comma (main.go:777-779, 1012)
@@ -502,33 +451,33 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) bvcf_rows_kernel(const RowsPa
           for (int i = 0; valid && i < tn; i++) valid = is_acgt(ta[i]);
           oa.alt_idx = alt_idx;
           if (!valid) {
-            if (!WRITE) push_diag(p, line_no, alt_idx + 1, 2, lane);
+            if (!WRITE) push_diag(p, line_no, alt_idx + 1, 2);
           } else if (ref_n == 1) {                                      // :786
             if (tn == 1) {
               oa.kind = 0; oa.ref = ref[0]; oa.alt_c = ta[0]; oa.pos_verbatim = true;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base, lane);
+              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
             } else if (ta[0] != ref[0]) {                               // :797
-              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 5, lane);
+              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 5);
             } else {                                                    // :803 simple insertion
               oa.kind = 1; oa.ref = ref[0]; oa.ins_p = ta + 1; oa.ins_n = tn - 1; oa.pos_verbatim = true;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base, lane);
+              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
             }
           } else if (!pos_ok) {                                         // :822-830 stop, keep what we have
-            if (!WRITE) push_diag(p, line_no, 0, 4, lane);
+            if (!WRITE) push_diag(p, line_no, 0, 4);
             break;
           } else if (tn == 1) {                                         // :832
             if (ta[0] != ref[0]) {
-              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 3, lane);
+              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 3);
             } else {
               oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n; oa.pos_verbatim = false;
               oa.pos_val = ipos + 1;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base, lane);
+              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
             }
           } else if (tn == ref_n) {                                     // :855 MNP / padded SNP
             for (int i = 0; i < ref_n; i++) {
               if (ref[i] != ta[i]) {
                 oa.kind = 0; oa.ref = ref[i]; oa.alt_c = ta[i]; oa.pos_verbatim = false; oa.pos_val = ipos + i;
-                emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base, lane);
+                emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
               }
             }
           } else if (tn > ref_n) {                                      // :899 insertion with padding
@@ -538,11 +487,11 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) bvcf_rows_kernel(const RowsPa
             bool pre = true;
             for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
             if (!pre) {
-              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 6, lane);
+              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 6);
             } else {
               oa.kind = 1; oa.ref = ref[off - 1]; oa.ins_p = ta + off; oa.ins_n = tn + r - off;
               oa.pos_verbatim = false; oa.pos_val = ipos + off - 1;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base, lane);
+              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
             }
           } else {                                                      // :971 deletion with padding
             int r = 0;
@@ -551,22 +500,99 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) bvcf_rows_kernel(const RowsPa
             bool pre = true;
             for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
             if (!pre) {
-              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 6, lane);
+              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 6);
             } else {
               oa.kind = 2; oa.ref = ref[off]; oa.del_n = -((long long)ref_n + r - off);
               oa.pos_verbatim = false; oa.pos_val = ipos + off;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base, lane);
+              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
             }
           }
           if (last) break;
         }
       }
     }
-    if (WRITE) {
-      w.flush();
-    } else if (lane == 0) {
+    if (!WRITE) {
       p.line_bytes[li] = (uint32_t)w.count;
       p.line_rows[li] = n_rows;
+    }
+  }
+}
+
+// ---- warp per row: sample-name lists + dosage row ----------------------------------------------------
+struct NamesParams {
+  const uint8_t *in;
+  DevCfg cfg;
+  const LineRec *lines;
+  const uint32_t *events;
+  const RowDesc *row_desc;
+  unsigned long long row_desc_cap;
+  uint8_t *out;
+  RunCounters *ctr;
+  int8_t *dosage;
+  unsigned long long dosage_cap_rows;
+};
+
+__global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
+  const DevCfg &cfg = p.cfg;
+  const int lane = threadIdx.x & 31;
+  if (p.ctr->out_overflow) return;
+  const unsigned long long row0 = p.ctr->chunk_row_base;
+  unsigned long long n_rows = p.ctr->row_cursor - row0;  // rows of this sub-chunk
+  if (n_rows > p.row_desc_cap) n_rows = p.row_desc_cap;
+  const uint32_t total_warps = gridDim.x * NAMES_WARPS;
+  const uint32_t dl = (uint32_t)cfg.delim_len;
+  const bool fixed = cfg.name_fixed_w > 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (unsigned long long r = blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5); r < n_rows; r += total_warps) {
+    const RowDesc rd = p.row_desc[r];
+    const LineRec rec = p.lines[rd.line];
+    const uint32_t *ev = p.events + rec.ev_start;
+    const uint8_t *L = p.in + rec.start;
+    const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
+    const uint32_t a = rd.allele;
+    int8_t *drow = nullptr;
+    if (cfg.want_dosage && (row0 + r) < p.dosage_cap_rows) {
+      drow = p.dosage + (row0 + r) * (unsigned long long)cfg.n_samples;
+      for (int i = lane; i < cfg.n_samples; i += 32) drow[i] = 0;
+      __syncwarp();
+    }
+    uint32_t run_n[3] = {0, 0, 0};
+    uint32_t run_b[3] = {0, 0, 0};
+    const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
+    for (uint32_t base = 0; base < rec.ev_count; base += 32) {
+      uint32_t samp, gtx, alt;
+      const uint32_t k = base + lane;
+      const int cls = classify_event(ev, k, rec.ev_count, L, content_len, a, samp, gtx, alt);
+      if (drow && k < rec.ev_count && !(ev[k] & EV_OFFSET_TAG))
+        drow[samp] = cls == 3 ? (int8_t)-1 : (int8_t)(alt > 127 ? 127 : alt);  // main.go:1172-1178
+      if (!cfg.want_tsv) continue;
+      const uint32_t nl = cls ? name_len(cfg, samp) : 0;
+      uint32_t my_off = 0, my_idx = 0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const uint32_t bal = __ballot_sync(FULL, cls == c + 1);
+        if (bal == 0) continue;
+        const uint32_t rank = __popc(bal & lt);
+        const uint32_t cnt = __popc(bal);
+        if (fixed) {
+          if (cls == c + 1) { my_idx = run_n[c] + rank; my_off = my_idx * (cfg.name_fixed_w + dl); }
+          run_n[c] += cnt;
+        } else {
+          const uint32_t v = cls == c + 1 ? nl + dl : 0;
+          const uint32_t incl = warp_incl_scan(v, lane);
+          if (cls == c + 1) { my_idx = run_n[c] + rank; my_off = run_b[c] + incl - v; }
+          run_n[c] += cnt;
+          run_b[c] += __shfl_sync(FULL, incl, 31);
+        }
+      }
+      if (cls) {
+        // item i occupies [delim if i>0] + name; my_off counts a delimiter per earlier item
+        uint8_t *d = p.out + dsts[cls - 1] + my_off;
+        if (my_idx > 0)
+          for (uint32_t i = 0; i < dl; i++) d[(int)i - (int)dl] = cfg.delim[i];
+        const uint8_t *src = name_ptr(cfg, samp);
+        for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
+      }
     }
   }
 }

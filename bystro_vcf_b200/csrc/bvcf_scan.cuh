@@ -4,15 +4,16 @@
 // shared-memory ring, 512 B per step), finds line boundaries and tab counts with SWAR byte compares +
 // __ballot_sync/__popc + warp prefix sums, and classifies every sample's GT token on the fly.  It owns the
 // lines that START in its range (it reads past the range end to finish the last one).  Products:
-//   * LineRec per record with the header's field count (main.go:449 len(record)==len(header)),
+//   * LineRec per record with the header's field count (main.go:449 len(record)==len(header)), including the
+//     offsets of its first nine tabs (the field index the rows kernel needs),
 //   * `an` of the fast-classified samples (main.go:1067-1169 totalGtCount),
 //   * one 32-bit event per non-reference sample, in header order (main.go:1057 loop order), which the
-//     rows kernel turns into the het/hom/missing lists and ac for each output allele.
+//     stats/names kernels turn into the het/hom/missing lists and ac for each output allele.
 // Replaces: strings.Split (main.go:535) + the sample loop of makeHetHomozygotes (main.go:1057-1191).
 //
 // Three tiers per 512-byte window, chosen warp-uniformly:
-//   T1  all 128 fields are "0|0\t" (or "0/0\t")  -> 4 compares + vote, nothing else
-//   T2  all 128 fields are "x|y\t" / "x/y\t", x,y in [0-9.] -> classify in registers, ballot-compact events
+//   T1  all 128 fields are "0|0\t" (or "0/0\t")  -> 4 XOR/OR + vote, nothing else
+//   T2  all 128 fields are "x|y\t" with x,y in [0-9.] -> SWAR classify in registers, ordered compaction of events
 //   T3  anything else (line start/end, fixed fields, FORMAT suffixes, odd widths): general path
 #pragma once
 #include "bvcf_common.cuh"
@@ -24,7 +25,7 @@ constexpr int STAGES = 8;                // ring stages per warp
 constexpr int RING = WIN * STAGES;       // 4 KiB per warp
 constexpr int PF = 6;                    // prefetch distance (windows in flight)
 constexpr int SCAN_WARPS = 8;            // warps per CTA
-constexpr uint64_t FS_NONE = ~0ull;
+constexpr int FS_NONE = 0x7FFFFFFF;      // "inside a field": no known field start
 
 struct ScanParams {
   const uint8_t *in;        // region base (>= 16-byte aligned)
@@ -44,12 +45,12 @@ struct ScanParams {
 
 struct WarpState {
   uint64_t line_start;
-  uint64_t fs;              // absolute offset of the first unprocessed field start, or FS_NONE (inside a field)
-  uint32_t col;             // field index of the field at fs == tabs of this line before fs
+  int fsr;                  // first unprocessed field start, relative to the current window; FS_NONE inside a field
+  uint32_t col;             // field index of the field at fsr == tabs of this line before it
   uint32_t an_lane, an_uni; // non-missing allele count: per-lane part and warp-uniform part
   uint32_t ev_w, line_ev_start;  // event write cursor (words, relative to this range's slice)
   uint32_t nrec, nlines;
-  uint32_t refpat;          // "0|0\t" or "0/0\t", adapted to the data
+  uint32_t refpat;          // "0|0\t" or "0/0\t", follows the data's separator
   int mode;                 // 0 seeking the first line start, 1 inside an owned line, 2 done
 };
 
@@ -64,17 +65,22 @@ __device__ __forceinline__ uint32_t tok_code(uint32_t c) {  // single-character 
   return c == '.' ? EV_CODE_MISSING : (d <= 9 ? d : 0u);
 }
 
+__device__ __forceinline__ void start_line(WarpState &st, uint64_t start, int rel) {
+  st.line_start = start; st.fsr = rel; st.col = 0;
+  st.an_lane = 0; st.an_uni = 0; st.line_ev_start = st.ev_w;
+}
+
 // ---- T3: the general window ------------------------------------------------------------------------
 template <bool HAS_SAMPLES>
 __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpState &st, const uint8_t *ring,
-                                                 uint32_t stage_off, const uint4 &v, uint64_t pos, uint64_t rend,
-                                                 int lane, LineRec *my_recs, uint32_t *my_events) {
+                                                    uint32_t stage_off, const uint4 &v, uint64_t pos, uint64_t rend,
+                                                    int lane, LineRec *my_recs, uint32_t *my_events) {
   const bool eol2 = p.eol_width == 2;
-  uint32_t tm = eq_mask16(v, 0x09090909u);
+  const uint32_t tm = eq_mask16(v, 0x09090909u);
   const uint32_t nm = eq_mask16(v, 0x0A0A0A0Au);
 
   int seg_lo = 0;
-  if (st.mode == 1 && st.fs != FS_NONE && st.fs > pos) seg_lo = (int)(st.fs - pos);  // bytes before fs are consumed
+  if (st.mode == 1 && st.fsr != FS_NONE && st.fsr > 0) seg_lo = st.fsr;  // bytes before the field start are consumed
 
   while (seg_lo < WIN) {
     // first newline at or after seg_lo
@@ -92,8 +98,7 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
       const uint64_t start = pos + nl + 1;
       if (start >= rend) { st.mode = 2; return; }
       st.mode = 1;
-      st.line_start = start; st.fs = start; st.col = 0;
-      st.an_lane = 0; st.an_uni = 0; st.line_ev_start = st.ev_w;
+      start_line(st, start, nl + 1);
       seg_lo = nl + 1;
       continue;
     }
@@ -106,13 +111,27 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
     const uint32_t excl = incl - cnt;
     const uint32_t total = __shfl_sync(FULL, incl, 31);
 
+    // field index: offsets of the record's first nine tabs (strings.Split, main.go:535)
+    if (st.col < 9 && st.nrec < p.slots_per_range) {
+      uint32_t m = tm_l;
+      uint32_t idx = st.col + excl;
+      while (m && idx < 9) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t off = pos + (uint64_t)(lane * 16 + b) - st.line_start;
+        my_recs[st.nrec].tab[idx] = off < 0xFFFFu ? (uint16_t)off : (uint16_t)0xFFFFu;
+        idx++;
+      }
+    }
+
     int last_end = -1;   // window-relative index of the '\t' that ends this lane's last field, if known
+    uint32_t last_sep = 0;
     uint32_t fm_all = 0;
     if (HAS_SAMPLES) {
-      // field starts owned by this lane: byte after a tab, or the carried-in start st.fs
+      // field starts owned by this lane: byte after a tab, or the carried-in start
       const uint32_t prev_hi = __shfl_up_sync(FULL, tm_l >> 15, 1);
       uint32_t fm = ((tm_l << 1) | (lane > 0 ? (prev_hi & 1u) : 0u)) & 0xFFFFu;
-      if (st.fs == pos + (uint64_t)seg_lo) {
+      if (st.fsr == seg_lo) {
         const int sl = seg_lo - lane * 16;
         if (sl >= 0 && sl < 16) fm |= 1u << sl;
       }
@@ -158,8 +177,8 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
             st.an_lane += 2;
             if (c1 | c2) evbuf[nev++] = ev_make(samp, c1, c2);
           }
-          if (b3 == '\t') last_end = s + 3;
-        } else {  // general grammar: resolved exactly by the rows kernel
+          if (b3 == '\t') { last_end = s + 3; last_sep = b1; }
+        } else {  // general grammar: resolved exactly by the stats/names kernels
           evbuf[nev++] = samp | EV_COMPLEX;
           evbuf[nev++] = EV_OFFSET_TAG | (uint32_t)(pos + (uint64_t)s - st.line_start);
         }
@@ -185,15 +204,13 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
       if (st.col == (uint32_t)(p.H - 1)) {
         if (st.nrec < p.slots_per_range) {
           if (lane == 0) {
-            LineRec r;
-            r.start = st.line_start;
-            r.len = (uint32_t)(pos + nl + 1 - st.line_start);
-            r.an = an;
-            r.ev_start = st.line_ev_start;
-            r.ev_count = st.ev_w - st.line_ev_start;
-            r.ord = st.nlines - 1;
-            r.pad = 0;
-            my_recs[st.nrec] = r;
+            LineRec *r = &my_recs[st.nrec];
+            r->start = st.line_start;
+            r->len = (uint32_t)(pos + nl + 1 - st.line_start);
+            r->an = an;
+            r->ev_start = st.line_ev_start;
+            r->ev_count = st.ev_w - st.line_ev_start;
+            r->ord = st.nlines - 1;
           }
         } else if (lane == 0) {
           p.ctr->slot_overflow = 1;
@@ -204,30 +221,35 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
       }
       const uint64_t start = pos + nl + 1;
       if (start >= rend) { st.mode = 2; return; }
-      st.line_start = start; st.fs = start; st.col = 0;
-      st.an_lane = 0; st.an_uni = 0; st.line_ev_start = st.ev_w;
+      start_line(st, start, nl + 1);
       seg_lo = nl + 1;
       continue;
     }
 
     // segment runs to the window end: hand the field phase over to the next window
-    uint64_t nfs = FS_NONE;
+    int nfs = FS_NONE;
     if (HAS_SAMPLES) {
       const uint32_t last_tab = __shfl_sync(FULL, tm_l >> 15, 31) & 1u;
       if (last_tab) {
-        nfs = pos + WIN;
+        nfs = 0;
       } else {
         const uint32_t have = __ballot_sync(FULL, fm_all != 0);
         if (have) {
           const int l = 31 - __clz(have);
           const int le = __shfl_sync(FULL, last_end, l);
-          if (le >= WIN) { nfs = pos + (uint64_t)le + 1; st.col += 1; }  // pre-count that tab
+          const uint32_t sp = __shfl_sync(FULL, last_sep, l);
+          if (le >= WIN) {
+            nfs = le + 1 - WIN; st.col += 1;  // pre-count that tab
+            if (sp) st.refpat = 0x09300030u | (sp << 8);
+          }
         }
       }
     }
-    st.fs = nfs;
+    st.fsr = nfs;
     return;
   }
+  // the last segment ended with a newline on the window's final byte: the next line starts the next window
+  if (st.mode == 1) st.fsr = seg_lo - WIN;
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
@@ -247,72 +269,90 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
   st.nrec = 0; st.nlines = 0; st.ev_w = 0; st.line_ev_start = 0;
   st.an_lane = 0; st.an_uni = 0; st.col = 0;
   st.refpat = 0x09307C30u;  // "0|0\t"
-  st.fs = FS_NONE; st.line_start = 0;
+  st.fsr = FS_NONE; st.line_start = 0;
   st.mode = 0;
   if (rstart >= p.end) {
     st.mode = 2;
   } else if (rstart <= p.begin) {  // first range: the region starts with a line
-    st.mode = 1; st.line_start = p.begin; st.fs = p.begin;
+    st.mode = 1; st.line_start = p.begin; st.fsr = (int)(p.begin - rstart);
   } else if (p.in[rstart - 1] == '\n') {
-    st.mode = 1; st.line_start = rstart; st.fs = rstart;
+    st.mode = 1; st.line_start = rstart; st.fsr = 0;
   }
 
-  uint8_t *ring = smem + warp * RING;
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-  auto issue = [&](uint32_t it) {
-    const uint64_t a = rstart + (uint64_t)it * WIN;
-    if (a + WIN <= p.buf_len) {
-      const uint32_t dst = ring_s + ((it & (STAGES - 1)) * WIN) + lane * 16;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(p.in + a + lane * 16));
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-
   if (st.mode != 2) {
+    uint8_t *ring = smem + warp * RING;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+    // windows this warp may touch: up to the end of the padded buffer (32-bit counters keep the loop lean)
+    const uint64_t avail64 = (p.buf_len - rstart) / WIN;
+    const uint32_t n_avail = avail64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)avail64;
+    const uint32_t seek_limit = (uint32_t)((rend - rstart + WIN - 1) / WIN);  // no owned line can start later
+    const uint8_t *gsrc = p.in + rstart + lane * 16;
+    uint32_t issued = 0;
+    auto issue = [&]() {
+      if (issued < n_avail)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring_s + ((issued & (STAGES - 1)) * WIN)), "l"(gsrc));
+      asm volatile("cp.async.commit_group;\n" ::);
+      gsrc += WIN;
+      issued++;
+    };
 #pragma unroll
-    for (int k = 0; k < PF; k++) issue(k);
-    for (uint32_t it = 0;; ++it) {
-      issue(it + PF);
+    for (int k = 0; k < PF; k++) issue();
+    for (uint32_t it = 0; it + 1 < n_avail; ++it) {
+      issue();
       asm volatile("cp.async.wait_group %0;\n" ::"n"(PF - 1));
       __syncwarp();
-      const uint64_t pos = rstart + (uint64_t)it * WIN;
-      if (pos + 2 * WIN > p.buf_len) break;  // safety: never run off the padded buffer
-      if (st.mode == 0 && pos >= rend) break;  // no line starts in this range
+      if (st.mode == 0 && it >= seek_limit) break;  // no line starts in this range
       const uint32_t stage_off = (it & (STAGES - 1)) * WIN;
       const uint4 v = *reinterpret_cast<const uint4 *>(ring + stage_off + lane * 16);
       bool handled = false;
-      if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (st.fs - pos) < 4ull) {
+      if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
         const uint32_t w4 = *reinterpret_cast<const uint32_t *>(ring + ((stage_off + lane * 16 + 16) & (RING - 1)));
-        const uint32_t sh = (uint32_t)(st.fs - pos) * 8u;
-        const uint32_t W0 = __funnelshift_r(v.x, v.y, sh), W1 = __funnelshift_r(v.y, v.z, sh);
-        const uint32_t W2 = __funnelshift_r(v.z, v.w, sh), W3 = __funnelshift_r(v.w, w4, sh);
+        const uint32_t sh = (uint32_t)st.fsr * 8u;
         const uint32_t rp = st.refpat;
-        // T1: every field of the window is the reference genotype
-        if (__all_sync(FULL, ((W0 ^ rp) | (W1 ^ rp) | (W2 ^ rp) | (W3 ^ rp)) == 0)) {
-          st.an_uni += 256; st.col += 128; st.fs += WIN;
+        // XOR with the reference pattern: 0 = reference genotype, digits differ only in the low nibble
+        const uint32_t t0 = __funnelshift_r(v.x, v.y, sh) ^ rp, t1 = __funnelshift_r(v.y, v.z, sh) ^ rp;
+        const uint32_t t2 = __funnelshift_r(v.z, v.w, sh) ^ rp, t3 = __funnelshift_r(v.w, w4, sh) ^ rp;
+        const uint32_t any = t0 | t1 | t2 | t3;
+        if (__all_sync(FULL, any == 0)) {  // T1: every field of the window is the reference genotype
+          st.an_uni += 256; st.col += 128;
           handled = true;
         } else {
-          // T2: every field is x|y\t or x/y\t with single-character alleles
-          const uint32_t Ws[4] = {W0, W1, W2, W3};
-          bool ok = true;
-          uint32_t ev[4];
-          uint32_t nev = 0, miss = 0;
-          const uint32_t samp0 = st.col - 9 + lane * 4;
+          // T2: separator and tab bytes unchanged, allele bytes in [0-9] (or '.', checked only if needed)
+          const uint32_t D = 0x00760076u, H = 0x00800080u, M = 0x00FF00FFu;
+          uint32_t bad = (any & ~M) | ((((t0 & M) + D) | ((t1 & M) + D) | ((t2 & M) + D) | ((t3 & M) + D)) & H);
+          bool dots = false;
+          if (!__all_sync(FULL, bad == 0)) {
+            // allow '.' ('.'^'0' == 0x1E) next to digits
+            const uint32_t ts[4] = {t0, t1, t2, t3};
+            bad = any & ~M;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const uint32_t W = Ws[j];
-            const uint32_t stc = W & 0xFF00FF00u;
-            const uint32_t x = W & 0xFF, y = (W >> 16) & 0xFF;
-            const uint32_t dx = x - '0', dy = y - '0';
-            const bool mx = x == '.', my = y == '.';
-            ok = ok && (stc == 0x09007C00u || stc == 0x09002F00u) && (dx <= 9 || mx) && (dy <= 9 || my);
-            uint32_t e = 0;
-            if (mx || my) { e = ev_make(samp0 + j, EV_CODE_MISSING, EV_CODE_MISSING); miss++; }
-            else if (dx | dy) e = ev_make(samp0 + j, dx, dy);
-            ev[j] = e;
-            nev += e != 0;
+            for (int j = 0; j < 4; j++) {
+              const uint32_t u = ts[j] & M;
+              const uint32_t d = u ^ 0x001E001Eu;
+              const uint32_t notdot = (((d & 0x007F007Fu) + 0x007F007Fu) | d) & H;  // 0x80 where the byte is not '.'
+              bad |= ((u + D) & H) & notdot;
+            }
+            dots = true;
           }
-          if (__all_sync(FULL, ok)) {
+          if (__all_sync(FULL, bad == 0)) {
+            const uint32_t ts[4] = {t0, t1, t2, t3};
+            uint32_t ev[4];
+            uint32_t nev = 0, miss = 0;
+            const uint32_t samp0 = st.col - 9 + lane * 4;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const uint32_t t = ts[j];
+              uint32_t e = 0;
+              if (t) {
+                e = (samp0 + j) + ((t & 0x1Fu) << 20) + ((t & 0x1F0000u) << 9);
+                if (dots && (((t & 0xFFu) == 0x1Eu) || ((t >> 16) == 0x1Eu))) {
+                  e = ev_make(samp0 + j, EV_CODE_MISSING, EV_CODE_MISSING);
+                  miss++;
+                }
+                nev++;
+              }
+              ev[j] = e;
+            }
             const uint32_t eincl = warp_incl_scan(nev, lane);
             const uint32_t etot = __shfl_sync(FULL, eincl, 31);
             if (st.ev_w + etot <= p.evcap_words) {
@@ -325,13 +365,13 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
             }
             st.ev_w += etot;
             st.an_uni += 256; st.an_lane -= 2 * miss;
-            st.col += 128; st.fs += WIN;
-            st.refpat = 0x09300030u | (__shfl_sync(FULL, W0, 0) & 0xFF00u);  // follow the data's separator
+            st.col += 128;
             handled = true;
           }
         }
       }
       if (!handled) {
+        const uint64_t pos = rstart + (uint64_t)it * WIN;
         scan_window_general<HAS_SAMPLES>(p, st, ring, stage_off, v, pos, rend, lane, my_recs, my_events);
         if (st.mode == 2) break;
       }

@@ -98,8 +98,10 @@ typedef struct {
 typedef struct {
   float scan_ms;     /* bvcf_scan_genotype_kernel: newline/tab index + per-sample GT classify  (north-star kernels 1+3) */
   float compact_ms;  /* line-table compaction + prefix sums */
-  float size_ms;     /* bvcf_rows_kernel<size>: FILTER + getAlleles + row sizing (kernels 2+4a) */
-  float emit_ms;     /* bvcf_rows_kernel<emit>: scatter-write rows (kernel 4b) */
+  float stats_ms;    /* bvcf_line_stats_kernel: het/hom/missing/ac/an per record (kernel 3, reduction half) */
+  float size_ms;     /* bvcf_rows_kernel<size>: FILTER + getAlleles + row sizing (kernels 2+4a) + offset scan */
+  float emit_ms;     /* bvcf_rows_kernel<emit>: fixed columns of every row (kernel 4b) */
+  float names_ms;    /* bvcf_names_kernel: sample-name lists + dosage rows (kernel 4b) */
   float total_ms;    /* first launch to last launch, whole run */
   uint32_t launches; /* kernels launched */
 } bvcf_kernel_times;

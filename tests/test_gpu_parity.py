@@ -104,3 +104,98 @@ def test_query_fixture_matches_oracle(query_fixture):
         got = gpu_rows(query_fixture, **kw)
         exp = oracle_rows(query_fixture, **kw)
         assert got == exp
+
+
+def test_dosage_matrix_vector():
+    """main_test.go:2911-2977 TestGenotypeMatrix through the C ABI (dosage batch of bvcf_collect)."""
+    from bystro_vcf_b200 import Config, Transformer, parse_preamble
+
+    vcf, loci, dos = V.DOSAGE_CASE
+    c = _cfg()
+    c.dosageMatrixOutPath = "unused.feather"
+    w, chrom, off = parse_preamble(vcf)
+    with Transformer(c, eol_width=w) as tr:
+        tr.set_header(chrom)
+        res = tr.process(vcf[off:])
+    assert res.loci == loci
+    assert res.dosage.tolist() == dos
+
+
+def test_dosage_matrix_chr1_vs_oracle(chr1_fixture):
+    import numpy as np
+
+    from bystro_vcf_b200 import Config, Transformer, parse_preamble
+    from oracle import oracle as O
+
+    n = chr1_fixture.index(b"\n", 30 << 20) + 1  # ~30 MB: header + ~2,900 records
+    data = chr1_fixture[:n]
+    ref = O.read_vcf(O.OracleConfig(want_dosage=True), data)
+    c = _cfg()
+    c.dosageMatrixOutPath = "unused.feather"
+    w, chrom, off = parse_preamble(data)
+    with Transformer(c, eol_width=w) as tr:
+        tr.set_header(chrom)
+        res = tr.process(data[off:])
+    assert res.tsv == ref.tsv
+    assert res.loci == ref.loci
+    assert np.array_equal(res.dosage, ref.dosage)
+
+
+def test_diagnostics_match_oracle():
+    """the reference's log.Printf sites (main.go:730-986) as (line, alt, code) triples"""
+    from bystro_vcf_b200 import Transformer, parse_preamble
+    from oracle import oracle as O
+
+    recs = [["1", "5", ".", "A", "A", ".", "PASS", "."], ["1", "6", ".", "A", "<DEL>", ".", "PASS", "."],
+            ["1", "7", ".", "AT", "G", ".", "PASS", "."], ["1", "x", ".", "AT", "A", ".", "PASS", "."],
+            ["1", "9", ".", "A", "GT,C,N", ".", "PASS", "."], ["1", "10", ".", "TAGCTT", "TAC,T", ".", "PASS", "."],
+            ["1", "y", ".", "AT", "A,ATT", ".", "PASS", "."], ["1", "12", ".", "AT", "C,ATT", ".", "PASS", "."]]
+    vcf = V._vcf(V.HDR8, recs)
+    ref = O.read_vcf(O.OracleConfig(), vcf)
+    w, chrom, off = parse_preamble(vcf)
+    with Transformer(_cfg(), eol_width=w) as tr:
+        tr.set_header(chrom)
+        res = tr.process(vcf[off:])
+    assert res.tsv == ref.tsv
+    assert sorted(res.diags) == sorted(ref.diags)
+    assert len(ref.diags) >= 8
+
+
+def test_long_fields_beyond_64k():
+    """tab offsets past 64 KiB (huge INFO / ALT): the rows kernel rescans the line itself"""
+    info = "X=" + "A" * 70000
+    ins = "A" + "ACGT" * 20000
+    hdr = V.HDR8 + ["FORMAT", "S1", "S2", "S3"]
+    recs = [["1", "100", "rs1", "A", "C", ".", "PASS", info, "GT", "0|1", "1|1", "0|0"],
+            ["1", "200", "rs2", "A", ins, ".", "PASS", "Y=1", "GT", "0|1", "0|0", ".|."],
+            ["1", "300", "rs3", "A", "G", ".", "PASS", "Z", "GT:PL", "0/1:" + "9," * 40000 + "9", "1/1:0", "0/0:1"]]
+    vcf = V._vcf(hdr, recs)
+    for kw in ({}, {"keep_info": True, "keep_id": True, "keep_pos": True}):
+        assert gpu_rows(vcf, **kw) == oracle_rows(vcf, **kw)
+
+
+def test_slash_separated_and_mixed_width_fields():
+    """'/'-separated 1000G-style block (T1/T2 tiers follow the separator) with odd-width fields mixed in"""
+    import random
+
+    rnd = random.Random(7)
+    ns = 700
+    hdr = V.HDR8 + ["FORMAT"] + ["N%04d" % i for i in range(ns)]
+    recs = []
+    for i in range(300):
+        sep = "/" if i % 3 else "|"
+        gts = []
+        for s in range(ns):
+            r = rnd.random()
+            if r < 0.9: g = "0" + sep + "0"
+            elif r < 0.95: g = "0" + sep + "1"
+            elif r < 0.97: g = "1" + sep + "1"
+            elif r < 0.98: g = "." + sep + "."
+            elif r < 0.985: g = "1"
+            elif r < 0.99: g = "10" + sep + "0"
+            elif r < 0.995: g = "0" + sep + "1" + sep + "1"
+            else: g = "0" + ("|" if sep == "/" else "/") + "1"
+            gts.append(g)
+        recs.append(["2", str(1000 + i), ".", "A", "C,G", ".", "PASS", ".", "GT"] + gts)
+    vcf = V._vcf(hdr, recs)
+    assert gpu_rows(vcf) == oracle_rows(vcf)
