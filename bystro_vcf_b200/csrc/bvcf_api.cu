@@ -75,7 +75,7 @@ struct bvcf_ctx {
   std::vector<std::string> allow, exclude;
   bool header_set = false;
   DevCfg dcfg{};
-  DevBuf d_filt_blob, d_filt_off, d_names, d_name_off;
+  DevBuf d_filt_blob, d_filt_off, d_names, d_name_off, d_name8;
   std::vector<Slot> slots;
   // resident path
   DevBuf r_in, r_out, r_dosage, r_loci;
@@ -159,7 +159,7 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
   if ((rc = dev_reserve(ctx, sc.partial, 2 * PFX_BLOCKS * 8))) return rc;
   if (ctx->dcfg.n_samples > 0) {
     sc.row_cap = std::max<uint64_t>(sc.row_cap, sc.max_records + sc.max_records / 4 + 1024);
-    if ((rc = dev_reserve(ctx, sc.stats1, sc.max_records * sizeof(GtStats)))) return rc;
+    if ((rc = dev_reserve(ctx, sc.stats1, sc.max_records * sizeof(LineStats)))) return rc;
     if ((rc = dev_reserve(ctx, sc.row_desc, sc.row_cap * sizeof(RowDesc)))) return rc;
   }
   return 0;
@@ -239,14 +239,14 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     // 3b. ALT #1 genotype summary per record (warp per record)
     if (dc.n_samples > 0) {
       StatsParams tp{};
-      tp.in = d_in; tp.cfg = dc; tp.lines = cp.dense; tp.events = sp.events; tp.stats1 = (GtStats *)sc.stats1.p; tp.ctr = d_ctr;
+      tp.in = d_in; tp.cfg = dc; tp.lines = cp.dense; tp.events = sp.events; tp.stats = (LineStats *)sc.stats1.p; tp.ctr = d_ctr;
       bvcf_line_stats_kernel<<<wgrid, 256, 0, st>>>(tp);
       ctx->launches++;
     }
     if (se) CK(cudaEventRecord(se->e[3], st));
     // 4. size pass (thread per record)
     RowsParams rp{};
-    rp.in = d_in; rp.cfg = dc; rp.lines = cp.dense; rp.events = sp.events; rp.stats1 = (const GtStats *)sc.stats1.p;
+    rp.in = d_in; rp.cfg = dc; rp.lines = cp.dense; rp.events = sp.events; rp.stats = (const LineStats *)sc.stats1.p;
     rp.line_bytes = (uint32_t *)sc.line_bytes.p; rp.line_rows = (uint32_t *)sc.line_rows.p;
     rp.line_off = (uint64_t *)sc.line_off.p; rp.row_off = (uint64_t *)sc.row_off.p;
     rp.out = d_out; rp.out_cap = out_cap; rp.ctr = d_ctr;
@@ -450,7 +450,7 @@ void bvcf_destroy(bvcf_ctx *ctx) {
     if (s.h_out) cudaFreeHost(s.h_out);
     if (s.h_dosage) cudaFreeHost(s.h_dosage);
   }
-  for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->r_in, &ctx->r_out,
+  for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->d_name8, &ctx->r_in, &ctx->r_out,
                     &ctx->r_dosage, &ctx->r_loci})
     dev_free(*b);
   scratch_free(ctx->r_sc);
@@ -497,6 +497,19 @@ int bvcf_set_header(bvcf_ctx *ctx, const char *chrom_line, size_t len) {
   ctx->dcfg.names = (const uint8_t *)ctx->d_names.p;
   ctx->dcfg.name_off = (const uint32_t *)ctx->d_name_off.p;
   ctx->dcfg.name_fixed_w = fixed_w;
+  ctx->dcfg.name8 = nullptr;
+  if (fixed_w == 7 && ctx->field_delim.size() == 1 && ns > 0) {
+    std::vector<unsigned long long> n8(ns);
+    for (int i = 0; i < ns; i++) {
+      unsigned long long v = 0;
+      for (int k = 0; k < 7; k++) v |= (unsigned long long)blob[(size_t)i * 7 + k] << (8 * k);
+      v |= (unsigned long long)(uint8_t)ctx->field_delim[0] << 56;
+      n8[i] = v;
+    }
+    if ((rc = dev_reserve(ctx, ctx->d_name8, n8.size() * 8))) return rc;
+    CK(cudaMemcpy(ctx->d_name8.p, n8.data(), n8.size() * 8, cudaMemcpyHostToDevice));
+    ctx->dcfg.name8 = (const unsigned long long *)ctx->d_name8.p;
+  }
   ctx->header_set = true;
   return BVCF_OK;
 }

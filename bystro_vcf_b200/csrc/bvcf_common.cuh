@@ -78,6 +78,8 @@ struct DevCfg {
   const uint8_t *names;       // sample names back to back
   const uint32_t *name_off;   // n_samples + 1
   int name_fixed_w;           // > 0 when every sample name has this length
+  const unsigned long long *name8;  // name + delimiter packed in 8 bytes per sample, when 7-char names and a
+                                    // 1-char delimiter make every list item exactly 8 bytes; else null
 };
 
 // ---- warp helpers --------------------------------------------------------------------------------

@@ -30,11 +30,20 @@ struct GtStats {
   uint32_t het_bytes, hom_bytes, miss_bytes;  // sum of the sample-name lengths per class
 };
 
+// warp-reduced summary of one record for ALT numbers 1..3 (99.99 % of real rows)
+constexpr int STAT_ALLELES = 3;
+struct __align__(16) LineStats {
+  uint32_t n_miss, an, miss_bytes, pad;
+  uint32_t n_het[STAT_ALLELES], n_hom[STAT_ALLELES], ac[STAT_ALLELES], het_bytes[STAT_ALLELES], hom_bytes[STAT_ALLELES];
+  uint32_t pad2;
+};
+
 // one emitted row, for the names kernel
 struct __align__(16) RowDesc {
   uint32_t line;        // record index in the dense line table
   uint32_t allele;      // ALT number (altIdx + 1)
   unsigned long long het_dst, hom_dst, miss_dst;  // absolute byte offsets of the three lists in the output
+  uint32_t n_het, n_hom, n_miss, pad;             // list lengths (names)
 };
 
 struct RowsParams {
@@ -42,7 +51,7 @@ struct RowsParams {
   DevCfg cfg;
   const LineRec *lines;      // dense, input order
   const uint32_t *events;    // sub-chunk event buffer
-  const GtStats *stats1;     // per record, ALT #1 (null when there are no samples)
+  const LineStats *stats;    // per record, ALT #1..3 (null when there are no samples)
   uint32_t *line_bytes;      // SIZE out
   uint32_t *line_rows;       // SIZE out
   const uint64_t *line_off;  // EMIT in: exclusive prefix of line_bytes
@@ -111,52 +120,76 @@ struct StatsParams {
   DevCfg cfg;
   const LineRec *lines;
   const uint32_t *events;
-  GtStats *stats1;
+  LineStats *stats;
   RunCounters *ctr;
 };
 
-__device__ __forceinline__ GtStats reduce_events_warp(const DevCfg &cfg, const LineRec &rec, const uint32_t *ev,
-                                                      const uint8_t *L, uint32_t content_len, uint32_t a, int lane) {
-  uint32_t n_het = 0, n_hom = 0, n_miss = 0, ac = 0, an_x = 0, hb = 0, mb = 0, ob = 0;
-  const bool fixed = cfg.name_fixed_w > 0;
-  for (uint32_t base = 0; base < rec.ev_count; base += 32) {
-    uint32_t samp, gtx, alt;
-    const int cls = classify_event(ev, base + lane, rec.ev_count, L, content_len, a, samp, gtx, alt);
-    n_het += __popc(__ballot_sync(FULL, cls == 1));
-    n_hom += __popc(__ballot_sync(FULL, cls == 2));
-    n_miss += __popc(__ballot_sync(FULL, cls == 3));
-    ac += alt;
-    an_x += gtx;
-    if (!fixed && cls) {
-      const uint32_t nl = name_len(cfg, samp);
-      if (cls == 1) hb += nl; else if (cls == 2) ob += nl; else mb += nl;
-    }
-  }
-  GtStats s;
-  s.n_het = n_het; s.n_hom = n_hom; s.n_miss = n_miss;
-  s.ac = warp_sum(ac);
-  s.an = rec.an + warp_sum(an_x);
-  if (fixed) {
-    s.het_bytes = n_het * cfg.name_fixed_w; s.hom_bytes = n_hom * cfg.name_fixed_w; s.miss_bytes = n_miss * cfg.name_fixed_w;
-  } else {
-    s.het_bytes = warp_sum(hb); s.hom_bytes = warp_sum(ob); s.miss_bytes = warp_sum(mb);
-  }
-  return s;
-}
-
 __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams p) {
+  const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
   const uint32_t n_rec = p.ctr->chunk_records;
   const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+  const bool fixed = cfg.name_fixed_w > 0;
   for (uint32_t li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); li < n_rec; li += total_warps) {
     const LineRec rec = p.lines[li];
-    const uint32_t n = rec.len >= (uint32_t)p.cfg.eol_width ? rec.len - (uint32_t)p.cfg.eol_width : 0;
-    const GtStats s = reduce_events_warp(p.cfg, rec, p.events + rec.ev_start, p.in + rec.start, n, 1, lane);
-    if (lane == 0) p.stats1[li] = s;
+    const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
+    const uint32_t *ev = p.events + rec.ev_start;
+    const uint8_t *L = p.in + rec.start;
+    uint32_t n_het[STAT_ALLELES] = {0, 0, 0}, n_hom[STAT_ALLELES] = {0, 0, 0}, ac[STAT_ALLELES] = {0, 0, 0};
+    uint32_t hb[STAT_ALLELES] = {0, 0, 0}, ob[STAT_ALLELES] = {0, 0, 0};
+    uint32_t n_miss = 0, an_x = 0, mb = 0;
+    for (uint32_t base = 0; base < rec.ev_count; base += 32) {
+      const uint32_t k = base + lane;
+      uint32_t w = k < rec.ev_count ? ev[k] : EV_OFFSET_TAG;
+      const bool is_ev = !(w & EV_OFFSET_TAG);
+      const uint32_t samp = w & EV_SAMPLE_MASK;
+      const uint32_t nl = (is_ev && !fixed) ? name_len(cfg, samp) : 0;
+      int cls[STAT_ALLELES];
+      uint32_t alt[STAT_ALLELES];
+      uint32_t gtx = 0;
+      if (is_ev && (w & EV_COMPLEX)) {  // general GT grammar, exact (main.go:1126-1190)
+        const uint32_t off = ev[k + 1] & ~EV_OFFSET_TAG;
+#pragma unroll
+        for (int a = 0; a < STAT_ALLELES; a++)
+          cls[a] = classify_gt_general(L + off, content_len > off ? content_len - off : 0, a + 1, gtx, alt[a]);
+      } else {
+        const uint32_t c1 = (w >> 20) & 31, c2 = (w >> 25) & 31;
+        const bool miss = c1 == EV_CODE_MISSING;
+        const uint32_t gt = c2 == EV_CODE_ABSENT ? 1 : 2;
+#pragma unroll
+        for (int a = 0; a < STAT_ALLELES; a++) {
+          alt[a] = (is_ev && !miss) ? (c1 == (uint32_t)(a + 1)) + (c2 == (uint32_t)(a + 1)) : 0;
+          cls[a] = !is_ev ? 0 : (miss ? 3 : (alt[a] == 0 ? 0 : (alt[a] == gt ? 2 : 1)));
+        }
+      }
+      const uint32_t bm = __ballot_sync(FULL, cls[0] == 3);
+      n_miss += __popc(bm);
+      if (cls[0] == 3) mb += nl;
+      an_x += gtx;
+#pragma unroll
+      for (int a = 0; a < STAT_ALLELES; a++) {
+        n_het[a] += __popc(__ballot_sync(FULL, cls[a] == 1));
+        n_hom[a] += __popc(__ballot_sync(FULL, cls[a] == 2));
+        ac[a] += alt[a];
+        if (cls[a] == 1) hb[a] += nl; else if (cls[a] == 2) ob[a] += nl;
+      }
+    }
+    LineStats s;
+    s.n_miss = n_miss; s.pad = 0; s.pad2 = 0;
+    s.an = rec.an + warp_sum(an_x);
+    s.miss_bytes = fixed ? n_miss * cfg.name_fixed_w : warp_sum(mb);
+#pragma unroll
+    for (int a = 0; a < STAT_ALLELES; a++) {
+      s.n_het[a] = n_het[a]; s.n_hom[a] = n_hom[a];
+      s.ac[a] = warp_sum(ac[a]);
+      s.het_bytes[a] = fixed ? n_het[a] * cfg.name_fixed_w : warp_sum(hb[a]);
+      s.hom_bytes[a] = fixed ? n_hom[a] * cfg.name_fixed_w : warp_sum(ob[a]);
+    }
+    if (lane == 0) p.stats[li] = s;
   }
 }
 
-// the record's own thread reduces the events for an ALT number other than 1
+// the record's own thread reduces the events for ALT numbers beyond STAT_ALLELES
 __device__ __noinline__ GtStats reduce_events_thread(const DevCfg &cfg, const LineRec &rec, const uint32_t *ev,
                                                      const uint8_t *L, uint32_t content_len, uint32_t a) {
   GtStats s;
@@ -227,8 +260,14 @@ __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, c
   const uint32_t a = (uint32_t)oa.alt_idx + 1;
   if (cfg.n_samples > 0) {
     if (gs_idx != oa.alt_idx) {  // MNP bases share their ALT index: reduce once (main.go:865-868)
-      if (a == 1) gs = p.stats1[lc.li];
-      else gs = reduce_events_thread(cfg, rec, p.events + rec.ev_start, lc.L, lc.content_len, a);
+      if (a <= (uint32_t)STAT_ALLELES) {
+        const LineStats &ls = p.stats[lc.li];
+        gs.n_het = ls.n_het[a - 1]; gs.n_hom = ls.n_hom[a - 1]; gs.ac = ls.ac[a - 1];
+        gs.het_bytes = ls.het_bytes[a - 1]; gs.hom_bytes = ls.hom_bytes[a - 1];
+        gs.n_miss = ls.n_miss; gs.an = ls.an; gs.miss_bytes = ls.miss_bytes;
+      } else {
+        gs = reduce_events_thread(cfg, rec, p.events + rec.ev_start, lc.L, lc.content_len, a);
+      }
       gs_idx = oa.alt_idx;
     }
     if (gs.ac == 0) return;  // main.go:558
@@ -258,6 +297,7 @@ __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, c
   RowDesc rd;
   rd.line = lc.li; rd.allele = a;
   rd.het_dst = rd.hom_dst = rd.miss_dst = ~0ull;
+  rd.n_het = rd.n_hom = rd.n_miss = 0; rd.pad = 0;
 
   if (cfg.want_tsv) {
     // chrom (main.go:570-574)
@@ -302,6 +342,7 @@ __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, c
         w.byte('\t');
       }
       rd.het_dst = dsts[0]; rd.hom_dst = dsts[1]; rd.miss_dst = dsts[2];
+      rd.n_het = gs.n_het; rd.n_hom = gs.n_hom; rd.n_miss = gs.n_miss;
       w.dec(gs.ac); w.byte('\t');
       w.dec(gs.an); w.byte('\t');
       if (gs.ac == 0) w.byte('0');
@@ -533,6 +574,7 @@ struct NamesParams {
 };
 
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
+  __shared__ unsigned long long s_stage[NAMES_WARPS][32];
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
   if (p.ctr->out_overflow) return;
@@ -559,6 +601,64 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
     uint32_t run_n[3] = {0, 0, 0};
     uint32_t run_b[3] = {0, 0, 0};
     const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
+    if (cfg.name8 && cfg.want_tsv) {
+      // ---- fast path: every list item is exactly 8 bytes (name + delimiter).  Items of one class are
+      // ranked with ballot/popc, permuted into rank order through shared memory and written as ALIGNED
+      // 64-bit words (each word = tail of item m-1 | head of item m), so a batch of 32 names is one
+      // fully coalesced 256-byte store instead of 256 single-byte stores. ----
+      unsigned long long *stg = s_stage[threadIdx.x >> 5];
+      const uint32_t totals[3] = {rd.n_het, rd.n_hom, rd.n_miss};
+      unsigned long long carry[3] = {0, 0, 0};
+      for (uint32_t base = 0; base < rec.ev_count; base += 32) {
+        uint32_t samp, gtx, alt;
+        const uint32_t k = base + lane;
+        const int cls = classify_event(ev, k, rec.ev_count, L, content_len, a, samp, gtx, alt);
+        if (drow && k < rec.ev_count && !(ev[k] & EV_OFFSET_TAG))
+          drow[samp] = cls == 3 ? (int8_t)-1 : (int8_t)(alt > 127 ? 127 : alt);  // main.go:1172-1178
+        const unsigned long long item = cls ? cfg.name8[samp] : 0ull;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const uint32_t bal = __ballot_sync(FULL, cls == c + 1);
+          if (bal == 0) continue;
+          const uint32_t cnt = __popc(bal);
+          if (cls == c + 1) stg[__popc(bal & lt)] = item;
+          __syncwarp();
+          unsigned long long it = lane < cnt ? stg[lane] : 0ull;
+          const uint32_t m = run_n[c] + lane;           // index of this lane's item in the list
+          if (m + 1 == totals[c]) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
+          unsigned long long prev = __shfl_up_sync(FULL, it, 1);
+          if (lane == 0) prev = carry[c];
+          carry[c] = __shfl_sync(FULL, it, cnt - 1);
+          const uint32_t sh = (uint32_t)(dsts[c] & 7ull);
+          unsigned long long *wp = reinterpret_cast<unsigned long long *>(p.out + (dsts[c] - sh)) + m;
+          if (lane < cnt) {
+            if (sh == 0) {
+              *wp = it;
+            } else if (m > 0) {
+              *wp = (prev >> (8 * (8 - sh))) | (it << (8 * sh));
+            } else {  // first item of the list: only its leading 8-sh bytes belong to word 0
+              uint8_t *d = p.out + dsts[c];
+              for (uint32_t i = 0; i < 8 - sh; i++) d[i] = (uint8_t)(it >> (8 * i));
+            }
+          }
+          run_n[c] += cnt;
+          __syncwarp();
+        }
+      }
+      // tails: the last sh bytes of the last item of each list
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const uint32_t sh = (uint32_t)(dsts[c] & 7ull);
+          if (run_n[c] && sh) {
+            uint8_t *d = p.out + (dsts[c] - sh) + 8ull * run_n[c];
+            const unsigned long long tail = carry[c] >> (8 * (8 - sh));
+            for (uint32_t i = 0; i < sh; i++) d[i] = (uint8_t)(tail >> (8 * i));
+          }
+        }
+      }
+      continue;
+    }
     for (uint32_t base = 0; base < rec.ev_count; base += 32) {
       uint32_t samp, gtx, alt;
       const uint32_t k = base + lane;
