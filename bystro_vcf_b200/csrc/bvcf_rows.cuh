@@ -92,12 +92,11 @@ __device__ __forceinline__ const uint8_t *name_ptr(const DevCfg &c, uint32_t s) 
 
 // classify one event word for allele number a; returns class 0..3 (none/het/hom/missing) and gt/alt.
 // Complex events read the next word and re-parse the field with the general GT grammar.
-__device__ __forceinline__ int classify_event(const uint32_t *ev, uint32_t k, uint32_t n, const uint8_t *L,
-                                              uint32_t content_len, uint32_t a, uint32_t &samp, uint32_t &gt_extra,
-                                              uint32_t &alt) {
+// classify_word takes the (possibly prefetched) event word; out-of-range lanes pass EV_OFFSET_TAG.
+__device__ __forceinline__ int classify_word(uint32_t w, const uint32_t *ev, uint32_t k, const uint8_t *L,
+                                             uint32_t content_len, uint32_t a, uint32_t &samp, uint32_t &gt_extra,
+                                             uint32_t &alt) {
   gt_extra = 0; alt = 0; samp = 0;
-  if (k >= n) return 0;
-  const uint32_t w = ev[k];
   if (w & EV_OFFSET_TAG) return 0;
   samp = w & EV_SAMPLE_MASK;
   if (w & EV_COMPLEX) {
@@ -113,6 +112,11 @@ __device__ __forceinline__ int classify_event(const uint32_t *ev, uint32_t k, ui
   const uint32_t gt = c2 == EV_CODE_ABSENT ? 1 : 2;
   return alt == 0 ? 0 : (alt == gt ? 2 : 1);
 }
+__device__ __forceinline__ int classify_event(const uint32_t *ev, uint32_t k, uint32_t n, const uint8_t *L,
+                                              uint32_t content_len, uint32_t a, uint32_t &samp, uint32_t &gt_extra,
+                                              uint32_t &alt) {
+  return classify_word(k < n ? ev[k] : EV_OFFSET_TAG, ev, k, L, content_len, a, samp, gt_extra, alt);
+}
 
 // ---- warp per record: ALT #1 summary ---------------------------------------------------------------
 struct StatsParams {
@@ -124,68 +128,128 @@ struct StatsParams {
   RunCounters *ctr;
 };
 
+// one event word classified against ALT numbers 1..STAT_ALLELES at once
+struct Ev3 {
+  int cls[STAT_ALLELES];
+  uint32_t alt[STAT_ALLELES];
+  uint32_t gtx, samp;
+  bool is_ev;
+};
+__device__ __forceinline__ void classify3w(uint32_t w, const uint32_t *ev, uint32_t k, const uint8_t *L,
+                                           uint32_t content_len, Ev3 &o) {
+  o.is_ev = !(w & EV_OFFSET_TAG);
+  o.samp = w & EV_SAMPLE_MASK;
+  o.gtx = 0;
+  if (o.is_ev && (w & EV_COMPLEX)) {  // general GT grammar, exact (main.go:1126-1190)
+    const uint32_t off = ev[k + 1] & ~EV_OFFSET_TAG;
+#pragma unroll
+    for (int a = 0; a < STAT_ALLELES; a++)
+      o.cls[a] = classify_gt_general(L + off, content_len > off ? content_len - off : 0, a + 1, o.gtx, o.alt[a]);
+  } else {
+    const uint32_t c1 = (w >> 20) & 31, c2 = (w >> 25) & 31;
+    const bool miss = c1 == EV_CODE_MISSING;
+    const uint32_t gt = c2 == EV_CODE_ABSENT ? 1 : 2;
+#pragma unroll
+    for (int a = 0; a < STAT_ALLELES; a++) {
+      o.alt[a] = (o.is_ev && !miss) ? (c1 == (uint32_t)(a + 1)) + (c2 == (uint32_t)(a + 1)) : 0;
+      o.cls[a] = !o.is_ev ? 0 : (miss ? 3 : (o.alt[a] == 0 ? 0 : (o.alt[a] == gt ? 2 : 1)));
+    }
+  }
+}
+
+__device__ __forceinline__ void classify3(const uint32_t *ev, uint32_t k, uint32_t n, const uint8_t *L,
+                                          uint32_t content_len, Ev3 &o) {
+  classify3w(k < n ? ev[k] : EV_OFFSET_TAG, ev, k, L, content_len, o);
+}
+
+constexpr uint32_t SMALL_EVENTS = 12;  // records with at most this many event words are reduced by one lane
+
+// Hybrid granularity: a warp takes 32 consecutive records.  Each lane reduces its own record when it has
+// few events (most of real data: singletons and rare variants); records with long event lists are then
+// reduced one at a time by the whole warp with ballot/popc.
 __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams p) {
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
   const uint32_t n_rec = p.ctr->chunk_records;
   const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
   const bool fixed = cfg.name_fixed_w > 0;
-  for (uint32_t li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); li < n_rec; li += total_warps) {
-    const LineRec rec = p.lines[li];
-    const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
-    const uint32_t *ev = p.events + rec.ev_start;
-    const uint8_t *L = p.in + rec.start;
-    uint32_t n_het[STAT_ALLELES] = {0, 0, 0}, n_hom[STAT_ALLELES] = {0, 0, 0}, ac[STAT_ALLELES] = {0, 0, 0};
-    uint32_t hb[STAT_ALLELES] = {0, 0, 0}, ob[STAT_ALLELES] = {0, 0, 0};
-    uint32_t n_miss = 0, an_x = 0, mb = 0;
-    for (uint32_t base = 0; base < rec.ev_count; base += 32) {
-      const uint32_t k = base + lane;
-      uint32_t w = k < rec.ev_count ? ev[k] : EV_OFFSET_TAG;
-      const bool is_ev = !(w & EV_OFFSET_TAG);
-      const uint32_t samp = w & EV_SAMPLE_MASK;
-      const uint32_t nl = (is_ev && !fixed) ? name_len(cfg, samp) : 0;
-      int cls[STAT_ALLELES];
-      uint32_t alt[STAT_ALLELES];
-      uint32_t gtx = 0;
-      if (is_ev && (w & EV_COMPLEX)) {  // general GT grammar, exact (main.go:1126-1190)
-        const uint32_t off = ev[k + 1] & ~EV_OFFSET_TAG;
+  for (uint32_t lb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; lb < n_rec; lb += total_warps * 32) {
+    const uint32_t li = lb + lane;
+    const bool valid = li < n_rec;
+    LineRec rec;
+    rec.start = 0; rec.len = 0; rec.an = 0; rec.ev_start = 0; rec.ev_count = 0;
+    if (valid) rec = p.lines[li];
+    const bool small = valid && rec.ev_count <= SMALL_EVENTS;
+    if (small) {  // ---- lane-serial ----
+      const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
+      const uint32_t *ev = p.events + rec.ev_start;
+      LineStats s;
+      s.n_miss = 0; s.an = rec.an; s.miss_bytes = 0; s.pad = 0; s.pad2 = 0;
 #pragma unroll
-        for (int a = 0; a < STAT_ALLELES; a++)
-          cls[a] = classify_gt_general(L + off, content_len > off ? content_len - off : 0, a + 1, gtx, alt[a]);
-      } else {
-        const uint32_t c1 = (w >> 20) & 31, c2 = (w >> 25) & 31;
-        const bool miss = c1 == EV_CODE_MISSING;
-        const uint32_t gt = c2 == EV_CODE_ABSENT ? 1 : 2;
+      for (int a = 0; a < STAT_ALLELES; a++) { s.n_het[a] = s.n_hom[a] = s.ac[a] = s.het_bytes[a] = s.hom_bytes[a] = 0; }
+      for (uint32_t k = 0; k < rec.ev_count; k++) {
+        Ev3 e;
+        classify3(ev, k, rec.ev_count, p.in + rec.start, content_len, e);
+        if (!e.is_ev) continue;
+        const uint32_t nl = name_len(cfg, e.samp);
+        s.an += e.gtx;
+        if (e.cls[0] == 3) { s.n_miss++; s.miss_bytes += nl; }
 #pragma unroll
         for (int a = 0; a < STAT_ALLELES; a++) {
-          alt[a] = (is_ev && !miss) ? (c1 == (uint32_t)(a + 1)) + (c2 == (uint32_t)(a + 1)) : 0;
-          cls[a] = !is_ev ? 0 : (miss ? 3 : (alt[a] == 0 ? 0 : (alt[a] == gt ? 2 : 1)));
+          s.ac[a] += e.alt[a];
+          if (e.cls[a] == 1) { s.n_het[a]++; s.het_bytes[a] += nl; }
+          else if (e.cls[a] == 2) { s.n_hom[a]++; s.hom_bytes[a] += nl; }
         }
       }
-      const uint32_t bm = __ballot_sync(FULL, cls[0] == 3);
-      n_miss += __popc(bm);
-      if (cls[0] == 3) mb += nl;
-      an_x += gtx;
+      p.stats[li] = s;
+    }
+    // ---- warp-cooperative for the long ones ----
+    uint32_t big = __ballot_sync(FULL, valid && !small);
+    while (big) {
+      const int l = __ffs(big) - 1;
+      big &= big - 1;
+      const uint64_t start = __shfl_sync(FULL, rec.start, l);
+      const uint32_t len = __shfl_sync(FULL, rec.len, l);
+      const uint32_t an0 = __shfl_sync(FULL, rec.an, l);
+      const uint32_t ev_start = __shfl_sync(FULL, rec.ev_start, l);
+      const uint32_t ev_count = __shfl_sync(FULL, rec.ev_count, l);
+      const uint32_t content_len = len >= (uint32_t)cfg.eol_width ? len - (uint32_t)cfg.eol_width : 0;
+      const uint32_t *ev = p.events + ev_start;
+      const uint8_t *L = p.in + start;
+      uint32_t n_het[STAT_ALLELES] = {0, 0, 0}, n_hom[STAT_ALLELES] = {0, 0, 0}, ac[STAT_ALLELES] = {0, 0, 0};
+      uint32_t hb[STAT_ALLELES] = {0, 0, 0}, ob[STAT_ALLELES] = {0, 0, 0};
+      uint32_t n_miss = 0, an_x = 0, mb = 0;
+      uint32_t w_next = lane < ev_count ? ev[lane] : EV_OFFSET_TAG;
+      for (uint32_t base = 0; base < ev_count; base += 32) {
+        const uint32_t w_cur = w_next;  // software pipelining: the next batch's words are already in flight
+        w_next = base + 32 + lane < ev_count ? ev[base + 32 + lane] : EV_OFFSET_TAG;
+        Ev3 e;
+        classify3w(w_cur, ev, base + lane, L, content_len, e);
+        const uint32_t nl = (e.is_ev && !fixed) ? name_len(cfg, e.samp) : 0;
+        n_miss += __popc(__ballot_sync(FULL, e.cls[0] == 3));
+        if (e.cls[0] == 3) mb += nl;
+        an_x += e.gtx;
+#pragma unroll
+        for (int a = 0; a < STAT_ALLELES; a++) {
+          n_het[a] += __popc(__ballot_sync(FULL, e.cls[a] == 1));
+          n_hom[a] += __popc(__ballot_sync(FULL, e.cls[a] == 2));
+          ac[a] += e.alt[a];
+          if (e.cls[a] == 1) hb[a] += nl; else if (e.cls[a] == 2) ob[a] += nl;
+        }
+      }
+      LineStats s;
+      s.n_miss = n_miss; s.pad = 0; s.pad2 = 0;
+      s.an = an0 + warp_sum(an_x);
+      s.miss_bytes = fixed ? n_miss * cfg.name_fixed_w : warp_sum(mb);
 #pragma unroll
       for (int a = 0; a < STAT_ALLELES; a++) {
-        n_het[a] += __popc(__ballot_sync(FULL, cls[a] == 1));
-        n_hom[a] += __popc(__ballot_sync(FULL, cls[a] == 2));
-        ac[a] += alt[a];
-        if (cls[a] == 1) hb[a] += nl; else if (cls[a] == 2) ob[a] += nl;
+        s.n_het[a] = n_het[a]; s.n_hom[a] = n_hom[a];
+        s.ac[a] = warp_sum(ac[a]);
+        s.het_bytes[a] = fixed ? n_het[a] * cfg.name_fixed_w : warp_sum(hb[a]);
+        s.hom_bytes[a] = fixed ? n_hom[a] * cfg.name_fixed_w : warp_sum(ob[a]);
       }
+      if (lane == 0) p.stats[lb + l] = s;
     }
-    LineStats s;
-    s.n_miss = n_miss; s.pad = 0; s.pad2 = 0;
-    s.an = rec.an + warp_sum(an_x);
-    s.miss_bytes = fixed ? n_miss * cfg.name_fixed_w : warp_sum(mb);
-#pragma unroll
-    for (int a = 0; a < STAT_ALLELES; a++) {
-      s.n_het[a] = n_het[a]; s.n_hom[a] = n_hom[a];
-      s.ac[a] = warp_sum(ac[a]);
-      s.het_bytes[a] = fixed ? n_het[a] * cfg.name_fixed_w : warp_sum(hb[a]);
-      s.hom_bytes[a] = fixed ? n_hom[a] * cfg.name_fixed_w : warp_sum(ob[a]);
-    }
-    if (lane == 0) p.stats[li] = s;
   }
 }
 
@@ -573,19 +637,14 @@ struct NamesParams {
   unsigned long long dosage_cap_rows;
 };
 
-__global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
-  __shared__ unsigned long long s_stage[NAMES_WARPS][32];
+// one row, whole warp: ballot/popc ranks, ordered scatter of the names (and the dosage row)
+__device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned long long r, unsigned long long row0,
+                                               int lane, unsigned long long *stg) {
   const DevCfg &cfg = p.cfg;
-  const int lane = threadIdx.x & 31;
-  if (p.ctr->out_overflow) return;
-  const unsigned long long row0 = p.ctr->chunk_row_base;
-  unsigned long long n_rows = p.ctr->row_cursor - row0;  // rows of this sub-chunk
-  if (n_rows > p.row_desc_cap) n_rows = p.row_desc_cap;
-  const uint32_t total_warps = gridDim.x * NAMES_WARPS;
   const uint32_t dl = (uint32_t)cfg.delim_len;
   const bool fixed = cfg.name_fixed_w > 0;
   const uint32_t lt = (1u << lane) - 1u;
-  for (unsigned long long r = blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5); r < n_rows; r += total_warps) {
+  {
     const RowDesc rd = p.row_desc[r];
     const LineRec rec = p.lines[rd.line];
     const uint32_t *ev = p.events + rec.ev_start;
@@ -606,14 +665,17 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
       // ranked with ballot/popc, permuted into rank order through shared memory and written as ALIGNED
       // 64-bit words (each word = tail of item m-1 | head of item m), so a batch of 32 names is one
       // fully coalesced 256-byte store instead of 256 single-byte stores. ----
-      unsigned long long *stg = s_stage[threadIdx.x >> 5];
+      
       const uint32_t totals[3] = {rd.n_het, rd.n_hom, rd.n_miss};
       unsigned long long carry[3] = {0, 0, 0};
+      uint32_t w_next = lane < rec.ev_count ? ev[lane] : EV_OFFSET_TAG;
       for (uint32_t base = 0; base < rec.ev_count; base += 32) {
         uint32_t samp, gtx, alt;
         const uint32_t k = base + lane;
-        const int cls = classify_event(ev, k, rec.ev_count, L, content_len, a, samp, gtx, alt);
-        if (drow && k < rec.ev_count && !(ev[k] & EV_OFFSET_TAG))
+        const uint32_t w_cur = w_next;  // software pipelining: the next batch's words are already in flight
+        w_next = k + 32 < rec.ev_count ? ev[k + 32] : EV_OFFSET_TAG;
+        const int cls = classify_word(w_cur, ev, k, L, content_len, a, samp, gtx, alt);
+        if (drow && !(w_cur & EV_OFFSET_TAG))
           drow[samp] = cls == 3 ? (int8_t)-1 : (int8_t)(alt > 127 ? 127 : alt);  // main.go:1172-1178
         const unsigned long long item = cls ? cfg.name8[samp] : 0ull;
 #pragma unroll
@@ -657,7 +719,7 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
           }
         }
       }
-      continue;
+      return;
     }
     for (uint32_t base = 0; base < rec.ev_count; base += 32) {
       uint32_t samp, gtx, alt;
@@ -693,6 +755,71 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
         const uint8_t *src = name_ptr(cfg, samp);
         for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
       }
+    }
+  }
+}
+
+// one row, one lane: rows whose record has only a handful of events (singletons, rare variants)
+__device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDesc &rd, const LineRec &rec) {
+  const DevCfg &cfg = p.cfg;
+  const uint32_t *ev = p.events + rec.ev_start;
+  const uint8_t *L = p.in + rec.start;
+  const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
+  const uint32_t dl = (uint32_t)cfg.delim_len;
+  const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
+  uint32_t run_n[3] = {0, 0, 0}, run_b[3] = {0, 0, 0};
+  for (uint32_t k = 0; k < rec.ev_count; k++) {
+    uint32_t samp, gtx, alt;
+    const int cls = classify_event(ev, k, rec.ev_count, L, content_len, rd.allele, samp, gtx, alt);
+    if (!cls) continue;
+    const int c = cls - 1;
+    uint8_t *d = p.out + dsts[c] + run_b[c];
+    if (run_n[c] > 0) {
+      for (uint32_t i = 0; i < dl; i++) d[i] = cfg.delim[i];
+      d += dl; run_b[c] += dl;
+    }
+    const uint32_t nl = name_len(cfg, samp);
+    if (cfg.name8) {
+      const unsigned long long it = cfg.name8[samp];
+#pragma unroll
+      for (int i = 0; i < 7; i++) d[i] = (uint8_t)(it >> (8 * i));
+    } else {
+      const uint8_t *src = name_ptr(cfg, samp);
+      for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
+    }
+    run_b[c] += nl;
+    run_n[c]++;
+  }
+}
+
+// Hybrid granularity (as in the stats kernel): a warp takes 32 consecutive rows; short ones lane-serial,
+// long ones warp-cooperative.
+__global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
+  __shared__ unsigned long long s_stage[NAMES_WARPS][32];
+  const DevCfg &cfg = p.cfg;
+  const int lane = threadIdx.x & 31;
+  if (p.ctr->out_overflow) return;
+  const unsigned long long row0 = p.ctr->chunk_row_base;
+  unsigned long long n_rows = p.ctr->row_cursor - row0;  // rows of this sub-chunk
+  if (n_rows > p.row_desc_cap) n_rows = p.row_desc_cap;
+  const unsigned long long total_warps = (unsigned long long)gridDim.x * NAMES_WARPS;
+  unsigned long long *stg = s_stage[threadIdx.x >> 5];
+  for (unsigned long long rb = ((unsigned long long)blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5)) * 32; rb < n_rows;
+       rb += total_warps * 32) {
+    const unsigned long long r = rb + lane;
+    const bool valid = r < n_rows;
+    bool small = false;
+    if (valid && !cfg.want_dosage && cfg.want_tsv) {
+      const RowDesc rd = p.row_desc[r];
+      const LineRec rec = p.lines[rd.line];
+      small = rec.ev_count <= SMALL_EVENTS;
+      if (small) names_row_lane(p, rd, rec);
+    }
+    uint32_t big = __ballot_sync(FULL, valid && !small);
+    while (big) {
+      const int l = __ffs(big) - 1;
+      big &= big - 1;
+      names_row_warp(p, rb + l, row0, lane, stg);
     }
   }
 }
