@@ -19,9 +19,11 @@ struct __align__(16) LineRec {
   uint32_t ord;       // ordinal of this line among ALL lines that start in its range
   uint16_t tab[9];    // offsets of the first nine tabs from `start` (0xFFFF: beyond 64 KiB, rescan); only
                       // the first min(H-1, 9) entries are meaningful
-  uint16_t pad;
+  uint16_t flags;     // bit 0: some sample carries an ALT number > 1 or needs the general GT grammar, so the
+                      // inline ALT #1 summary below is not the whole story (bvcf_line_stats_kernel serves it)
+  uint32_t n_het1, n_hom1, n_miss, ac1;  // ALT #1 summary over the fast-classified samples (main.go:1042-1194)
 };
-static_assert(sizeof(LineRec) == 48, "LineRec layout");
+static_assert(sizeof(LineRec) == 64, "LineRec layout");
 
 // ---- genotype events ----------------------------------------------------------------------------
 // The scan kernel emits one 32-bit event per sample whose GT is not plain reference:

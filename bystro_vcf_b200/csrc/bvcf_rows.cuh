@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams 
     const uint32_t li = lb + lane;
     const bool valid = li < n_rec;
     LineRec rec;
-    rec.start = 0; rec.len = 0; rec.an = 0; rec.ev_start = 0; rec.ev_count = 0;
+    rec.start = 0; rec.len = 0; rec.an = 0; rec.ev_start = 0; rec.ev_count = 0; rec.flags = 0;
     if (valid) rec = p.lines[li];
-    const bool small = valid && rec.ev_count <= SMALL_EVENTS;
+    // records whose inline summary (scan kernel) is complete need nothing here
+    const bool needed = valid && (!fixed || (rec.flags & 1));
+    const bool small = needed && rec.ev_count <= SMALL_EVENTS;
     if (small) {  // ---- lane-serial ----
       const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
       const uint32_t *ev = p.events + rec.ev_start;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams 
       p.stats[li] = s;
     }
     // ---- warp-cooperative for the long ones ----
-    uint32_t big = __ballot_sync(FULL, valid && !small);
+    uint32_t big = __ballot_sync(FULL, needed && !small);
     while (big) {
       const int l = __ffs(big) - 1;
       big &= big - 1;
@@ -324,7 +326,13 @@ __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, c
   const uint32_t a = (uint32_t)oa.alt_idx + 1;
   if (cfg.n_samples > 0) {
     if (gs_idx != oa.alt_idx) {  // MNP bases share their ALT index: reduce once (main.go:865-868)
-      if (a <= (uint32_t)STAT_ALLELES) {
+      if (cfg.name_fixed_w > 0 && !(rec.flags & 1)) {
+        // the scan kernel's inline summary is complete: only ALT #1 occurs among the samples
+        gs.n_het = a == 1 ? rec.n_het1 : 0; gs.n_hom = a == 1 ? rec.n_hom1 : 0; gs.ac = a == 1 ? rec.ac1 : 0;
+        gs.n_miss = rec.n_miss; gs.an = rec.an;
+        gs.het_bytes = gs.n_het * cfg.name_fixed_w; gs.hom_bytes = gs.n_hom * cfg.name_fixed_w;
+        gs.miss_bytes = gs.n_miss * cfg.name_fixed_w;
+      } else if (a <= (uint32_t)STAT_ALLELES) {
         const LineStats &ls = p.stats[lc.li];
         gs.n_het = ls.n_het[a - 1]; gs.n_hom = ls.n_hom[a - 1]; gs.ac = ls.ac[a - 1];
         gs.het_bytes = ls.het_bytes[a - 1]; gs.hom_bytes = ls.hom_bytes[a - 1];

@@ -5,16 +5,18 @@
 // __ballot_sync/__popc + warp prefix sums, and classifies every sample's GT token on the fly.  It owns the
 // lines that START in its range (it reads past the range end to finish the last one).  Products:
 //   * LineRec per record with the header's field count (main.go:449 len(record)==len(header)), including the
-//     offsets of its first nine tabs (the field index the rows kernel needs),
-//   * `an` of the fast-classified samples (main.go:1067-1169 totalGtCount),
-//   * one 32-bit event per non-reference sample, in header order (main.go:1057 loop order), which the
-//     stats/names kernels turn into the het/hom/missing lists and ac for each output allele.
+//     offsets of its first nine tabs (the field index the rows kernel needs) and the ALT #1 genotype
+//     summary (het/hom/missing counts, ac, an -- main.go:1042-1194),
+//   * one 32-bit event per non-reference sample, in header order (main.go:1057 loop order), from which the
+//     names kernel writes the het/hom/missing lists (and the stats kernel serves the other ALT numbers).
 // Replaces: strings.Split (main.go:535) + the sample loop of makeHetHomozygotes (main.go:1057-1191).
 //
 // Three tiers per 512-byte window, chosen warp-uniformly:
-//   T1  all 128 fields are "0|0\t" (or "0/0\t")  -> 4 XOR/OR + vote, nothing else
+//   T1  all 128 fields are "0|0\t" (or "0/0\t")  -> 5 XOR/OR on the raw words + vote, nothing else
 //   T2  all 128 fields are "x|y\t" with x,y in [0-9.] -> SWAR classify in registers, ordered compaction of events
-//   T3  anything else (line start/end, fixed fields, FORMAT suffixes, odd widths): general path
+//   T3  anything else (line start/end, fixed fields, FORMAT suffixes, odd widths): tab/newline masks, ballots
+//       and prefix sums; its sample zone is still classified with the T2 vector code when it is regular,
+//       field by field otherwise
 #pragma once
 #include "bvcf_common.cuh"
 
@@ -43,16 +45,36 @@ struct ScanParams {
   int H, eol_width;
 };
 
+// per-line accumulators; *_l are per-lane partial sums reduced when the line ends
+struct LineAcc {
+  uint32_t an_l, an_uni;    // non-missing allele count (main.go:1067,1169)
+  uint32_t het_l, hom_l;    // ALT #1 heterozygotes / homozygotes (main.go:1080-1109,1185)
+  uint32_t ac_l;            // ALT #1 allele count
+  uint32_t miss_l;          // missing samples (main.go:1113,1150)
+  uint32_t flag_l;          // 1: an event carries another ALT number or needs the general GT grammar
+};
+
 struct WarpState {
   uint64_t line_start;
   int fsr;                  // first unprocessed field start, relative to the current window; FS_NONE inside a field
   uint32_t col;             // field index of the field at fsr == tabs of this line before it
-  uint32_t an_lane, an_uni; // non-missing allele count: per-lane part and warp-uniform part
   uint32_t ev_w, line_ev_start;  // event write cursor (words, relative to this range's slice)
   uint32_t nrec, nlines;
   uint32_t refpat;          // "0|0\t" or "0/0\t", follows the data's separator
   int mode;                 // 0 seeking the first line start, 1 inside an owned line, 2 done
+  LineAcc a;
 };
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a));
+  return v;
+}
 
 __device__ __forceinline__ uint32_t bits_range16(int lo, int hi) {  // bits [lo, hi) clipped to [0,16)
   lo = lo < 0 ? 0 : lo;
@@ -67,12 +89,91 @@ __device__ __forceinline__ uint32_t tok_code(uint32_t c) {  // single-character 
 
 __device__ __forceinline__ void start_line(WarpState &st, uint64_t start, int rel) {
   st.line_start = start; st.fsr = rel; st.col = 0;
-  st.an_lane = 0; st.an_uni = 0; st.line_ev_start = st.ev_w;
+  st.a.an_l = st.a.an_uni = st.a.het_l = st.a.hom_l = st.a.ac_l = st.a.miss_l = st.a.flag_l = 0;
+  st.line_ev_start = st.ev_w;
+}
+
+// ALT #1 bookkeeping for one fast-classified sample with allele codes c1,c2 (c2 == EV_CODE_ABSENT: haploid)
+__device__ __forceinline__ void acc_sample(LineAcc &a, uint32_t c1, uint32_t c2) {
+  const uint32_t hap = c2 == EV_CODE_ABSENT;
+  const uint32_t alt = (c1 == 1) + (c2 == 1);
+  a.ac_l += alt;
+  a.hom_l += hap ? alt : (alt >> 1);
+  a.het_l += hap ? 0u : (alt & 1u);
+  a.flag_l |= (c1 > 1) | (!hap && c2 > 1);
+}
+
+// ---- the T2 vector code: four realigned fields per lane, XORed with the reference pattern -------------
+// t[j] == 0: reference genotype.  Structure (separator, tab) already verified by the caller; allele bytes are
+// digits (t byte <= 9) or, when `dots`, '.' (0x1E).  zone: which of the four words are sample fields.
+// Returns the lane's event count; events in ev[] in field order (0 = none).
+__device__ __forceinline__ uint32_t classify_words4(const uint32_t t[4], uint32_t zone, int samp0, bool dots, LineAcc &a,
+                                                    uint32_t ev[4]) {
+  uint32_t nev = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t tt = (zone >> j) & 1u ? (t[j] & 0x00FF00FFu) : 0u;
+    uint32_t e = 0;
+    if (tt) {
+      const uint32_t c1 = tt & 0xFFu, c2 = tt >> 16;
+      if (dots && (c1 == 0x1Eu || c2 == 0x1Eu)) {
+        e = ev_make((uint32_t)(samp0 + j), EV_CODE_MISSING, EV_CODE_MISSING);
+        a.miss_l++;
+        a.an_l -= 2;
+      } else {
+        e = (uint32_t)(samp0 + j) | (c1 << 20) | (c2 << 25);
+        const uint32_t alt = (c1 == 1) + (c2 == 1);
+        a.ac_l += alt;
+        a.hom_l += alt >> 1;
+        a.het_l += alt & 1u;
+        a.flag_l |= (c1 | c2) > 1;
+      }
+      nev++;
+    }
+    ev[j] = e;
+  }
+  return nev;
+}
+
+// ordered warp compaction of up to four events per lane into the range's event slice
+__device__ __forceinline__ void push_events4(const ScanParams &p, WarpState &st, uint32_t *my_events, const uint32_t ev[4],
+                                             uint32_t nev, int lane) {
+  const uint32_t eincl = warp_incl_scan(nev, lane);
+  const uint32_t etot = __shfl_sync(FULL, eincl, 31);
+  if (etot == 0) return;
+  if (st.ev_w + etot <= p.evcap_words) {
+    uint32_t *dst = my_events + st.ev_w + (eincl - nev);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (ev[j]) *dst++ = ev[j];
+  } else if (lane == 0) {
+    p.ctr->ev_overflow = 1;
+  }
+  st.ev_w += etot;
+}
+
+// SWAR validity of four XORed fields: separator/tab bytes unchanged, allele bytes digits (or '.')
+__device__ __forceinline__ uint32_t bad_digits4(const uint32_t t[4], uint32_t keep_mask3) {
+  const uint32_t D = 0x00760076u, H = 0x00800080u, M = 0x00FF00FFu;
+  const uint32_t any = t[0] | t[1] | t[2] | (t[3] & keep_mask3);
+  return (any & ~M) | ((((t[0] & M) + D) | ((t[1] & M) + D) | ((t[2] & M) + D) | ((t[3] & M) + D)) & H);
+}
+__device__ __forceinline__ uint32_t bad_digits_or_dots4(const uint32_t t[4], uint32_t keep_mask3) {
+  const uint32_t D = 0x00760076u, H = 0x00800080u, M = 0x00FF00FFu;
+  uint32_t bad = (t[0] | t[1] | t[2] | (t[3] & keep_mask3)) & ~M;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t u = t[j] & M;
+    const uint32_t d = u ^ 0x001E001Eu;
+    const uint32_t notdot = (((d & 0x007F007Fu) + 0x007F007Fu) | d) & H;  // 0x80 where the byte is not '.'
+    bad |= ((u + D) & H) & notdot;
+  }
+  return bad;
 }
 
 // ---- T3: the general window ------------------------------------------------------------------------
 template <bool HAS_SAMPLES>
-__device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpState &st, const uint8_t *ring,
+__device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpState &st, uint32_t ring_base_s,
                                                     uint32_t stage_off, const uint4 &v, uint64_t pos, uint64_t rend,
                                                     int lane, LineRec *my_recs, uint32_t *my_events) {
   const bool eol2 = p.eol_width == 2;
@@ -124,83 +225,177 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
       }
     }
 
-    int last_end = -1;   // window-relative index of the '\t' that ends this lane's last field, if known
-    uint32_t last_sep = 0;
-    uint32_t fm_all = 0;
+    int nfs = FS_NONE;       // hand-over to the next window when this segment reaches the window end
+    uint32_t col_extra = 0;
     if (HAS_SAMPLES) {
-      // field starts owned by this lane: byte after a tab, or the carried-in start
-      const uint32_t prev_hi = __shfl_up_sync(FULL, tm_l >> 15, 1);
-      uint32_t fm = ((tm_l << 1) | (lane > 0 ? (prev_hi & 1u) : 0u)) & 0xFFFFu;
-      if (st.fsr == seg_lo) {
-        const int sl = seg_lo - lane * 16;
-        if (sl >= 0 && sl < 16) fm |= 1u << sl;
+      // ---- where do this segment's sample fields begin? ----
+      int s9 = -1;           // window-relative start of the first sample field of the segment
+      uint32_t samp_base = 0;
+      if (st.col >= 9) {
+        if (st.fsr == seg_lo) { s9 = seg_lo; samp_base = st.col - 9; }
+      } else if (st.col + total >= 9) {
+        const uint32_t k9 = 8 - st.col;  // in-segment index of the ninth tab
+        const bool mine = k9 >= excl && k9 < excl + cnt;
+        const uint32_t who = __ballot_sync(FULL, mine);
+        int pos9 = 0;
+        if (mine) pos9 = lane * 16 + (int)__fns(tm_l, 0, (int)(k9 - excl) + 1);
+        s9 = __shfl_sync(FULL, pos9, __ffs(who) - 1) + 1;
       }
-      fm_all = fm;
-      uint32_t evbuf[16];
-      int nev = 0;
-      while (fm) {
-        const int sl = __ffs(fm) - 1;
-        fm &= fm - 1;
-        const uint32_t fidx = st.col + excl + __popc(tm_l & ((1u << sl) - 1u));
-        last_end = -1;
-        if (fidx < 9) continue;
-        const uint32_t samp = fidx - 9;
-        const int s = lane * 16 + sl;
-        // 5 bytes at s from the ring (s+4 may reach into the next window: already loaded)
-        const uint32_t a = stage_off + (uint32_t)s;
-        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(ring + ((a & ~3u) & (RING - 1)));
-        const uint32_t w1 = *reinterpret_cast<const uint32_t *>(ring + (((a & ~3u) + 4u) & (RING - 1)));
-        const uint32_t sh = (a & 3u) * 8u;
-        const uint32_t lo = __funnelshift_r(w0, w1, sh);
-        const uint32_t b0 = lo & 0xFF, b1 = (lo >> 8) & 0xFF, b2 = (lo >> 16) & 0xFF, b3 = lo >> 24;
-        const uint32_t b4 = (w1 >> sh) & 0xFF;
-        auto is_end = [&](uint32_t c, uint32_t nx) { return c == '\t' || c == '\n' || c == ':' || (eol2 && nx == '\n'); };
-        auto is_sep = [](uint32_t c) { return c == '|' || c == '/'; };
-        const bool e0 = is_end(b0, b1), e1 = is_end(b1, b2), e2 = is_end(b2, b3), e3 = is_end(b3, b4);
-        if (e0) {  // empty GT: one token "" (main.go:1143,1166)
-          st.an_lane += 1;
-          if (b0 == '\t') last_end = s;
-        } else if (!is_sep(b0) && e1) {  // haploid, one single-character token
-          const uint32_t c = tok_code(b0);
-          if (c == EV_CODE_MISSING) {
-            evbuf[nev++] = ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
+      const int zone_end = nl;  // sample fields of this segment live in [s9, zone_end)
+      bool vector_ok = false;
+      if (s9 >= 0 && s9 < zone_end && !(eol2 && nl < WIN)) {
+        // ---- regular zone? classify it with the T2 vector code ----
+        const uint32_t w4 = lds32(ring_base_s + ((stage_off + lane * 16 + 16) & (RING - 1)));
+        const uint32_t sh = (uint32_t)(s9 & 3) * 8u;
+        const uint32_t rp = st.refpat;
+        uint32_t t[4] = {__funnelshift_r(v.x, v.y, sh) ^ rp, __funnelshift_r(v.y, v.z, sh) ^ rp,
+                         __funnelshift_r(v.z, v.w, sh) ^ rp, __funnelshift_r(v.w, w4, sh) ^ rp};
+        const int ws0 = lane * 16 + (s9 & 3);  // start of this lane's first realigned word
+        uint32_t zone = 0;
+        bool bad_shape = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int ws = ws0 + 4 * j;
+          if (ws >= s9 && ws < zone_end) {
+            zone |= 1u << j;
+            if (nl < WIN) {
+              if (ws + 3 == nl) t[j] ^= 0x03000000u;       // last field of the line ends with '\n', not '\t'
+              else if (ws + 3 > nl) bad_shape = true;       // short last field
+            }
           } else {
-            st.an_lane += 1;
-            if (c) evbuf[nev++] = ev_make(samp, c, EV_CODE_ABSENT);
+            t[j] = 0;
           }
-          if (b1 == '\t') last_end = s + 1;
-        } else if (!is_sep(b0) && is_sep(b1) && !e2 && !is_sep(b2) && e3) {  // diploid x|y or x/y
-          const uint32_t c1 = tok_code(b0), c2 = tok_code(b2);
-          if (c1 == EV_CODE_MISSING || c2 == EV_CODE_MISSING) {
-            evbuf[nev++] = ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
-          } else {
-            st.an_lane += 2;
-            if (c1 | c2) evbuf[nev++] = ev_make(samp, c1, c2);
+        }
+        uint32_t bad = bad_digits4(t, 0xFFFFFFFFu) | (bad_shape ? 1u : 0u);
+        bool dots = false;
+        if (!__all_sync(FULL, bad == 0)) {
+          bad = bad_digits_or_dots4(t, 0xFFFFFFFFu) | (bad_shape ? 1u : 0u);
+          dots = true;
+        }
+        if (__all_sync(FULL, bad == 0)) {
+          vector_ok = true;
+          uint32_t ev[4];
+          const int samp0 = (int)samp_base + ((ws0 - s9) >> 2);  // arithmetic shift: negative before the zone
+          st.a.an_l += 2 * __popc(zone);
+          const uint32_t nev = classify_words4(t, zone, samp0, dots, st.a, ev);
+          push_events4(p, st, my_events, ev, nev, lane);
+          if (nl == WIN) {  // zone runs to the window end: the next window continues in the same phase
+            const int n_words = (WIN - s9 + 3) >> 2;
+            const int ws_last = s9 + 4 * (n_words - 1);
+            nfs = ws_last + 4 - WIN;
+            col_extra = ws_last + 3 >= WIN ? 1u : 0u;  // that field's tab lies in the next window: pre-count it
           }
-          if (b3 == '\t') { last_end = s + 3; last_sep = b1; }
-        } else {  // general grammar: resolved exactly by the stats/names kernels
-          evbuf[nev++] = samp | EV_COMPLEX;
-          evbuf[nev++] = EV_OFFSET_TAG | (uint32_t)(pos + (uint64_t)s - st.line_start);
         }
       }
-      // ordered compaction of this segment's events
-      const uint32_t eincl = warp_incl_scan((uint32_t)nev, lane);
-      const uint32_t etot = __shfl_sync(FULL, eincl, 31);
-      if (etot) {
-        if (st.ev_w + etot <= p.evcap_words) {
-          uint32_t *dst = my_events + st.ev_w + (eincl - nev);
-          for (int k = 0; k < nev; k++) dst[k] = evbuf[k];
-        } else if (lane == 0) {
-          p.ctr->ev_overflow = 1;
+      if (!vector_ok) {
+        // ---- field by field ----
+        int last_end = -1;   // window-relative index of the '\t' that ends this lane's last field, if known
+        uint32_t last_sep = 0;
+        const uint32_t prev_hi = __shfl_up_sync(FULL, tm_l >> 15, 1);
+        uint32_t fm = ((tm_l << 1) | (lane > 0 ? (prev_hi & 1u) : 0u)) & 0xFFFFu;
+        if (st.fsr == seg_lo) {
+          const int sl = seg_lo - lane * 16;
+          if (sl >= 0 && sl < 16) fm |= 1u << sl;
         }
-        st.ev_w += etot;
+        const uint32_t fm_all = fm;
+        uint32_t evbuf[16];
+        int nev = 0;
+        while (fm) {
+          const int sl = __ffs(fm) - 1;
+          fm &= fm - 1;
+          const uint32_t fidx = st.col + excl + __popc(tm_l & ((1u << sl) - 1u));
+          last_end = -1;
+          if (fidx < 9) continue;
+          const uint32_t samp = fidx - 9;
+          const int s = lane * 16 + sl;
+          // 5 bytes at s from the ring (s+4 may reach into the next window: already loaded)
+          const uint32_t a = stage_off + (uint32_t)s;
+          const uint32_t w0 = lds32(ring_base_s + ((a & ~3u) & (RING - 1)));
+          const uint32_t w1 = lds32(ring_base_s + (((a & ~3u) + 4u) & (RING - 1)));
+          const uint32_t sh = (a & 3u) * 8u;
+          const uint32_t lo = __funnelshift_r(w0, w1, sh);
+          const uint32_t b0 = lo & 0xFF, b1 = (lo >> 8) & 0xFF, b2 = (lo >> 16) & 0xFF, b3 = lo >> 24;
+          const uint32_t b4 = (w1 >> sh) & 0xFF;
+          auto is_end = [&](uint32_t c, uint32_t nx) { return c == '\t' || c == '\n' || c == ':' || (eol2 && nx == '\n'); };
+          auto is_sep = [](uint32_t c) { return c == '|' || c == '/'; };
+          const bool e0 = is_end(b0, b1), e1 = is_end(b1, b2), e2 = is_end(b2, b3), e3 = is_end(b3, b4);
+          if (e0) {  // empty GT: one token "" (main.go:1143,1166)
+            st.a.an_l += 1;
+            if (b0 == '\t') last_end = s;
+          } else if (!is_sep(b0) && e1) {  // haploid, one single-character token
+            const uint32_t c = tok_code(b0);
+            if (c == EV_CODE_MISSING) {
+              evbuf[nev++] = ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
+              st.a.miss_l++;
+            } else {
+              st.a.an_l += 1;
+              if (c) { evbuf[nev++] = ev_make(samp, c, EV_CODE_ABSENT); acc_sample(st.a, c, EV_CODE_ABSENT); }
+            }
+            if (b1 == '\t') last_end = s + 1;
+          } else if (!is_sep(b0) && is_sep(b1) && !e2 && !is_sep(b2) && e3) {  // diploid x|y or x/y
+            const uint32_t c1 = tok_code(b0), c2 = tok_code(b2);
+            if (c1 == EV_CODE_MISSING || c2 == EV_CODE_MISSING) {
+              evbuf[nev++] = ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
+              st.a.miss_l++;
+            } else {
+              st.a.an_l += 2;
+              if (c1 | c2) { evbuf[nev++] = ev_make(samp, c1, c2); acc_sample(st.a, c1, c2); }
+            }
+            if (b3 == '\t') { last_end = s + 3; last_sep = b1; }
+          } else {  // general grammar: resolved exactly by the stats/names kernels
+            evbuf[nev++] = samp | EV_COMPLEX;
+            evbuf[nev++] = EV_OFFSET_TAG | (uint32_t)(pos + (uint64_t)s - st.line_start);
+            st.a.flag_l |= 1;
+          }
+        }
+        // ordered compaction of this segment's events
+        const uint32_t eincl = warp_incl_scan((uint32_t)nev, lane);
+        const uint32_t etot = __shfl_sync(FULL, eincl, 31);
+        if (etot) {
+          if (st.ev_w + etot <= p.evcap_words) {
+            uint32_t *dst = my_events + st.ev_w + (eincl - nev);
+            for (int k = 0; k < nev; k++) dst[k] = evbuf[k];
+          } else if (lane == 0) {
+            p.ctr->ev_overflow = 1;
+          }
+          st.ev_w += etot;
+        }
+        if (nl == WIN) {  // hand the field phase over to the next window
+          const uint32_t last_tab = __shfl_sync(FULL, tm_l >> 15, 31) & 1u;
+          if (last_tab) {
+            nfs = 0;
+          } else {
+            const uint32_t have = __ballot_sync(FULL, fm_all != 0);
+            if (have) {
+              const int l = 31 - __clz(have);
+              const int le = __shfl_sync(FULL, last_end, l);
+              const uint32_t sp = __shfl_sync(FULL, last_sep, l);
+              if (le >= WIN) {
+                nfs = le + 1 - WIN; col_extra = 1;  // pre-count that tab
+                if (sp) st.refpat = 0x09300030u | (sp << 8);
+              }
+            }
+          }
+        }
       }
     }
     st.col += total;
 
     if (nl < WIN) {  // the line ends inside this window
       st.nlines++;
-      const uint32_t an = warp_sum(st.an_lane) + st.an_uni;
+      const LineAcc &a = st.a;
+      const uint32_t an = warp_sum(a.an_l) + a.an_uni;
+      uint32_t n_het = 0, n_hom = 0, n_miss = 0, ac = 0, flag = 0;
+      if (HAS_SAMPLES) {
+        flag = __any_sync(FULL, a.flag_l != 0);
+        if (__any_sync(FULL, (a.het_l | a.hom_l | a.miss_l) != 0)) {
+          // two 16-bit halves per reduction would overflow at biobank width: reduce 64-bit pairs
+          const unsigned long long s1 = warp_sum64((unsigned long long)a.het_l | ((unsigned long long)a.hom_l << 32));
+          const unsigned long long s2 = warp_sum64((unsigned long long)a.ac_l | ((unsigned long long)a.miss_l << 32));
+          n_het = (uint32_t)s1; n_hom = (uint32_t)(s1 >> 32);
+          ac = (uint32_t)s2; n_miss = (uint32_t)(s2 >> 32);
+        }
+      }
       if (st.col == (uint32_t)(p.H - 1)) {
         if (st.nrec < p.slots_per_range) {
           if (lane == 0) {
@@ -211,6 +406,8 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
             r->ev_start = st.line_ev_start;
             r->ev_count = st.ev_w - st.line_ev_start;
             r->ord = st.nlines - 1;
+            r->flags = (uint16_t)flag;
+            r->n_het1 = n_het; r->n_hom1 = n_hom; r->n_miss = n_miss; r->ac1 = ac;
           }
         } else if (lane == 0) {
           p.ctr->slot_overflow = 1;
@@ -225,26 +422,8 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
       seg_lo = nl + 1;
       continue;
     }
-
-    // segment runs to the window end: hand the field phase over to the next window
-    int nfs = FS_NONE;
-    if (HAS_SAMPLES) {
-      const uint32_t last_tab = __shfl_sync(FULL, tm_l >> 15, 31) & 1u;
-      if (last_tab) {
-        nfs = 0;
-      } else {
-        const uint32_t have = __ballot_sync(FULL, fm_all != 0);
-        if (have) {
-          const int l = 31 - __clz(have);
-          const int le = __shfl_sync(FULL, last_end, l);
-          const uint32_t sp = __shfl_sync(FULL, last_sep, l);
-          if (le >= WIN) {
-            nfs = le + 1 - WIN; st.col += 1;  // pre-count that tab
-            if (sp) st.refpat = 0x09300030u | (sp << 8);
-          }
-        }
-      }
-    }
+    // segment ran to the window end
+    st.col += col_extra;
     st.fsr = nfs;
     return;
   }
@@ -266,11 +445,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
   uint32_t *my_events = p.events + (size_t)rl * p.evcap_words;
 
   WarpState st;
-  st.nrec = 0; st.nlines = 0; st.ev_w = 0; st.line_ev_start = 0;
-  st.an_lane = 0; st.an_uni = 0; st.col = 0;
+  st.nrec = 0; st.nlines = 0; st.ev_w = 0;
   st.refpat = 0x09307C30u;  // "0|0\t"
-  st.fsr = FS_NONE; st.line_start = 0;
   st.mode = 0;
+  start_line(st, 0, FS_NONE);
   if (rstart >= p.end) {
     st.mode = 2;
   } else if (rstart <= p.begin) {  // first range: the region starts with a line
@@ -280,8 +458,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
   }
 
   if (st.mode != 2) {
-    uint8_t *ring = smem + warp * RING;
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+    const uint32_t ring_base_s = (uint32_t)__cvta_generic_to_shared(smem + warp * RING);
+    const uint32_t ring_lane_s = ring_base_s + lane * 16;
     // windows this warp may touch: up to the end of the padded buffer (32-bit counters keep the loop lean)
     const uint64_t avail64 = (p.buf_len - rstart) / WIN;
     const uint32_t n_avail = avail64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)avail64;
@@ -290,91 +468,53 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
     uint32_t issued = 0;
     auto issue = [&]() {
       if (issued < n_avail)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring_s + ((issued & (STAGES - 1)) * WIN)), "l"(gsrc));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring_lane_s + ((issued & (STAGES - 1)) * WIN)), "l"(gsrc));
       asm volatile("cp.async.commit_group;\n" ::);
       gsrc += WIN;
       issued++;
     };
 #pragma unroll
     for (int k = 0; k < PF; k++) issue();
-    for (uint32_t it = 0; it + 1 < n_avail; ++it) {
+    uint32_t stage_off = 0;
+    for (uint32_t it = 0; it + 1 < n_avail; ++it, stage_off = (stage_off + WIN) & (RING - 1)) {
       issue();
       asm volatile("cp.async.wait_group %0;\n" ::"n"(PF - 1));
       __syncwarp();
       if (st.mode == 0 && it >= seek_limit) break;  // no line starts in this range
-      const uint32_t stage_off = (it & (STAGES - 1)) * WIN;
-      const uint4 v = *reinterpret_cast<const uint4 *>(ring + stage_off + lane * 16);
-      bool handled = false;
+      const uint4 v = lds128(ring_lane_s + stage_off);
       if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
-        const uint32_t w4 = *reinterpret_cast<const uint32_t *>(ring + ((stage_off + lane * 16 + 16) & (RING - 1)));
+        const uint32_t w4 = lds32(ring_base_s + ((stage_off + lane * 16 + 16) & (RING - 1)));
         const uint32_t sh = (uint32_t)st.fsr * 8u;
         const uint32_t rp = st.refpat;
-        // XOR with the reference pattern: 0 = reference genotype, digits differ only in the low nibble
-        const uint32_t t0 = __funnelshift_r(v.x, v.y, sh) ^ rp, t1 = __funnelshift_r(v.y, v.z, sh) ^ rp;
-        const uint32_t t2 = __funnelshift_r(v.z, v.w, sh) ^ rp, t3 = __funnelshift_r(v.w, w4, sh) ^ rp;
-        const uint32_t any = t0 | t1 | t2 | t3;
-        if (__all_sync(FULL, any == 0)) {  // T1: every field of the window is the reference genotype
-          st.an_uni += 256; st.col += 128;
-          handled = true;
-        } else {
-          // T2: separator and tab bytes unchanged, allele bytes in [0-9] (or '.', checked only if needed)
-          const uint32_t D = 0x00760076u, H = 0x00800080u, M = 0x00FF00FFu;
-          uint32_t bad = (any & ~M) | ((((t0 & M) + D) | ((t1 & M) + D) | ((t2 & M) + D) | ((t3 & M) + D)) & H);
-          bool dots = false;
-          if (!__all_sync(FULL, bad == 0)) {
-            // allow '.' ('.'^'0' == 0x1E) next to digits
-            const uint32_t ts[4] = {t0, t1, t2, t3};
-            bad = any & ~M;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const uint32_t u = ts[j] & M;
-              const uint32_t d = u ^ 0x001E001Eu;
-              const uint32_t notdot = (((d & 0x007F007Fu) + 0x007F007Fu) | d) & H;  // 0x80 where the byte is not '.'
-              bad |= ((u + D) & H) & notdot;
-            }
-            dots = true;
-          }
-          if (__all_sync(FULL, bad == 0)) {
-            const uint32_t ts[4] = {t0, t1, t2, t3};
-            uint32_t ev[4];
-            uint32_t nev = 0, miss = 0;
-            const uint32_t samp0 = st.col - 9 + lane * 4;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const uint32_t t = ts[j];
-              uint32_t e = 0;
-              if (t) {
-                e = (samp0 + j) + ((t & 0x1Fu) << 20) + ((t & 0x1F0000u) << 9);
-                if (dots && (((t & 0xFFu) == 0x1Eu) || ((t >> 16) == 0x1Eu))) {
-                  e = ev_make(samp0 + j, EV_CODE_MISSING, EV_CODE_MISSING);
-                  miss++;
-                }
-                nev++;
-              }
-              ev[j] = e;
-            }
-            const uint32_t eincl = warp_incl_scan(nev, lane);
-            const uint32_t etot = __shfl_sync(FULL, eincl, 31);
-            if (st.ev_w + etot <= p.evcap_words) {
-              uint32_t *dst = my_events + st.ev_w + (eincl - nev);
-#pragma unroll
-              for (int j = 0; j < 4; j++)
-                if (ev[j]) *dst++ = ev[j];
-            } else if (lane == 0) {
-              p.ctr->ev_overflow = 1;
-            }
-            st.ev_w += etot;
-            st.an_uni += 256; st.an_lane -= 2 * miss;
-            st.col += 128;
-            handled = true;
-          }
+        const uint32_t rot = __funnelshift_l(rp, rp, sh);  // the pattern as the unaligned raw words see it
+        // T1: every byte of the window (and the 4 bytes after it) repeats the reference genotype.
+        // The vote also orders this window's shared-memory reads before the refill two iterations later.
+        if (__all_sync(FULL, ((v.x ^ rot) | (v.y ^ rot) | (v.z ^ rot) | (v.w ^ rot) | (w4 ^ rot)) == 0)) {
+          st.a.an_uni += 256; st.col += 128;
+          continue;
+        }
+        // T2: separator and tab bytes unchanged, allele bytes in [0-9] (or '.', checked only if needed)
+        const uint32_t t[4] = {__funnelshift_r(v.x, v.y, sh) ^ rp, __funnelshift_r(v.y, v.z, sh) ^ rp,
+                               __funnelshift_r(v.z, v.w, sh) ^ rp, __funnelshift_r(v.w, w4, sh) ^ rp};
+        uint32_t bad = bad_digits4(t, 0xFFFFFFFFu);
+        bool dots = false;
+        if (!__all_sync(FULL, bad == 0)) {
+          bad = bad_digits_or_dots4(t, 0xFFFFFFFFu);
+          dots = true;
+        }
+        if (__all_sync(FULL, bad == 0)) {
+          uint32_t ev[4];
+          st.a.an_uni += 256;
+          const uint32_t nev = classify_words4(t, 0xFu, (int)(st.col - 9) + lane * 4, dots, st.a, ev);
+          push_events4(p, st, my_events, ev, nev, lane);
+          st.col += 128;
+          __syncwarp();
+          continue;
         }
       }
-      if (!handled) {
-        const uint64_t pos = rstart + (uint64_t)it * WIN;
-        scan_window_general<HAS_SAMPLES>(p, st, ring, stage_off, v, pos, rend, lane, my_recs, my_events);
-        if (st.mode == 2) break;
-      }
+      const uint64_t pos = rstart + (uint64_t)it * WIN;
+      scan_window_general<HAS_SAMPLES>(p, st, ring_base_s, stage_off, v, pos, rend, lane, my_recs, my_events);
+      if (st.mode == 2) break;
       __syncwarp();  // everyone is done with this stage before it is refilled
     }
   }
