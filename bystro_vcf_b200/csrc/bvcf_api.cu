@@ -212,6 +212,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     sp.recs = (LineRec *)sc.recs.p; sp.range_nrec = (uint32_t *)sc.range_nrec.p;
     sp.range_nlines = (uint32_t *)sc.range_nlines.p; sp.events = (uint32_t *)sc.events.p;
     sp.ctr = d_ctr; sp.H = dc.H; sp.eol_width = dc.eol_width;
+    { const char *tv = getenv("BVCF_TUNE"); sp.tune = tv ? atoi(tv) : 0; }
     const unsigned grid = (nr + SCAN_WARPS - 1) / SCAN_WARPS;
     if (dc.n_samples > 0)
       bvcf_scan_genotype_kernel<true><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);
@@ -235,7 +236,9 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     bvcf_compact_lines_kernel<<<(nr + 7) / 8, 256, 0, st>>>(cp);
     ctx->launches += 4;
     if (se) CK(cudaEventRecord(se->e[2], st));
-    const unsigned wgrid = (unsigned)n_sm * 8;
+    // many more CTAs than SMs: each warp gets about one block of 32 records/rows and the hardware
+    // scheduler evens out the very different row sizes (1 .. 2,500 names)
+    const unsigned wgrid = (unsigned)n_sm * 64;
     // 3b. ALT #1 genotype summary per record (warp per record)
     if (dc.n_samples > 0) {
       StatsParams tp{};
@@ -307,7 +310,7 @@ Slot *find_slot(bvcf_ctx *ctx, uint64_t seq) {
 
 int slot_enqueue(bvcf_ctx *ctx, Slot &s, bool upload) {
   const uint64_t len = s.len;
-  const uint64_t buf_len = round_up(len, 512) + 1024;
+  const uint64_t buf_len = round_up(len, 1024) + 2048;
   int rc;
   if ((rc = dev_reserve(ctx, s.d_in, buf_len))) return rc;
   if ((rc = scratch_reserve(ctx, s.sc, len, ctx->cfg.resident_subchunk_bytes))) return rc;
@@ -654,7 +657,7 @@ int bvcf_release(bvcf_ctx *ctx, uint64_t seq) {
 int bvcf_resident_alloc(bvcf_ctx *ctx, size_t in_bytes, size_t out_capacity, void **d_in, void **d_out) {
   if (!ctx) return BVCF_E_ARG;
   cudaSetDevice(ctx->device);
-  const uint64_t buf_len = round_up(in_bytes, 512) + 1024;
+  const uint64_t buf_len = round_up(in_bytes, 1024) + 2048;
   int rc;
   if ((rc = dev_reserve(ctx, ctx->r_in, buf_len))) return rc;
   if ((rc = dev_reserve(ctx, ctx->r_out, std::max<size_t>(out_capacity, 4096)))) return rc;
@@ -685,7 +688,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
     int rc;
     if ((rc = scratch_reserve(ctx, ctx->r_sc, len, ctx->cfg.resident_subchunk_bytes))) return rc;
     // the bytes after `len` must not look like data: pad (idempotent)
-    const uint64_t buf_len = std::min<uint64_t>(ctx->r_in.cap / 512 * 512, round_up(len, 512) + 1024);
+    const uint64_t buf_len = std::min<uint64_t>(ctx->r_in.cap / 1024 * 1024, round_up(len, 1024) + 2048);
     CK(cudaMemsetAsync(ctx->r_d_ctr, 0, sizeof(RunCounters), ctx->r_stream));
     uint64_t dos_rows = 0;
     if (dc.want_dosage && dc.n_samples > 0) dos_rows = ctx->r_dosage.cap / (uint64_t)dc.n_samples;

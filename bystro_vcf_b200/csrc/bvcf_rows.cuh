@@ -645,9 +645,37 @@ struct NamesParams {
   unsigned long long dosage_cap_rows;
 };
 
+// 8 bytes to an arbitrarily aligned address with the widest naturally aligned pieces (2-4 stores)
+__device__ __forceinline__ void store8_unaligned(uint8_t *d, unsigned long long v) {
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  switch ((uintptr_t)d & 3u) {
+    case 0:
+      *reinterpret_cast<uint32_t *>(d) = lo;
+      *reinterpret_cast<uint32_t *>(d + 4) = hi;
+      break;
+    case 2:
+      *reinterpret_cast<uint16_t *>(d) = (uint16_t)lo;
+      *reinterpret_cast<uint32_t *>(d + 2) = (uint32_t)(v >> 16);
+      *reinterpret_cast<uint16_t *>(d + 6) = (uint16_t)(hi >> 16);
+      break;
+    case 1:
+      d[0] = (uint8_t)lo;
+      *reinterpret_cast<uint16_t *>(d + 1) = (uint16_t)(lo >> 8);
+      *reinterpret_cast<uint32_t *>(d + 3) = (uint32_t)(v >> 24);
+      d[7] = (uint8_t)(hi >> 24);
+      break;
+    default:
+      d[0] = (uint8_t)lo;
+      *reinterpret_cast<uint32_t *>(d + 1) = (uint32_t)(v >> 8);
+      *reinterpret_cast<uint16_t *>(d + 5) = (uint16_t)(hi >> 8);
+      d[7] = (uint8_t)(hi >> 24);
+      break;
+  }
+}
+
 // one row, whole warp: ballot/popc ranks, ordered scatter of the names (and the dosage row)
 __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned long long r, unsigned long long row0,
-                                               int lane, unsigned long long *stg) {
+                                               int lane) {
   const DevCfg &cfg = p.cfg;
   const uint32_t dl = (uint32_t)cfg.delim_len;
   const bool fixed = cfg.name_fixed_w > 0;
@@ -669,13 +697,10 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
     uint32_t run_b[3] = {0, 0, 0};
     const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
     if (cfg.name8 && cfg.want_tsv) {
-      // ---- fast path: every list item is exactly 8 bytes (name + delimiter).  Items of one class are
-      // ranked with ballot/popc, permuted into rank order through shared memory and written as ALIGNED
-      // 64-bit words (each word = tail of item m-1 | head of item m), so a batch of 32 names is one
-      // fully coalesced 256-byte store instead of 256 single-byte stores. ----
-      
+      // ---- fast path: every list item is exactly 8 bytes (name + delimiter).  Each lane ranks its item
+      // within its class with ballot/popc and stores the 8 bytes itself with the widest aligned pieces the
+      // destination allows (2-4 stores): all three classes go out in the same instructions. ----
       const uint32_t totals[3] = {rd.n_het, rd.n_hom, rd.n_miss};
-      unsigned long long carry[3] = {0, 0, 0};
       uint32_t w_next = lane < rec.ev_count ? ev[lane] : EV_OFFSET_TAG;
       for (uint32_t base = 0; base < rec.ev_count; base += 32) {
         uint32_t samp, gtx, alt;
@@ -685,47 +710,17 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
         const int cls = classify_word(w_cur, ev, k, L, content_len, a, samp, gtx, alt);
         if (drow && !(w_cur & EV_OFFSET_TAG))
           drow[samp] = cls == 3 ? (int8_t)-1 : (int8_t)(alt > 127 ? 127 : alt);  // main.go:1172-1178
-        const unsigned long long item = cls ? cfg.name8[samp] : 0ull;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const uint32_t bal = __ballot_sync(FULL, cls == c + 1);
-          if (bal == 0) continue;
-          const uint32_t cnt = __popc(bal);
-          if (cls == c + 1) stg[__popc(bal & lt)] = item;
-          __syncwarp();
-          unsigned long long it = lane < cnt ? stg[lane] : 0ull;
-          const uint32_t m = run_n[c] + lane;           // index of this lane's item in the list
-          if (m + 1 == totals[c]) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
-          unsigned long long prev = __shfl_up_sync(FULL, it, 1);
-          if (lane == 0) prev = carry[c];
-          carry[c] = __shfl_sync(FULL, it, cnt - 1);
-          const uint32_t sh = (uint32_t)(dsts[c] & 7ull);
-          unsigned long long *wp = reinterpret_cast<unsigned long long *>(p.out + (dsts[c] - sh)) + m;
-          if (lane < cnt) {
-            if (sh == 0) {
-              *wp = it;
-            } else if (m > 0) {
-              *wp = (prev >> (8 * (8 - sh))) | (it << (8 * sh));
-            } else {  // first item of the list: only its leading 8-sh bytes belong to word 0
-              uint8_t *d = p.out + dsts[c];
-              for (uint32_t i = 0; i < 8 - sh; i++) d[i] = (uint8_t)(it >> (8 * i));
-            }
-          }
-          run_n[c] += cnt;
-          __syncwarp();
+        const uint32_t b1 = __ballot_sync(FULL, cls == 1), b2 = __ballot_sync(FULL, cls == 2), b3 = __ballot_sync(FULL, cls == 3);
+        if (cls) {
+          const int c = cls - 1;
+          const uint32_t mine = c == 0 ? b1 : (c == 1 ? b2 : b3);
+          const uint32_t idx = (c == 0 ? run_n[0] : (c == 1 ? run_n[1] : run_n[2])) + __popc(mine & lt);
+          const uint32_t tot = c == 0 ? totals[0] : (c == 1 ? totals[1] : totals[2]);
+          unsigned long long it = cfg.name8[samp];
+          if (idx + 1 == tot) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
+          store8_unaligned(p.out + (c == 0 ? dsts[0] : (c == 1 ? dsts[1] : dsts[2])) + 8ull * idx, it);
         }
-      }
-      // tails: the last sh bytes of the last item of each list
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const uint32_t sh = (uint32_t)(dsts[c] & 7ull);
-          if (run_n[c] && sh) {
-            uint8_t *d = p.out + (dsts[c] - sh) + 8ull * run_n[c];
-            const unsigned long long tail = carry[c] >> (8 * (8 - sh));
-            for (uint32_t i = 0; i < sh; i++) d[i] = (uint8_t)(tail >> (8 * i));
-          }
-        }
+        run_n[0] += __popc(b1); run_n[1] += __popc(b2); run_n[2] += __popc(b3);
       }
       return;
     }
@@ -788,9 +783,10 @@ __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDe
     }
     const uint32_t nl = name_len(cfg, samp);
     if (cfg.name8) {
-      const unsigned long long it = cfg.name8[samp];
-#pragma unroll
-      for (int i = 0; i < 7; i++) d[i] = (uint8_t)(it >> (8 * i));
+      unsigned long long it = cfg.name8[samp];
+      const uint32_t tot = c == 0 ? rd.n_het : (c == 1 ? rd.n_hom : rd.n_miss);
+      if (run_n[c] + 1 == tot) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
+      store8_unaligned(d, it);
     } else {
       const uint8_t *src = name_ptr(cfg, samp);
       for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
@@ -803,7 +799,6 @@ __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDe
 // Hybrid granularity (as in the stats kernel): a warp takes 32 consecutive rows; short ones lane-serial,
 // long ones warp-cooperative.
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
-  __shared__ unsigned long long s_stage[NAMES_WARPS][32];
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
   if (p.ctr->out_overflow) return;
@@ -811,7 +806,6 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
   unsigned long long n_rows = p.ctr->row_cursor - row0;  // rows of this sub-chunk
   if (n_rows > p.row_desc_cap) n_rows = p.row_desc_cap;
   const unsigned long long total_warps = (unsigned long long)gridDim.x * NAMES_WARPS;
-  unsigned long long *stg = s_stage[threadIdx.x >> 5];
   for (unsigned long long rb = ((unsigned long long)blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5)) * 32; rb < n_rows;
        rb += total_warps * 32) {
     const unsigned long long r = rb + lane;
@@ -827,7 +821,7 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
     while (big) {
       const int l = __ffs(big) - 1;
       big &= big - 1;
-      names_row_warp(p, rb + l, row0, lane, stg);
+      names_row_warp(p, rb + l, row0, lane);
     }
   }
 }

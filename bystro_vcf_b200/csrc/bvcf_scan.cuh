@@ -25,7 +25,7 @@ namespace bvcf {
 constexpr int WIN = 512;                 // bytes per warp step
 constexpr int STAGES = 8;                // ring stages per warp
 constexpr int RING = WIN * STAGES;       // 4 KiB per warp
-constexpr int PF = 6;                    // prefetch distance (windows in flight)
+constexpr int PF = 5;                    // prefetch distance (windows in flight beyond the pair being read)
 constexpr int SCAN_WARPS = 8;            // warps per CTA
 constexpr int FS_NONE = 0x7FFFFFFF;      // "inside a field": no known field start
 
@@ -43,6 +43,7 @@ struct ScanParams {
   uint32_t *events;         // n_ranges * evcap_words
   RunCounters *ctr;
   int H, eol_width;
+  int tune;                 // bit 0: never try the two-window reference test (experiments)
 };
 
 // per-line accumulators; *_l are per-lane partial sums reduced when the line ends
@@ -105,49 +106,41 @@ __device__ __forceinline__ void acc_sample(LineAcc &a, uint32_t c1, uint32_t c2)
 
 // ---- the T2 vector code: four realigned fields per lane, XORed with the reference pattern -------------
 // t[j] == 0: reference genotype.  Structure (separator, tab) already verified by the caller; allele bytes are
-// digits (t byte <= 9) or, when `dots`, '.' (0x1E).  zone: which of the four words are sample fields.
-// Returns the lane's event count; events in ev[] in field order (0 = none).
-__device__ __forceinline__ uint32_t classify_words4(const uint32_t t[4], uint32_t zone, int samp0, bool dots, LineAcc &a,
-                                                    uint32_t ev[4]) {
-  uint32_t nev = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const uint32_t tt = (zone >> j) & 1u ? (t[j] & 0x00FF00FFu) : 0u;
-    uint32_t e = 0;
-    if (tt) {
-      const uint32_t c1 = tt & 0xFFu, c2 = tt >> 16;
-      if (dots && (c1 == 0x1Eu || c2 == 0x1Eu)) {
-        e = ev_make((uint32_t)(samp0 + j), EV_CODE_MISSING, EV_CODE_MISSING);
-        a.miss_l++;
-        a.an_l -= 2;
-      } else {
-        e = (uint32_t)(samp0 + j) | (c1 << 20) | (c2 << 25);
-        const uint32_t alt = (c1 == 1) + (c2 == 1);
-        a.ac_l += alt;
-        a.hom_l += alt >> 1;
-        a.het_l += alt & 1u;
-        a.flag_l |= (c1 | c2) > 1;
-      }
-      nev++;
-    }
-    ev[j] = e;
-  }
-  return nev;
-}
-
-// ordered warp compaction of up to four events per lane into the range's event slice
-__device__ __forceinline__ void push_events4(const ScanParams &p, WarpState &st, uint32_t *my_events, const uint32_t ev[4],
-                                             uint32_t nev, int lane) {
+// digits (t byte <= 9) or, when `dots`, '.' (0x1E).  Words outside the sample zone arrive zeroed.
+// Non-reference fields are sparse, so they are visited with a find-first-set loop (a lane usually has 0 or 1)
+// and compacted in order into the range's event slice with a warp prefix sum.
+__device__ __forceinline__ void classify_push_words4(const ScanParams &p, WarpState &st, uint32_t *my_events,
+                                                     const uint32_t t[4], int samp0, bool dots, int lane) {
+  uint32_t nz = (t[0] & 0x00FF00FFu ? 1u : 0u) | (t[1] & 0x00FF00FFu ? 2u : 0u) | (t[2] & 0x00FF00FFu ? 4u : 0u) |
+                (t[3] & 0x00FF00FFu ? 8u : 0u);
+  const uint32_t nev = __popc(nz);
   const uint32_t eincl = warp_incl_scan(nev, lane);
   const uint32_t etot = __shfl_sync(FULL, eincl, 31);
   if (etot == 0) return;
-  if (st.ev_w + etot <= p.evcap_words) {
-    uint32_t *dst = my_events + st.ev_w + (eincl - nev);
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-      if (ev[j]) *dst++ = ev[j];
-  } else if (lane == 0) {
-    p.ctr->ev_overflow = 1;
+  const bool room = st.ev_w + etot <= p.evcap_words;
+  if (!room && lane == 0) p.ctr->ev_overflow = 1;
+  uint32_t k = st.ev_w + (eincl - nev);
+  LineAcc &a = st.a;
+  while (nz) {
+    const int j = __ffs(nz) - 1;
+    nz &= nz - 1;
+    const uint32_t tt = (j == 0 ? t[0] : j == 1 ? t[1] : j == 2 ? t[2] : t[3]) & 0x00FF00FFu;
+    const uint32_t c1 = tt & 0xFFu, c2 = tt >> 16;
+    uint32_t e;
+    if (dots && (c1 == 0x1Eu || c2 == 0x1Eu)) {
+      e = ev_make((uint32_t)(samp0 + j), EV_CODE_MISSING, EV_CODE_MISSING);
+      a.miss_l++;
+      a.an_l -= 2;
+    } else {
+      e = (uint32_t)(samp0 + j) | (c1 << 20) | (c2 << 25);
+      const uint32_t alt = (c1 == 1) + (c2 == 1);
+      a.ac_l += alt;
+      a.hom_l += alt >> 1;
+      a.het_l += alt & 1u;
+      a.flag_l |= (c1 | c2) > 1;
+    }
+    if (room) my_events[k] = e;
+    k++;
   }
   st.ev_w += etot;
 }
@@ -274,11 +267,9 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
         }
         if (__all_sync(FULL, bad == 0)) {
           vector_ok = true;
-          uint32_t ev[4];
           const int samp0 = (int)samp_base + ((ws0 - s9) >> 2);  // arithmetic shift: negative before the zone
           st.a.an_l += 2 * __popc(zone);
-          const uint32_t nev = classify_words4(t, zone, samp0, dots, st.a, ev);
-          push_events4(p, st, my_events, ev, nev, lane);
+          classify_push_words4(p, st, my_events, t, samp0, dots, lane);  // out-of-zone words are zero
           if (nl == WIN) {  // zone runs to the window end: the next window continues in the same phase
             const int n_words = (WIN - s9 + 3) >> 2;
             const int ws_last = s9 + 4 * (n_words - 1);
@@ -475,47 +466,69 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
     };
 #pragma unroll
     for (int k = 0; k < PF; k++) issue();
+    // One loop iteration = one 1 KiB pair of windows.  Pairs that are all-reference (the bulk of real
+    // data) cost one 9-compare vote; anything else falls through to the per-window dispatcher.
     uint32_t stage_off = 0;
-    for (uint32_t it = 0; it + 1 < n_avail; ++it, stage_off = (stage_off + WIN) & (RING - 1)) {
+    uint32_t pair_skip = (p.tune & 1) ? 0x7FFFFFFFu : 0u;
+    bool done = false;
+    for (uint32_t it = 0; it + 2 < n_avail && !done; it += 2, stage_off = (stage_off + 2 * WIN) & (RING - 1)) {
       issue();
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(PF - 1));
+      issue();
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(PF - 1));  // windows it, it+1 and it+2 have landed
       __syncwarp();
-      if (st.mode == 0 && it >= seek_limit) break;  // no line starts in this range
-      const uint4 v = lds128(ring_lane_s + stage_off);
-      if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
-        const uint32_t w4 = lds32(ring_base_s + ((stage_off + lane * 16 + 16) & (RING - 1)));
-        const uint32_t sh = (uint32_t)st.fsr * 8u;
+      if (pair_skip) {
+        pair_skip--;  // dense-genotype stretch: do not pay for the pair test again right away
+      } else if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
+        const uint4 va = lds128(ring_lane_s + stage_off);
+        const uint4 vb = lds128(ring_lane_s + ((stage_off + WIN) & (RING - 1)));
+        const uint32_t w4 = lds32(ring_base_s + ((stage_off + WIN + lane * 16 + 16) & (RING - 1)));
         const uint32_t rp = st.refpat;
-        const uint32_t rot = __funnelshift_l(rp, rp, sh);  // the pattern as the unaligned raw words see it
-        // T1: every byte of the window (and the 4 bytes after it) repeats the reference genotype.
-        // The vote also orders this window's shared-memory reads before the refill two iterations later.
-        if (__all_sync(FULL, ((v.x ^ rot) | (v.y ^ rot) | (v.z ^ rot) | (v.w ^ rot) | (w4 ^ rot)) == 0)) {
-          st.a.an_uni += 256; st.col += 128;
+        const uint32_t rot = __funnelshift_l(rp, rp, (uint32_t)st.fsr * 8u);  // the pattern as the raw words see it
+        // T1 x2: every byte of both windows (and the 4 bytes after them) repeats the reference genotype.
+        // The vote also orders these shared-memory reads before the stages are refilled.
+        const uint32_t diff = (va.x ^ rot) | (va.y ^ rot) | (va.z ^ rot) | (va.w ^ rot) | (vb.x ^ rot) | (vb.y ^ rot) |
+                              (vb.z ^ rot) | (vb.w ^ rot) | (w4 ^ rot);
+        if (__all_sync(FULL, diff == 0)) {
+          st.a.an_uni += 512; st.col += 256;
           continue;
         }
-        // T2: separator and tab bytes unchanged, allele bytes in [0-9] (or '.', checked only if needed)
-        const uint32_t t[4] = {__funnelshift_r(v.x, v.y, sh) ^ rp, __funnelshift_r(v.y, v.z, sh) ^ rp,
-                               __funnelshift_r(v.z, v.w, sh) ^ rp, __funnelshift_r(v.w, w4, sh) ^ rp};
-        uint32_t bad = bad_digits4(t, 0xFFFFFFFFu);
-        bool dots = false;
-        if (!__all_sync(FULL, bad == 0)) {
-          bad = bad_digits_or_dots4(t, 0xFFFFFFFFu);
-          dots = true;
-        }
-        if (__all_sync(FULL, bad == 0)) {
-          uint32_t ev[4];
-          st.a.an_uni += 256;
-          const uint32_t nev = classify_words4(t, 0xFu, (int)(st.col - 9) + lane * 4, dots, st.a, ev);
-          push_events4(p, st, my_events, ev, nev, lane);
-          st.col += 128;
-          __syncwarp();
-          continue;
-        }
+        pair_skip = 3;
       }
-      const uint64_t pos = rstart + (uint64_t)it * WIN;
-      scan_window_general<HAS_SAMPLES>(p, st, ring_base_s, stage_off, v, pos, rend, lane, my_recs, my_events);
-      if (st.mode == 2) break;
-      __syncwarp();  // everyone is done with this stage before it is refilled
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {
+        const uint32_t wi = it + h;
+        const uint32_t so = (stage_off + h * WIN) & (RING - 1);
+        if (st.mode == 0 && wi >= seek_limit) { done = true; break; }  // no line starts in this range
+        const uint4 v = lds128(ring_lane_s + so);
+        if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
+          const uint32_t w4 = lds32(ring_base_s + ((so + lane * 16 + 16) & (RING - 1)));
+          const uint32_t sh = (uint32_t)st.fsr * 8u;
+          const uint32_t rp = st.refpat;
+          const uint32_t t[4] = {__funnelshift_r(v.x, v.y, sh) ^ rp, __funnelshift_r(v.y, v.z, sh) ^ rp,
+                                 __funnelshift_r(v.z, v.w, sh) ^ rp, __funnelshift_r(v.w, w4, sh) ^ rp};
+          if (__all_sync(FULL, (t[0] | t[1] | t[2] | t[3]) == 0)) {  // T1
+            st.a.an_uni += 256; st.col += 128;
+            continue;
+          }
+          // T2: separator and tab bytes unchanged, allele bytes in [0-9] (or '.', checked only if needed)
+          uint32_t bad = bad_digits4(t, 0xFFFFFFFFu);
+          bool dots = false;
+          if (!__all_sync(FULL, bad == 0)) {
+            bad = bad_digits_or_dots4(t, 0xFFFFFFFFu);
+            dots = true;
+          }
+          if (__all_sync(FULL, bad == 0)) {
+            st.a.an_uni += 256;
+            classify_push_words4(p, st, my_events, t, (int)(st.col - 9) + lane * 4, dots, lane);
+            st.col += 128;
+            continue;
+          }
+        }
+        const uint64_t pos = rstart + (uint64_t)wi * WIN;
+        scan_window_general<HAS_SAMPLES>(p, st, ring_base_s, so, v, pos, rend, lane, my_recs, my_events);
+        if (st.mode == 2) { done = true; break; }
+      }
+      __syncwarp();  // everyone is done with these stages before they are refilled
     }
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
