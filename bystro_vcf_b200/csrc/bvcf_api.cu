@@ -37,7 +37,7 @@ struct Scratch {
   uint64_t max_records = 0;
   uint64_t row_cap = 0;       // RowDesc slots (rows one sub-chunk may emit)
   DevBuf recs, range_nrec, range_nlines, rec_base, line_base, events, dense, line_bytes, line_rows, line_off,
-      row_off, partial, stats1, row_desc;
+      row_off, partial, stats1, row_desc, big_recs, big_rows;
 };
 
 struct Slot {
@@ -161,12 +161,15 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
     sc.row_cap = std::max<uint64_t>(sc.row_cap, sc.max_records + sc.max_records / 4 + 1024);
     if ((rc = dev_reserve(ctx, sc.stats1, sc.max_records * sizeof(LineStats)))) return rc;
     if ((rc = dev_reserve(ctx, sc.row_desc, sc.row_cap * sizeof(RowDesc)))) return rc;
+    if ((rc = dev_reserve(ctx, sc.big_recs, sc.max_records * 4))) return rc;
+    if ((rc = dev_reserve(ctx, sc.big_rows, sc.row_cap * 4))) return rc;
   }
   return 0;
 }
 void scratch_free(Scratch &sc) {
   for (DevBuf *b : {&sc.recs, &sc.range_nrec, &sc.range_nlines, &sc.rec_base, &sc.line_base, &sc.events, &sc.dense,
-                    &sc.line_bytes, &sc.line_rows, &sc.line_off, &sc.row_off, &sc.partial, &sc.stats1, &sc.row_desc})
+                    &sc.line_bytes, &sc.line_rows, &sc.line_off, &sc.row_off, &sc.partial, &sc.stats1, &sc.row_desc, &sc.big_recs,
+                    &sc.big_rows})
     dev_free(*b);
 }
 
@@ -243,8 +246,10 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     if (dc.n_samples > 0) {
       StatsParams tp{};
       tp.in = d_in; tp.cfg = dc; tp.lines = cp.dense; tp.events = sp.events; tp.stats = (LineStats *)sc.stats1.p; tp.ctr = d_ctr;
+      tp.big_recs = (uint32_t *)sc.big_recs.p;
       bvcf_line_stats_kernel<<<wgrid, 256, 0, st>>>(tp);
-      ctx->launches++;
+      bvcf_line_stats_big_kernel<<<wgrid, 256, 0, st>>>(tp);
+      ctx->launches += 2;
     }
     if (se) CK(cudaEventRecord(se->e[3], st));
     // 4. size pass (thread per record)
@@ -278,8 +283,10 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       NamesParams np{};
       np.in = d_in; np.cfg = dc; np.lines = cp.dense; np.events = sp.events; np.row_desc = (const RowDesc *)sc.row_desc.p;
       np.row_desc_cap = sc.row_cap; np.out = d_out; np.ctr = d_ctr; np.dosage = d_dosage; np.dosage_cap_rows = dosage_cap_rows;
+      np.big_rows = (uint32_t *)sc.big_rows.p;
       bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
-      ctx->launches++;
+      bvcf_names_big_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
+      ctx->launches += 2;
     }
     if (se) CK(cudaEventRecord(se->e[6], st));
   }
@@ -735,7 +742,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->size_ms += ms;
       cudaEventElapsedTime(&ms, t.e[4], t.e[5]); times->emit_ms += ms;
       cudaEventElapsedTime(&ms, t.e[5], t.e[6]); times->names_ms += ms;
-      times->launches += ctx->dcfg.n_samples > 0 ? 12 : 10;
+      times->launches += ctx->dcfg.n_samples > 0 ? 14 : 10;
     }
     if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[N_STAGE_EV - 1]);
     for (auto &t : timing)

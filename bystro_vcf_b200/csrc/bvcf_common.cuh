@@ -54,6 +54,8 @@ struct RunCounters {
   unsigned int out_overflow;       // output region too small
   unsigned int n_diags;
   unsigned int row_overflow;       // a sub-chunk emitted more rows than RowDesc slots
+  unsigned int n_big_recs;         // work list of the stats kernel: records with long event lists (per sub-chunk)
+  unsigned int n_big_rows;         // work list of the names kernel: rows with long event lists (per sub-chunk)
   unsigned int pad0;
   unsigned long long chunk_out_base;  // out_cursor before this sub-chunk (set by the scan-finalize kernel)
   unsigned long long chunk_row_base;

@@ -23,6 +23,7 @@ namespace bvcf {
 constexpr int ROWS_THREADS = 128;
 constexpr int NAMES_WARPS = 8;
 constexpr int FILT_SMEM = 1024;      // FILTER table bytes kept in shared memory
+constexpr uint32_t ROW_STAGE_BYTES = 6144;  // per-warp staging of 32 sample-less rows (EMIT pass)
 
 // genotype summary of one (record, ALT number)
 struct GtStats {
@@ -126,6 +127,7 @@ struct StatsParams {
   const uint32_t *events;
   LineStats *stats;
   RunCounters *ctr;
+  uint32_t *big_recs;        // work list: records reduced by a whole warp (bvcf_line_stats_big_kernel)
 };
 
 // one event word classified against ALT numbers 1..STAT_ALLELES at once
@@ -205,16 +207,32 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams 
       }
       p.stats[li] = s;
     }
-    // ---- warp-cooperative for the long ones ----
-    uint32_t big = __ballot_sync(FULL, needed && !small);
-    while (big) {
-      const int l = __ffs(big) - 1;
-      big &= big - 1;
-      const uint64_t start = __shfl_sync(FULL, rec.start, l);
-      const uint32_t len = __shfl_sync(FULL, rec.len, l);
-      const uint32_t an0 = __shfl_sync(FULL, rec.an, l);
-      const uint32_t ev_start = __shfl_sync(FULL, rec.ev_start, l);
-      const uint32_t ev_count = __shfl_sync(FULL, rec.ev_count, l);
+    // ---- the long ones go to the work list of the warp-per-record kernel (one atomic per warp) ----
+    const uint32_t big = __ballot_sync(FULL, needed && !small);
+    if (big) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&p.ctr->n_big_recs, (unsigned int)__popc(big));
+      base = __shfl_sync(FULL, base, 0);
+      if (needed && !small) p.big_recs[base + __popc(big & ((1u << lane) - 1u))] = li;
+    }
+  }
+}
+
+// warp per record: the records the hybrid kernel queued (long event lists), ballot/popc reductions
+__global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsParams p) {
+  const DevCfg &cfg = p.cfg;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_big = p.ctr->n_big_recs;
+  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+  const bool fixed = cfg.name_fixed_w > 0;
+  for (uint32_t wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < n_big; wi += total_warps) {
+    const uint32_t li = p.big_recs[wi];
+    const LineRec rec = p.lines[li];
+    {
+      const uint64_t start = rec.start;
+      const uint32_t len = rec.len, an0 = rec.an, ev_start = rec.ev_start, ev_count = rec.ev_count;
+      const int l = 0;
+      const uint32_t lb = li;
       const uint32_t content_len = len >= (uint32_t)cfg.eol_width ? len - (uint32_t)cfg.eol_width : 0;
       const uint32_t *ev = p.events + ev_start;
       const uint8_t *L = p.in + start;
@@ -439,11 +457,147 @@ __device__ __forceinline__ void push_diag(const RowsParams &p, unsigned long lon
   }
 }
 
+// ---- getAlleles (main.go:723-1038) as a generator -----------------------------------------------------
+// gen_begin does the whole-line checks (REF == ALT, site type); gen_next yields one output allele per call,
+// in the order the reference appends them, so that all lanes of a warp meet at a single emit_row call.
+struct AlleleGen {
+  const uint8_t *ref, *alt, *ta;  // ta/tn: the equal-length allele being decomposed base by base
+  int ref_n, alt_n, tn;
+  int s;          // cursor in ALT: start of the next comma-separated allele
+  int alt_idx;    // its index in the ALT list
+  int mnp_i;      // >= 0: resume the MNP decomposition at this base
+  long long ipos;
+  bool pos_ok, last, done;
+};
+
+__device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const RowsParams &p, unsigned long long line_no,
+                                          bool diag) {
+  bool same = g.alt_n == g.ref_n;
+  for (int i = 0; same && i < g.alt_n; i++) same = g.alt[i] == g.ref[i];
+  if (same) {                                                         // :729
+    if (diag) push_diag(p, line_no, 0, 1);
+    g.done = true;
+    return;
+  }
+  bool multi = false;                                                 // :777-779, 1012: ALT holds a comma
+  for (int i = 0; i < g.alt_n; i++) multi = multi || g.alt[i] == ',';
+  lc.multi = multi;
+  lc.site_type = T_MULTI;
+  if (!multi) {  // a single allele: type from its shape (main.go:742,764,1018-1037)
+    if (g.alt_n == 1) lc.site_type = g.ref_n == 1 ? T_SNP : T_DEL;
+    else if (g.ref_n == 1 || g.alt_n > g.ref_n) lc.site_type = T_INS;
+    else if (g.alt_n < g.ref_n) lc.site_type = T_DEL;
+    else {
+      int nd = 0;
+      for (int i = 0; i < g.ref_n; i++) nd += g.ref[i] != g.alt[i];
+      lc.site_type = nd > 1 ? T_MNP : T_SNP;
+    }
+  }
+}
+
+__device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const RowsParams &p, unsigned long long line_no,
+                                         bool diag) {
+  const uint8_t *ref = g.ref;
+  const int ref_n = g.ref_n;
+  for (;;) {
+    if (g.done) return false;
+    if (g.mnp_i >= 0) {                                               // :855-873 one row per differing base
+      for (int i = g.mnp_i; i < ref_n; i++) {
+        if (ref[i] != g.ta[i]) {
+          oa.kind = 0; oa.ref = ref[i]; oa.alt_c = g.ta[i]; oa.pos_verbatim = false; oa.pos_val = g.ipos + i;
+          g.mnp_i = i + 1;
+          return true;
+        }
+      }
+      g.mnp_i = -1;
+      if (g.last) { g.done = true; return false; }
+      continue;
+    }
+    if (g.alt_n == 1) {                                               // :735 the single one-base ALT
+      g.done = true;
+      const uint8_t a0 = g.alt[0];
+      oa.alt_idx = 0;
+      if (!is_acgt(a0)) { if (diag) push_diag(p, line_no, 1, 2); return false; }
+      if (ref_n == 1) {                                               // :742 SNP, POS text verbatim
+        oa.kind = 0; oa.ref = ref[0]; oa.alt_c = a0; oa.pos_verbatim = true;
+        return true;
+      }
+      if (a0 != ref[0]) { if (diag) push_diag(p, line_no, 1, 3); return false; }   // :747
+      if (!g.pos_ok) { if (diag) push_diag(p, line_no, 1, 4); return false; }      // :752
+      oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n;               // :764
+      oa.pos_verbatim = false; oa.pos_val = g.ipos + 1;
+      return true;
+    }
+    // next comma-separated allele                                    // :774
+    int e = g.s;
+    while (e < g.alt_n && g.alt[e] != ',') e++;
+    const uint8_t *ta = g.alt + g.s;
+    const int tn = e - g.s;
+    const bool last = e >= g.alt_n;
+    const int alt_idx = g.alt_idx;
+    g.s = e + 1;
+    g.alt_idx = alt_idx + 1;
+    g.last = last;
+    if (last) g.done = true;  // cleared again below when an MNP still has bases to yield
+    oa.alt_idx = alt_idx;
+    bool valid = tn > 0;                                              // altIsValid :456-474
+    for (int i = 0; valid && i < tn; i++) valid = is_acgt(ta[i]);
+    if (!valid) { if (diag) push_diag(p, line_no, alt_idx + 1, 2); continue; }
+    if (ref_n == 1) {                                                 // :786
+      if (tn == 1) {
+        oa.kind = 0; oa.ref = ref[0]; oa.alt_c = ta[0]; oa.pos_verbatim = true;
+        return true;
+      }
+      if (ta[0] != ref[0]) { if (diag) push_diag(p, line_no, alt_idx + 1, 5); continue; }   // :797
+      oa.kind = 1; oa.ref = ref[0]; oa.ins_p = ta + 1; oa.ins_n = tn - 1; oa.pos_verbatim = true;  // :803
+      return true;
+    }
+    if (!g.pos_ok) {                                                  // :822-830 stop, keep what we have
+      if (diag) push_diag(p, line_no, 0, 4);
+      g.done = true;
+      return false;
+    }
+    if (tn == 1) {                                                    // :832
+      if (ta[0] != ref[0]) { if (diag) push_diag(p, line_no, alt_idx + 1, 3); continue; }
+      oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n; oa.pos_verbatim = false;
+      oa.pos_val = g.ipos + 1;
+      return true;
+    }
+    if (tn == ref_n) {                                                // :855 MNP / padded SNP
+      g.ta = ta; g.tn = tn; g.mnp_i = 0; g.done = false;
+      continue;
+    }
+    if (tn > ref_n) {                                                 // :899 insertion with padding
+      int r = 0;
+      while (tn + r > 0 && ref_n + r > 1 && ta[tn + r - 1] == ref[ref_n + r - 1]) r--;
+      const int off = ref_n + r;                                      // :932
+      bool pre = true;
+      for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
+      if (!pre) { if (diag) push_diag(p, line_no, alt_idx + 1, 6); continue; }
+      oa.kind = 1; oa.ref = ref[off - 1]; oa.ins_p = ta + off; oa.ins_n = tn + r - off;
+      oa.pos_verbatim = false; oa.pos_val = g.ipos + off - 1;
+      return true;
+    }
+    {                                                                 // :971 deletion with padding
+      int r = 0;
+      while (tn + r > 1 && ref_n + r > 0 && ta[tn + r - 1] == ref[ref_n + r - 1]) r--;
+      const int off = tn + r;                                         // :984
+      bool pre = true;
+      for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
+      if (!pre) { if (diag) push_diag(p, line_no, alt_idx + 1, 6); continue; }
+      oa.kind = 2; oa.ref = ref[off]; oa.del_n = -((long long)ref_n + r - off);
+      oa.pos_verbatim = false; oa.pos_val = g.ipos + off;
+      return true;
+    }
+  }
+}
+
 // ---- thread per record, grid-stride, record count read from device memory ----------------------------
 template <bool WRITE>
 __global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_kernel(const RowsParams p) {
   __shared__ uint8_t s_filt[FILT_SMEM];
   __shared__ uint32_t s_filt_off[65];
+  __shared__ __align__(16) uint8_t s_rowstage[WRITE ? ROWS_THREADS / 32 : 1][WRITE ? ROW_STAGE_BYTES : 16];
   const DevCfg &cfg = p.cfg;
   // FILTER allow/exclude table -> shared memory
   const int n_filt = cfg.n_allow + cfg.n_excl;
@@ -455,14 +609,35 @@ __global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_kernel(const RowsParam
   const unsigned long long out_base = p.ctr->chunk_out_base;
   const uint32_t total_threads = gridDim.x * blockDim.x;
 
-  for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_rec; li += total_threads) {
+  const int lane = threadIdx.x & 31;
+  uint8_t *stage = s_rowstage[threadIdx.x >> 5];
+  for (uint32_t li_base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); li_base < n_rec; li_base += total_threads) {
+    const uint32_t li = li_base + lane;
+    const bool valid = li < n_rec;
+    // Without sample lists the rows of 32 consecutive records are one contiguous span of the output: compose
+    // them in shared memory and copy the span out with aligned 16-byte stores instead of byte stores.
+    bool staged = false;
+    unsigned long long span_base = 0;
+    uint32_t span = 0, my_rel = 0, mis = 0;
+    if (WRITE && cfg.n_samples == 0) {
+      const unsigned long long off = valid ? p.line_off[li] : 0;
+      const unsigned long long end = valid ? off + p.line_bytes[li] : 0;
+      span_base = __shfl_sync(FULL, off, 0);
+      const uint32_t last = n_rec - li_base > 32 ? 31 : n_rec - li_base - 1;
+      const unsigned long long span64 = __shfl_sync(FULL, end, last) - span_base;
+      mis = (uint32_t)((uintptr_t)(p.out + out_base + span_base) & 15u);
+      staged = span64 + mis <= ROW_STAGE_BYTES;
+      span = (uint32_t)span64;
+      my_rel = (uint32_t)(off - span_base);
+    }
+    if (valid) {
     const LineRec rec = p.lines[li];
     const uint8_t *L = p.in + rec.start;
     const uint32_t n = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;  // main.go:535
 
     RowWriter<WRITE> w;
     w.count = 0;
-    w.g = WRITE ? p.out + out_base + p.line_off[li] : nullptr;
+    w.g = WRITE ? (staged ? stage + mis + my_rel : p.out + out_base + p.line_off[li]) : nullptr;
     uint32_t n_rows = 0;
     const unsigned long long row_base = WRITE ? p.row_off[li] : 0;  // row number within the sub-chunk
 
@@ -507,126 +682,38 @@ __global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_kernel(const RowsParam
       if (in_excl) pass = false;
     }
 
-    // ---- getAlleles (main.go:723-1038) ----
-    if (pass && ref_n > 0 && alt_n > 0) {
+    // ---- getAlleles (main.go:723-1038) as a resumable generator: one converged emit_row call site ----
+    {
+      AlleleGen g;
+      g.ref = ref; g.alt = alt; g.ref_n = ref_n; g.alt_n = alt_n;
+      g.s = 0; g.alt_idx = 0; g.mnp_i = -1; g.ta = alt; g.tn = 0; g.last = false;
+      g.done = !(pass && ref_n > 0 && alt_n > 0);
+      g.ipos = 0;
+      g.pos_ok = g.done ? false : atoi_go(lc.pos, lc.pos_n, g.ipos);
       const unsigned long long line_no = p.ctr->chunk_line_base + rec.ord;
+      if (!g.done) gen_begin(g, lc, p, line_no, !WRITE);
       GtStats gs;
       int gs_idx = -1;
       OutAllele oa;
       oa.ins_p = nullptr; oa.ins_n = 0; oa.del_n = 0; oa.pos_val = 0;
-      long long ipos = 0;
-      const bool pos_ok = atoi_go(lc.pos, lc.pos_n, ipos);
-      bool same = alt_n == ref_n;
-      for (int i = 0; same && i < alt_n; i++) same = alt[i] == ref[i];
-      if (same) {                                                       // :729
-        if (!WRITE) push_diag(p, line_no, 0, 1);
-      } else if (alt_n == 1) {                                          // :735
-        if (!is_acgt(alt[0])) {
-          if (!WRITE) push_diag(p, line_no, 1, 2);
-        } else if (ref_n == 1) {                                        // :742 SNP, POS text verbatim
-          lc.site_type = T_SNP;
-          oa.kind = 0; oa.ref = ref[0]; oa.alt_c = alt[0]; oa.alt_idx = 0; oa.pos_verbatim = true;
-          emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-        } else if (alt[0] != ref[0]) {                                  // :747
-          if (!WRITE) push_diag(p, line_no, 1, 3);
-        } else if (!pos_ok) {                                           // :752
-          if (!WRITE) push_diag(p, line_no, 1, 4);
-        } else {                                                        // :764 simple deletion
-          lc.site_type = T_DEL;
-          oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n; oa.alt_idx = 0;
-          oa.pos_verbatim = false; oa.pos_val = ipos + 1;
-          emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-        }
-      } else {
-        // multi == the ALT field holds a comma (main.go:777-779, 1012)
-        bool multi = false;
-        for (int i = 0; i < alt_n; i++) multi = multi || alt[i] == ',';
-        lc.multi = multi;
-        lc.site_type = T_MULTI;
-        if (!multi) {  // a single allele: type from its shape (main.go:1018-1037)
-          if (ref_n == 1 || alt_n > ref_n) lc.site_type = T_INS;
-          else if (alt_n < ref_n) lc.site_type = T_DEL;
-          else {
-            int nd = 0;
-            for (int i = 0; i < ref_n; i++) nd += ref[i] != alt[i];
-            lc.site_type = nd > 1 ? T_MNP : T_SNP;
-          }
-        }
-        int s = 0;
-        for (int alt_idx = 0;; alt_idx++) {                             // :774
-          int e = s;
-          while (e < alt_n && alt[e] != ',') e++;
-          const uint8_t *ta = alt + s;
-          const int tn = e - s;
-          const bool last = e >= alt_n;
-          s = e + 1;
-          bool valid = tn > 0;                                          // altIsValid :456-474
-          for (int i = 0; valid && i < tn; i++) valid = is_acgt(ta[i]);
-          oa.alt_idx = alt_idx;
-          if (!valid) {
-            if (!WRITE) push_diag(p, line_no, alt_idx + 1, 2);
-          } else if (ref_n == 1) {                                      // :786
-            if (tn == 1) {
-              oa.kind = 0; oa.ref = ref[0]; oa.alt_c = ta[0]; oa.pos_verbatim = true;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-            } else if (ta[0] != ref[0]) {                               // :797
-              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 5);
-            } else {                                                    // :803 simple insertion
-              oa.kind = 1; oa.ref = ref[0]; oa.ins_p = ta + 1; oa.ins_n = tn - 1; oa.pos_verbatim = true;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-            }
-          } else if (!pos_ok) {                                         // :822-830 stop, keep what we have
-            if (!WRITE) push_diag(p, line_no, 0, 4);
-            break;
-          } else if (tn == 1) {                                         // :832
-            if (ta[0] != ref[0]) {
-              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 3);
-            } else {
-              oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n; oa.pos_verbatim = false;
-              oa.pos_val = ipos + 1;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-            }
-          } else if (tn == ref_n) {                                     // :855 MNP / padded SNP
-            for (int i = 0; i < ref_n; i++) {
-              if (ref[i] != ta[i]) {
-                oa.kind = 0; oa.ref = ref[i]; oa.alt_c = ta[i]; oa.pos_verbatim = false; oa.pos_val = ipos + i;
-                emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-              }
-            }
-          } else if (tn > ref_n) {                                      // :899 insertion with padding
-            int r = 0;
-            while (tn + r > 0 && ref_n + r > 1 && ta[tn + r - 1] == ref[ref_n + r - 1]) r--;
-            const int off = ref_n + r;                                  // :932
-            bool pre = true;
-            for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
-            if (!pre) {
-              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 6);
-            } else {
-              oa.kind = 1; oa.ref = ref[off - 1]; oa.ins_p = ta + off; oa.ins_n = tn + r - off;
-              oa.pos_verbatim = false; oa.pos_val = ipos + off - 1;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-            }
-          } else {                                                      // :971 deletion with padding
-            int r = 0;
-            while (tn + r > 1 && ref_n + r > 0 && ta[tn + r - 1] == ref[ref_n + r - 1]) r--;
-            const int off = tn + r;                                     // :984
-            bool pre = true;
-            for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
-            if (!pre) {
-              if (!WRITE) push_diag(p, line_no, alt_idx + 1, 6);
-            } else {
-              oa.kind = 2; oa.ref = ref[off]; oa.del_n = -((long long)ref_n + r - off);
-              oa.pos_verbatim = false; oa.pos_val = ipos + off;
-              emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-            }
-          }
-          if (last) break;
-        }
-      }
+      while (gen_next(g, oa, p, line_no, !WRITE)) emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
     }
     if (!WRITE) {
       p.line_bytes[li] = (uint32_t)w.count;
       p.line_rows[li] = n_rows;
+    }
+    }  // valid
+    if (WRITE && staged) {
+      __syncwarp();
+      uint8_t *gb = p.out + out_base + span_base;
+      const uint8_t *sb = stage + mis;
+      const uint32_t head = span < ((16u - mis) & 15u) ? span : ((16u - mis) & 15u);
+      for (uint32_t i = lane; i < head; i += 32) gb[i] = sb[i];
+      const uint32_t nvec = (span - head) >> 4;
+      for (uint32_t v = lane; v < nvec; v += 32)
+        *reinterpret_cast<uint4 *>(gb + head + 16 * v) = *reinterpret_cast<const uint4 *>(sb + head + 16 * v);
+      for (uint32_t i = head + 16 * nvec + lane; i < span; i += 32) gb[i] = sb[i];
+      __syncwarp();
     }
   }
 }
@@ -643,6 +730,7 @@ struct NamesParams {
   RunCounters *ctr;
   int8_t *dosage;
   unsigned long long dosage_cap_rows;
+  uint32_t *big_rows;        // work list: rows written by a whole warp (bvcf_names_big_kernel)
 };
 
 // 8 bytes to an arbitrarily aligned address with the widest naturally aligned pieces (2-4 stores)
@@ -817,13 +905,26 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
       small = rec.ev_count <= SMALL_EVENTS;
       if (small) names_row_lane(p, rd, rec);
     }
-    uint32_t big = __ballot_sync(FULL, valid && !small);
-    while (big) {
-      const int l = __ffs(big) - 1;
-      big &= big - 1;
-      names_row_warp(p, rb + l, row0, lane);
+    // long rows go to the work list of the warp-per-row kernel (one atomic per warp)
+    const uint32_t big = __ballot_sync(FULL, valid && !small);
+    if (big) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&p.ctr->n_big_rows, (unsigned int)__popc(big));
+      base = __shfl_sync(FULL, base, 0);
+      if (valid && !small) p.big_rows[base + __popc(big & ((1u << lane) - 1u))] = (uint32_t)r;
     }
   }
+}
+
+// warp per row: the rows the hybrid kernel queued
+__global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_big_kernel(const NamesParams p) {
+  const int lane = threadIdx.x & 31;
+  if (p.ctr->out_overflow) return;
+  const unsigned long long row0 = p.ctr->chunk_row_base;
+  const uint32_t n_big = p.ctr->n_big_rows;
+  const uint32_t total_warps = gridDim.x * NAMES_WARPS;
+  for (uint32_t wi = blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5); wi < n_big; wi += total_warps)
+    names_row_warp(p, p.big_rows[wi], row0, lane);
 }
 
 }  // namespace bvcf

@@ -145,6 +145,54 @@ __device__ __forceinline__ void classify_push_words4(const ScanParams &p, WarpSt
   st.ev_w += etot;
 }
 
+// Two adjacent windows at once: events of window A (all lanes) precede those of window B; one packed
+// prefix sum (A count in the low half, B count in the high half) serves both.
+__device__ __forceinline__ void emit_words4(const ScanParams &p, WarpState &st, uint32_t *my_events, const uint32_t t[4],
+                                            uint32_t nz, int samp0, bool dots, bool room, uint32_t k) {
+  LineAcc &a = st.a;
+  while (nz) {
+    const int j = __ffs(nz) - 1;
+    nz &= nz - 1;
+    const uint32_t tt = (j == 0 ? t[0] : j == 1 ? t[1] : j == 2 ? t[2] : t[3]) & 0x00FF00FFu;
+    const uint32_t c1 = tt & 0xFFu, c2 = tt >> 16;
+    uint32_t e;
+    if (dots && (c1 == 0x1Eu || c2 == 0x1Eu)) {
+      e = ev_make((uint32_t)(samp0 + j), EV_CODE_MISSING, EV_CODE_MISSING);
+      a.miss_l++;
+      a.an_l -= 2;
+    } else {
+      e = (uint32_t)(samp0 + j) | (c1 << 20) | (c2 << 25);
+      const uint32_t alt = (c1 == 1) + (c2 == 1);
+      a.ac_l += alt;
+      a.hom_l += alt >> 1;
+      a.het_l += alt & 1u;
+      a.flag_l |= (c1 | c2) > 1;
+    }
+    if (room) my_events[k] = e;
+    k++;
+  }
+}
+__device__ __forceinline__ uint32_t nz_mask4(const uint32_t t[4]) {
+  return (t[0] & 0x00FF00FFu ? 1u : 0u) | (t[1] & 0x00FF00FFu ? 2u : 0u) | (t[2] & 0x00FF00FFu ? 4u : 0u) |
+         (t[3] & 0x00FF00FFu ? 8u : 0u);
+}
+__device__ __forceinline__ void classify_push_pair(const ScanParams &p, WarpState &st, uint32_t *my_events,
+                                                   const uint32_t ta[4], const uint32_t tb[4], int samp0, bool dots,
+                                                   int lane) {
+  const uint32_t nza = nz_mask4(ta), nzb = nz_mask4(tb);
+  const uint32_t packed = __popc(nza) | (__popc(nzb) << 16);
+  const uint32_t incl = warp_incl_scan(packed, lane);
+  const uint32_t tot = __shfl_sync(FULL, incl, 31);
+  if (tot == 0) return;
+  const uint32_t tot_a = tot & 0xFFFFu, tot_b = tot >> 16;
+  const bool room = st.ev_w + tot_a + tot_b <= p.evcap_words;
+  if (!room && lane == 0) p.ctr->ev_overflow = 1;
+  const uint32_t excl = incl - packed;
+  emit_words4(p, st, my_events, ta, nza, samp0, dots, room, st.ev_w + (excl & 0xFFFFu));
+  emit_words4(p, st, my_events, tb, nzb, samp0 + 128, dots, room, st.ev_w + tot_a + (excl >> 16));
+  st.ev_w += tot_a + tot_b;
+}
+
 // SWAR validity of four XORed fields: separator/tab bytes unchanged, allele bytes digits (or '.')
 __device__ __forceinline__ uint32_t bad_digits4(const uint32_t t[4], uint32_t keep_mask3) {
   const uint32_t D = 0x00760076u, H = 0x00800080u, M = 0x00FF00FFu;
@@ -469,30 +517,47 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
     // One loop iteration = one 1 KiB pair of windows.  Pairs that are all-reference (the bulk of real
     // data) cost one 9-compare vote; anything else falls through to the per-window dispatcher.
     uint32_t stage_off = 0;
-    uint32_t pair_skip = (p.tune & 1) ? 0x7FFFFFFFu : 0u;
     bool done = false;
     for (uint32_t it = 0; it + 2 < n_avail && !done; it += 2, stage_off = (stage_off + 2 * WIN) & (RING - 1)) {
       issue();
       issue();
       asm volatile("cp.async.wait_group %0;\n" ::"n"(PF - 1));  // windows it, it+1 and it+2 have landed
       __syncwarp();
-      if (pair_skip) {
-        pair_skip--;  // dense-genotype stretch: do not pay for the pair test again right away
-      } else if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
+      if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u && !(p.tune & 1)) {
+        const uint32_t so_b = (stage_off + WIN) & (RING - 1);
         const uint4 va = lds128(ring_lane_s + stage_off);
-        const uint4 vb = lds128(ring_lane_s + ((stage_off + WIN) & (RING - 1)));
-        const uint32_t w4 = lds32(ring_base_s + ((stage_off + WIN + lane * 16 + 16) & (RING - 1)));
+        const uint4 vb = lds128(ring_lane_s + so_b);
+        const uint32_t w4b = lds32(ring_base_s + ((so_b + lane * 16 + 16) & (RING - 1)));
         const uint32_t rp = st.refpat;
-        const uint32_t rot = __funnelshift_l(rp, rp, (uint32_t)st.fsr * 8u);  // the pattern as the raw words see it
+        const uint32_t sh = (uint32_t)st.fsr * 8u;
+        const uint32_t rot = __funnelshift_l(rp, rp, sh);  // the pattern as the unaligned raw words see it
         // T1 x2: every byte of both windows (and the 4 bytes after them) repeats the reference genotype.
         // The vote also orders these shared-memory reads before the stages are refilled.
         const uint32_t diff = (va.x ^ rot) | (va.y ^ rot) | (va.z ^ rot) | (va.w ^ rot) | (vb.x ^ rot) | (vb.y ^ rot) |
-                              (vb.z ^ rot) | (vb.w ^ rot) | (w4 ^ rot);
+                              (vb.z ^ rot) | (vb.w ^ rot) | (w4b ^ rot);
         if (__all_sync(FULL, diff == 0)) {
           st.a.an_uni += 512; st.col += 256;
           continue;
         }
-        pair_skip = 3;
+        // T2 x2: both windows regular -> one ordered compaction for the 256 fields
+        const uint32_t w4a = lds32(ring_base_s + ((stage_off + lane * 16 + 16) & (RING - 1)));
+        const uint32_t ta[4] = {__funnelshift_r(va.x, va.y, sh) ^ rp, __funnelshift_r(va.y, va.z, sh) ^ rp,
+                                __funnelshift_r(va.z, va.w, sh) ^ rp, __funnelshift_r(va.w, w4a, sh) ^ rp};
+        const uint32_t tb[4] = {__funnelshift_r(vb.x, vb.y, sh) ^ rp, __funnelshift_r(vb.y, vb.z, sh) ^ rp,
+                                __funnelshift_r(vb.z, vb.w, sh) ^ rp, __funnelshift_r(vb.w, w4b, sh) ^ rp};
+        uint32_t bad = bad_digits4(ta, 0xFFFFFFFFu) | bad_digits4(tb, 0xFFFFFFFFu);
+        bool dots = false;
+        if (!__all_sync(FULL, bad == 0)) {
+          bad = bad_digits_or_dots4(ta, 0xFFFFFFFFu) | bad_digits_or_dots4(tb, 0xFFFFFFFFu);
+          dots = true;
+        }
+        if (__all_sync(FULL, bad == 0)) {
+          st.a.an_uni += 512;
+          classify_push_pair(p, st, my_events, ta, tb, (int)(st.col - 9) + lane * 4, dots, lane);
+          st.col += 256;
+          __syncwarp();
+          continue;
+        }
       }
 #pragma unroll 1
       for (int h = 0; h < 2; h++) {
