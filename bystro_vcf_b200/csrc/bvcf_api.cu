@@ -132,6 +132,12 @@ uint32_t choose_range_bytes(uint64_t total) {
 int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t sub_limit) {
   const int H = ctx->dcfg.H;
   sc.range_bytes = choose_range_bytes(total_bytes);
+  // a record is scanned by the one warp that owns its start: with biobank-width lines (4+ bytes per sample)
+  // ranges shorter than a line would leave most warps idle, so make a range hold at least ~1.25 lines
+  {
+    const uint64_t min_r = round_up(5ull * (uint64_t)std::max(ctx->dcfg.n_samples, 0), 512);
+    if (min_r > sc.range_bytes) sc.range_bytes = (uint32_t)std::min<uint64_t>(min_r, 64ull << 20);
+  }
   uint64_t sub = std::min<uint64_t>(round_up(total_bytes + 512, sc.range_bytes), round_up(sub_limit, sc.range_bytes));
   sc.sub_bytes = sub;
   sc.n_ranges = (uint32_t)(sub / sc.range_bytes);
@@ -560,8 +566,15 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
     CK(cudaEventSynchronize(s->done));
     const RunCounters &c = *s->h_ctr;
     bool again = false;
-    if (c.ev_overflow) { ctx->ev_factor *= 4; again = true; }           // dense genotype block: more event slots
     if (c.slot_overflow) return BVCF_E_TOO_LARGE;                       // cannot happen: slots cover the minimum line
+    if (c.ev_overflow) {                                                // dense genotype block: more event slots
+      ctx->ev_factor *= 4;
+      s->retries++;
+      if (s->retries > 8) return BVCF_E_TOO_LARGE;
+      const int rc = slot_enqueue(ctx, *s, false);
+      if (rc) return rc;
+      continue;
+    }
     if (c.row_overflow) { s->sc.row_cap = s->sc.row_cap * 4 + c.row_cursor; again = true; }  // MNP/multi-ALT heavy block
     if (c.out_overflow) {
       int rc = dev_reserve(ctx, s->d_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096));
@@ -710,8 +723,12 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
     CK(cudaStreamSynchronize(ctx->r_stream));
     const RunCounters &c = *ctx->r_h_ctr;
     bool again = false;
-    if (c.ev_overflow) { ctx->ev_factor *= 4; again = true; }
     if (c.slot_overflow) return BVCF_E_TOO_LARGE;
+    if (c.ev_overflow) {  // dense genotype block: more event slots, run again
+      ctx->ev_factor *= 4;
+      if (++retries > 8) return BVCF_E_TOO_LARGE;
+      continue;
+    }
     if (c.row_overflow) { ctx->r_sc.row_cap = ctx->r_sc.row_cap * 4 + c.row_cursor; again = true; }
     if (c.out_overflow) {
       if ((rc = dev_reserve(ctx, ctx->r_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096)))) return rc;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(1024) bvcf_prefix_spine_kernel(const PrefixPar
       c->n_big_recs = 0;
       c->n_records += sa[t];
       c->n_lines += sb[t];
-    } else {
+    } else if (!(c->ev_overflow | c->slot_overflow)) {  // sizes are garbage after a scratch overflow: leave the cursors
       c->n_big_rows = 0;
       c->chunk_out_base = c->out_cursor;
       c->chunk_row_base = c->row_cursor;

@@ -172,6 +172,7 @@ constexpr uint32_t SMALL_EVENTS = 12;  // records with at most this many event w
 __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams p) {
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
+  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;  // the host grows the scratch and re-runs the chunk
   const uint32_t n_rec = p.ctr->chunk_records;
   const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
   const bool fixed = cfg.name_fixed_w > 0;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams 
 __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsParams p) {
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
+  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const uint32_t n_big = p.ctr->n_big_recs;
   const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
   const bool fixed = cfg.name_fixed_w > 0;
@@ -605,6 +607,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_kernel(const RowsParam
   for (int i = threadIdx.x; i <= n_filt && i < 65; i += blockDim.x) s_filt_off[i] = cfg.filt_off[i];
   __syncthreads();
   if (WRITE && p.ctr->out_overflow) return;
+  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;  // the host grows the scratch and re-runs the chunk
   const uint32_t n_rec = p.ctr->chunk_records;
   const unsigned long long out_base = p.ctr->chunk_out_base;
   const uint32_t total_threads = gridDim.x * blockDim.x;
@@ -889,7 +892,7 @@ __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDe
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
-  if (p.ctr->out_overflow) return;
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const unsigned long long row0 = p.ctr->chunk_row_base;
   unsigned long long n_rows = p.ctr->row_cursor - row0;  // rows of this sub-chunk
   if (n_rows > p.row_desc_cap) n_rows = p.row_desc_cap;
@@ -919,7 +922,7 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
 // warp per row: the rows the hybrid kernel queued
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_big_kernel(const NamesParams p) {
   const int lane = threadIdx.x & 31;
-  if (p.ctr->out_overflow) return;
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const unsigned long long row0 = p.ctr->chunk_row_base;
   const uint32_t n_big = p.ctr->n_big_rows;
   const uint32_t total_warps = gridDim.x * NAMES_WARPS;

@@ -199,3 +199,22 @@ def test_slash_separated_and_mixed_width_fields():
         recs.append(["2", str(1000 + i), ".", "A", "C,G", ".", "PASS", ".", "GT"] + gts)
     vcf = V._vcf(hdr, recs)
     assert gpu_rows(vcf) == oracle_rows(vcf)
+
+
+def test_dense_genotype_block_grows_event_scratch():
+    """every sample non-reference and haploid: 4 event bytes per 2 input bytes overflows the default event
+    slice; the library must notice, grow the scratch and re-run the chunk (retries > 0), byte-identically"""
+    from bystro_vcf_b200 import Transformer, parse_preamble
+    from oracle import oracle as O
+
+    ns = 6000
+    hdr = V.HDR8 + ["FORMAT"] + ["H%05d" % i for i in range(ns)]
+    recs = [["3", str(100 + i), ".", "A", "C", ".", "PASS", ".", "GT"] + ["1"] * ns for i in range(200)]
+    vcf = V._vcf(hdr, recs)
+    ref = O.read_vcf(O.OracleConfig(), vcf)
+    w, chrom, off = parse_preamble(vcf)
+    with Transformer(_cfg(), eol_width=w) as tr:
+        tr.set_header(chrom)
+        res = tr.process(vcf[off:])
+    assert res.retries > 0
+    assert res.tsv == ref.tsv
