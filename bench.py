@@ -39,35 +39,41 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe):
+    one long-running `nvidia-smi -lms 100` started before the region and stopped after it."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
-        self._t = None
-
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self._p = None
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                        "--format=csv,noheader,nounits", "-lms", "100"],
+                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.25)  # let the first sample land before the timed region starts
+        except Exception:
+            self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._p is None:
+            return
+        time.sleep(0.12)
+        self._p.terminate()
+        try:
+            out, _ = self._p.communicate(timeout=5)
+        except Exception:
+            self._p.kill()
+            out = ""
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6:
+                self.rows.append(f)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -76,6 +82,18 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(self.rows)}
+
+
+def scan_traffic_ratio():
+    """DRAM bytes (read+write) per algorithmic byte of the scan kernel, from the committed ncu --set full
+    capture (profiles/r01_scan_traffic.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r01_scan_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["algorithmic_bytes"], d.get("source", p)
+    except Exception:
+        return None, None
 
 
 def newline_cuts(view, total: int, chunk: int):
@@ -207,6 +225,10 @@ def run_ours(args):
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
                 "algorithmic_bytes_per_step": need, "avg_ms_per_step": scan_ms}
         roof["frac"] = roof["achieved"] / peak
+        ratio, src = scan_traffic_ratio()
+        if ratio is not None:  # per launch (= per step here: one launch per sub-chunk), scaled from the ncu capture
+            roof["traffic"] = ratio * need
+            roof["traffic_source"] = src
         pipe = {"achieved": alg_bytes / (dev_ms / args.steps / 1e3) / 1e9, "unit": "GB/s",
                 "algorithmic_bytes_per_step": alg_bytes, "bytes_per_variant": alg_bytes / n_lines}
         pipe["frac"] = pipe["achieved"] / peak

@@ -291,7 +291,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       np.row_desc_cap = sc.row_cap; np.out = d_out; np.ctr = d_ctr; np.dosage = d_dosage; np.dosage_cap_rows = dosage_cap_rows;
       np.big_rows = (uint32_t *)sc.big_rows.p;
       bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
-      bvcf_names_big_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
+      bvcf_names_big_kernel<<<wgrid * 4, NAMES_WARPS * 32, 0, st>>>(np);
       ctx->launches += 2;
     }
     if (se) CK(cudaEventRecord(se->e[6], st));

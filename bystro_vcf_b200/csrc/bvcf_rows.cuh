@@ -21,7 +21,7 @@
 namespace bvcf {
 
 constexpr int ROWS_THREADS = 128;
-constexpr int NAMES_WARPS = 8;
+constexpr int NAMES_WARPS = 2;   // small CTAs: rows differ wildly in size, a finished warp must not pin the others' slots
 constexpr int FILT_SMEM = 1024;      // FILTER table bytes kept in shared memory
 constexpr uint32_t ROW_STAGE_BYTES = 6144;  // per-warp staging of 32 sample-less rows (EMIT pass)
 
@@ -790,28 +790,39 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
     if (cfg.name8 && cfg.want_tsv) {
       // ---- fast path: every list item is exactly 8 bytes (name + delimiter).  Each lane ranks its item
       // within its class with ballot/popc and stores the 8 bytes itself with the widest aligned pieces the
-      // destination allows (2-4 stores): all three classes go out in the same instructions. ----
+      // destination allows (2-4 stores; the alignment is uniform per class, so no divergence). ----
       const uint32_t totals[3] = {rd.n_het, rd.n_hom, rd.n_miss};
       uint32_t w_next = lane < rec.ev_count ? ev[lane] : EV_OFFSET_TAG;
       for (uint32_t base = 0; base < rec.ev_count; base += 32) {
-        uint32_t samp, gtx, alt;
         const uint32_t k = base + lane;
         const uint32_t w_cur = w_next;  // software pipelining: the next batch's words are already in flight
         w_next = k + 32 < rec.ev_count ? ev[k + 32] : EV_OFFSET_TAG;
-        const int cls = classify_word(w_cur, ev, k, L, content_len, a, samp, gtx, alt);
+        int cls;
+        uint32_t samp, alt;
+        if (__any_sync(FULL, (w_cur & (EV_COMPLEX | EV_OFFSET_TAG)) == EV_COMPLEX)) {
+          uint32_t gtx;  // a sample in this batch needs the general GT grammar
+          cls = classify_word(w_cur, ev, k, L, content_len, a, samp, gtx, alt);
+        } else {
+          const uint32_t c1 = (w_cur >> 20) & 31, c2 = (w_cur >> 25) & 31;
+          samp = w_cur & EV_SAMPLE_MASK;
+          alt = (c1 == a) + (c2 == a);
+          const bool dip = c2 != EV_CODE_ABSENT;
+          cls = (w_cur & EV_OFFSET_TAG) ? 0 : (c1 == EV_CODE_MISSING ? 3 : (alt == 0 ? 0 : ((alt == 2 || !dip) ? 2 : 1)));
+        }
         if (drow && !(w_cur & EV_OFFSET_TAG))
           drow[samp] = cls == 3 ? (int8_t)-1 : (int8_t)(alt > 127 ? 127 : alt);  // main.go:1172-1178
-        const uint32_t b1 = __ballot_sync(FULL, cls == 1), b2 = __ballot_sync(FULL, cls == 2), b3 = __ballot_sync(FULL, cls == 3);
-        if (cls) {
-          const int c = cls - 1;
-          const uint32_t mine = c == 0 ? b1 : (c == 1 ? b2 : b3);
-          const uint32_t idx = (c == 0 ? run_n[0] : (c == 1 ? run_n[1] : run_n[2])) + __popc(mine & lt);
-          const uint32_t tot = c == 0 ? totals[0] : (c == 1 ? totals[1] : totals[2]);
-          unsigned long long it = cfg.name8[samp];
-          if (idx + 1 == tot) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
-          store8_unaligned(p.out + (c == 0 ? dsts[0] : (c == 1 ? dsts[1] : dsts[2])) + 8ull * idx, it);
+        unsigned long long it = cls ? cfg.name8[samp] : 0ull;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const uint32_t bal = __ballot_sync(FULL, cls == c + 1);
+          if (bal == 0) continue;  // warp-uniform
+          if (cls == c + 1) {
+            const uint32_t idx = run_n[c] + __popc(bal & lt);
+            if (idx + 1 == totals[c]) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
+            store8_unaligned(p.out + dsts[c] + 8ull * idx, it);
+          }
+          run_n[c] += __popc(bal);
         }
-        run_n[0] += __popc(b1); run_n[1] += __popc(b2); run_n[2] += __popc(b3);
       }
       return;
     }
