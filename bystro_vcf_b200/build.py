@@ -55,5 +55,20 @@ def build(force: bool = False, verbose: bool = False) -> None:
         subprocess.check_call(cmd)
 
 
+def build_host(force: bool = False) -> str:
+    """g++ build of the C++ host binary (the reference's main()/readVcf over the C ABI)."""
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    out = os.path.join(bindir, "bystro-vcf-b200")
+    src = os.path.join(CSRC, "bvcf_host.cpp")
+    lib = os.path.join(LIBDIR, "libbvcf.so")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(lib)):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", out, src, "-L", LIBDIR, "-lbvcf", "-Wl,-rpath,$ORIGIN/../lib"]
+        print("[build]", " ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_host(force="--force" in sys.argv)

@@ -555,12 +555,12 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Rows
       return true;
     }
     if (!g.pos_ok) {                                                  // :822-830 stop, keep what we have
-      if (diag) push_diag(p, line_no, 0, 4);
+      if (diag) push_diag(p, line_no, 0, 8);
       g.done = true;
       return false;
     }
     if (tn == 1) {                                                    // :832
-      if (ta[0] != ref[0]) { if (diag) push_diag(p, line_no, alt_idx + 1, 3); continue; }
+      if (ta[0] != ref[0]) { if (diag) push_diag(p, line_no, alt_idx + 1, 7); continue; }
       oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n; oa.pos_verbatim = false;
       oa.pos_val = g.ipos + 1;
       return true;

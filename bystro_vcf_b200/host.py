@@ -27,7 +27,21 @@ DIAG_TEXT = {
     4: "Invalid POS",
     5: "1st base ALT != REF",
     6: "Mixed indel/snp sites not supported",
+    7: "1st base REF != ALT",   # inside the ALT list: logged as "ALT#%d" (main.go:835)
+    8: "Invalid POS",           # inside the ALT list: logged without an ALT number (main.go:827)
 }
+
+
+def format_diag(chrom: str, pos: str, alt_no: int, code: int) -> str:
+    """The reference's log.Printf line for one diagnostic (formats differ per call site, main.go:730-986)."""
+    msg = DIAG_TEXT.get(code, "?")
+    if code == 1:
+        return "%s:%s : %s" % (chrom, pos, msg)
+    if code in (6, 7):
+        return "%s:%s ALT#%d %s" % (chrom, pos, alt_no, msg)
+    if code == 8:
+        return "%s:%s %s" % (chrom, pos, msg)
+    return "%s:%s ALT #%d %s" % (chrom, pos, alt_no, msg)
 
 # parse.Header of github.com/bystrogenomics/bystro-utils (pinned by main_test.go:79-80)
 PARSE_HEADER = ["chrom", "pos", "type", "ref", "alt", "trTv", "heterozygotes", "heterozygosity", "homozygotes",

@@ -63,12 +63,14 @@ enum {
 
 /* diagnostics: what the reference logs with log.Printf and then skips (main.go:41-51,730-986) */
 enum {
-  BVCF_DIAG_SAME = 1,    /* "REF == ALT" */
-  BVCF_DIAG_BAD_ALT = 2, /* "ALT not ACTG" */
-  BVCF_DIAG_DEL1 = 3,    /* "1st base REF != ALT" */
-  BVCF_DIAG_POS = 4,     /* "Invalid POS" */
-  BVCF_DIAG_INS1 = 5,    /* "1st base ALT != REF" */
-  BVCF_DIAG_MIXED = 6    /* "Mixed indel/snp sites not supported" */
+  BVCF_DIAG_SAME = 1,    /* "REF == ALT"            "%s:%s : %s"        main.go:730 */
+  BVCF_DIAG_BAD_ALT = 2, /* "ALT not ACTG"          "%s:%s ALT #%d %s"  main.go:737,782 */
+  BVCF_DIAG_DEL1 = 3,    /* "1st base REF != ALT"   "%s:%s ALT #1 %s"   main.go:748 */
+  BVCF_DIAG_POS = 4,     /* "Invalid POS"           "%s:%s ALT #1 %s"   main.go:755 */
+  BVCF_DIAG_INS1 = 5,    /* "1st base ALT != REF"   "%s:%s ALT #%d %s"  main.go:798 */
+  BVCF_DIAG_MIXED = 6,   /* "Mixed indel/snp sites not supported"   "%s:%s ALT#%d %s"  main.go:934,986 */
+  BVCF_DIAG_DEL1_LIST = 7, /* DEL1 inside the ALT list: "%s:%s ALT#%d %s" (no space)  main.go:835 */
+  BVCF_DIAG_POS_LIST = 8   /* POS inside the ALT list:  "%s:%s %s"                    main.go:827 */
 };
 typedef struct {
   uint64_t line_no; /* 0-based data-line index within the chunk */

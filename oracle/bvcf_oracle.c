@@ -263,14 +263,14 @@ static void get_alleles(sv pos, sv ref, sv alt, allele_list *out, diag_sink *ds)
       }
       if (ip == 0) { /* :822 */
         if (go_atoi(pos, &ip)) {
-          diag(ds, 0, ORACLE_DIAG_POS);
+          diag(ds, 0, ORACLE_DIAG_POS_LIST);
           last = 2; /* break out of the allele loop, keep what we have :828 */
           break;
         }
       }
       if (t.n == 1) { /* :832 */
         if (t.p[0] != ref.p[0]) {
-          diag(ds, alt_idx + 1, ORACLE_DIAG_DEL1);
+          diag(ds, alt_idx + 1, ORACLE_DIAG_DEL1_LIST);
           break;
         }
         al_push_int(out, ip + 1, ref.p[1], 1 - (long long)ref.n, alt_idx);

@@ -50,7 +50,9 @@ enum {
   ORACLE_DIAG_DEL1 = 3,      /* "1st base REF != ALT"              main.go:748,835 */
   ORACLE_DIAG_POS = 4,       /* "Invalid POS"                      main.go:755,827 */
   ORACLE_DIAG_INS1 = 5,      /* "1st base ALT != REF"              main.go:798 */
-  ORACLE_DIAG_MIXED = 6      /* "Mixed indel/snp sites not supported" main.go:934,986 */
+  ORACLE_DIAG_MIXED = 6,     /* "Mixed indel/snp sites not supported" main.go:934,986 */
+  ORACLE_DIAG_DEL1_LIST = 7, /* delError1 inside the ALT list, "ALT#%d" format   main.go:835 */
+  ORACLE_DIAG_POS_LIST = 8   /* posError inside the ALT list, no ALT number      main.go:827 */
 };
 
 typedef struct {
