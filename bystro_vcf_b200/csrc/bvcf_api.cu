@@ -125,7 +125,9 @@ uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 uint32_t choose_range_bytes(uint64_t total) {
   uint64_t r = total / (148ull * 32 * 3);
   r = round_up(std::max<uint64_t>(r, 1), 512);
-  r = std::min<uint64_t>(std::max<uint64_t>(r, 16 * 1024), 256 * 1024);
+  uint64_t cap_r = 256 * 1024;
+  if (const char *e = getenv("BVCF_RANGE_KB")) cap_r = std::max(16, atoi(e)) * 1024ull;  // experiments
+  r = std::min<uint64_t>(std::max<uint64_t>(r, 16 * 1024), cap_r);
   return (uint32_t)r;
 }
 
@@ -408,7 +410,7 @@ int bvcf_create(bvcf_ctx **out, int cuda_device, const bvcf_config *cfg) {
   if (ctx->allow.size() + ctx->exclude.size() > 64) { delete ctx; return BVCF_E_TOO_LARGE; }
   if (ctx->cfg.n_slots <= 0) ctx->cfg.n_slots = 3;
   if (ctx->cfg.max_chunk_bytes == 0) ctx->cfg.max_chunk_bytes = 256ull << 20;
-  if (ctx->cfg.resident_subchunk_bytes == 0) ctx->cfg.resident_subchunk_bytes = 4ull << 30;
+  if (ctx->cfg.resident_subchunk_bytes == 0) ctx->cfg.resident_subchunk_bytes = 16ull << 30;
   ctx->cfg.allow = nullptr; ctx->cfg.exclude = nullptr; ctx->cfg.empty_field = nullptr; ctx->cfg.field_delim = nullptr;
 
   auto fail = [&](int rc) { *out = ctx; bvcf_destroy(ctx); *out = nullptr; return rc; };

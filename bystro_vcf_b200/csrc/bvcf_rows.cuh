@@ -787,6 +787,51 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
     uint32_t run_n[3] = {0, 0, 0};
     uint32_t run_b[3] = {0, 0, 0};
     const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
+    if (cfg.name8 && cfg.want_tsv && !drow && !(rec.flags & 1) && a == 1) {
+      // ---- the common row: ALT #1 of a record whose samples only carry alleles 0/1 (or are missing), 8-byte
+      // items, no dosage.  The class is read straight off the event's code bits; ballot/popc give the rank;
+      // each lane stores its own item (alignment uniform per class). ----
+      uint8_t *const base_h = p.out + rd.het_dst, *const base_o = p.out + rd.hom_dst, *const base_m = p.out + rd.miss_dst;
+      uint32_t run_h = 0, run_o = 0, run_m = 0;
+      uint32_t w_next = lane < rec.ev_count ? ev[lane] : EV_OFFSET_TAG;
+      for (uint32_t base = 0; base < rec.ev_count; base += 32) {
+        const uint32_t w = w_next;  // software pipelining: the next batch's words are already in flight
+        const uint32_t kn = base + 32 + lane;
+        w_next = kn < rec.ev_count ? ev[kn] : EV_OFFSET_TAG;
+        const bool valid = !(w & EV_OFFSET_TAG);
+        const uint32_t x = (w >> 20) & 0x3FFu;  // c1 | c2 << 5
+        const bool is_m = valid && x == (EV_CODE_MISSING | (EV_CODE_MISSING << 5));
+        const bool is_o = valid && (x == (1u | (1u << 5)) || x == (1u | (EV_CODE_ABSENT << 5)));
+        const bool is_h = valid && !is_m && !is_o;
+        const uint32_t bh = __ballot_sync(FULL, is_h), bo = __ballot_sync(FULL, is_o), bm = __ballot_sync(FULL, is_m);
+        unsigned long long it = valid ? cfg.name8[w & EV_SAMPLE_MASK] : 0ull;
+        if (bh) {
+          if (is_h) {
+            const uint32_t idx = run_h + __popc(bh & lt);
+            if (idx + 1 == rd.n_het) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);
+            store8_unaligned(base_h + 8ull * idx, it);
+          }
+          run_h += __popc(bh);
+        }
+        if (bo) {
+          if (is_o) {
+            const uint32_t idx = run_o + __popc(bo & lt);
+            if (idx + 1 == rd.n_hom) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);
+            store8_unaligned(base_o + 8ull * idx, it);
+          }
+          run_o += __popc(bo);
+        }
+        if (bm) {
+          if (is_m) {
+            const uint32_t idx = run_m + __popc(bm & lt);
+            if (idx + 1 == rd.n_miss) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);
+            store8_unaligned(base_m + 8ull * idx, it);
+          }
+          run_m += __popc(bm);
+        }
+      }
+      return;
+    }
     if (cfg.name8 && cfg.want_tsv) {
       // ---- fast path: every list item is exactly 8 bytes (name + delimiter).  Each lane ranks its item
       // within its class with ballot/popc and stores the 8 bytes itself with the widest aligned pieces the
