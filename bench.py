@@ -179,6 +179,13 @@ def run_ours(args):
     nl = np.flatnonzero(hview[max(0, probe - (1 << 20)):probe] == 10)
     e2e_bytes = max(0, probe - (1 << 20)) + int(nl[-1]) + 1
     cuts = newline_cuts(hview, e2e_bytes, args.chunk_mb << 20)
+    # PCIe H2D bound, measured in the same run: pinned -> device copies of the slice
+    tr.resident_upload(0, (host_ptr.value, min(e2e_bytes, 1 << 30)))  # warm
+    tp0 = time.perf_counter()
+    n_up = 3
+    for _ in range(n_up):
+        tr.resident_upload(0, (host_ptr.value, e2e_bytes))
+    pcie_gbs = n_up * e2e_bytes / (time.perf_counter() - tp0) / 1e9
     e2e_ms = None
     e2e_nlines = 0
     e2e_out = 0
@@ -250,6 +257,8 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "variants/s", "h2d_bytes_per_step": e2e_bytes,
                     "d2h_bytes_per_step": e2e_out_per_step, "variants_per_step": e2e_lines_per_step,
                     "input_gb_per_s": world * e2e_bytes * args.steps / (e2e_ms / 1e3) / 1e9,
+                    "pcie_h2d_gbs_measured": pcie_gbs,
+                    "frac_of_pcie_h2d_bound": (e2e_bytes * args.steps / (e2e_ms / 1e3) / 1e9) / pcie_gbs,
                     "sample": "first %d variants of each rank's shard, pinned host memory, %d MiB chunks, 3 slots"
                               % (e2e_lines_per_step, args.chunk_mb)},
             "gpu_launches": int(gpu_launches),

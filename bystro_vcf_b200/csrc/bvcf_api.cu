@@ -192,7 +192,8 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
                      uint8_t *d_loci, uint32_t *d_diags, std::vector<StageEvents> *timing) {
   const DevCfg &dc = ctx->dcfg;
   const uint64_t total_ranges = (len + sc.range_bytes - 1) / sc.range_bytes;
-  const int smem = SCAN_WARPS * RING;
+  int smem = SCAN_WARPS * RING;
+  if (const char *e = getenv("BVCF_SCAN_SMEM_KB")) smem = std::max(smem, atoi(e) * 1024);  // experiments: cap CTAs/SM
   cudaFuncSetAttribute(bvcf_scan_genotype_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(bvcf_scan_genotype_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int n_sm = 148;

@@ -218,3 +218,32 @@ def test_dense_genotype_block_grows_event_scratch():
         res = tr.process(vcf[off:])
     assert res.retries > 0
     assert res.tsv == ref.tsv
+
+
+def test_dosage_arrow_file_like_reference(tmp_path):
+    """main_test.go:2911-2977 TestGenotypeMatrix end to end: --dosageOutput writes an Arrow IPC file (zstd) with
+    schema locus: utf8 + one non-nullable int8 column per sample; read it back like the reference test does."""
+    import pyarrow as pa
+
+    from bystro_vcf_b200 import read_vcf
+
+    vcf, loci, dos = V.DOSAGE_CASE
+    path = tmp_path / "dosage.feather"
+    c = _cfg()
+    c.dosageMatrixOutPath = str(path)
+    out = io.BytesIO()
+    read_vcf(c, io.BytesIO(vcf), out)
+    with pa.OSFile(str(path), "rb") as f:
+        t = pa.ipc.open_file(f).read_all()
+    assert t.schema.names == ["locus", "S1", "S2", "S3"]
+    assert t.schema.field("locus").type == pa.string() and not t.schema.field("locus").nullable
+    assert all(t.schema.field(n).type == pa.int8() and not t.schema.field(n).nullable for n in ("S1", "S2", "S3"))
+    got = {l: [t.column(n)[i].as_py() for n in ("S1", "S2", "S3")] for i, l in enumerate(t.column("locus").to_pylist())}
+    assert got == {l.decode(): d for l, d in zip(loci, dos)}
+    # TestNoOut (main_test.go:2980-3029): --noOut still writes the matrix and no TSV
+    c.noOut = True
+    out2 = io.BytesIO()
+    read_vcf(c, io.BytesIO(vcf), out2)
+    assert out2.getvalue() == b""
+    with pa.OSFile(str(path), "rb") as f:
+        assert pa.ipc.open_file(f).read_all().num_rows == 3
