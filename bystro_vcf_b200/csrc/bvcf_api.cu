@@ -146,7 +146,7 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
   sc.slots = sc.range_bytes / (uint32_t)std::max(H, 16) + 2;
   uint64_t evb = (uint64_t)(sc.range_bytes * ctx->ev_factor) + 16 * 1024;
   if (ctx->dcfg.n_samples == 0) evb = 64;
-  sc.evcap_words = (uint32_t)(evb / 4);
+  sc.evcap_words = (uint32_t)(evb / 4) & ~1u;  // quad events are 8-byte aligned
   while ((uint64_t)sc.n_ranges * sc.evcap_words >= (1ull << 32)) {  // event indices are 32-bit
     sc.n_ranges /= 2;
     sc.sub_bytes = (uint64_t)sc.n_ranges * sc.range_bytes;

@@ -15,7 +15,7 @@ struct __align__(16) LineRec {
   uint32_t len;       // length including the EOL
   uint32_t an;        // non-missing allele count of the fast-classified samples (main.go:1067,1169)
   uint32_t ev_start;  // first event word of this line
-  uint32_t ev_count;  // event words of this line
+  uint32_t ev_count;  // event words of this line (two per quad event)
   uint32_t ord;       // ordinal of this line among ALL lines that start in its range
   uint16_t tab[9];    // offsets of the first nine tabs from `start` (0xFFFF: beyond 64 KiB, rescan); only
                       // the first min(H-1, 9) entries are meaningful
@@ -26,21 +26,42 @@ struct __align__(16) LineRec {
 static_assert(sizeof(LineRec) == 64, "LineRec layout");
 
 // ---- genotype events ----------------------------------------------------------------------------
-// The scan kernel emits one 32-bit event per sample whose GT is not plain reference:
-//   bits  0..19  sample index (header order)
-//   bits 20..24  c1, bits 25..29  c2 : allele codes; 0 = ref/other token, 1..9 = that allele number,
-//                30 = absent (haploid), 31 = '.' (sample missing)
-//   bit  30      complex: GT needs the general grammar (polyploid, allele >= 10, mixed separators);
-//                the NEXT word is (1u<<31 | byte offset of the field from the line start)
-//   bit  31      set only on the offset word that follows a complex event
+// The scan kernel emits one 64-bit "quad" event (two 32-bit words, 8-byte aligned) per group of four
+// consecutive samples of which at least one is not plain reference, in header order:
+//   word 0  bits  0..19  base sample index + EV_BASE_BIAS (the first of the four samples; may be -3..-1 for the
+//                        group that straddles the start of a line's sample zone)
+//           bit  30      complex: ONE sample (slot 0) whose GT needs the general grammar (polyploid, allele >= 10,
+//                        mixed separators); word 1 is then the byte offset of the field from the line start
+//   word 1  eight 4-bit allele codes: nibble k (k = 0..3) = first allele of sample base+k, nibble 4+k = its
+//           second allele.  0 = reference / any other token, 1..9 = that allele number, 0xE = '.',
+//           0xF = absent (haploid sample, second nibble only).  A sample whose two nibbles are 0 carries nothing.
+// Consumers expand a slot to the 32-bit "slot word" below (sample | c1 << 20 | c2 << 25) with ev_slot_word().
 constexpr uint32_t EV_SAMPLE_MASK = 0xFFFFFu;
 constexpr uint32_t EV_COMPLEX = 1u << 30;
-constexpr uint32_t EV_OFFSET_TAG = 1u << 31;
-constexpr uint32_t EV_CODE_ABSENT = 30, EV_CODE_MISSING = 31;
-constexpr uint32_t MAX_SAMPLES = 1u << 20;
+constexpr uint32_t EV_OFFSET_TAG = 1u << 31;   // slot word only: "no sample in this slot"
+constexpr uint32_t EV_CODE_ABSENT = 30, EV_CODE_MISSING = 31;   // slot-word codes
+constexpr uint32_t EV_NIB_MISSING = 0xEu, EV_NIB_ABSENT = 0xFu; // payload nibbles
+constexpr uint32_t EV_BASE_BIAS = 3;
+constexpr uint32_t MAX_SAMPLES = (1u << 20) - 16;
 
 __device__ __forceinline__ uint32_t ev_make(uint32_t sample, uint32_t c1, uint32_t c2) {
   return sample | (c1 << 20) | (c2 << 25);
+}
+// one-sample quad (slot 0) from slot-word codes
+__device__ __forceinline__ uint32_t ev_single_payload(uint32_t c1, uint32_t c2) {
+  const uint32_t n1 = c1 == EV_CODE_MISSING ? EV_NIB_MISSING : c1;
+  const uint32_t n2 = c2 == EV_CODE_MISSING ? EV_NIB_MISSING : (c2 == EV_CODE_ABSENT ? EV_NIB_ABSENT : c2);
+  return n1 | (n2 << 16);
+}
+// slot j (0..3) of the quad (h, pl) as a slot word; EV_OFFSET_TAG when the slot carries nothing.
+// Complex quads yield `sample | EV_COMPLEX` in slot 0 (the field offset is pl).
+__device__ __forceinline__ uint32_t ev_slot_word(uint32_t h, uint32_t pl, int j) {
+  const uint32_t samp = (h & EV_SAMPLE_MASK) + (uint32_t)j - EV_BASE_BIAS;
+  if (h & EV_COMPLEX) return j == 0 ? (samp | EV_COMPLEX) : EV_OFFSET_TAG;
+  const uint32_t n1 = (pl >> (4 * j)) & 0xFu, n2 = (pl >> (16 + 4 * j)) & 0xFu;
+  if ((n1 | n2) == 0) return EV_OFFSET_TAG;
+  if (n1 == EV_NIB_MISSING || n2 == EV_NIB_MISSING) return ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
+  return ev_make(samp, n1, n2 == EV_NIB_ABSENT ? EV_CODE_ABSENT : n2);
 }
 
 // ---- flags written by kernels, read by the host after the run -----------------------------------

@@ -91,17 +91,27 @@ __device__ __forceinline__ const uint8_t *name_ptr(const DevCfg &c, uint32_t s) 
   return c.names + (c.name_fixed_w > 0 ? (size_t)s * c.name_fixed_w : (size_t)c.name_off[s]);
 }
 
-// classify one event word for allele number a; returns class 0..3 (none/het/hom/missing) and gt/alt.
-// Complex events read the next word and re-parse the field with the general GT grammar.
-// classify_word takes the (possibly prefetched) event word; out-of-range lanes pass EV_OFFSET_TAG.
-__device__ __forceinline__ int classify_word(uint32_t w, const uint32_t *ev, uint32_t k, const uint8_t *L,
+// Events are quads (bvcf_common.cuh); consumers walk the "virtual slots" v = 4 * quad + j of a record:
+// slot_load returns the slot word of slot v (EV_OFFSET_TAG when empty / out of range) and, for a complex
+// sample, the byte offset of its field.
+__device__ __forceinline__ uint32_t slot_load(const uint32_t *ev, uint32_t v, uint32_t n_words, uint32_t &off) {
+  const uint32_t q = v >> 2;
+  off = 0;
+  if (2 * q + 1 >= n_words) return EV_OFFSET_TAG;
+  const uint2 e = *reinterpret_cast<const uint2 *>(ev + 2 * q);
+  off = e.y;
+  return ev_slot_word(e.x, e.y, (int)(v & 3u));
+}
+
+// classify one slot word for allele number a; returns class 0..3 (none/het/hom/missing) and gt/alt.
+// Complex samples re-parse the field at `off` with the general GT grammar.
+__device__ __forceinline__ int classify_word(uint32_t w, uint32_t off, const uint8_t *L,
                                              uint32_t content_len, uint32_t a, uint32_t &samp, uint32_t &gt_extra,
                                              uint32_t &alt) {
   gt_extra = 0; alt = 0; samp = 0;
   if (w & EV_OFFSET_TAG) return 0;
   samp = w & EV_SAMPLE_MASK;
   if (w & EV_COMPLEX) {
-    const uint32_t off = ev[k + 1] & ~EV_OFFSET_TAG;
     uint32_t gt;
     const int cls = classify_gt_general(L + off, content_len > off ? content_len - off : 0, a, gt, alt);
     gt_extra = gt;  // the scan kernel left this sample out of `an`
@@ -113,10 +123,14 @@ __device__ __forceinline__ int classify_word(uint32_t w, const uint32_t *ev, uin
   const uint32_t gt = c2 == EV_CODE_ABSENT ? 1 : 2;
   return alt == 0 ? 0 : (alt == gt ? 2 : 1);
 }
-__device__ __forceinline__ int classify_event(const uint32_t *ev, uint32_t k, uint32_t n, const uint8_t *L,
+// slot v of a record's events
+__device__ __forceinline__ int classify_event(const uint32_t *ev, uint32_t v, uint32_t n_words, const uint8_t *L,
                                               uint32_t content_len, uint32_t a, uint32_t &samp, uint32_t &gt_extra,
-                                              uint32_t &alt) {
-  return classify_word(k < n ? ev[k] : EV_OFFSET_TAG, ev, k, L, content_len, a, samp, gt_extra, alt);
+                                              uint32_t &alt, bool &is_ev) {
+  uint32_t off;
+  const uint32_t w = slot_load(ev, v, n_words, off);
+  is_ev = !(w & EV_OFFSET_TAG);
+  return classify_word(w, off, L, content_len, a, samp, gt_extra, alt);
 }
 
 // ---- warp per record: ALT #1 summary ---------------------------------------------------------------
@@ -137,13 +151,12 @@ struct Ev3 {
   uint32_t gtx, samp;
   bool is_ev;
 };
-__device__ __forceinline__ void classify3w(uint32_t w, const uint32_t *ev, uint32_t k, const uint8_t *L,
+__device__ __forceinline__ void classify3w(uint32_t w, uint32_t off, const uint8_t *L,
                                            uint32_t content_len, Ev3 &o) {
   o.is_ev = !(w & EV_OFFSET_TAG);
   o.samp = w & EV_SAMPLE_MASK;
   o.gtx = 0;
   if (o.is_ev && (w & EV_COMPLEX)) {  // general GT grammar, exact (main.go:1126-1190)
-    const uint32_t off = ev[k + 1] & ~EV_OFFSET_TAG;
 #pragma unroll
     for (int a = 0; a < STAT_ALLELES; a++)
       o.cls[a] = classify_gt_general(L + off, content_len > off ? content_len - off : 0, a + 1, o.gtx, o.alt[a]);
@@ -159,9 +172,11 @@ __device__ __forceinline__ void classify3w(uint32_t w, const uint32_t *ev, uint3
   }
 }
 
-__device__ __forceinline__ void classify3(const uint32_t *ev, uint32_t k, uint32_t n, const uint8_t *L,
+__device__ __forceinline__ void classify3(const uint32_t *ev, uint32_t v, uint32_t n_words, const uint8_t *L,
                                           uint32_t content_len, Ev3 &o) {
-  classify3w(k < n ? ev[k] : EV_OFFSET_TAG, ev, k, L, content_len, o);
+  uint32_t off;
+  const uint32_t w = slot_load(ev, v, n_words, off);
+  classify3w(w, off, L, content_len, o);
 }
 
 constexpr uint32_t SMALL_EVENTS = 12;  // records with at most this many event words are reduced by one lane
@@ -192,7 +207,7 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams 
       s.n_miss = 0; s.an = rec.an; s.miss_bytes = 0; s.pad = 0; s.pad2 = 0;
 #pragma unroll
       for (int a = 0; a < STAT_ALLELES; a++) { s.n_het[a] = s.n_hom[a] = s.ac[a] = s.het_bytes[a] = s.hom_bytes[a] = 0; }
-      for (uint32_t k = 0; k < rec.ev_count; k++) {
+      for (uint32_t k = 0; k < 2 * rec.ev_count; k++) {
         Ev3 e;
         classify3(ev, k, rec.ev_count, p.in + rec.start, content_len, e);
         if (!e.is_ev) continue;
@@ -241,12 +256,13 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsPar
       uint32_t n_het[STAT_ALLELES] = {0, 0, 0}, n_hom[STAT_ALLELES] = {0, 0, 0}, ac[STAT_ALLELES] = {0, 0, 0};
       uint32_t hb[STAT_ALLELES] = {0, 0, 0}, ob[STAT_ALLELES] = {0, 0, 0};
       uint32_t n_miss = 0, an_x = 0, mb = 0;
-      uint32_t w_next = lane < ev_count ? ev[lane] : EV_OFFSET_TAG;
-      for (uint32_t base = 0; base < ev_count; base += 32) {
-        const uint32_t w_cur = w_next;  // software pipelining: the next batch's words are already in flight
-        w_next = base + 32 + lane < ev_count ? ev[base + 32 + lane] : EV_OFFSET_TAG;
+      uint32_t off_next;
+      uint32_t w_next = slot_load(ev, lane, ev_count, off_next);
+      for (uint32_t base = 0; base < 2 * ev_count; base += 32) {
+        const uint32_t w_cur = w_next, off_cur = off_next;  // software pipelining: the next batch is already in flight
+        w_next = slot_load(ev, base + 32 + lane, ev_count, off_next);
         Ev3 e;
-        classify3w(w_cur, ev, base + lane, L, content_len, e);
+        classify3w(w_cur, off_cur, L, content_len, e);
         const uint32_t nl = (e.is_ev && !fixed) ? name_len(cfg, e.samp) : 0;
         n_miss += __popc(__ballot_sync(FULL, e.cls[0] == 3));
         if (e.cls[0] == 3) mb += nl;
@@ -281,9 +297,10 @@ __device__ __noinline__ GtStats reduce_events_thread(const DevCfg &cfg, const Li
   GtStats s;
   s.n_het = s.n_hom = s.n_miss = s.ac = 0; s.an = rec.an;
   s.het_bytes = s.hom_bytes = s.miss_bytes = 0;
-  for (uint32_t k = 0; k < rec.ev_count; k++) {
+  for (uint32_t k = 0; k < 2 * rec.ev_count; k++) {
     uint32_t samp, gtx, alt;
-    const int cls = classify_event(ev, k, rec.ev_count, L, content_len, a, samp, gtx, alt);
+    bool is_ev;
+    const int cls = classify_event(ev, k, rec.ev_count, L, content_len, a, samp, gtx, alt, is_ev);
     s.ac += alt;
     s.an += gtx;
     if (cls) {
@@ -793,11 +810,11 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
       // each lane stores its own item (alignment uniform per class). ----
       uint8_t *const base_h = p.out + rd.het_dst, *const base_o = p.out + rd.hom_dst, *const base_m = p.out + rd.miss_dst;
       uint32_t run_h = 0, run_o = 0, run_m = 0;
-      uint32_t w_next = lane < rec.ev_count ? ev[lane] : EV_OFFSET_TAG;
-      for (uint32_t base = 0; base < rec.ev_count; base += 32) {
+      uint32_t off_unused;
+      uint32_t w_next = slot_load(ev, lane, rec.ev_count, off_unused);
+      for (uint32_t base = 0; base < 2 * rec.ev_count; base += 32) {
         const uint32_t w = w_next;  // software pipelining: the next batch's words are already in flight
-        const uint32_t kn = base + 32 + lane;
-        w_next = kn < rec.ev_count ? ev[kn] : EV_OFFSET_TAG;
+        w_next = slot_load(ev, base + 32 + lane, rec.ev_count, off_unused);
         const bool valid = !(w & EV_OFFSET_TAG);
         const uint32_t x = (w >> 20) & 0x3FFu;  // c1 | c2 << 5
         const bool is_m = valid && x == (EV_CODE_MISSING | (EV_CODE_MISSING << 5));
@@ -837,16 +854,17 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
       // within its class with ballot/popc and stores the 8 bytes itself with the widest aligned pieces the
       // destination allows (2-4 stores; the alignment is uniform per class, so no divergence). ----
       const uint32_t totals[3] = {rd.n_het, rd.n_hom, rd.n_miss};
-      uint32_t w_next = lane < rec.ev_count ? ev[lane] : EV_OFFSET_TAG;
-      for (uint32_t base = 0; base < rec.ev_count; base += 32) {
+      uint32_t off_next;
+      uint32_t w_next = slot_load(ev, lane, rec.ev_count, off_next);
+      for (uint32_t base = 0; base < 2 * rec.ev_count; base += 32) {
         const uint32_t k = base + lane;
-        const uint32_t w_cur = w_next;  // software pipelining: the next batch's words are already in flight
-        w_next = k + 32 < rec.ev_count ? ev[k + 32] : EV_OFFSET_TAG;
+        const uint32_t w_cur = w_next, off_cur = off_next;  // software pipelining: the next batch is already in flight
+        w_next = slot_load(ev, k + 32, rec.ev_count, off_next);
         int cls;
         uint32_t samp, alt;
         if (__any_sync(FULL, (w_cur & (EV_COMPLEX | EV_OFFSET_TAG)) == EV_COMPLEX)) {
           uint32_t gtx;  // a sample in this batch needs the general GT grammar
-          cls = classify_word(w_cur, ev, k, L, content_len, a, samp, gtx, alt);
+          cls = classify_word(w_cur, off_cur, L, content_len, a, samp, gtx, alt);
         } else {
           const uint32_t c1 = (w_cur >> 20) & 31, c2 = (w_cur >> 25) & 31;
           samp = w_cur & EV_SAMPLE_MASK;
@@ -871,11 +889,12 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
       }
       return;
     }
-    for (uint32_t base = 0; base < rec.ev_count; base += 32) {
+    for (uint32_t base = 0; base < 2 * rec.ev_count; base += 32) {
       uint32_t samp, gtx, alt;
       const uint32_t k = base + lane;
-      const int cls = classify_event(ev, k, rec.ev_count, L, content_len, a, samp, gtx, alt);
-      if (drow && k < rec.ev_count && !(ev[k] & EV_OFFSET_TAG))
+      bool is_ev;
+      const int cls = classify_event(ev, k, rec.ev_count, L, content_len, a, samp, gtx, alt, is_ev);
+      if (drow && is_ev)
         drow[samp] = cls == 3 ? (int8_t)-1 : (int8_t)(alt > 127 ? 127 : alt);  // main.go:1172-1178
       if (!cfg.want_tsv) continue;
       const uint32_t nl = cls ? name_len(cfg, samp) : 0;
@@ -918,9 +937,10 @@ __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDe
   const uint32_t dl = (uint32_t)cfg.delim_len;
   const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
   uint32_t run_n[3] = {0, 0, 0}, run_b[3] = {0, 0, 0};
-  for (uint32_t k = 0; k < rec.ev_count; k++) {
+  for (uint32_t k = 0; k < 2 * rec.ev_count; k++) {
     uint32_t samp, gtx, alt;
-    const int cls = classify_event(ev, k, rec.ev_count, L, content_len, rd.allele, samp, gtx, alt);
+    bool is_ev;
+    const int cls = classify_event(ev, k, rec.ev_count, L, content_len, rd.allele, samp, gtx, alt, is_ev);
     if (!cls) continue;
     const int c = cls - 1;
     uint8_t *d = p.out + dsts[c] + run_b[c];

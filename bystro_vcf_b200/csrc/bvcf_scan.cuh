@@ -107,90 +107,75 @@ __device__ __forceinline__ void acc_sample(LineAcc &a, uint32_t c1, uint32_t c2)
 // ---- the T2 vector code: four realigned fields per lane, XORed with the reference pattern -------------
 // t[j] == 0: reference genotype.  Structure (separator, tab) already verified by the caller; allele bytes are
 // digits (t byte <= 9) or, when `dots`, '.' (0x1E).  Words outside the sample zone arrive zeroed.
-// Non-reference fields are sparse, so they are visited with a find-first-set loop (a lane usually has 0 or 1)
-// and compacted in order into the range's event slice with a warp prefix sum.
+// The lane's four fields become ONE quad event (eight 4-bit allele codes, bvcf_common.cuh): no per-sample
+// loop, the compaction is a ballot + popc, the ALT #1 summary is nibble-parallel arithmetic.
+__device__ __forceinline__ uint32_t pack_quad(const uint32_t t[4], bool dots) {
+  if (dots) {
+    const uint32_t K = 0x000F000Fu;  // '.' ^ '0' = 0x1E -> nibble 0xE
+    return (t[0] & K) | ((t[1] & K) << 4) | ((t[2] & K) << 8) | ((t[3] & K) << 12);
+  }
+  return t[0] | (t[1] << 4) | (t[2] << 8) | (t[3] << 12);  // digits: every allele byte is already a nibble
+}
+// ALT #1 bookkeeping of one quad payload (diploid fields only: the vector path)
+__device__ __forceinline__ void acc_quad(LineAcc &a, uint32_t pl, bool dots) {
+  const uint32_t y = pl ^ 0x11111111u;
+  uint32_t one = ~(((y & 0x77777777u) + 0x77777777u) | y) & 0x88888888u;  // bit 3 of every nibble equal to 1
+  uint32_t big = pl & 0xEEEEEEEEu;                                         // nibbles >= 2
+  if (dots) {
+    const uint32_t d = pl ^ 0xEEEEEEEEu;
+    const uint32_t dot = ~(((d & 0x77777777u) + 0x77777777u) | d) & 0x88888888u;  // nibbles equal to 0xE
+    const uint32_t mf = (dot | (dot >> 16)) & 0x8888u;    // samples with a '.' token: missing (main.go:1113,1150)
+    const uint32_t nm = __popc(mf);
+    a.miss_l += nm;
+    a.an_l -= 2 * nm;
+    const uint32_t gone = ((mf | (mf << 16)) >> 3) * 15u;  // all eight bits of both nibbles of a missing sample
+    one &= ~gone;
+    big &= ~gone;
+  }
+  const uint32_t both = one & (one >> 16);
+  const uint32_t n1 = __popc(one), n2 = __popc(both);
+  a.ac_l += n1;
+  a.hom_l += n2;
+  a.het_l += n1 - 2 * n2;
+  a.flag_l |= big;
+}
 __device__ __forceinline__ void classify_push_words4(const ScanParams &p, WarpState &st, uint32_t *my_events,
                                                      const uint32_t t[4], int samp0, bool dots, int lane) {
-  uint32_t nz = (t[0] & 0x00FF00FFu ? 1u : 0u) | (t[1] & 0x00FF00FFu ? 2u : 0u) | (t[2] & 0x00FF00FFu ? 4u : 0u) |
-                (t[3] & 0x00FF00FFu ? 8u : 0u);
-  const uint32_t nev = __popc(nz);
-  const uint32_t eincl = warp_incl_scan(nev, lane);
-  const uint32_t etot = __shfl_sync(FULL, eincl, 31);
-  if (etot == 0) return;
-  const bool room = st.ev_w + etot <= p.evcap_words;
-  if (!room && lane == 0) p.ctr->ev_overflow = 1;
-  uint32_t k = st.ev_w + (eincl - nev);
-  LineAcc &a = st.a;
-  while (nz) {
-    const int j = __ffs(nz) - 1;
-    nz &= nz - 1;
-    const uint32_t tt = (j == 0 ? t[0] : j == 1 ? t[1] : j == 2 ? t[2] : t[3]) & 0x00FF00FFu;
-    const uint32_t c1 = tt & 0xFFu, c2 = tt >> 16;
-    uint32_t e;
-    if (dots && (c1 == 0x1Eu || c2 == 0x1Eu)) {
-      e = ev_make((uint32_t)(samp0 + j), EV_CODE_MISSING, EV_CODE_MISSING);
-      a.miss_l++;
-      a.an_l -= 2;
-    } else {
-      e = (uint32_t)(samp0 + j) | (c1 << 20) | (c2 << 25);
-      const uint32_t alt = (c1 == 1) + (c2 == 1);
-      a.ac_l += alt;
-      a.hom_l += alt >> 1;
-      a.het_l += alt & 1u;
-      a.flag_l |= (c1 | c2) > 1;
-    }
-    if (room) my_events[k] = e;
-    k++;
+  const uint32_t pl = pack_quad(t, dots);
+  const uint32_t bal = __ballot_sync(FULL, pl != 0);
+  if (bal == 0) return;
+  const uint32_t n = 2 * __popc(bal);
+  if (st.ev_w + n <= p.evcap_words) {
+    if (pl)
+      *reinterpret_cast<uint2 *>(my_events + st.ev_w + 2 * __popc(bal & ((1u << lane) - 1u))) =
+          make_uint2((uint32_t)(samp0 + (int)EV_BASE_BIAS), pl);
+  } else if (lane == 0) {
+    p.ctr->ev_overflow = 1;
   }
-  st.ev_w += etot;
+  if (pl) acc_quad(st.a, pl, dots);
+  st.ev_w += n;
 }
 
-// Two adjacent windows at once: events of window A (all lanes) precede those of window B; one packed
-// prefix sum (A count in the low half, B count in the high half) serves both.
-__device__ __forceinline__ void emit_words4(const ScanParams &p, WarpState &st, uint32_t *my_events, const uint32_t t[4],
-                                            uint32_t nz, int samp0, bool dots, bool room, uint32_t k) {
-  LineAcc &a = st.a;
-  while (nz) {
-    const int j = __ffs(nz) - 1;
-    nz &= nz - 1;
-    const uint32_t tt = (j == 0 ? t[0] : j == 1 ? t[1] : j == 2 ? t[2] : t[3]) & 0x00FF00FFu;
-    const uint32_t c1 = tt & 0xFFu, c2 = tt >> 16;
-    uint32_t e;
-    if (dots && (c1 == 0x1Eu || c2 == 0x1Eu)) {
-      e = ev_make((uint32_t)(samp0 + j), EV_CODE_MISSING, EV_CODE_MISSING);
-      a.miss_l++;
-      a.an_l -= 2;
-    } else {
-      e = (uint32_t)(samp0 + j) | (c1 << 20) | (c2 << 25);
-      const uint32_t alt = (c1 == 1) + (c2 == 1);
-      a.ac_l += alt;
-      a.hom_l += alt >> 1;
-      a.het_l += alt & 1u;
-      a.flag_l |= (c1 | c2) > 1;
-    }
-    if (room) my_events[k] = e;
-    k++;
-  }
-}
-__device__ __forceinline__ uint32_t nz_mask4(const uint32_t t[4]) {
-  return (t[0] & 0x00FF00FFu ? 1u : 0u) | (t[1] & 0x00FF00FFu ? 2u : 0u) | (t[2] & 0x00FF00FFu ? 4u : 0u) |
-         (t[3] & 0x00FF00FFu ? 8u : 0u);
-}
+// Two adjacent windows at once: the quads of window A (all lanes) precede those of window B.
 __device__ __forceinline__ void classify_push_pair(const ScanParams &p, WarpState &st, uint32_t *my_events,
                                                    const uint32_t ta[4], const uint32_t tb[4], int samp0, bool dots,
                                                    int lane) {
-  const uint32_t nza = nz_mask4(ta), nzb = nz_mask4(tb);
-  const uint32_t packed = __popc(nza) | (__popc(nzb) << 16);
-  const uint32_t incl = warp_incl_scan(packed, lane);
-  const uint32_t tot = __shfl_sync(FULL, incl, 31);
-  if (tot == 0) return;
-  const uint32_t tot_a = tot & 0xFFFFu, tot_b = tot >> 16;
-  const bool room = st.ev_w + tot_a + tot_b <= p.evcap_words;
-  if (!room && lane == 0) p.ctr->ev_overflow = 1;
-  const uint32_t excl = incl - packed;
-  emit_words4(p, st, my_events, ta, nza, samp0, dots, room, st.ev_w + (excl & 0xFFFFu));
-  emit_words4(p, st, my_events, tb, nzb, samp0 + 128, dots, room, st.ev_w + tot_a + (excl >> 16));
-  st.ev_w += tot_a + tot_b;
+  const uint32_t pa = pack_quad(ta, dots), pb = pack_quad(tb, dots);
+  const uint32_t ba = __ballot_sync(FULL, pa != 0), bb = __ballot_sync(FULL, pb != 0);
+  if ((ba | bb) == 0) return;
+  const uint32_t na = 2 * __popc(ba), n = na + 2 * __popc(bb);
+  const uint32_t lt = (1u << lane) - 1u;
+  if (st.ev_w + n <= p.evcap_words) {
+    uint32_t *dst = my_events + st.ev_w;
+    if (pa) *reinterpret_cast<uint2 *>(dst + 2 * __popc(ba & lt)) = make_uint2((uint32_t)(samp0 + (int)EV_BASE_BIAS), pa);
+    if (pb)
+      *reinterpret_cast<uint2 *>(dst + na + 2 * __popc(bb & lt)) = make_uint2((uint32_t)(samp0 + 128 + (int)EV_BASE_BIAS), pb);
+  } else if (lane == 0) {
+    p.ctr->ev_overflow = 1;
+  }
+  if (pa) acc_quad(st.a, pa, dots);
+  if (pb) acc_quad(st.a, pb, dots);
+  st.ev_w += n;
 }
 
 // SWAR validity of four XORed fields: separator/tab bytes unchanged, allele bytes digits (or '.')
@@ -364,26 +349,32 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
           } else if (!is_sep(b0) && e1) {  // haploid, one single-character token
             const uint32_t c = tok_code(b0);
             if (c == EV_CODE_MISSING) {
-              evbuf[nev++] = ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
+              evbuf[nev++] = samp + EV_BASE_BIAS; evbuf[nev++] = ev_single_payload(EV_CODE_MISSING, EV_CODE_MISSING);
               st.a.miss_l++;
             } else {
               st.a.an_l += 1;
-              if (c) { evbuf[nev++] = ev_make(samp, c, EV_CODE_ABSENT); acc_sample(st.a, c, EV_CODE_ABSENT); }
+              if (c) {
+                evbuf[nev++] = samp + EV_BASE_BIAS; evbuf[nev++] = ev_single_payload(c, EV_CODE_ABSENT);
+                acc_sample(st.a, c, EV_CODE_ABSENT);
+              }
             }
             if (b1 == '\t') last_end = s + 1;
           } else if (!is_sep(b0) && is_sep(b1) && !e2 && !is_sep(b2) && e3) {  // diploid x|y or x/y
             const uint32_t c1 = tok_code(b0), c2 = tok_code(b2);
             if (c1 == EV_CODE_MISSING || c2 == EV_CODE_MISSING) {
-              evbuf[nev++] = ev_make(samp, EV_CODE_MISSING, EV_CODE_MISSING);
+              evbuf[nev++] = samp + EV_BASE_BIAS; evbuf[nev++] = ev_single_payload(EV_CODE_MISSING, EV_CODE_MISSING);
               st.a.miss_l++;
             } else {
               st.a.an_l += 2;
-              if (c1 | c2) { evbuf[nev++] = ev_make(samp, c1, c2); acc_sample(st.a, c1, c2); }
+              if (c1 | c2) {
+                evbuf[nev++] = samp + EV_BASE_BIAS; evbuf[nev++] = ev_single_payload(c1, c2);
+                acc_sample(st.a, c1, c2);
+              }
             }
             if (b3 == '\t') { last_end = s + 3; last_sep = b1; }
           } else {  // general grammar: resolved exactly by the stats/names kernels
-            evbuf[nev++] = samp | EV_COMPLEX;
-            evbuf[nev++] = EV_OFFSET_TAG | (uint32_t)(pos + (uint64_t)s - st.line_start);
+            evbuf[nev++] = (samp + EV_BASE_BIAS) | EV_COMPLEX;
+            evbuf[nev++] = (uint32_t)(pos + (uint64_t)s - st.line_start);
             st.a.flag_l |= 1;
           }
         }
