@@ -19,6 +19,7 @@
 #include "bvcf_common.cuh"
 #include "bvcf_prefix.cuh"
 #include "bvcf_rows.cuh"
+#include "bvcf_names.cuh"
 #include "bvcf_scan.cuh"
 
 using namespace bvcf;
@@ -287,14 +288,23 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     bvcf_rows_kernel<true><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
     ctx->launches++;
     if (se) CK(cudaEventRecord(se->e[5], st));
-    // 7. sample-name lists + dosage rows (warp per row)
+    // 7. sample-name lists + dosage rows: short rows lane-serially, the queued long rows by a warp each --
+    // as aligned vectors when every list item is 8 bytes and no dosage row is wanted (bvcf_names.cuh)
     if (dc.n_samples > 0) {
       NamesParams np{};
       np.in = d_in; np.cfg = dc; np.lines = cp.dense; np.events = sp.events; np.row_desc = (const RowDesc *)sc.row_desc.p;
       np.row_desc_cap = sc.row_cap; np.out = d_out; np.ctr = d_ctr; np.dosage = d_dosage; np.dosage_cap_rows = dosage_cap_rows;
       np.big_rows = (uint32_t *)sc.big_rows.p;
       bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
-      bvcf_names_big_kernel<<<wgrid * 4, NAMES_WARPS * 32, 0, st>>>(np);
+      static const bool no_vec = getenv("BVCF_NO_NAMES_VEC") != nullptr;  // experiments
+      if (dc.name8 && dc.want_tsv && !dc.want_dosage && !no_vec) {
+        if (dc.n_samples <= 65000)
+          bvcf_names_vec_kernel<uint16_t><<<wgrid * 4, NVEC_WARPS * 32, 0, st>>>(np);
+        else
+          bvcf_names_vec_kernel<uint32_t><<<wgrid * 4, NVEC_WARPS * 32, 0, st>>>(np);
+      } else {
+        bvcf_names_big_kernel<<<wgrid * 4, NAMES_WARPS * 32, 0, st>>>(np);
+      }
       ctx->launches += 2;
     }
     if (se) CK(cudaEventRecord(se->e[6], st));

@@ -1,0 +1,210 @@
+// bvcf_names.cuh -- north-star kernel (4b), sample-name lists of the long rows as aligned 16-byte vectors.
+//
+// bvcf_names_kernel (bvcf_rows.cuh) writes the lists of short rows lane-serially and queues the others.  When
+// every list item is 8 bytes (7-character names + 1-character delimiter: the 1000 Genomes / biobank layout) and
+// no dosage row is wanted, bvcf_names_vec_kernel takes the queue instead of bvcf_names_big_kernel:
+//   pass 1  one sweep over the row's quad events: het / hom / missing slots as nibble masks (general GT grammar for
+//           complex samples, main.go:1126-1190), ranks from one packed warp prefix sum per 32 quads, the sample
+//           indices of the three lists compacted into shared memory in header order (main.go:1057 loop order);
+//   pass 2  each list (main.go:617,639,653 strings.Join) leaves as aligned uint4 stores, every vector assembled
+//           from the two or three neighbouring 8-byte items it overlaps; byte stores only at the ragged ends.
+// The old kernel stored each item with 2-4 narrow unaligned stores (0.6 store sectors per clock per SM: the LSU
+// limit, not HBM).
+#pragma once
+#include "bvcf_rows.cuh"
+
+namespace bvcf {
+
+constexpr int NVEC_WARPS = 2;
+constexpr int NVEC_IDX_BYTES = 6144;   // per-warp index buffer: 3072 samples (16-bit) / 1536 (32-bit) per sweep
+
+__device__ __forceinline__ uint32_t nib_eq(uint32_t x, uint32_t pat) {  // bit 3 of every nibble of x equal to pat's
+  const uint32_t y = x ^ pat;
+  return ~(((y & 0x77777777u) + 0x77777777u) | y) & 0x88888888u;
+}
+
+// het / hom / missing slots of one quad for allele number a, as nibble flags (bit 4j+3 = sample base+j).
+// `simple`: the record only carries alleles 0 / 1 / '.' / absent and a == 1 (LineRec.flags bit 0 clear).
+__device__ __forceinline__ void quad_masks(uint32_t h, uint32_t pl, uint32_t a, bool simple, const uint8_t *L,
+                                           uint32_t content_len, bool valid, uint32_t &mh, uint32_t &mo, uint32_t &mm) {
+  mh = mo = mm = 0;
+  if (!valid) return;
+  uint32_t one1, one2, dot, hap;
+  if (simple) {  // nibbles are 0, 1, 0xE or 0xF: two bit planes tell them apart
+    const uint32_t b0 = pl << 3, b3 = pl;
+    const uint32_t one = b0 & ~b3 & 0x88888888u, dt = b3 & ~b0 & 0x88888888u;
+    one1 = one & 0x8888u; one2 = one >> 16;
+    dot = dt | (dt >> 16);
+    hap = (b3 & b0 & 0x88888888u) >> 16;
+  } else {
+    if (h & EV_COMPLEX) {
+      uint32_t gt, alt;
+      const int cls = classify_gt_general(L + pl, content_len > pl ? content_len - pl : 0, a, gt, alt);
+      if (cls == 1) mh = 8u; else if (cls == 2) mo = 8u; else if (cls == 3) mm = 8u;
+      return;
+    }
+    const uint32_t eq = a <= 9 ? nib_eq(pl, a * 0x11111111u) : 0u;
+    const uint32_t dt = nib_eq(pl, 0xEEEEEEEEu);
+    one1 = eq & 0x8888u; one2 = eq >> 16;
+    dot = dt | (dt >> 16);
+    hap = nib_eq(pl, 0xFFFFFFFFu) >> 16;
+  }
+  mm = dot & 0x8888u;
+  mo = one1 & (one2 | hap) & ~mm;
+  mh = (one1 ^ one2) & ~hap & ~mm & 0x8888u;
+}
+
+// `n` names, given by sample index in idx[0, n) (shared memory), as list bytes [g, g + len) of the output,
+// len <= 8 n
+template <typename IdxT>
+__device__ __forceinline__ void emit_name_vectors(const unsigned long long *__restrict__ name8, uint8_t *g, const IdxT *idx,
+                                                  uint32_t n, uint32_t len, int lane) {
+  const uint32_t head = (16u - (uint32_t)((uintptr_t)g & 15u)) & 15u;
+  const uint32_t h = head < len ? head : len;
+  for (uint32_t b = lane; b < h; b += 32) g[b] = (uint8_t)(name8[idx[b >> 3]] >> (8 * (b & 7u)));
+  if (h == len) return;
+  const uint32_t nvec = (len - h) >> 4;
+  const uint32_t sh = (h & 7u) * 8u;  // every vector starts at stream offset h + 16 v: same phase within an item
+  uint4 *gv = reinterpret_cast<uint4 *>(g + h);
+  const uint32_t k00 = h >> 3;
+  if (sh == 0) {
+    for (uint32_t v = lane; v < nvec; v += 32) {
+      const uint32_t k0 = k00 + 2 * v;
+      const unsigned long long i0 = name8[idx[k0]];
+      const unsigned long long i1 = k0 + 1 < n ? name8[idx[k0 + 1]] : 0ull;
+      gv[v] = make_uint4((uint32_t)i0, (uint32_t)(i0 >> 32), (uint32_t)i1, (uint32_t)(i1 >> 32));
+    }
+  } else {
+    for (uint32_t v = lane; v < nvec; v += 32) {
+      const uint32_t k0 = k00 + 2 * v;
+      const unsigned long long i0 = name8[idx[k0]];
+      const unsigned long long i1 = k0 + 1 < n ? name8[idx[k0 + 1]] : 0ull;
+      const unsigned long long i2 = k0 + 2 < n ? name8[idx[k0 + 2]] : 0ull;
+      const unsigned long long lo = (i0 >> sh) | (i1 << (64u - sh)), hi = (i1 >> sh) | (i2 << (64u - sh));
+      gv[v] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    }
+  }
+  for (uint32_t b = h + 16u * nvec + lane; b < len; b += 32) g[b] = (uint8_t)(name8[idx[b >> 3]] >> (8 * (b & 7u)));
+}
+
+struct RowEvents {
+  const uint32_t *ev;
+  uint32_t n_words;
+  const uint8_t *L;
+  uint32_t content_len, a;
+  bool simple;
+};
+
+// all three lists of one row in one sweep: index lists at idx[0,n_het) | [n_het, n_het+n_hom) | [.., +n_miss)
+template <typename IdxT>
+__device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx, uint32_t base_o, uint32_t base_m, int lane) {
+  const uint32_t nq = re.n_words >> 1;
+  uint32_t run_h = 0, run_o = base_o, run_m = base_m;
+  uint2 e_next = make_uint2(0u, 0u);
+  if ((uint32_t)lane < nq) e_next = *reinterpret_cast<const uint2 *>(re.ev + 2 * lane);
+  for (uint32_t base = 0; base < nq; base += 32) {
+    const uint2 e = e_next;  // software pipelining: the next batch is already in flight
+    const bool valid = base + lane < nq;
+    if (base + 32 + lane < nq) e_next = *reinterpret_cast<const uint2 *>(re.ev + 2 * (base + 32 + lane));
+    uint32_t mh, mo, mm;
+    quad_masks(e.x, e.y, re.a, re.simple, re.L, re.content_len, valid, mh, mo, mm);
+    const uint32_t s0 = (e.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
+    const uint32_t cnt = __popc(mh) | (__popc(mo) << 10) | (__popc(mm) << 20);
+    const uint32_t incl = warp_incl_scan(cnt, lane);
+    const uint32_t tot = __shfl_sync(FULL, incl, 31);
+    const uint32_t excl = incl - cnt;
+    uint32_t kh = run_h + (excl & 1023u), ko = run_o + ((excl >> 10) & 1023u), km = run_m + (excl >> 20);
+    const uint32_t any = mh | mo | mm;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t bit = 8u << (4 * j);
+      if (any & bit) {
+        const uint32_t d = (mh & bit) ? kh++ : ((mo & bit) ? ko++ : km++);
+        idx[d] = (IdxT)(s0 + (uint32_t)j);
+      }
+    }
+    run_h += tot & 1023u; run_o += (tot >> 10) & 1023u; run_m += tot >> 20;
+  }
+}
+
+// one list, rows with more names than the index buffer holds: `cap` indices at a time
+template <typename IdxT>
+__device__ __forceinline__ void stream_list(const unsigned long long *__restrict__ name8, const RowEvents &re, int cls,
+                                            uint32_t n_total, IdxT *idx, uint32_t cap, uint8_t *g, int lane) {
+  const uint32_t nq = re.n_words >> 1;
+  uint32_t fill = 0, written = 0, seen = 0;
+  uint2 e_next = make_uint2(0u, 0u);
+  if ((uint32_t)lane < nq) e_next = *reinterpret_cast<const uint2 *>(re.ev + 2 * lane);
+  for (uint32_t base = 0; base < nq; base += 32) {
+    const uint2 e = e_next;
+    const bool valid = base + lane < nq;
+    if (base + 32 + lane < nq) e_next = *reinterpret_cast<const uint2 *>(re.ev + 2 * (base + 32 + lane));
+    uint32_t mh, mo, mm;
+    quad_masks(e.x, e.y, re.a, re.simple, re.L, re.content_len, valid, mh, mo, mm);
+    uint32_t m = cls == 0 ? mh : (cls == 1 ? mo : mm);
+    const uint32_t s0 = (e.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
+    const uint32_t cnt = __popc(m);
+    const uint32_t incl = warp_incl_scan(cnt, lane);
+    const uint32_t tot = __shfl_sync(FULL, incl, 31);
+    uint32_t k = fill + incl - cnt;
+    while (m) { const int j = (__ffs(m) - 1) >> 2; m &= m - 1; idx[k++] = (IdxT)(s0 + (uint32_t)j); }
+    fill += tot; seen += tot;
+    const bool last = base + 32 >= nq;
+    if (fill + 128 > cap || last) {
+      __syncwarp();
+      if (fill) {
+        const uint32_t len = 8u * fill - ((last || seen >= n_total) ? 1u : 0u);  // n names, n-1 delimiters
+        emit_name_vectors<IdxT>(name8, g + written, idx, fill, len, lane);
+        written += len;
+      }
+      fill = 0;
+      __syncwarp();
+    }
+  }
+}
+
+template <typename IdxT>
+__device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned long long r, IdxT *idx, int lane) {
+  const DevCfg &cfg = p.cfg;
+  const RowDesc rd = p.row_desc[r];
+  const LineRec rec = p.lines[rd.line];
+  RowEvents re;
+  re.ev = p.events + rec.ev_start; re.n_words = rec.ev_count; re.L = p.in + rec.start;
+  re.content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
+  re.a = rd.allele; re.simple = !(rec.flags & 1) && rd.allele == 1;
+  const unsigned long long *name8 = cfg.name8;
+  const uint32_t cap = NVEC_IDX_BYTES / sizeof(IdxT);
+  const uint32_t n_tot = rd.n_het + rd.n_hom + rd.n_miss;
+  const uint32_t ns[3] = {rd.n_het, rd.n_hom, rd.n_miss};
+  const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
+  if (n_tot <= cap) {
+    index_lists_once<IdxT>(re, idx, rd.n_het, rd.n_het + rd.n_hom, lane);
+    __syncwarp();
+    uint32_t b = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (ns[c]) emit_name_vectors<IdxT>(name8, p.out + dsts[c], idx + b, ns[c], 8u * ns[c] - 1u, lane);
+      b += ns[c];
+    }
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      if (ns[c]) stream_list<IdxT>(name8, re, c, ns[c], idx, cap, p.out + dsts[c], lane);
+  }
+}
+
+// warp per queued row (requires cfg.name8, TSV output, no dosage matrix)
+template <typename IdxT>
+__global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const NamesParams p) {
+  __shared__ __align__(16) uint8_t s_idx[NVEC_WARPS][NVEC_IDX_BYTES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  const uint32_t n_big = p.ctr->n_big_rows;
+  const uint32_t total_warps = gridDim.x * NVEC_WARPS;
+  IdxT *idx = reinterpret_cast<IdxT *>(s_idx[warp]);
+  for (uint32_t wi = blockIdx.x * NVEC_WARPS + warp; wi < n_big; wi += total_warps)
+    names_row_vec<IdxT>(p, p.big_rows[wi], idx, lane);
+}
+
+}  // namespace bvcf

@@ -314,10 +314,22 @@ __device__ __noinline__ GtStats reduce_events_thread(const DevCfg &cfg, const Li
 }
 
 // ---- row writer: counts in the SIZE pass, byte stores in the EMIT pass --------------------------------
+// Writer policy of emit_row: kWrite (bytes are produced), kGlobal (bytes go to the output buffer: loci and
+// RowDesc are written too).  span_in() is a span of the INPUT line (long ones may be referenced, not copied);
+// list() reserves the bytes of one sample-name list; lists_done() ends the three lists of a row.
 template <bool WRITE>
 struct RowWriter {
+  static constexpr bool kWrite = WRITE, kGlobal = WRITE;
   uint8_t *g;                // global cursor (EMIT)
   unsigned long long count;  // bytes (SIZE)
+  const uint8_t *out0;       // output base (EMIT): list destinations are offsets from it
+  __device__ __forceinline__ void span_in(const uint8_t *p, int len) { span(p, len); }
+  __device__ __forceinline__ unsigned long long list(int, uint32_t, unsigned long long bytes, uint32_t) {
+    const unsigned long long d = WRITE ? (unsigned long long)(g - out0) : 0ull;
+    skip(bytes);  // filled by the names kernel
+    return d;
+  }
+  __device__ __forceinline__ void lists_done(uint32_t) {}
   __device__ __forceinline__ void byte(uint8_t c) { if (WRITE) *g++ = c; else count++; }
   __device__ __forceinline__ void span(const uint8_t *p, int len) {
     if (WRITE) { for (int i = 0; i < len; i++) g[i] = p[i]; g += len; } else count += len;
@@ -355,10 +367,11 @@ struct LineCtx {
   uint32_t li;
 };
 
-template <bool WRITE>
+template <class W>
 __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, const LineCtx &lc, const OutAllele &oa,
-                                      GtStats &gs, int &gs_idx, RowWriter<WRITE> &w, uint32_t &n_rows,
+                                      GtStats &gs, int &gs_idx, W &w, uint32_t &n_rows,
                                       unsigned long long row_base) {
+  constexpr bool WRITE = W::kGlobal;
   const DevCfg &cfg = p.cfg;
   const uint32_t a = (uint32_t)oa.alt_idx + 1;
   if (cfg.n_samples > 0) {
@@ -411,16 +424,16 @@ __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, c
   if (cfg.want_tsv) {
     // chrom (main.go:570-574)
     if (lc.chrom_n < 4 || lc.chrom[0] != 'c') { w.byte('c'); w.byte('h'); w.byte('r'); }
-    w.span(lc.chrom, lc.chrom_n);
+    w.span_in(lc.chrom, lc.chrom_n);
     w.byte('\t');
-    if (oa.pos_verbatim) w.span(lc.pos, lc.pos_n); else w.dec(oa.pos_val);
+    if (oa.pos_verbatim) w.span_in(lc.pos, lc.pos_n); else w.dec(oa.pos_val);
     w.byte('\t');
     w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
     w.byte('\t');
     w.byte(oa.ref);
     w.byte('\t');
     if (oa.kind == 0) w.byte(oa.alt_c);
-    else if (oa.kind == 1) { w.byte('+'); w.span(oa.ins_p, oa.ins_n); }
+    else if (oa.kind == 1) { w.byte('+'); w.span_in(oa.ins_p, oa.ins_n); }
     else w.dec(oa.del_n);
     w.byte('\t');
     w.byte(lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0'));  // main.go:602-606
@@ -441,8 +454,7 @@ __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, c
         if (cnts[k] == 0) {
           w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0');
         } else {
-          if (WRITE) dsts[k] = (unsigned long long)(w.g - p.out);
-          w.skip((unsigned long long)nb[k] + (unsigned long long)(cnts[k] - 1) * dl);  // filled by the names kernel
+          dsts[k] = w.list(k, cnts[k], (unsigned long long)nb[k] + (unsigned long long)(cnts[k] - 1) * dl, a);
           w.byte('\t');
           int fl;
           const uint64_t ft = format_ratio_g3(cnts[k], den[k], fl);
@@ -450,6 +462,7 @@ __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, c
         }
         w.byte('\t');
       }
+      w.lists_done(a);
       rd.het_dst = dsts[0]; rd.hom_dst = dsts[1]; rd.miss_dst = dsts[2];
       rd.n_het = gs.n_het; rd.n_hom = gs.n_hom; rd.n_miss = gs.n_miss;
       w.dec(gs.ac); w.byte('\t');
@@ -457,9 +470,9 @@ __device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, c
       if (gs.ac == 0) w.byte('0');
       else { int fl; const uint64_t ft = format_ratio_g3(gs.ac, gs.an, fl); w.packed(ft, fl); }
     }
-    if (cfg.keep_pos) { w.byte('\t'); w.span(lc.pos, lc.pos_n); }
-    if (cfg.keep_id) { w.byte('\t'); w.span(lc.id, lc.id_n); }
-    if (cfg.keep_info) { w.byte('\t'); w.dec(oa.alt_idx); w.byte('\t'); w.span(lc.info, lc.info_n); }
+    if (cfg.keep_pos) { w.byte('\t'); w.span_in(lc.pos, lc.pos_n); }
+    if (cfg.keep_id) { w.byte('\t'); w.span_in(lc.id, lc.id_n); }
+    if (cfg.keep_info) { w.byte('\t'); w.dec(oa.alt_idx); w.byte('\t'); w.span_in(lc.info, lc.info_n); }
     w.byte('\n');
   }
   if (WRITE && cfg.n_samples > 0 && r < p.row_desc_cap) p.row_desc[r] = rd;
@@ -611,6 +624,74 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Rows
   }
 }
 
+// ---- one record: field index, linePasses, getAlleles, one emit_row per output allele ------------------
+template <class W>
+__device__ __forceinline__ void process_record(const RowsParams &p, uint32_t li, const LineRec &rec, W &w,
+                                               const uint8_t *s_filt, const uint32_t *s_filt_off, uint32_t &n_rows,
+                                               unsigned long long row_base, bool diag) {
+  const DevCfg &cfg = p.cfg;
+  const int n_filt = cfg.n_allow + cfg.n_excl;
+  const uint8_t *L = p.in + rec.start;
+  const uint32_t n = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;  // main.go:535
+  // ---- first eight/nine tabs (strings.Split, main.go:535) ----
+  const int need = cfg.H - 1 < 9 ? cfg.H - 1 : 9;
+  uint32_t t[9];
+  int found = need;
+  bool far = false;  // a tab beyond 64 KiB from the line start: the scan kernel could not record it
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    t[k] = rec.tab[k];
+    far = far || (k < need && t[k] == 0xFFFFu);
+  }
+  if (far) {
+    found = 0;
+    for (uint32_t i = 0; i < n && found < need; i++)
+      if (L[i] == '\t') t[found++] = i;
+  }
+  bool pass = found >= need;  // always true for scan-kernel records; defensive
+  for (int k = found; k < 9; k++) t[k] = n;
+  LineCtx lc;
+  lc.L = L; lc.content_len = n; lc.li = li;
+  lc.chrom = L; lc.chrom_n = (int)t[0];
+  lc.pos = L + t[0] + 1; lc.pos_n = (int)(t[1] - t[0] - 1);
+  lc.id = L + t[1] + 1; lc.id_n = (int)(t[2] - t[1] - 1);
+  const uint8_t *ref = L + t[2] + 1; const int ref_n = (int)(t[3] - t[2] - 1);
+  const uint8_t *alt = L + t[3] + 1; const int alt_n = (int)(t[4] - t[3] - 1);
+  const uint8_t *filt = L + t[5] + 1; const int filt_n = (int)(t[6] - t[5] - 1);
+  lc.info = L + t[6] + 1; lc.info_n = (int)(t[7] - t[6] - 1);
+  lc.multi = false; lc.site_type = T_SNP;
+
+  // ---- linePasses (main.go:447-454): exact whole-field match against the shared-memory table ----
+  if (pass && (!cfg.allow_all || cfg.n_excl > 0)) {
+    bool in_allow = false, in_excl = false;
+    for (int k = 0; k < n_filt; k++) {
+      const uint32_t o = s_filt_off[k], ln = s_filt_off[k + 1] - o;
+      bool eq = (int)ln == filt_n;
+      for (int i = 0; eq && i < filt_n; i++) eq = s_filt[o + i] == filt[i];
+      if (eq) { if (k < cfg.n_allow) in_allow = true; else in_excl = true; }
+    }
+    if (!cfg.allow_all && !in_allow) pass = false;
+    if (in_excl) pass = false;
+  }
+
+  // ---- getAlleles (main.go:723-1038) as a resumable generator: one converged emit_row call site ----
+  {
+    AlleleGen g;
+    g.ref = ref; g.alt = alt; g.ref_n = ref_n; g.alt_n = alt_n;
+    g.s = 0; g.alt_idx = 0; g.mnp_i = -1; g.ta = alt; g.tn = 0; g.last = false;
+    g.done = !(pass && ref_n > 0 && alt_n > 0);
+    g.ipos = 0;
+    g.pos_ok = g.done ? false : atoi_go(lc.pos, lc.pos_n, g.ipos);
+    const unsigned long long line_no = p.ctr->chunk_line_base + rec.ord;
+    if (!g.done) gen_begin(g, lc, p, line_no, diag);
+    GtStats gs;
+    int gs_idx = -1;
+    OutAllele oa;
+    oa.ins_p = nullptr; oa.ins_n = 0; oa.del_n = 0; oa.pos_val = 0;
+    while (gen_next(g, oa, p, line_no, diag)) emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
+  }
+}
+
 // ---- thread per record, grid-stride, record count read from device memory ----------------------------
 template <bool WRITE>
 __global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_kernel(const RowsParams p) {
@@ -652,72 +733,15 @@ __global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_kernel(const RowsParam
     }
     if (valid) {
     const LineRec rec = p.lines[li];
-    const uint8_t *L = p.in + rec.start;
-    const uint32_t n = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;  // main.go:535
 
     RowWriter<WRITE> w;
     w.count = 0;
+    w.out0 = p.out;
     w.g = WRITE ? (staged ? stage + mis + my_rel : p.out + out_base + p.line_off[li]) : nullptr;
     uint32_t n_rows = 0;
     const unsigned long long row_base = WRITE ? p.row_off[li] : 0;  // row number within the sub-chunk
 
-    // ---- first eight/nine tabs (strings.Split, main.go:535) ----
-    const int need = cfg.H - 1 < 9 ? cfg.H - 1 : 9;
-    uint32_t t[9];
-    int found = need;
-    bool far = false;  // a tab beyond 64 KiB from the line start: the scan kernel could not record it
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-      t[k] = rec.tab[k];
-      far = far || (k < need && t[k] == 0xFFFFu);
-    }
-    if (far) {
-      found = 0;
-      for (uint32_t i = 0; i < n && found < need; i++)
-        if (L[i] == '\t') t[found++] = i;
-    }
-    bool pass = found >= need;  // always true for scan-kernel records; defensive
-    for (int k = found; k < 9; k++) t[k] = n;
-    LineCtx lc;
-    lc.L = L; lc.content_len = n; lc.li = li;
-    lc.chrom = L; lc.chrom_n = (int)t[0];
-    lc.pos = L + t[0] + 1; lc.pos_n = (int)(t[1] - t[0] - 1);
-    lc.id = L + t[1] + 1; lc.id_n = (int)(t[2] - t[1] - 1);
-    const uint8_t *ref = L + t[2] + 1; const int ref_n = (int)(t[3] - t[2] - 1);
-    const uint8_t *alt = L + t[3] + 1; const int alt_n = (int)(t[4] - t[3] - 1);
-    const uint8_t *filt = L + t[5] + 1; const int filt_n = (int)(t[6] - t[5] - 1);
-    lc.info = L + t[6] + 1; lc.info_n = (int)(t[7] - t[6] - 1);
-    lc.multi = false; lc.site_type = T_SNP;
-
-    // ---- linePasses (main.go:447-454): exact whole-field match against the shared-memory table ----
-    if (pass && (!cfg.allow_all || cfg.n_excl > 0)) {
-      bool in_allow = false, in_excl = false;
-      for (int k = 0; k < n_filt; k++) {
-        const uint32_t o = s_filt_off[k], ln = s_filt_off[k + 1] - o;
-        bool eq = (int)ln == filt_n;
-        for (int i = 0; eq && i < filt_n; i++) eq = s_filt[o + i] == filt[i];
-        if (eq) { if (k < cfg.n_allow) in_allow = true; else in_excl = true; }
-      }
-      if (!cfg.allow_all && !in_allow) pass = false;
-      if (in_excl) pass = false;
-    }
-
-    // ---- getAlleles (main.go:723-1038) as a resumable generator: one converged emit_row call site ----
-    {
-      AlleleGen g;
-      g.ref = ref; g.alt = alt; g.ref_n = ref_n; g.alt_n = alt_n;
-      g.s = 0; g.alt_idx = 0; g.mnp_i = -1; g.ta = alt; g.tn = 0; g.last = false;
-      g.done = !(pass && ref_n > 0 && alt_n > 0);
-      g.ipos = 0;
-      g.pos_ok = g.done ? false : atoi_go(lc.pos, lc.pos_n, g.ipos);
-      const unsigned long long line_no = p.ctr->chunk_line_base + rec.ord;
-      if (!g.done) gen_begin(g, lc, p, line_no, !WRITE);
-      GtStats gs;
-      int gs_idx = -1;
-      OutAllele oa;
-      oa.ins_p = nullptr; oa.ins_n = 0; oa.del_n = 0; oa.pos_val = 0;
-      while (gen_next(g, oa, p, line_no, !WRITE)) emit_row<WRITE>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-    }
+    process_record<RowWriter<WRITE>>(p, li, rec, w, s_filt, s_filt_off, n_rows, row_base, !WRITE);
     if (!WRITE) {
       p.line_bytes[li] = (uint32_t)w.count;
       p.line_rows[li] = n_rows;
