@@ -179,10 +179,15 @@ __device__ __forceinline__ void classify_push_pair(const ScanParams &p, WarpStat
 }
 
 // SWAR validity of four XORed fields: separator/tab bytes unchanged, allele bytes digits (or '.')
+// Quick test on the OR of the words (no false negatives: the OR of nibbles is >= each of them; a false positive,
+// e.g. alleles 8 and 2 in one lane, only costs the exact test below).
 __device__ __forceinline__ uint32_t bad_digits4(const uint32_t t[4], uint32_t keep_mask3) {
-  const uint32_t D = 0x00760076u, H = 0x00800080u, M = 0x00FF00FFu;
-  const uint32_t any = t[0] | t[1] | t[2] | (t[3] & keep_mask3);
-  return (any & ~M) | ((((t[0] & M) + D) | ((t[1] & M) + D) | ((t[2] & M) + D) | ((t[3] & M) + D)) & H);
+  const uint32_t o = t[0] | t[1] | t[2] | (t[3] & keep_mask3);
+  return (o & 0xFFF0FFF0u) | (((o & 0x000F000Fu) + 0x00060006u) & 0x00100010u);
+}
+__device__ __forceinline__ uint32_t bad_digits8(const uint32_t ta[4], const uint32_t tb[4]) {
+  const uint32_t o = ta[0] | ta[1] | ta[2] | ta[3] | tb[0] | tb[1] | tb[2] | tb[3];
+  return (o & 0xFFF0FFF0u) | (((o & 0x000F000Fu) + 0x00060006u) & 0x00100010u);
 }
 __device__ __forceinline__ uint32_t bad_digits_or_dots4(const uint32_t t[4], uint32_t keep_mask3) {
   const uint32_t D = 0x00760076u, H = 0x00800080u, M = 0x00FF00FFu;
@@ -234,9 +239,18 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
     if (eol2 && nl < WIN && nl > 0) tab_hi = nl - 1;  // row[:len-2] strips the byte before '\n' (main.go:535)
     const uint32_t tm_l = tm & bits_range16(lo_l, tab_hi - lane * 16);
     const uint32_t cnt = __popc(tm_l);
-    const uint32_t incl = warp_incl_scan(cnt, lane);
-    const uint32_t excl = incl - cnt;
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    // the per-lane field index (prefix sum) is only needed while the fixed fields go by, or field by field
+    // below; a segment that lies in the sample zone just needs its tab count (one REDUX)
+    uint32_t excl = 0, total;
+    bool have_excl = false;
+    if (st.col < 9) {
+      const uint32_t incl = warp_incl_scan(cnt, lane);
+      excl = incl - cnt;
+      total = __shfl_sync(FULL, incl, 31);
+      have_excl = true;
+    } else {
+      total = __reduce_add_sync(FULL, cnt);
+    }
 
     // field index: offsets of the record's first nine tabs (strings.Split, main.go:535)
     if (st.col < 9 && st.nrec < p.slots_per_range) {
@@ -264,7 +278,11 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
         const bool mine = k9 >= excl && k9 < excl + cnt;
         const uint32_t who = __ballot_sync(FULL, mine);
         int pos9 = 0;
-        if (mine) pos9 = lane * 16 + (int)__fns(tm_l, 0, (int)(k9 - excl) + 1);
+        if (mine) {  // the (k9 - excl)-th set bit of tm_l: drop the lower ones
+          uint32_t m9 = tm_l;
+          for (uint32_t d = k9 - excl; d > 0; d--) m9 &= m9 - 1;
+          pos9 = lane * 16 + __ffs(m9) - 1;
+        }
         s9 = __shfl_sync(FULL, pos9, __ffs(who) - 1) + 1;
       }
       const int zone_end = nl;  // sample fields of this segment live in [s9, zone_end)
@@ -313,6 +331,7 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
       }
       if (!vector_ok) {
         // ---- field by field ----
+        if (!have_excl) excl = warp_incl_scan(cnt, lane) - cnt;
         int last_end = -1;   // window-relative index of the '\t' that ends this lane's last field, if known
         uint32_t last_sep = 0;
         const uint32_t prev_hi = __shfl_up_sync(FULL, tm_l >> 15, 1);
@@ -414,16 +433,13 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
     if (nl < WIN) {  // the line ends inside this window
       st.nlines++;
       const LineAcc &a = st.a;
-      const uint32_t an = warp_sum(a.an_l) + a.an_uni;
+      const uint32_t an = __reduce_add_sync(FULL, a.an_l) + a.an_uni;
       uint32_t n_het = 0, n_hom = 0, n_miss = 0, ac = 0, flag = 0;
       if (HAS_SAMPLES) {
         flag = __any_sync(FULL, a.flag_l != 0);
         if (__any_sync(FULL, (a.het_l | a.hom_l | a.miss_l) != 0)) {
-          // two 16-bit halves per reduction would overflow at biobank width: reduce 64-bit pairs
-          const unsigned long long s1 = warp_sum64((unsigned long long)a.het_l | ((unsigned long long)a.hom_l << 32));
-          const unsigned long long s2 = warp_sum64((unsigned long long)a.ac_l | ((unsigned long long)a.miss_l << 32));
-          n_het = (uint32_t)s1; n_hom = (uint32_t)(s1 >> 32);
-          ac = (uint32_t)s2; n_miss = (uint32_t)(s2 >> 32);
+          n_het = __reduce_add_sync(FULL, a.het_l); n_hom = __reduce_add_sync(FULL, a.hom_l);  // REDUX
+          ac = __reduce_add_sync(FULL, a.ac_l); n_miss = __reduce_add_sync(FULL, a.miss_l);
         }
       }
       if (st.col == (uint32_t)(p.H - 1)) {
@@ -536,7 +552,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
                                 __funnelshift_r(va.z, va.w, sh) ^ rp, __funnelshift_r(va.w, w4a, sh) ^ rp};
         const uint32_t tb[4] = {__funnelshift_r(vb.x, vb.y, sh) ^ rp, __funnelshift_r(vb.y, vb.z, sh) ^ rp,
                                 __funnelshift_r(vb.z, vb.w, sh) ^ rp, __funnelshift_r(vb.w, w4b, sh) ^ rp};
-        uint32_t bad = bad_digits4(ta, 0xFFFFFFFFu) | bad_digits4(tb, 0xFFFFFFFFu);
+        uint32_t bad = bad_digits8(ta, tb);
         bool dots = false;
         if (!__all_sync(FULL, bad == 0)) {
           bad = bad_digits_or_dots4(ta, 0xFFFFFFFFu) | bad_digits_or_dots4(tb, 0xFFFFFFFFu);
