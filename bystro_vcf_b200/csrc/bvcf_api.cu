@@ -121,6 +121,9 @@ void dev_free(DevBuf &b) {
 
 uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 
+// the scan kernel prefetches up to eight 512-byte windows past the last one it reads: allocated, never used
+constexpr uint64_t IN_SLACK = 8192;
+
 // choose the range size for `total` bytes: enough ranges to fill 148 SMs x 32 warps a few times over,
 // large enough that re-reading one line per range boundary stays cheap
 uint32_t choose_range_bytes(uint64_t total) {
@@ -338,7 +341,7 @@ int slot_enqueue(bvcf_ctx *ctx, Slot &s, bool upload) {
   const uint64_t len = s.len;
   const uint64_t buf_len = round_up(len, 1024) + 2048;
   int rc;
-  if ((rc = dev_reserve(ctx, s.d_in, buf_len))) return rc;
+  if ((rc = dev_reserve(ctx, s.d_in, buf_len + IN_SLACK))) return rc;
   if ((rc = scratch_reserve(ctx, s.sc, len, ctx->cfg.resident_subchunk_bytes))) return rc;
   if (s.d_out.cap == 0) {
     if ((rc = dev_reserve(ctx, s.d_out, std::max<size_t>(len / 2, 1 << 20)))) return rc;
@@ -692,7 +695,7 @@ int bvcf_resident_alloc(bvcf_ctx *ctx, size_t in_bytes, size_t out_capacity, voi
   cudaSetDevice(ctx->device);
   const uint64_t buf_len = round_up(in_bytes, 1024) + 2048;
   int rc;
-  if ((rc = dev_reserve(ctx, ctx->r_in, buf_len))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->r_in, buf_len + IN_SLACK))) return rc;
   if ((rc = dev_reserve(ctx, ctx->r_out, std::max<size_t>(out_capacity, 4096)))) return rc;
   CK(cudaMemset((uint8_t *)ctx->r_in.p + in_bytes, '\n', ctx->r_in.cap - in_bytes));
   ctx->r_in_bytes = in_bytes;
@@ -721,7 +724,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
     int rc;
     if ((rc = scratch_reserve(ctx, ctx->r_sc, len, ctx->cfg.resident_subchunk_bytes))) return rc;
     // the bytes after `len` must not look like data: pad (idempotent)
-    const uint64_t buf_len = std::min<uint64_t>(ctx->r_in.cap / 1024 * 1024, round_up(len, 1024) + 2048);
+    const uint64_t buf_len = std::min<uint64_t>((ctx->r_in.cap - IN_SLACK) / 1024 * 1024, round_up(len, 1024) + 2048);
     CK(cudaMemsetAsync(ctx->r_d_ctr, 0, sizeof(RunCounters), ctx->r_stream));
     uint64_t dos_rows = 0;
     if (dc.want_dosage && dc.n_samples > 0) dos_rows = ctx->r_dosage.cap / (uint64_t)dc.n_samples;

@@ -25,7 +25,7 @@ namespace bvcf {
 constexpr int WIN = 512;                 // bytes per warp step
 constexpr int STAGES = 8;                // ring stages per warp
 constexpr int RING = WIN * STAGES;       // 4 KiB per warp
-constexpr int PF = 5;                    // prefetch distance (windows in flight beyond the pair being read)
+constexpr int PF_PAIRS = 3;              // pairs of windows in flight beyond the pair being read
 constexpr int SCAN_WARPS = 8;            // warps per CTA
 constexpr int FS_NONE = 0x7FFFFFFF;      // "inside a field": no known field start
 
@@ -511,24 +511,25 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
     const uint32_t n_avail = avail64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)avail64;
     const uint32_t seek_limit = (uint32_t)((rend - rstart + WIN - 1) / WIN);  // no owned line can start later
     const uint8_t *gsrc = p.in + rstart + lane * 16;
-    uint32_t issued = 0;
-    auto issue = [&]() {
-      if (issued < n_avail)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring_lane_s + ((issued & (STAGES - 1)) * WIN)), "l"(gsrc));
+    uint32_t issue_off = 0;  // ring offset of the next pair of windows
+    // one commit group per 1 KiB pair; the buffer carries 8 KiB of slack, so the prefetch needs no bounds test
+    auto issue_pair = [&]() {
+      const uint32_t d = ring_lane_s + issue_off;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + WIN), "l"(gsrc + WIN));
       asm volatile("cp.async.commit_group;\n" ::);
-      gsrc += WIN;
-      issued++;
+      gsrc += 2 * WIN;
+      issue_off = (issue_off + 2 * WIN) & (RING - 1);
     };
 #pragma unroll
-    for (int k = 0; k < PF; k++) issue();
+    for (int k = 0; k < PF_PAIRS; k++) issue_pair();
     // One loop iteration = one 1 KiB pair of windows.  Pairs that are all-reference (the bulk of real
     // data) cost one 9-compare vote; anything else falls through to the per-window dispatcher.
     uint32_t stage_off = 0;
     bool done = false;
     for (uint32_t it = 0; it + 2 < n_avail && !done; it += 2, stage_off = (stage_off + 2 * WIN) & (RING - 1)) {
-      issue();
-      issue();
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(PF - 1));  // windows it, it+1 and it+2 have landed
+      issue_pair();
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(PF_PAIRS - 1));  // windows it .. it+3 have landed
       __syncwarp();
       if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u && !(p.tune & 1)) {
         const uint32_t so_b = (stage_off + WIN) & (RING - 1);
