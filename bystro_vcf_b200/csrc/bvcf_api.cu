@@ -261,7 +261,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       tp.in = d_in; tp.cfg = dc; tp.lines = cp.dense; tp.events = sp.events; tp.stats = (LineStats *)sc.stats1.p; tp.ctr = d_ctr;
       tp.big_recs = (uint32_t *)sc.big_recs.p;
       bvcf_line_stats_kernel<<<wgrid, 256, 0, st>>>(tp);
-      bvcf_line_stats_big_kernel<<<wgrid, 256, 0, st>>>(tp);
+      bvcf_line_stats_big_kernel<<<(unsigned)n_sm * 4, 256, 0, st>>>(tp);
       ctx->launches += 2;
     }
     if (se) CK(cudaEventRecord(se->e[3], st));
@@ -302,9 +302,9 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       static const bool no_vec = getenv("BVCF_NO_NAMES_VEC") != nullptr;  // experiments
       if (dc.name8 && dc.want_tsv && !dc.want_dosage && !no_vec) {
         if (dc.n_samples <= 65000)
-          bvcf_names_vec_kernel<uint16_t><<<wgrid * 4, NVEC_WARPS * 32, 0, st>>>(np);
+          bvcf_names_vec_kernel<uint16_t><<<(unsigned)n_sm * 16, NVEC_WARPS * 32, 0, st>>>(np);
         else
-          bvcf_names_vec_kernel<uint32_t><<<wgrid * 4, NVEC_WARPS * 32, 0, st>>>(np);
+          bvcf_names_vec_kernel<uint32_t><<<(unsigned)n_sm * 16, NVEC_WARPS * 32, 0, st>>>(np);
       } else {
         bvcf_names_big_kernel<<<wgrid * 4, NAMES_WARPS * 32, 0, st>>>(np);
       }

@@ -77,12 +77,12 @@ struct RunCounters {
   unsigned int row_overflow;       // a sub-chunk emitted more rows than RowDesc slots
   unsigned int n_big_recs;         // work list of the stats kernel: records with long event lists (per sub-chunk)
   unsigned int n_big_rows;         // work list of the names kernel: rows with long event lists (per sub-chunk)
-  unsigned int pad0;
+  unsigned int big_row_cursor;     // next entry of the names work list to be taken (dynamic scheduling)
   unsigned long long chunk_out_base;  // out_cursor before this sub-chunk (set by the scan-finalize kernel)
   unsigned long long chunk_row_base;
   unsigned long long chunk_line_base; // n_lines before this sub-chunk (diagnostic line numbers)
   unsigned int chunk_records;      // records in the current sub-chunk (device-side n for grid-stride kernels)
-  unsigned int pad;
+  unsigned int big_rec_cursor;     // next entry of the stats work list to be taken
 };
 
 // ---- configuration as the kernels see it ---------------------------------------------------------

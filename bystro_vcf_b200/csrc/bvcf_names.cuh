@@ -201,10 +201,15 @@ __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const N
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const uint32_t n_big = p.ctr->n_big_rows;
-  const uint32_t total_warps = gridDim.x * NVEC_WARPS;
   IdxT *idx = reinterpret_cast<IdxT *>(s_idx[warp]);
-  for (uint32_t wi = blockIdx.x * NVEC_WARPS + warp; wi < n_big; wi += total_warps)
+  // rows differ by three orders of magnitude in size: warps take the next queued row from a shared cursor
+  for (;;) {
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(&p.ctr->big_row_cursor, 1u);
+    wi = __shfl_sync(FULL, wi, 0);
+    if (wi >= n_big) break;
     names_row_vec<IdxT>(p, p.big_rows[wi], idx, lane);
+  }
 }
 
 }  // namespace bvcf

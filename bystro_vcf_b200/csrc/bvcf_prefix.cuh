@@ -84,10 +84,12 @@ __global__ void __launch_bounds__(1024) bvcf_prefix_spine_kernel(const PrefixPar
       c->chunk_records = (unsigned int)sa[t];
       c->chunk_line_base = c->n_lines;
       c->n_big_recs = 0;
+      c->big_rec_cursor = 0;
       c->n_records += sa[t];
       c->n_lines += sb[t];
     } else if (!(c->ev_overflow | c->slot_overflow)) {  // sizes are garbage after a scratch overflow: leave the cursors
       c->n_big_rows = 0;
+      c->big_row_cursor = 0;
       c->chunk_out_base = c->out_cursor;
       c->chunk_row_base = c->row_cursor;
       c->out_cursor += sa[t];

@@ -240,9 +240,12 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsPar
   const int lane = threadIdx.x & 31;
   if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const uint32_t n_big = p.ctr->n_big_recs;
-  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
   const bool fixed = cfg.name_fixed_w > 0;
-  for (uint32_t wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < n_big; wi += total_warps) {
+  for (;;) {  // warps take the next queued record from a shared cursor
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(&p.ctr->big_rec_cursor, 1u);
+    wi = __shfl_sync(FULL, wi, 0);
+    if (wi >= n_big) break;
     const uint32_t li = p.big_recs[wi];
     const LineRec rec = p.lines[li];
     {
