@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
       issue_pair();
       asm volatile("cp.async.wait_group %0;\n" ::"n"(PF_PAIRS - 1));  // windows it .. it+3 have landed
       __syncwarp();
+      int hint = 0;  // 1: window A was regular and is done, B is known not to be; 2: A is known not to be regular
       if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u && !(p.tune & 1)) {
         const uint32_t so_b = (stage_off + WIN) & (RING - 1);
         const uint4 va = lds128(ring_lane_s + stage_off);
@@ -553,10 +554,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
                                 __funnelshift_r(va.z, va.w, sh) ^ rp, __funnelshift_r(va.w, w4a, sh) ^ rp};
         const uint32_t tb[4] = {__funnelshift_r(vb.x, vb.y, sh) ^ rp, __funnelshift_r(vb.y, vb.z, sh) ^ rp,
                                 __funnelshift_r(vb.z, vb.w, sh) ^ rp, __funnelshift_r(vb.w, w4b, sh) ^ rp};
-        uint32_t bad = bad_digits8(ta, tb);
+        uint32_t bad = bad_digits8(ta, tb), bad_a = 0;
         bool dots = false;
         if (!__all_sync(FULL, bad == 0)) {
-          bad = bad_digits_or_dots4(ta, 0xFFFFFFFFu) | bad_digits_or_dots4(tb, 0xFFFFFFFFu);
+          bad_a = bad_digits_or_dots4(ta, 0xFFFFFFFFu);
+          bad = bad_a | bad_digits_or_dots4(tb, 0xFFFFFFFFu);
           dots = true;
         }
         if (__all_sync(FULL, bad == 0)) {
@@ -566,14 +568,25 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
           __syncwarp();
           continue;
         }
+        // Not regular as a pair (a line ends in it, typically).  What the exact test said about window A spares
+        // the per-window dispatcher below its own T1/T2 attempts.
+        if (__all_sync(FULL, bad_a == 0)) {
+          st.a.an_uni += 256;
+          classify_push_words4(p, st, my_events, ta, (int)(st.col - 9) + lane * 4, true, lane);
+          st.col += 128;
+          hint = 1;
+        } else {
+          hint = 2;
+        }
       }
 #pragma unroll 1
       for (int h = 0; h < 2; h++) {
+        if (hint == 1 && h == 0) continue;
         const uint32_t wi = it + h;
         const uint32_t so = (stage_off + h * WIN) & (RING - 1);
         if (st.mode == 0 && wi >= seek_limit) { done = true; break; }  // no line starts in this range
         const uint4 v = lds128(ring_lane_s + so);
-        if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
+        if (HAS_SAMPLES && hint != 2 - h && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
           const uint32_t w4 = lds32(ring_base_s + ((so + lane * 16 + 16) & (RING - 1)));
           const uint32_t sh = (uint32_t)st.fsr * 8u;
           const uint32_t rp = st.refpat;
