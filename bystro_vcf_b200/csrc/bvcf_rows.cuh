@@ -697,7 +697,7 @@ __device__ __forceinline__ void process_record(const RowsParams &p, uint32_t li,
 
 // ---- thread per record, grid-stride, record count read from device memory ----------------------------
 template <bool WRITE>
-__global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_kernel(const RowsParams p) {
+__global__ void __launch_bounds__(ROWS_THREADS, WRITE ? 4 : 5) bvcf_rows_kernel(const __grid_constant__ RowsParams p) {
   __shared__ uint8_t s_filt[FILT_SMEM];
   __shared__ uint32_t s_filt_off[65];
   __shared__ __align__(16) uint8_t s_rowstage[WRITE ? ROWS_THREADS / 32 : 1][WRITE ? ROW_STAGE_BYTES : 16];
