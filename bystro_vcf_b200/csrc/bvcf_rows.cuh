@@ -341,9 +341,22 @@ struct RowWriter {
     if (WRITE) { for (int i = 0; i < len; i++) g[i] = (uint8_t)(chars >> (8 * i)); g += len; } else count += len;
   }
   __device__ __forceinline__ void dec(long long v) {
-    uint8_t buf[24];
-    const int len = itoa_dec(v, buf);
-    if (WRITE) { for (int i = 0; i < len; i++) g[i] = buf[i]; g += len; } else count += len;
+    if (!WRITE) {
+      count += (v < 0 ? 1 : 0) + dec_len(v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v);
+      return;
+    }
+    unsigned long long lo, hi;
+    const int len = itoa_pack(v, lo, hi);  // registers, no byte buffer in local memory
+    if (len >= 0) {
+      for (int i = 0; i < len && i < 8; i++) g[i] = (uint8_t)(lo >> (8 * i));
+      for (int i = 8; i < len; i++) g[i] = (uint8_t)(hi >> (8 * (i - 8)));
+      g += len;
+    } else {
+      uint8_t buf[24];
+      const int l2 = itoa_dec(v, buf);
+      for (int i = 0; i < l2; i++) g[i] = buf[i];
+      g += l2;
+    }
   }
   __device__ __forceinline__ void skip(unsigned long long len) { if (WRITE) g += len; else count += len; }
 };
@@ -371,7 +384,7 @@ struct LineCtx {
 };
 
 template <class W>
-__device__ __noinline__ void emit_row(const RowsParams &p, const LineRec &rec, const LineCtx &lc, const OutAllele &oa,
+__device__ __forceinline__ void emit_row(const RowsParams &p, const LineRec &rec, const LineCtx &lc, const OutAllele &oa,
                                       GtStats &gs, int &gs_idx, W &w, uint32_t &n_rows,
                                       unsigned long long row_base) {
   constexpr bool WRITE = W::kGlobal;
@@ -649,10 +662,15 @@ __device__ __forceinline__ void process_record(const RowsParams &p, uint32_t li,
   if (far) {
     found = 0;
     for (uint32_t i = 0; i < n && found < need; i++)
-      if (L[i] == '\t') t[found++] = i;
+      if (L[i] == '\t') {
+#pragma unroll
+        for (int k = 0; k < 9; k++) if (k == found) t[k] = i;  // static indexing keeps t[] in registers
+        found++;
+      }
   }
   bool pass = found >= need;  // always true for scan-kernel records; defensive
-  for (int k = found; k < 9; k++) t[k] = n;
+#pragma unroll
+  for (int k = 0; k < 9; k++) if (k >= found) t[k] = n;
   LineCtx lc;
   lc.L = L; lc.content_len = n; lc.li = li;
   lc.chrom = L; lc.chrom_n = (int)t[0];

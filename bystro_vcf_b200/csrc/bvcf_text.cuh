@@ -75,7 +75,40 @@ __device__ __forceinline__ int itoa_dec(long long v, uint8_t *buf) {
 }
 __device__ __forceinline__ int dec_len(unsigned long long u) {
   int n = 1;
+  if ((u >> 32) == 0) {  // 32-bit arithmetic for the common case (POS, ac, an)
+    uint32_t w = (uint32_t)u;
+    while (w >= 10) { w /= 10; n++; }
+    return n;
+  }
   while (u >= 10) { u /= 10; n++; }
+  return n;
+}
+// strconv.Itoa without a byte buffer: the text of v packed little-endian in (lo, hi), at most 16 characters.
+// Returns the length, or -1 when the text is longer (callers fall back to itoa_dec).
+__device__ __forceinline__ int itoa_pack(long long v, unsigned long long &lo, unsigned long long &hi) {
+  unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+  if (u >= 1000000000000000ull) return -1;
+  lo = 0; hi = 0;
+  int n = 0;
+  // digits come least significant first; each one is shifted in below the previous, so byte 0 ends up the
+  // most significant digit
+  if ((u >> 32) == 0) {
+    uint32_t w = (uint32_t)u;
+    do {
+      const uint32_t q = w / 10;
+      hi = (hi << 8) | (lo >> 56);
+      lo = (lo << 8) | (unsigned long long)('0' + (w - q * 10));
+      w = q; n++;
+    } while (w);
+  } else {
+    do {
+      const unsigned long long q = u / 10;
+      hi = (hi << 8) | (lo >> 56);
+      lo = (lo << 8) | (unsigned long long)('0' + (uint32_t)(u - q * 10));
+      u = q; n++;
+    } while (u);
+  }
+  if (v < 0) { hi = (hi << 8) | (lo >> 56); lo = (lo << 8) | (unsigned long long)'-'; n++; }
   return n;
 }
 
