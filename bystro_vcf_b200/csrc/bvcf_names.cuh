@@ -18,42 +18,6 @@ namespace bvcf {
 constexpr int NVEC_WARPS = 2;
 constexpr int NVEC_IDX_BYTES = 6144;   // per-warp index buffer: 3072 samples (16-bit) / 1536 (32-bit) per sweep
 
-__device__ __forceinline__ uint32_t nib_eq(uint32_t x, uint32_t pat) {  // bit 3 of every nibble of x equal to pat's
-  const uint32_t y = x ^ pat;
-  return ~(((y & 0x77777777u) + 0x77777777u) | y) & 0x88888888u;
-}
-
-// het / hom / missing slots of one quad for allele number a, as nibble flags (bit 4j+3 = sample base+j).
-// `simple`: the record only carries alleles 0 / 1 / '.' / absent and a == 1 (LineRec.flags bit 0 clear).
-__device__ __forceinline__ void quad_masks(uint32_t h, uint32_t pl, uint32_t a, bool simple, const uint8_t *L,
-                                           uint32_t content_len, bool valid, uint32_t &mh, uint32_t &mo, uint32_t &mm) {
-  mh = mo = mm = 0;
-  if (!valid) return;
-  uint32_t one1, one2, dot, hap;
-  if (simple) {  // nibbles are 0, 1, 0xE or 0xF: two bit planes tell them apart
-    const uint32_t b0 = pl << 3, b3 = pl;
-    const uint32_t one = b0 & ~b3 & 0x88888888u, dt = b3 & ~b0 & 0x88888888u;
-    one1 = one & 0x8888u; one2 = one >> 16;
-    dot = dt | (dt >> 16);
-    hap = (b3 & b0 & 0x88888888u) >> 16;
-  } else {
-    if (h & EV_COMPLEX) {
-      uint32_t gt, alt;
-      const int cls = classify_gt_general(L + pl, content_len > pl ? content_len - pl : 0, a, gt, alt);
-      if (cls == 1) mh = 8u; else if (cls == 2) mo = 8u; else if (cls == 3) mm = 8u;
-      return;
-    }
-    const uint32_t eq = a <= 9 ? nib_eq(pl, a * 0x11111111u) : 0u;
-    const uint32_t dt = nib_eq(pl, 0xEEEEEEEEu);
-    one1 = eq & 0x8888u; one2 = eq >> 16;
-    dot = dt | (dt >> 16);
-    hap = nib_eq(pl, 0xFFFFFFFFu) >> 16;
-  }
-  mm = dot & 0x8888u;
-  mo = one1 & (one2 | hap) & ~mm;
-  mh = (one1 ^ one2) & ~hap & ~mm & 0x8888u;
-}
-
 // `n` names, given by sample index in idx[0, n) (shared memory), as list bytes [g, g + len) of the output,
 // len <= 8 n
 template <typename IdxT>

@@ -133,6 +133,43 @@ __device__ __forceinline__ int classify_event(const uint32_t *ev, uint32_t v, ui
   return classify_word(w, off, L, content_len, a, samp, gt_extra, alt);
 }
 
+// ---- nibble-parallel classification of a quad event ---------------------------------------------------
+__device__ __forceinline__ uint32_t nib_eq(uint32_t x, uint32_t pat) {  // bit 3 of every nibble of x equal to pat's
+  const uint32_t y = x ^ pat;
+  return ~(((y & 0x77777777u) + 0x77777777u) | y) & 0x88888888u;
+}
+
+// het / hom / missing slots of one quad for allele number a, as nibble flags (bit 4j+3 = sample base+j).
+// `simple`: the record only carries alleles 0 / 1 / '.' / absent and a == 1 (LineRec.flags bit 0 clear).
+__device__ __forceinline__ void quad_masks(uint32_t h, uint32_t pl, uint32_t a, bool simple, const uint8_t *L,
+                                           uint32_t content_len, bool valid, uint32_t &mh, uint32_t &mo, uint32_t &mm) {
+  mh = mo = mm = 0;
+  if (!valid) return;
+  uint32_t one1, one2, dot, hap;
+  if (simple) {  // nibbles are 0, 1, 0xE or 0xF: two bit planes tell them apart
+    const uint32_t b0 = pl << 3, b3 = pl;
+    const uint32_t one = b0 & ~b3 & 0x88888888u, dt = b3 & ~b0 & 0x88888888u;
+    one1 = one & 0x8888u; one2 = one >> 16;
+    dot = dt | (dt >> 16);
+    hap = (b3 & b0 & 0x88888888u) >> 16;
+  } else {
+    if (h & EV_COMPLEX) {
+      uint32_t gt, alt;
+      const int cls = classify_gt_general(L + pl, content_len > pl ? content_len - pl : 0, a, gt, alt);
+      if (cls == 1) mh = 8u; else if (cls == 2) mo = 8u; else if (cls == 3) mm = 8u;
+      return;
+    }
+    const uint32_t eq = a <= 9 ? nib_eq(pl, a * 0x11111111u) : 0u;
+    const uint32_t dt = nib_eq(pl, 0xEEEEEEEEu);
+    one1 = eq & 0x8888u; one2 = eq >> 16;
+    dot = dt | (dt >> 16);
+    hap = nib_eq(pl, 0xFFFFFFFFu) >> 16;
+  }
+  mm = dot & 0x8888u;
+  mo = one1 & (one2 | hap) & ~mm;
+  mh = (one1 ^ one2) & ~hap & ~mm & 0x8888u;
+}
+
 // ---- warp per record: ALT #1 summary ---------------------------------------------------------------
 struct StatsParams {
   const uint8_t *in;
@@ -259,6 +296,39 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsPar
       uint32_t n_het[STAT_ALLELES] = {0, 0, 0}, n_hom[STAT_ALLELES] = {0, 0, 0}, ac[STAT_ALLELES] = {0, 0, 0};
       uint32_t hb[STAT_ALLELES] = {0, 0, 0}, ob[STAT_ALLELES] = {0, 0, 0};
       uint32_t n_miss = 0, an_x = 0, mb = 0;
+      if (fixed) {
+        // fixed-width names: no per-sample lengths are needed, so a lane takes a whole quad (four samples) and
+        // counts with nibble masks; one REDUX per counter at the end
+        const uint32_t nq = ev_count >> 1;
+        uint32_t lh[STAT_ALLELES] = {0, 0, 0}, lo_[STAT_ALLELES] = {0, 0, 0}, lm = 0;
+        for (uint32_t q = lane; q < nq; q += 32) {
+          const uint2 e = *reinterpret_cast<const uint2 *>(ev + 2 * q);
+          if (e.x & EV_COMPLEX) {
+#pragma unroll
+            for (int a = 0; a < STAT_ALLELES; a++) {
+              uint32_t gt, alt;
+              const int cls = classify_gt_general(L + e.y, content_len > e.y ? content_len - e.y : 0, a + 1, gt, alt);
+              lh[a] += cls == 1; lo_[a] += cls == 2; ac[a] += alt;
+              if (a == 0) { lm += cls == 3; an_x += gt; }
+            }
+          } else {
+            const uint32_t dt = nib_eq(e.y, 0xEEEEEEEEu);
+            const uint32_t ms = (dt | (dt >> 16)) & 0x8888u;             // samples with a '.' token
+            const uint32_t gone = ((ms | (ms << 16)) >> 3) * 15u;        // both nibbles of those samples
+            lm += __popc(ms);
+#pragma unroll
+            for (int a = 0; a < STAT_ALLELES; a++) {
+              uint32_t mh, mo, mm;
+              quad_masks(e.x, e.y, a + 1, false, L, content_len, true, mh, mo, mm);
+              lh[a] += __popc(mh); lo_[a] += __popc(mo);
+              ac[a] += __popc(nib_eq(e.y, (uint32_t)(a + 1) * 0x11111111u) & ~gone);
+            }
+          }
+        }
+        n_miss = __reduce_add_sync(FULL, lm);
+#pragma unroll
+        for (int a = 0; a < STAT_ALLELES; a++) { n_het[a] = __reduce_add_sync(FULL, lh[a]); n_hom[a] = __reduce_add_sync(FULL, lo_[a]); }
+      } else {
       uint32_t off_next;
       uint32_t w_next = slot_load(ev, lane, ev_count, off_next);
       for (uint32_t base = 0; base < 2 * ev_count; base += 32) {
@@ -277,6 +347,7 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsPar
           ac[a] += e.alt[a];
           if (e.cls[a] == 1) hb[a] += nl; else if (e.cls[a] == 2) ob[a] += nl;
         }
+      }
       }
       LineStats s;
       s.n_miss = n_miss; s.pad = 0; s.pad2 = 0;
@@ -980,31 +1051,41 @@ __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDe
   const uint8_t *L = p.in + rec.start;
   const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
   const uint32_t dl = (uint32_t)cfg.delim_len;
-  const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
-  uint32_t run_n[3] = {0, 0, 0}, run_b[3] = {0, 0, 0};
-  for (uint32_t k = 0; k < 2 * rec.ev_count; k++) {
-    uint32_t samp, gtx, alt;
-    bool is_ev;
-    const int cls = classify_event(ev, k, rec.ev_count, L, content_len, rd.allele, samp, gtx, alt, is_ev);
-    if (!cls) continue;
-    const int c = cls - 1;
-    uint8_t *d = p.out + dsts[c] + run_b[c];
-    if (run_n[c] > 0) {
-      for (uint32_t i = 0; i < dl; i++) d[i] = cfg.delim[i];
-      d += dl; run_b[c] += dl;
+  const bool simple = !(rec.flags & 1) && rd.allele == 1;
+  // per-class cursors in scalars (a runtime-indexed array would live in local memory)
+  uint32_t nh = 0, no = 0, nm = 0, bh = 0, bo = 0, bm = 0;
+  for (uint32_t q = 0; 2 * q + 1 < rec.ev_count; q++) {
+    const uint2 e = *reinterpret_cast<const uint2 *>(ev + 2 * q);
+    uint32_t mh, mo, mm;
+    quad_masks(e.x, e.y, rd.allele, simple, L, content_len, true, mh, mo, mm);
+    const uint32_t s0 = (e.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
+    uint32_t any = mh | mo | mm;
+    while (any) {
+      const uint32_t bit = any & (0u - any);
+      any &= any - 1;
+      const uint32_t samp = s0 + ((uint32_t)(__ffs(bit) - 1) >> 2);
+      const bool is_h = (mh & bit) != 0, is_o = (mo & bit) != 0;
+      const uint32_t rn = is_h ? nh : (is_o ? no : nm), rb = is_h ? bh : (is_o ? bo : bm);
+      const unsigned long long dst = is_h ? rd.het_dst : (is_o ? rd.hom_dst : rd.miss_dst);
+      const uint32_t tot = is_h ? rd.n_het : (is_o ? rd.n_hom : rd.n_miss);
+      uint8_t *d = p.out + dst + rb;
+      uint32_t adv = 0;
+      if (rn > 0) {
+        for (uint32_t i = 0; i < dl; i++) d[i] = cfg.delim[i];
+        d += dl; adv = dl;
+      }
+      const uint32_t nl = name_len(cfg, samp);
+      if (cfg.name8) {
+        unsigned long long it = cfg.name8[samp];
+        if (rn + 1 == tot) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
+        store8_unaligned(d, it);
+      } else {
+        const uint8_t *src = name_ptr(cfg, samp);
+        for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
+      }
+      adv += nl;
+      if (is_h) { nh++; bh += adv; } else if (is_o) { no++; bo += adv; } else { nm++; bm += adv; }
     }
-    const uint32_t nl = name_len(cfg, samp);
-    if (cfg.name8) {
-      unsigned long long it = cfg.name8[samp];
-      const uint32_t tot = c == 0 ? rd.n_het : (c == 1 ? rd.n_hom : rd.n_miss);
-      if (run_n[c] + 1 == tot) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
-      store8_unaligned(d, it);
-    } else {
-      const uint8_t *src = name_ptr(cfg, samp);
-      for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
-    }
-    run_b[c] += nl;
-    run_n[c]++;
   }
 }
 
