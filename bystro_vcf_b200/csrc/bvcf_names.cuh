@@ -59,32 +59,47 @@ struct RowEvents {
   bool simple;
 };
 
-// all three lists of one row in one sweep: index lists at idx[0,n_het) | [n_het, n_het+n_hom) | [.., +n_miss)
+// all three lists of one row in one sweep: index lists at idx[0,n_het) | [n_het, n_het+n_hom) | [.., +n_miss).
+// A lane takes two consecutive quads (eight samples) per step, so one packed prefix sum ranks 256 samples.
 template <typename IdxT>
 __device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx, uint32_t base_o, uint32_t base_m, int lane) {
   const uint32_t nq = re.n_words >> 1;
+  const uint2 *ev2 = reinterpret_cast<const uint2 *>(re.ev);
   uint32_t run_h = 0, run_o = base_o, run_m = base_m;
-  uint2 e_next = make_uint2(0u, 0u);
-  if ((uint32_t)lane < nq) e_next = *reinterpret_cast<const uint2 *>(re.ev + 2 * lane);
-  for (uint32_t base = 0; base < nq; base += 32) {
-    const uint2 e = e_next;  // software pipelining: the next batch is already in flight
-    const bool valid = base + lane < nq;
-    if (base + 32 + lane < nq) e_next = *reinterpret_cast<const uint2 *>(re.ev + 2 * (base + 32 + lane));
-    uint32_t mh, mo, mm;
-    quad_masks(e.x, e.y, re.a, re.simple, re.L, re.content_len, valid, mh, mo, mm);
-    const uint32_t s0 = (e.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
-    const uint32_t cnt = __popc(mh) | (__popc(mo) << 10) | (__popc(mm) << 20);
+  uint2 n0 = make_uint2(0u, 0u), n1 = make_uint2(0u, 0u);
+  if (2u * lane < nq) n0 = ev2[2 * lane];
+  if (2u * lane + 1 < nq) n1 = ev2[2 * lane + 1];
+  for (uint32_t base = 0; base < nq; base += 64) {
+    const uint2 e0 = n0, e1 = n1;  // software pipelining: the next step's quads are already in flight
+    const uint32_t q0 = base + 2 * lane;
+    const bool v0 = q0 < nq, v1 = q0 + 1 < nq;
+    n0 = make_uint2(0u, 0u); n1 = make_uint2(0u, 0u);
+    if (q0 + 64 < nq) n0 = ev2[q0 + 64];
+    if (q0 + 65 < nq) n1 = ev2[q0 + 65];
+    uint32_t mh0, mo0, mm0, mh1, mo1, mm1;
+    quad_masks(e0.x, e0.y, re.a, re.simple, re.L, re.content_len, v0, mh0, mo0, mm0);
+    quad_masks(e1.x, e1.y, re.a, re.simple, re.L, re.content_len, v1, mh1, mo1, mm1);
+    const uint32_t cnt = (__popc(mh0) + __popc(mh1)) | ((__popc(mo0) + __popc(mo1)) << 10) | ((__popc(mm0) + __popc(mm1)) << 20);
     const uint32_t incl = warp_incl_scan(cnt, lane);
     const uint32_t tot = __shfl_sync(FULL, incl, 31);
     const uint32_t excl = incl - cnt;
     uint32_t kh = run_h + (excl & 1023u), ko = run_o + ((excl >> 10) & 1023u), km = run_m + (excl >> 20);
-    const uint32_t any = mh | mo | mm;
+    const uint32_t s0 = (e0.x & EV_SAMPLE_MASK) - EV_BASE_BIAS, s1 = (e1.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
+    const uint32_t any0 = mh0 | mo0 | mm0, any1 = mh1 | mo1 | mm1;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const uint32_t bit = 8u << (4 * j);
-      if (any & bit) {
-        const uint32_t d = (mh & bit) ? kh++ : ((mo & bit) ? ko++ : km++);
+      if (any0 & bit) {
+        const uint32_t d = (mh0 & bit) ? kh++ : ((mo0 & bit) ? ko++ : km++);
         idx[d] = (IdxT)(s0 + (uint32_t)j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t bit = 8u << (4 * j);
+      if (any1 & bit) {
+        const uint32_t d = (mh1 & bit) ? kh++ : ((mo1 & bit) ? ko++ : km++);
+        idx[d] = (IdxT)(s1 + (uint32_t)j);
       }
     }
     run_h += tot & 1023u; run_o += (tot >> 10) & 1023u; run_m += tot >> 20;
