@@ -388,6 +388,34 @@ __device__ __noinline__ GtStats reduce_events_thread(const DevCfg &cfg, const Li
 }
 
 // ---- row writer: counts in the SIZE pass, byte stores in the EMIT pass --------------------------------
+// 8 bytes to an arbitrarily aligned address with the widest naturally aligned pieces (2-4 stores)
+__device__ __forceinline__ void store8_unaligned(uint8_t *d, unsigned long long v) {
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  switch ((uintptr_t)d & 3u) {
+    case 0:
+      *reinterpret_cast<uint32_t *>(d) = lo;
+      *reinterpret_cast<uint32_t *>(d + 4) = hi;
+      break;
+    case 2:
+      *reinterpret_cast<uint16_t *>(d) = (uint16_t)lo;
+      *reinterpret_cast<uint32_t *>(d + 2) = (uint32_t)(v >> 16);
+      *reinterpret_cast<uint16_t *>(d + 6) = (uint16_t)(hi >> 16);
+      break;
+    case 1:
+      d[0] = (uint8_t)lo;
+      *reinterpret_cast<uint16_t *>(d + 1) = (uint16_t)(lo >> 8);
+      *reinterpret_cast<uint32_t *>(d + 3) = (uint32_t)(v >> 24);
+      d[7] = (uint8_t)(hi >> 24);
+      break;
+    default:
+      d[0] = (uint8_t)lo;
+      *reinterpret_cast<uint32_t *>(d + 1) = (uint32_t)(v >> 8);
+      *reinterpret_cast<uint16_t *>(d + 5) = (uint16_t)(hi >> 8);
+      d[7] = (uint8_t)(hi >> 24);
+      break;
+  }
+}
+
 // Writer policy of emit_row: kWrite (bytes are produced), kGlobal (bytes go to the output buffer: loci and
 // RowDesc are written too).  span_in() is a span of the INPUT line (long ones may be referenced, not copied);
 // list() reserves the bytes of one sample-name list; lists_done() ends the three lists of a row.
@@ -397,20 +425,43 @@ struct RowWriter {
   uint8_t *g;                // global cursor (EMIT)
   unsigned long long count;  // bytes (SIZE)
   const uint8_t *out0;       // output base (EMIT): list destinations are offsets from it
-  __device__ __forceinline__ void span_in(const uint8_t *p, int len) { span(p, len); }
-  __device__ __forceinline__ unsigned long long list(int, uint32_t, unsigned long long bytes, uint32_t) {
-    const unsigned long long d = WRITE ? (unsigned long long)(g - out0) : 0ull;
-    skip(bytes);  // filled by the names kernel
-    return d;
+  // EMIT: bytes gather in a 64-bit register and leave eight at a time (2-4 aligned stores instead of 8 byte
+  // stores: every store of a thread is a transaction of its own, the pass was bound by them)
+  unsigned long long acc;    // pending bytes, little-endian
+  int fill;                  // how many (0..7); they belong at g[0..fill)
+  __device__ __forceinline__ void begin(uint8_t *dst) { g = dst; acc = 0; fill = 0; }
+  __device__ __forceinline__ void flush() {
+    if (WRITE) {
+      for (int i = 0; i < fill; i++) g[i] = (uint8_t)(acc >> (8 * i));
+      g += fill; acc = 0; fill = 0;
+    }
   }
-  __device__ __forceinline__ void lists_done(uint32_t) {}
-  __device__ __forceinline__ void byte(uint8_t c) { if (WRITE) *g++ = c; else count++; }
-  __device__ __forceinline__ void span(const uint8_t *p, int len) {
-    if (WRITE) { for (int i = 0; i < len; i++) g[i] = p[i]; g += len; } else count += len;
-  }
+  __device__ __forceinline__ void finish() { flush(); }
+  // up to 8 characters packed little-endian; bytes at and above len must be zero
   __device__ __forceinline__ void packed(uint64_t chars, int len) {
-    if (WRITE) { for (int i = 0; i < len; i++) g[i] = (uint8_t)(chars >> (8 * i)); g += len; } else count += len;
+    if (!WRITE) { count += len; return; }
+    acc |= chars << (8 * fill);
+    int nf = fill + len;
+    if (nf >= 8) {
+      store8_unaligned(g, acc);
+      g += 8;
+      acc = fill ? chars >> (8 * (8 - fill)) : 0ull;
+      nf -= 8;
+    }
+    fill = nf;
   }
+  __device__ __forceinline__ void byte(uint8_t c) { if (WRITE) packed((uint64_t)c, 1); else count++; }
+  __device__ __forceinline__ void span(const uint8_t *p, int len) {
+    if (!WRITE) { count += len; return; }
+    for (int i = 0; i < len; i += 8) {
+      const int n = len - i < 8 ? len - i : 8;
+      unsigned long long v = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) if (k < n) v |= (unsigned long long)p[i + k] << (8 * k);
+      packed(v, n);
+    }
+  }
+  __device__ __forceinline__ void span_in(const uint8_t *p, int len) { span(p, len); }
   __device__ __forceinline__ void dec(long long v) {
     if (!WRITE) {
       count += (v < 0 ? 1 : 0) + dec_len(v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v);
@@ -419,17 +470,22 @@ struct RowWriter {
     unsigned long long lo, hi;
     const int len = itoa_pack(v, lo, hi);  // registers, no byte buffer in local memory
     if (len >= 0) {
-      for (int i = 0; i < len && i < 8; i++) g[i] = (uint8_t)(lo >> (8 * i));
-      for (int i = 8; i < len; i++) g[i] = (uint8_t)(hi >> (8 * (i - 8)));
-      g += len;
+      packed(lo, len < 8 ? len : 8);
+      if (len > 8) packed(hi, len - 8);
     } else {
       uint8_t buf[24];
       const int l2 = itoa_dec(v, buf);
-      for (int i = 0; i < l2; i++) g[i] = buf[i];
-      g += l2;
+      for (int i = 0; i < l2; i++) byte(buf[i]);
     }
   }
-  __device__ __forceinline__ void skip(unsigned long long len) { if (WRITE) g += len; else count += len; }
+  __device__ __forceinline__ void skip(unsigned long long len) { if (WRITE) { flush(); g += len; } else count += len; }
+  __device__ __forceinline__ unsigned long long list(int, uint32_t, unsigned long long bytes, uint32_t) {
+    if (WRITE) flush();
+    const unsigned long long d = WRITE ? (unsigned long long)(g - out0) : 0ull;
+    skip(bytes);  // filled by the names kernel
+    return d;
+  }
+  __device__ __forceinline__ void lists_done(uint32_t) {}
 };
 
 // ---- one output allele of getAlleles ------------------------------------------------------------
@@ -829,11 +885,12 @@ __global__ void __launch_bounds__(ROWS_THREADS, WRITE ? 4 : 5) bvcf_rows_kernel(
     RowWriter<WRITE> w;
     w.count = 0;
     w.out0 = p.out;
-    w.g = WRITE ? (staged ? stage + mis + my_rel : p.out + out_base + p.line_off[li]) : nullptr;
+    w.begin(WRITE ? (staged ? stage + mis + my_rel : p.out + out_base + p.line_off[li]) : nullptr);
     uint32_t n_rows = 0;
     const unsigned long long row_base = WRITE ? p.row_off[li] : 0;  // row number within the sub-chunk
 
     process_record<RowWriter<WRITE>>(p, li, rec, w, s_filt, s_filt_off, n_rows, row_base, !WRITE);
+    w.finish();
     if (!WRITE) {
       p.line_bytes[li] = (uint32_t)w.count;
       p.line_rows[li] = n_rows;
@@ -868,34 +925,6 @@ struct NamesParams {
   unsigned long long dosage_cap_rows;
   uint32_t *big_rows;        // work list: rows written by a whole warp (bvcf_names_big_kernel)
 };
-
-// 8 bytes to an arbitrarily aligned address with the widest naturally aligned pieces (2-4 stores)
-__device__ __forceinline__ void store8_unaligned(uint8_t *d, unsigned long long v) {
-  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-  switch ((uintptr_t)d & 3u) {
-    case 0:
-      *reinterpret_cast<uint32_t *>(d) = lo;
-      *reinterpret_cast<uint32_t *>(d + 4) = hi;
-      break;
-    case 2:
-      *reinterpret_cast<uint16_t *>(d) = (uint16_t)lo;
-      *reinterpret_cast<uint32_t *>(d + 2) = (uint32_t)(v >> 16);
-      *reinterpret_cast<uint16_t *>(d + 6) = (uint16_t)(hi >> 16);
-      break;
-    case 1:
-      d[0] = (uint8_t)lo;
-      *reinterpret_cast<uint16_t *>(d + 1) = (uint16_t)(lo >> 8);
-      *reinterpret_cast<uint32_t *>(d + 3) = (uint32_t)(v >> 24);
-      d[7] = (uint8_t)(hi >> 24);
-      break;
-    default:
-      d[0] = (uint8_t)lo;
-      *reinterpret_cast<uint32_t *>(d + 1) = (uint32_t)(v >> 8);
-      *reinterpret_cast<uint16_t *>(d + 5) = (uint16_t)(hi >> 8);
-      d[7] = (uint8_t)(hi >> 24);
-      break;
-  }
-}
 
 // one row, whole warp: ballot/popc ranks, ordered scatter of the names (and the dosage row)
 __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned long long r, unsigned long long row0,
