@@ -228,7 +228,6 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     sp.recs = (LineRec *)sc.recs.p; sp.range_nrec = (uint32_t *)sc.range_nrec.p;
     sp.range_nlines = (uint32_t *)sc.range_nlines.p; sp.events = (uint32_t *)sc.events.p;
     sp.ctr = d_ctr; sp.H = dc.H; sp.eol_width = dc.eol_width;
-    { const char *tv = getenv("BVCF_TUNE"); sp.tune = tv ? atoi(tv) : 0; }
     const unsigned grid = (nr + SCAN_WARPS - 1) / SCAN_WARPS;
     if (dc.n_samples > 0)
       bvcf_scan_genotype_kernel<true><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);

@@ -43,7 +43,6 @@ struct ScanParams {
   uint32_t *events;         // n_ranges * evcap_words
   RunCounters *ctr;
   int H, eol_width;
-  int tune;                 // bit 0: never try the two-window reference test (experiments)
 };
 
 // per-line accumulators; *_l are per-lane partial sums reduced when the line ends
@@ -527,12 +526,15 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
     // data) cost one 9-compare vote; anything else falls through to the per-window dispatcher.
     uint32_t stage_off = 0;
     bool done = false;
+    // the vector tiers apply while the warp is inside a line's sample zone with a known field phase; only the
+    // general window changes that, so the test is kept as one flag
+    bool fast = HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u;
     for (uint32_t it = 0; it + 2 < n_avail && !done; it += 2, stage_off = (stage_off + 2 * WIN) & (RING - 1)) {
       issue_pair();
       asm volatile("cp.async.wait_group %0;\n" ::"n"(PF_PAIRS - 1));  // windows it .. it+3 have landed
       __syncwarp();
       int hint = 0;  // 1: window A was regular and is done, B is known not to be; 2: A is known not to be regular
-      if (HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u && !(p.tune & 1)) {
+      if (fast) {
         const uint32_t so_b = (stage_off + WIN) & (RING - 1);
         const uint4 va = lds128(ring_lane_s + stage_off);
         const uint4 vb = lds128(ring_lane_s + so_b);
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
         const uint32_t so = (stage_off + h * WIN) & (RING - 1);
         if (st.mode == 0 && wi >= seek_limit) { done = true; break; }  // no line starts in this range
         const uint4 v = lds128(ring_lane_s + so);
-        if (HAS_SAMPLES && hint != 2 - h && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u) {
+        if (fast && hint != 2 - h) {
           const uint32_t w4 = lds32(ring_base_s + ((so + lane * 16 + 16) & (RING - 1)));
           const uint32_t sh = (uint32_t)st.fsr * 8u;
           const uint32_t rp = st.refpat;
@@ -613,6 +615,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
         const uint64_t pos = rstart + (uint64_t)wi * WIN;
         scan_window_general<HAS_SAMPLES>(p, st, ring_base_s, so, v, pos, rend, lane, my_recs, my_events);
         if (st.mode == 2) { done = true; break; }
+        fast = HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u;
       }
       __syncwarp();  // everyone is done with these stages before they are refilled
     }
