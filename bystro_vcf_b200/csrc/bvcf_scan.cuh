@@ -253,13 +253,14 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
 
     // field index: offsets of the record's first nine tabs (strings.Split, main.go:535)
     if (st.col < 9 && st.nrec < p.slots_per_range) {
+      uint16_t *const tabp = my_recs[st.nrec].tab;
+      const uint32_t off0 = (uint32_t)(pos - st.line_start) + (uint32_t)(lane * 16);  // a line is < 4 GiB (LineRec.len)
       uint32_t m = tm_l;
       uint32_t idx = st.col + excl;
       while (m && idx < 9) {
-        const int b = __ffs(m) - 1;
+        const uint32_t off = off0 + (uint32_t)(__ffs(m) - 1);
         m &= m - 1;
-        const uint64_t off = pos + (uint64_t)(lane * 16 + b) - st.line_start;
-        my_recs[st.nrec].tab[idx] = off < 0xFFFFu ? (uint16_t)off : (uint16_t)0xFFFFu;
+        tabp[idx] = off < 0xFFFFu ? (uint16_t)off : (uint16_t)0xFFFFu;
         idx++;
       }
     }
@@ -294,19 +295,22 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
         uint32_t t[4] = {__funnelshift_r(v.x, v.y, sh) ^ rp, __funnelshift_r(v.y, v.z, sh) ^ rp,
                          __funnelshift_r(v.z, v.w, sh) ^ rp, __funnelshift_r(v.w, w4, sh) ^ rp};
         const int ws0 = lane * 16 + (s9 & 3);  // start of this lane's first realigned word
-        uint32_t zone = 0;
-        bool bad_shape = false;
+        // word j of this lane starts at ws0 + 4 j, in phase with s9; it is in the zone iff s9 <= ws < zone_end
+        int jlo = (s9 - ws0 + 3) >> 2, jhi = (zone_end - ws0 + 3) >> 2;  // arithmetic shifts: ceilings
+        jlo = jlo < 0 ? 0 : jlo;
+        jhi = jhi > 4 ? 4 : jhi;
+        const uint32_t zone = jhi > jlo ? (((1u << jhi) - 1u) & ~((1u << jlo) - 1u)) : 0u;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int ws = ws0 + 4 * j;
-          if (ws >= s9 && ws < zone_end) {
-            zone |= 1u << j;
-            if (nl < WIN) {
-              if (ws + 3 == nl) t[j] ^= 0x03000000u;       // last field of the line ends with '\n', not '\t'
-              else if (ws + 3 > nl) bad_shape = true;       // short last field
-            }
-          } else {
-            t[j] = 0;
+        for (int j = 0; j < 4; j++) t[j] = (zone >> j) & 1u ? t[j] : 0u;
+        bool bad_shape = false;
+        if (nl < WIN) {  // the line ends here: where does the newline fall within its field?  (warp-uniform)
+          const int r = (nl - s9) & 3;
+          if (r == 3) {  // "x|y\n": the last field ends with '\n', not '\t'
+            const int jn = (nl - 3 - ws0) >> 2;
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j == jn) t[j] ^= 0x03000000u & (0u - ((zone >> j) & 1u));
+          } else if (r != 0) {
+            bad_shape = true;  // short last field (r == 0: an empty last field, the field count will tell)
           }
         }
         uint32_t bad = bad_digits4(t, 0xFFFFFFFFu) | (bad_shape ? 1u : 0u);
