@@ -208,21 +208,24 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
                                                     int lane, LineRec *my_recs, uint32_t *my_events) {
   const bool eol2 = p.eol_width == 2;
   const uint32_t tm = eq_mask16(v, 0x09090909u);
-  const uint32_t nm = eq_mask16(v, 0x0A0A0A0Au);
+  uint32_t nm = eq_mask16(v, 0x0A0A0A0Au);  // newlines not yet consumed: each segment takes the lowest one
 
   int seg_lo = 0;
-  if (st.mode == 1 && st.fsr != FS_NONE && st.fsr > 0) seg_lo = st.fsr;  // bytes before the field start are consumed
+  if (st.mode == 1 && st.fsr != FS_NONE && st.fsr > 0) {  // bytes before the field start are consumed
+    seg_lo = st.fsr;
+    nm &= bits_range16(seg_lo - lane * 16, 16);
+  }
 
   while (seg_lo < WIN) {
     // first newline at or after seg_lo
     const int lo_l = seg_lo - lane * 16;
-    const uint32_t nm_l = nm & bits_range16(lo_l, 16);
-    const uint32_t ball = __ballot_sync(FULL, nm_l != 0);
+    const uint32_t ball = __ballot_sync(FULL, nm != 0);
     int nl = WIN;
     if (ball) {
       const int l = __ffs(ball) - 1;
-      const uint32_t m = __shfl_sync(FULL, nm_l, l);
+      const uint32_t m = __shfl_sync(FULL, nm, l);
       nl = l * 16 + __ffs(m) - 1;
+      if (lane == l) nm &= nm - 1;
     }
     if (st.mode == 0) {  // seeking the first owned line start
       if (nl == WIN) return;
