@@ -38,7 +38,7 @@ struct Scratch {
   uint64_t max_records = 0;
   uint64_t row_cap = 0;       // RowDesc slots (rows one sub-chunk may emit)
   DevBuf recs, range_nrec, range_nlines, rec_base, line_base, events, dense, line_bytes, line_rows, line_off,
-      row_off, partial, stats1, row_desc, big_recs, big_rows;
+      row_off, partial, stats1, row_desc, big_recs, big_rows, multi_recs;
 };
 
 struct Slot {
@@ -169,6 +169,7 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
   if ((rc = dev_reserve(ctx, sc.line_off, sc.max_records * 8))) return rc;
   if ((rc = dev_reserve(ctx, sc.row_off, sc.max_records * 8))) return rc;
   if ((rc = dev_reserve(ctx, sc.partial, 2 * PFX_BLOCKS * 8))) return rc;
+  if ((rc = dev_reserve(ctx, sc.multi_recs, sc.max_records * 4))) return rc;
   if (ctx->dcfg.n_samples > 0) {
     sc.row_cap = std::max<uint64_t>(sc.row_cap, sc.max_records + sc.max_records / 4 + 1024);
     if ((rc = dev_reserve(ctx, sc.stats1, sc.max_records * sizeof(LineStats)))) return rc;
@@ -181,7 +182,7 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
 void scratch_free(Scratch &sc) {
   for (DevBuf *b : {&sc.recs, &sc.range_nrec, &sc.range_nlines, &sc.rec_base, &sc.line_base, &sc.events, &sc.dense,
                     &sc.line_bytes, &sc.line_rows, &sc.line_off, &sc.row_off, &sc.partial, &sc.stats1, &sc.row_desc, &sc.big_recs,
-                    &sc.big_rows})
+                    &sc.big_rows, &sc.multi_recs})
     dev_free(*b);
 }
 
@@ -273,8 +274,12 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     rp.row_desc = (RowDesc *)sc.row_desc.p; rp.row_desc_cap = dc.n_samples > 0 ? sc.row_cap : 0;
     rp.dosage_cap_rows = dosage_cap_rows; rp.loci = d_loci; rp.loci_stride = LOCI_STRIDE;
     rp.diags = d_diags; rp.diag_cap = DIAG_CAP;
+    rp.multi_recs = (uint32_t *)sc.multi_recs.p;
+    const bool defer_multi = dc.n_samples == 0;  // see RowsParams::multi_recs
     const unsigned rgrid = (unsigned)n_sm * 16;
-    bvcf_rows_kernel<false><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
+    if (defer_multi) bvcf_rows_kernel<false, true><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
+    else bvcf_rows_kernel<false, false><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
+    if (defer_multi) bvcf_rows_list_kernel<false><<<(unsigned)n_sm * 8, ROWS_THREADS, 0, st>>>(rp);  // the queued multi-row records
     // 5. row offsets
     PrefixParams pq{};
     pq.a = rp.line_bytes; pq.b = rp.line_rows; pq.out_a = (uint64_t *)sc.line_off.p; pq.out_b = (uint64_t *)sc.row_off.p;
@@ -284,11 +289,13 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     bvcf_prefix_reduce_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pq);
     bvcf_prefix_spine_kernel<<<1, 1024, 0, st>>>(pq);
     bvcf_prefix_scan_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pq);
-    ctx->launches += 4;
+    ctx->launches += defer_multi ? 5 : 4;
     if (se) CK(cudaEventRecord(se->e[4], st));
     // 6. emit pass: every non-list byte + one RowDesc per row
-    bvcf_rows_kernel<true><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
-    ctx->launches++;
+    if (defer_multi) bvcf_rows_kernel<true, true><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
+    else bvcf_rows_kernel<true, false><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
+    if (defer_multi) bvcf_rows_list_kernel<true><<<(unsigned)n_sm * 8, ROWS_THREADS, 0, st>>>(rp);
+    ctx->launches += defer_multi ? 2 : 1;
     if (se) CK(cudaEventRecord(se->e[5], st));
     // 7. sample-name lists + dosage rows: short rows lane-serially, the queued long rows by a warp each --
     // as aligned vectors when every list item is 8 bytes and no dosage row is wanted (bvcf_names.cuh)
@@ -774,7 +781,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->size_ms += ms;
       cudaEventElapsedTime(&ms, t.e[4], t.e[5]); times->emit_ms += ms;
       cudaEventElapsedTime(&ms, t.e[5], t.e[6]); times->names_ms += ms;
-      times->launches += ctx->dcfg.n_samples > 0 ? 14 : 10;
+      times->launches += ctx->dcfg.n_samples > 0 ? 14 : 12;
     }
     if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[N_STAGE_EV - 1]);
     for (auto &t : timing)

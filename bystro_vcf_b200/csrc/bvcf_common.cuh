@@ -83,6 +83,8 @@ struct RunCounters {
   unsigned long long chunk_line_base; // n_lines before this sub-chunk (diagnostic line numbers)
   unsigned int chunk_records;      // records in the current sub-chunk (device-side n for grid-stride kernels)
   unsigned int big_rec_cursor;     // next entry of the stats work list to be taken
+  unsigned int n_multi_recs;       // work list of bvcf_rows_list_kernel: records that may yield several rows
+  unsigned int pad1;
 };
 
 // ---- configuration as the kernels see it ---------------------------------------------------------

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(1024) bvcf_prefix_spine_kernel(const PrefixPar
       c->chunk_line_base = c->n_lines;
       c->n_big_recs = 0;
       c->big_rec_cursor = 0;
+      c->n_multi_recs = 0;
       c->n_records += sa[t];
       c->n_lines += sb[t];
     } else if (!(c->ev_overflow | c->slot_overflow)) {  // sizes are garbage after a scratch overflow: leave the cursors

@@ -69,6 +69,12 @@ struct RowsParams {
   // diagnostics (main.go:730-986 log.Printf sites)
   uint32_t *diags;           // 4 words each: line_lo, line_hi, alt_no, code
   uint32_t diag_cap;
+  // DEFER kernels: records that can yield several rows (comma in ALT, equal-length REF/ALT longer than one base) are
+  // queued by the SIZE pass and handled by bvcf_rows_list_kernel in both passes, so that the main kernels call
+  // emit_row once per warp instead of once per row of their widest record.  Pays off for sites-only input (cheap
+  // rows, many multi-allelic lines: -17 % on C3); with samples such records are rare and a short list kernel is a
+  // serial tail, so the host leaves it off there.
+  uint32_t *multi_recs;
 };
 
 // site types (bystro-utils parse.Snp/Ins/Del/Mnp/Multi)
@@ -768,8 +774,9 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Rows
 }
 
 // ---- one record: field index, linePasses, getAlleles, one emit_row per output allele ------------------
-template <class W>
-__device__ __forceinline__ void process_record(const RowsParams &p, uint32_t li, const LineRec &rec, W &w,
+// DEFER: return true, doing nothing, when the record may yield more than one row.
+template <class W, bool DEFER>
+__device__ __forceinline__ bool process_record(const RowsParams &p, uint32_t li, const LineRec &rec, W &w,
                                                const uint8_t *s_filt, const uint32_t *s_filt_off, uint32_t &n_rows,
                                                unsigned long long row_base, bool diag) {
   const DevCfg &cfg = p.cfg;
@@ -836,12 +843,18 @@ __device__ __forceinline__ void process_record(const RowsParams &p, uint32_t li,
     int gs_idx = -1;
     OutAllele oa;
     oa.ins_p = nullptr; oa.ins_n = 0; oa.del_n = 0; oa.pos_val = 0;
-    while (gen_next(g, oa, p, line_no, diag)) emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
+    if (DEFER) {
+      if (!g.done && (lc.multi || (alt_n == ref_n && ref_n > 1))) return true;
+      if (gen_next(g, oa, p, line_no, diag)) emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);  // at most one row
+    } else {
+      while (gen_next(g, oa, p, line_no, diag)) emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
+    }
   }
+  return false;
 }
 
 // ---- thread per record, grid-stride, record count read from device memory ----------------------------
-template <bool WRITE>
+template <bool WRITE, bool DEFER>
 __global__ void __launch_bounds__(ROWS_THREADS, WRITE ? 4 : 5) bvcf_rows_kernel(const __grid_constant__ RowsParams p) {
   __shared__ uint8_t s_filt[FILT_SMEM];
   __shared__ uint32_t s_filt_off[65];
@@ -879,6 +892,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, WRITE ? 4 : 5) bvcf_rows_kernel(
       span = (uint32_t)span64;
       my_rel = (uint32_t)(off - span_base);
     }
+    bool deferred = false;
     if (valid) {
     const LineRec rec = p.lines[li];
 
@@ -889,13 +903,22 @@ __global__ void __launch_bounds__(ROWS_THREADS, WRITE ? 4 : 5) bvcf_rows_kernel(
     uint32_t n_rows = 0;
     const unsigned long long row_base = WRITE ? p.row_off[li] : 0;  // row number within the sub-chunk
 
-    process_record<RowWriter<WRITE>>(p, li, rec, w, s_filt, s_filt_off, n_rows, row_base, !WRITE);
+    deferred = process_record<RowWriter<WRITE>, DEFER>(p, li, rec, w, s_filt, s_filt_off, n_rows, row_base, !WRITE);
     w.finish();
-    if (!WRITE) {
+    if (!WRITE && !deferred) {
       p.line_bytes[li] = (uint32_t)w.count;
       p.line_rows[li] = n_rows;
     }
     }  // valid
+    if (!WRITE && DEFER) {  // queue the multi-row records (one atomic per warp)
+      const uint32_t dm = __ballot_sync(FULL, deferred);
+      if (dm) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&p.ctr->n_multi_recs, (unsigned int)__popc(dm));
+        base = __shfl_sync(FULL, base, 0);
+        if (deferred) p.multi_recs[base + __popc(dm & ((1u << lane) - 1u))] = li;
+      }
+    }
     if (WRITE && staged) {
       __syncwarp();
       uint8_t *gb = p.out + out_base + span_base;
@@ -907,6 +930,38 @@ __global__ void __launch_bounds__(ROWS_THREADS, WRITE ? 4 : 5) bvcf_rows_kernel(
         *reinterpret_cast<uint4 *>(gb + head + 16 * v) = *reinterpret_cast<const uint4 *>(sb + head + 16 * v);
       for (uint32_t i = head + 16 * nvec + lane; i < span; i += 32) gb[i] = sb[i];
       __syncwarp();
+    }
+  }
+}
+
+// the queued multi-row records, thread per record, both passes
+template <bool WRITE>
+__global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_list_kernel(const __grid_constant__ RowsParams p) {
+  __shared__ uint8_t s_filt[FILT_SMEM];
+  __shared__ uint32_t s_filt_off[65];
+  const DevCfg &cfg = p.cfg;
+  const int n_filt = cfg.n_allow + cfg.n_excl;
+  for (int i = threadIdx.x; i < cfg.filt_bytes && i < FILT_SMEM; i += blockDim.x) s_filt[i] = cfg.filt_blob[i];
+  for (int i = threadIdx.x; i <= n_filt && i < 65; i += blockDim.x) s_filt_off[i] = cfg.filt_off[i];
+  __syncthreads();
+  if (WRITE && p.ctr->out_overflow) return;
+  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  const uint32_t n = p.ctr->n_multi_recs;
+  const unsigned long long out_base = p.ctr->chunk_out_base;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t li = p.multi_recs[i];
+    const LineRec rec = p.lines[li];
+    RowWriter<WRITE> w;
+    w.count = 0;
+    w.out0 = p.out;
+    w.begin(WRITE ? p.out + out_base + p.line_off[li] : nullptr);
+    uint32_t n_rows = 0;
+    const unsigned long long row_base = WRITE ? p.row_off[li] : 0;
+    process_record<RowWriter<WRITE>, false>(p, li, rec, w, s_filt, s_filt_off, n_rows, row_base, !WRITE);
+    w.finish();
+    if (!WRITE) {
+      p.line_bytes[li] = (uint32_t)w.count;
+      p.line_rows[li] = n_rows;
     }
   }
 }
