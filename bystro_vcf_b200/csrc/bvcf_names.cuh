@@ -106,37 +106,78 @@ __device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx,
   }
 }
 
-// one list, rows with more names than the index buffer holds: `cap` indices at a time
+// Rows with more names than the index buffer holds (wide cohorts): still ONE sweep over the quads.  The buffer
+// is cut into three regions; a list whose region cannot take another step (256 names) is written out as a chunk
+// of vectors and its region starts over.  n names make 8 n - 1 bytes: the final chunk of a list drops the
+// trailing delimiter.
 template <typename IdxT>
-__device__ __forceinline__ void stream_list(const unsigned long long *__restrict__ name8, const RowEvents &re, int cls,
-                                            uint32_t n_total, IdxT *idx, uint32_t cap, uint8_t *g, int lane) {
+__device__ __forceinline__ void sweep_lists_chunked(const unsigned long long *__restrict__ name8, const RowEvents &re,
+                                                    IdxT *idx, uint32_t cap3, uint8_t *g_h, uint8_t *g_o, uint8_t *g_m,
+                                                    uint32_t n_h, uint32_t n_o, uint32_t n_m, int lane) {
   const uint32_t nq = re.n_words >> 1;
-  uint32_t fill = 0, written = 0, seen = 0;
-  uint2 e_next = make_uint2(0u, 0u);
-  if ((uint32_t)lane < nq) e_next = *reinterpret_cast<const uint2 *>(re.ev + 2 * lane);
-  for (uint32_t base = 0; base < nq; base += 32) {
-    const uint2 e = e_next;
-    const bool valid = base + lane < nq;
-    if (base + 32 + lane < nq) e_next = *reinterpret_cast<const uint2 *>(re.ev + 2 * (base + 32 + lane));
-    uint32_t mh, mo, mm;
-    quad_masks(e.x, e.y, re.a, re.simple, re.L, re.content_len, valid, mh, mo, mm);
-    uint32_t m = cls == 0 ? mh : (cls == 1 ? mo : mm);
-    const uint32_t s0 = (e.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
-    const uint32_t cnt = __popc(m);
+  const uint2 *ev2 = reinterpret_cast<const uint2 *>(re.ev);
+  IdxT *const ih = idx, *const io = idx + cap3, *const im = idx + 2 * cap3;
+  uint32_t fh = 0, fo = 0, fm = 0;          // names waiting in each region
+  uint32_t sh = 0, so = 0, sm = 0;          // names seen so far per list
+  uint2 n0 = make_uint2(0u, 0u), n1 = make_uint2(0u, 0u);
+  if (2u * lane < nq) n0 = ev2[2 * lane];
+  if (2u * lane + 1 < nq) n1 = ev2[2 * lane + 1];
+  for (uint32_t base = 0; base < nq; base += 64) {
+    const uint2 e0 = n0, e1 = n1;
+    const uint32_t q0 = base + 2 * lane;
+    const bool v0 = q0 < nq, v1 = q0 + 1 < nq;
+    n0 = make_uint2(0u, 0u); n1 = make_uint2(0u, 0u);
+    if (q0 + 64 < nq) n0 = ev2[q0 + 64];
+    if (q0 + 65 < nq) n1 = ev2[q0 + 65];
+    uint32_t mh0, mo0, mm0, mh1, mo1, mm1;
+    quad_masks(e0.x, e0.y, re.a, re.simple, re.L, re.content_len, v0, mh0, mo0, mm0);
+    quad_masks(e1.x, e1.y, re.a, re.simple, re.L, re.content_len, v1, mh1, mo1, mm1);
+    const uint32_t cnt = (__popc(mh0) + __popc(mh1)) | ((__popc(mo0) + __popc(mo1)) << 10) | ((__popc(mm0) + __popc(mm1)) << 20);
     const uint32_t incl = warp_incl_scan(cnt, lane);
     const uint32_t tot = __shfl_sync(FULL, incl, 31);
-    uint32_t k = fill + incl - cnt;
-    while (m) { const int j = (__ffs(m) - 1) >> 2; m &= m - 1; idx[k++] = (IdxT)(s0 + (uint32_t)j); }
-    fill += tot; seen += tot;
-    const bool last = base + 32 >= nq;
-    if (fill + 128 > cap || last) {
-      __syncwarp();
-      if (fill) {
-        const uint32_t len = 8u * fill - ((last || seen >= n_total) ? 1u : 0u);  // n names, n-1 delimiters
-        emit_name_vectors<IdxT>(name8, g + written, idx, fill, len, lane);
-        written += len;
+    const uint32_t excl = incl - cnt;
+    uint32_t kh = fh + (excl & 1023u), ko = fo + ((excl >> 10) & 1023u), km = fm + (excl >> 20);
+    const uint32_t s0 = (e0.x & EV_SAMPLE_MASK) - EV_BASE_BIAS, s1 = (e1.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
+    const uint32_t any0 = mh0 | mo0 | mm0, any1 = mh1 | mo1 | mm1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t bit = 8u << (4 * j);
+      if (any0 & bit) {
+        if (mh0 & bit) ih[kh++] = (IdxT)(s0 + (uint32_t)j);
+        else if (mo0 & bit) io[ko++] = (IdxT)(s0 + (uint32_t)j);
+        else im[km++] = (IdxT)(s0 + (uint32_t)j);
       }
-      fill = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t bit = 8u << (4 * j);
+      if (any1 & bit) {
+        if (mh1 & bit) ih[kh++] = (IdxT)(s1 + (uint32_t)j);
+        else if (mo1 & bit) io[ko++] = (IdxT)(s1 + (uint32_t)j);
+        else im[km++] = (IdxT)(s1 + (uint32_t)j);
+      }
+    }
+    const uint32_t th = tot & 1023u, to = (tot >> 10) & 1023u, tm = tot >> 20;
+    fh += th; fo += to; fm += tm;
+    sh += th; so += to; sm += tm;
+    const bool last = base + 64 >= nq;
+    if (last || fh + 256 > cap3 || fo + 256 > cap3 || fm + 256 > cap3) {
+      __syncwarp();
+      if (fh && (last || fh + 256 > cap3)) {
+        const uint32_t len = 8u * fh - (sh >= n_h ? 1u : 0u);
+        emit_name_vectors<IdxT>(name8, g_h, ih, fh, len, lane);
+        g_h += len; fh = 0;
+      }
+      if (fo && (last || fo + 256 > cap3)) {
+        const uint32_t len = 8u * fo - (so >= n_o ? 1u : 0u);
+        emit_name_vectors<IdxT>(name8, g_o, io, fo, len, lane);
+        g_o += len; fo = 0;
+      }
+      if (fm && (last || fm + 256 > cap3)) {
+        const uint32_t len = 8u * fm - (sm >= n_m ? 1u : 0u);
+        emit_name_vectors<IdxT>(name8, g_m, im, fm, len, lane);
+        g_m += len; fm = 0;
+      }
       __syncwarp();
     }
   }
@@ -167,9 +208,8 @@ __device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned lon
     }
     __syncwarp();
   } else {
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-      if (ns[c]) stream_list<IdxT>(name8, re, c, ns[c], idx, cap, p.out + dsts[c], lane);
+    sweep_lists_chunked<IdxT>(name8, re, idx, cap / 3, p.out + rd.het_dst, p.out + rd.hom_dst, p.out + rd.miss_dst, rd.n_het,
+                              rd.n_hom, rd.n_miss, lane);
   }
 }
 
