@@ -277,17 +277,23 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams 
   }
 }
 
-// warp per record: the records the hybrid kernel queued (long event lists), ballot/popc reductions
+// CTA per record: the records the hybrid kernel queued (long event lists: up to 50,000 quads at biobank width);
+// the eight warps take interleaved 32-quad batches, ballot/popc and REDUX per warp, shared-memory atomics across
 __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsParams p) {
+  __shared__ uint32_t s_wi;
+  __shared__ uint32_t s_acc[3 + 5 * STAT_ALLELES];
   const DevCfg &cfg = p.cfg;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr uint32_t NW = 8;  // warps per CTA (launch: 256 threads)
   if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const uint32_t n_big = p.ctr->n_big_recs;
   const bool fixed = cfg.name_fixed_w > 0;
-  for (;;) {  // warps take the next queued record from a shared cursor
-    uint32_t wi = 0;
-    if (lane == 0) wi = atomicAdd(&p.ctr->big_rec_cursor, 1u);
-    wi = __shfl_sync(FULL, wi, 0);
+  for (;;) {  // CTAs take the next queued record from a shared cursor
+    __syncthreads();
+    if (threadIdx.x == 0) s_wi = atomicAdd(&p.ctr->big_rec_cursor, 1u);
+    if (threadIdx.x < 3 + 5 * STAT_ALLELES) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t wi = s_wi;
     if (wi >= n_big) break;
     const uint32_t li = p.big_recs[wi];
     const LineRec rec = p.lines[li];
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsPar
         // counts with nibble masks; one REDUX per counter at the end
         const uint32_t nq = ev_count >> 1;
         uint32_t lh[STAT_ALLELES] = {0, 0, 0}, lo_[STAT_ALLELES] = {0, 0, 0}, lm = 0;
-        for (uint32_t q = lane; q < nq; q += 32) {
+        for (uint32_t q = warp * 32 + lane; q < nq; q += NW * 32) {
           const uint2 e = *reinterpret_cast<const uint2 *>(ev + 2 * q);
           if (e.x & EV_COMPLEX) {
 #pragma unroll
@@ -336,10 +342,10 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsPar
         for (int a = 0; a < STAT_ALLELES; a++) { n_het[a] = __reduce_add_sync(FULL, lh[a]); n_hom[a] = __reduce_add_sync(FULL, lo_[a]); }
       } else {
       uint32_t off_next;
-      uint32_t w_next = slot_load(ev, lane, ev_count, off_next);
-      for (uint32_t base = 0; base < 2 * ev_count; base += 32) {
+      uint32_t w_next = slot_load(ev, warp * 32 + lane, ev_count, off_next);
+      for (uint32_t base = warp * 32; base < 2 * ev_count; base += NW * 32) {
         const uint32_t w_cur = w_next, off_cur = off_next;  // software pipelining: the next batch is already in flight
-        w_next = slot_load(ev, base + 32 + lane, ev_count, off_next);
+        w_next = slot_load(ev, base + NW * 32 + lane, ev_count, off_next);
         Ev3 e;
         classify3w(w_cur, off_cur, L, content_len, e);
         const uint32_t nl = (e.is_ev && !fixed) ? name_len(cfg, e.samp) : 0;
@@ -355,18 +361,36 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsPar
         }
       }
       }
-      LineStats s;
-      s.n_miss = n_miss; s.pad = 0; s.pad2 = 0;
-      s.an = an0 + warp_sum(an_x);
-      s.miss_bytes = fixed ? n_miss * cfg.name_fixed_w : warp_sum(mb);
+      // warp totals -> shared memory (n_miss, n_het, n_hom are warp-uniform already)
+      const uint32_t w_an = __reduce_add_sync(FULL, an_x), w_mb = __reduce_add_sync(FULL, mb);
+      uint32_t w_ac[STAT_ALLELES], w_hb[STAT_ALLELES], w_ob[STAT_ALLELES];
 #pragma unroll
       for (int a = 0; a < STAT_ALLELES; a++) {
-        s.n_het[a] = n_het[a]; s.n_hom[a] = n_hom[a];
-        s.ac[a] = warp_sum(ac[a]);
-        s.het_bytes[a] = fixed ? n_het[a] * cfg.name_fixed_w : warp_sum(hb[a]);
-        s.hom_bytes[a] = fixed ? n_hom[a] * cfg.name_fixed_w : warp_sum(ob[a]);
+        w_ac[a] = __reduce_add_sync(FULL, ac[a]); w_hb[a] = __reduce_add_sync(FULL, hb[a]); w_ob[a] = __reduce_add_sync(FULL, ob[a]);
       }
-      if (lane == 0) p.stats[lb + l] = s;
+      if (lane == 0) {
+        atomicAdd(&s_acc[0], n_miss); atomicAdd(&s_acc[1], w_an); atomicAdd(&s_acc[2], w_mb);
+#pragma unroll
+        for (int a = 0; a < STAT_ALLELES; a++) {
+          atomicAdd(&s_acc[3 + 5 * a], n_het[a]); atomicAdd(&s_acc[4 + 5 * a], n_hom[a]); atomicAdd(&s_acc[5 + 5 * a], w_ac[a]);
+          atomicAdd(&s_acc[6 + 5 * a], w_hb[a]); atomicAdd(&s_acc[7 + 5 * a], w_ob[a]);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        LineStats s;
+        s.n_miss = s_acc[0]; s.pad = 0; s.pad2 = 0;
+        s.an = an0 + s_acc[1];
+        s.miss_bytes = fixed ? s.n_miss * cfg.name_fixed_w : s_acc[2];
+#pragma unroll
+        for (int a = 0; a < STAT_ALLELES; a++) {
+          s.n_het[a] = s_acc[3 + 5 * a]; s.n_hom[a] = s_acc[4 + 5 * a];
+          s.ac[a] = s_acc[5 + 5 * a];
+          s.het_bytes[a] = fixed ? s.n_het[a] * cfg.name_fixed_w : s_acc[6 + 5 * a];
+          s.hom_bytes[a] = fixed ? s.n_hom[a] * cfg.name_fixed_w : s_acc[7 + 5 * a];
+        }
+        p.stats[lb + l] = s;
+      }
     }
   }
 }
