@@ -595,6 +595,14 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
         const uint32_t so = (stage_off + h * WIN) & (RING - 1);
         if (st.mode == 0 && wi >= seek_limit) { done = true; break; }  // no line starts in this range
         const uint4 v = lds128(ring_lane_s + so);
+        if (st.mode == 0) {
+          // Seeking the first line that starts in this range (half a line on average, most of a range at biobank
+          // width): only a newline matters.  Exact zero-byte test on v ^ '\n', no mask compression.
+          const uint32_t K = 0x7F7F7F7Fu;
+          const uint32_t a = v.x ^ 0x0A0A0A0Au, b = v.y ^ 0x0A0A0A0Au, c = v.z ^ 0x0A0A0A0Au, d = v.w ^ 0x0A0A0A0Au;
+          const uint32_t z = ~((((a & K) + K) | a) & (((b & K) + K) | b) & (((c & K) + K) | c) & (((d & K) + K) | d)) & ~K;
+          if (!__any_sync(FULL, z != 0)) continue;
+        }
         if (fast && hint != 2 - h) {
           const uint32_t w4 = lds32(ring_base_s + ((so + lane * 16 + 16) & (RING - 1)));
           const uint32_t sh = (uint32_t)st.fsr * 8u;

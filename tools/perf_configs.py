@@ -28,7 +28,7 @@ def run(name, seed, ns, shape, n_lines, cfg_kw=None, reps=3):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["C3", "C4", "C5"]
     if "C3" in which: run("C3 sites-only", 50, 0, "sites", int(os.environ.get("C3_LINES", "20000000")))
-    if "C4" in which: run("C4 biobank 200k samples (slice)", 200000, 200000, "biobank", 4000)
+    if "C4" in which: run("C4 biobank 200k samples (slice)", 200000, 200000, "biobank", int(os.environ.get("C4_LINES", "4000")))
     if "C5" in which: run("C5 chr1 filters keepInfo dosage", 20130502, 2504, "chr1_filters", 600000,
                           {"keepInfo": True, "allowedFilters": None, "excludedFilters": {"LowQual": True}})
     if "C5d" in which: run("C5 + dosage", 20130502, 2504, "chr1_filters", 300000,
