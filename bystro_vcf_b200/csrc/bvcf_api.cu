@@ -304,13 +304,19 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       np.in = d_in; np.cfg = dc; np.lines = cp.dense; np.events = sp.events; np.row_desc = (const RowDesc *)sc.row_desc.p;
       np.row_desc_cap = sc.row_cap; np.out = d_out; np.ctr = d_ctr; np.dosage = d_dosage; np.dosage_cap_rows = dosage_cap_rows;
       np.big_rows = (uint32_t *)sc.big_rows.p;
-      bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
       static const bool no_vec = getenv("BVCF_NO_NAMES_VEC") != nullptr;  // experiments
-      if (dc.name8 && dc.want_tsv && !dc.want_dosage && !no_vec) {
-        if (dc.n_samples <= 65000)
+      const bool vec = dc.name8 && dc.want_tsv && !dc.want_dosage && !no_vec;
+      np.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
+      bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
+      if (vec) {
+        if (dc.n_samples <= 65000) {
           bvcf_names_vec_kernel<uint16_t><<<(unsigned)n_sm * 16, NVEC_WARPS * 32, 0, st>>>(np);
-        else
+          bvcf_names_long_kernel<uint16_t><<<(unsigned)n_sm * 2, NLONG_WARPS * 32, 0, st>>>(np);
+        } else {
           bvcf_names_vec_kernel<uint32_t><<<(unsigned)n_sm * 16, NVEC_WARPS * 32, 0, st>>>(np);
+          bvcf_names_long_kernel<uint32_t><<<(unsigned)n_sm * 2, NLONG_WARPS * 32, 0, st>>>(np);
+        }
+        ctx->launches++;
       } else {
         bvcf_names_big_kernel<<<wgrid * 4, NAMES_WARPS * 32, 0, st>>>(np);
       }
@@ -725,6 +731,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
   cudaSetDevice(ctx->device);
   const DevCfg &dc = ctx->dcfg;
   uint32_t retries = 0;
+  uint64_t launches0 = ctx->launches;
   std::vector<StageEvents> timing;
   for (;;) {
     int rc;
@@ -737,6 +744,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
     for (auto &t : timing)
       for (auto e : t.e) ctx->ev_pool.push_back(e);
     timing.clear();
+    launches0 = ctx->launches;
     rc = enqueue_pipeline(ctx, ctx->r_sc, ctx->r_stream, (const uint8_t *)ctx->r_in.p, len, buf_len,
                           (uint8_t *)ctx->r_out.p, ctx->r_out.cap, ctx->r_d_ctr, (int8_t *)ctx->r_dosage.p, dos_rows,
                           (uint8_t *)ctx->r_loci.p, nullptr, times ? &timing : nullptr);
@@ -781,9 +789,9 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->size_ms += ms;
       cudaEventElapsedTime(&ms, t.e[4], t.e[5]); times->emit_ms += ms;
       cudaEventElapsedTime(&ms, t.e[5], t.e[6]); times->names_ms += ms;
-      times->launches += ctx->dcfg.n_samples > 0 ? 14 : 12;
     }
     if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[N_STAGE_EV - 1]);
+    times->launches = (uint32_t)(ctx->launches - launches0);  // of the last (successful) attempt
     for (auto &t : timing)
       for (auto e : t.e) ctx->ev_pool.push_back(e);
   }

@@ -84,6 +84,8 @@ struct RunCounters {
   unsigned int chunk_records;      // records in the current sub-chunk (device-side n for grid-stride kernels)
   unsigned int big_rec_cursor;     // next entry of the stats work list to be taken
   unsigned int n_multi_recs;       // work list of bvcf_rows_list_kernel: records that may yield several rows
+  unsigned int n_long_rows;        // rows with very long event lists: written by a whole CTA (bvcf_names_long_kernel)
+  unsigned int long_row_cursor;
   unsigned int pad1;
 };
 

@@ -113,12 +113,13 @@ __device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx,
 template <typename IdxT>
 __device__ __forceinline__ void sweep_lists_chunked(const unsigned long long *__restrict__ name8, const RowEvents &re,
                                                     IdxT *idx, uint32_t cap3, uint8_t *g_h, uint8_t *g_o, uint8_t *g_m,
-                                                    uint32_t n_h, uint32_t n_o, uint32_t n_m, int lane) {
+                                                    uint32_t n_h, uint32_t n_o, uint32_t n_m, int lane,
+                                                    uint32_t sh = 0, uint32_t so = 0, uint32_t sm = 0) {
+  // sh, so, sm: names of each list before this stretch of quads (a CTA splits a very long row among its warps)
   const uint32_t nq = re.n_words >> 1;
   const uint2 *ev2 = reinterpret_cast<const uint2 *>(re.ev);
   IdxT *const ih = idx, *const io = idx + cap3, *const im = idx + 2 * cap3;
   uint32_t fh = 0, fo = 0, fm = 0;          // names waiting in each region
-  uint32_t sh = 0, so = 0, sm = 0;          // names seen so far per list
   uint2 n0 = make_uint2(0u, 0u), n1 = make_uint2(0u, 0u);
   if (2u * lane < nq) n0 = ev2[2 * lane];
   if (2u * lane + 1 < nq) n1 = ev2[2 * lane + 1];
@@ -228,6 +229,56 @@ __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const N
     wi = __shfl_sync(FULL, wi, 0);
     if (wi >= n_big) break;
     names_row_vec<IdxT>(p, p.big_rows[wi], idx, lane);
+  }
+}
+
+// CTA per very long row (biobank width: tens of thousands of quads, up to megabytes of names).  Each warp takes a
+// contiguous stretch of the row's quads: a counting sweep, a prefix over the eight warps, then the chunked sweep
+// writes the warp's part of the three lists at its offsets.
+constexpr int NLONG_WARPS = 8;
+constexpr int NLONG_IDX_BYTES = 5120;
+template <typename IdxT>
+__global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const NamesParams p) {
+  __shared__ __align__(16) uint8_t s_idx[NLONG_WARPS][NLONG_IDX_BYTES];
+  __shared__ uint32_t s_cnt[NLONG_WARPS][3];
+  __shared__ uint32_t s_wi;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  const DevCfg &cfg = p.cfg;
+  const uint32_t n_long = p.ctr->n_long_rows;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_wi = atomicAdd(&p.ctr->long_row_cursor, 1u);
+    __syncthreads();
+    const uint32_t wi = s_wi;
+    if (wi >= n_long) break;
+    const RowDesc rd = p.row_desc[p.big_rows[p.row_desc_cap - 1 - wi]];
+    const LineRec rec = p.lines[rd.line];
+    const uint32_t nq = rec.ev_count >> 1;
+    const uint32_t seg = ((nq + NLONG_WARPS - 1) / NLONG_WARPS + 63u) & ~63u;  // whole 64-quad steps
+    const uint32_t q_lo = warp * seg < nq ? warp * seg : nq, q_hi = q_lo + seg < nq ? q_lo + seg : nq;
+    RowEvents re;
+    re.ev = p.events + rec.ev_start + 2 * q_lo; re.n_words = 2 * (q_hi - q_lo); re.L = p.in + rec.start;
+    re.content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
+    re.a = rd.allele; re.simple = !(rec.flags & 1) && rd.allele == 1;
+    // counting sweep
+    uint32_t ch = 0, co = 0, cm = 0;
+    const uint2 *ev2 = reinterpret_cast<const uint2 *>(re.ev);
+    for (uint32_t q = lane; q < q_hi - q_lo; q += 32) {
+      const uint2 e = ev2[q];
+      uint32_t mh, mo, mm;
+      quad_masks(e.x, e.y, re.a, re.simple, re.L, re.content_len, true, mh, mo, mm);
+      ch += __popc(mh); co += __popc(mo); cm += __popc(mm);
+    }
+    ch = __reduce_add_sync(FULL, ch); co = __reduce_add_sync(FULL, co); cm = __reduce_add_sync(FULL, cm);
+    if (lane == 0) { s_cnt[warp][0] = ch; s_cnt[warp][1] = co; s_cnt[warp][2] = cm; }
+    __syncthreads();
+    uint32_t ph = 0, po = 0, pm = 0;
+    for (int w = 0; w < warp; w++) { ph += s_cnt[w][0]; po += s_cnt[w][1]; pm += s_cnt[w][2]; }
+    const uint32_t cap3 = (NLONG_IDX_BYTES / sizeof(IdxT)) / 3;
+    sweep_lists_chunked<IdxT>(cfg.name8, re, reinterpret_cast<IdxT *>(s_idx[warp]), cap3, p.out + rd.het_dst + 8ull * ph,
+                              p.out + rd.hom_dst + 8ull * po, p.out + rd.miss_dst + 8ull * pm, rd.n_het, rd.n_hom, rd.n_miss,
+                              lane, ph, po, pm);
   }
 }
 

@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(1024) bvcf_prefix_spine_kernel(const PrefixPar
     } else if (!(c->ev_overflow | c->slot_overflow)) {  // sizes are garbage after a scratch overflow: leave the cursors
       c->n_big_rows = 0;
       c->big_row_cursor = 0;
+      c->n_long_rows = 0;
+      c->long_row_cursor = 0;
       c->chunk_out_base = c->out_cursor;
       c->chunk_row_base = c->row_cursor;
       c->out_cursor += sa[t];

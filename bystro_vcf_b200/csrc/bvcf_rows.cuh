@@ -1002,7 +1002,10 @@ struct NamesParams {
   RunCounters *ctr;
   int8_t *dosage;
   unsigned long long dosage_cap_rows;
-  uint32_t *big_rows;        // work list: rows written by a whole warp (bvcf_names_big_kernel)
+  uint32_t *big_rows;        // work list: rows written by a whole warp (bvcf_names_big_kernel / _vec_)
+  // rows with more than long_words event words are queued from the END of big_rows (row_desc_cap entries) for
+  // bvcf_names_long_kernel, a CTA per row; 0: no such kernel follows
+  uint32_t long_words;
 };
 
 // one row, whole warp: ballot/popc ranks, ordered scatter of the names (and the dosage row)
@@ -1212,19 +1215,30 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
     const unsigned long long r = rb + lane;
     const bool valid = r < n_rows;
     bool small = false;
+    uint32_t ev_words = 0;
     if (valid && !cfg.want_dosage && cfg.want_tsv) {
       const RowDesc rd = p.row_desc[r];
       const LineRec rec = p.lines[rd.line];
+      ev_words = rec.ev_count;
       small = rec.ev_count <= SMALL_EVENTS;
       if (small) names_row_lane(p, rd, rec);
     }
-    // long rows go to the work list of the warp-per-row kernel (one atomic per warp)
-    const uint32_t big = __ballot_sync(FULL, valid && !small);
+    // long rows go to the work list of the warp-per-row kernel (one atomic per warp), very long ones to the
+    // CTA-per-row kernel's
+    const bool very = valid && !small && p.long_words && ev_words > p.long_words;
+    const uint32_t big = __ballot_sync(FULL, valid && !small && !very);
     if (big) {
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(&p.ctr->n_big_rows, (unsigned int)__popc(big));
       base = __shfl_sync(FULL, base, 0);
-      if (valid && !small) p.big_rows[base + __popc(big & ((1u << lane) - 1u))] = (uint32_t)r;
+      if (valid && !small && !very) p.big_rows[base + __popc(big & ((1u << lane) - 1u))] = (uint32_t)r;
+    }
+    const uint32_t vm = __ballot_sync(FULL, very);
+    if (vm) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&p.ctr->n_long_rows, (unsigned int)__popc(vm));
+      base = __shfl_sync(FULL, base, 0);
+      if (very) p.big_rows[p.row_desc_cap - 1 - (base + __popc(vm & ((1u << lane) - 1u)))] = (uint32_t)r;
     }
   }
 }
