@@ -188,17 +188,18 @@ __device__ __forceinline__ uint32_t bad_digits8(const uint32_t ta[4], const uint
   const uint32_t o = ta[0] | ta[1] | ta[2] | ta[3] | tb[0] | tb[1] | tb[2] | tb[3];
   return (o & 0xFFF0FFF0u) | (((o & 0x000F000Fu) + 0x00060006u) & 0x00100010u);
 }
+// Exact test with '.' allowed: every allele byte (XORed with '0') is 0..9 or 0x1E, every other byte 0.
+// With all bytes below 0x20 (first term), b + 22 carries into bit 5 iff b >= 10, b + 2 iff b >= 30, b + 1 iff b == 31:
+// bad iff 10 <= b <= 29 or b == 31.
 __device__ __forceinline__ uint32_t bad_digits_or_dots4(const uint32_t t[4], uint32_t keep_mask3) {
-  const uint32_t D = 0x00760076u, H = 0x00800080u, M = 0x00FF00FFu;
-  uint32_t bad = (t[0] | t[1] | t[2] | (t[3] & keep_mask3)) & ~M;
+  const uint32_t o = t[0] | t[1] | t[2] | (t[3] & keep_mask3);
+  uint32_t acc = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const uint32_t u = t[j] & M;
-    const uint32_t d = u ^ 0x001E001Eu;
-    const uint32_t notdot = (((d & 0x007F007Fu) + 0x007F007Fu) | d) & H;  // 0x80 where the byte is not '.'
-    bad |= ((u + D) & H) & notdot;
+    const uint32_t x = t[j] + 0x00160016u, y = t[j] + 0x00020002u, z = t[j] + 0x00010001u;
+    acc |= (x & ~y) | z;
   }
-  return bad;
+  return (o & 0xFFE0FFE0u) | (acc & 0x00200020u);
 }
 
 // ---- T3: the general window ------------------------------------------------------------------------
