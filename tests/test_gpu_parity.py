@@ -247,3 +247,39 @@ def test_dosage_arrow_file_like_reference(tmp_path):
     assert out2.getvalue() == b""
     with pa.OSFile(str(path), "rb") as f:
         assert pa.ipc.open_file(f).read_all().num_rows == 3
+
+
+def test_odd_bytes_in_regular_genotype_zones():
+    """Bytes that are neither a digit nor '.' where an allele belongs, inside otherwise regular `x|y` zones (the
+    vector tiers of the scan kernel must hand such windows to the field-by-field path): high-bit bytes whose low
+    nibble looks like a digit, '/', ':' and letters, next to missing and multi-allelic samples."""
+    import random
+
+    rng = random.Random(7)
+    n = 700  # several 512-byte windows per line
+    hdr = V.HDR8 + ["FORMAT"] + ["ZZ%05d" % i for i in range(n)]  # 7-character names: the vector names path
+    odd = [b"\xba", b"\xbf", b"\x8a", b"/", b"?", b"N", b"\x1e", b"\x3a", b"\xb1", b"\xfe"]
+    recs = []
+    for r in range(40):
+        fields = []
+        for i in range(n):
+            u = rng.random()
+            if u < 0.90:
+                f = b"0|0"
+            elif u < 0.93:
+                f = b"0|1" if rng.random() < 0.5 else b"1|1"
+            elif u < 0.95:
+                f = b".|." if rng.random() < 0.5 else b"0|."
+            elif u < 0.97:
+                f = b"2|1"
+            else:
+                a = odd[rng.randrange(len(odd))]
+                f = (a + b"|1") if rng.random() < 0.5 else (b"1|" + a)
+            fields.append(f)
+        fixed = [b"1", str(1000 + r).encode(), b".", b"A", b"C,G", b".", b"PASS", b".", b"GT"]
+        recs.append(b"\t".join(fixed + fields))
+    vcf = (V.VERSION + "\n" + "\t".join(hdr) + "\n").encode() + b"\n".join(recs) + b"\n"
+    got = gpu_rows(vcf)
+    exp = oracle_rows(vcf)
+    assert got == exp
+    assert len(got) > 1000
