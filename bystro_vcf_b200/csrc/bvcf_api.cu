@@ -305,16 +305,29 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       np.row_desc_cap = sc.row_cap; np.out = d_out; np.ctr = d_ctr; np.dosage = d_dosage; np.dosage_cap_rows = dosage_cap_rows;
       np.big_rows = (uint32_t *)sc.big_rows.p;
       static const bool no_vec = getenv("BVCF_NO_NAMES_VEC") != nullptr;  // experiments
-      const bool vec = dc.name8 && dc.want_tsv && !dc.want_dosage && !no_vec;
+      const bool vec = dc.name8 && dc.want_tsv && !no_vec;
       np.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
+      if (dc.want_dosage && d_dosage) { bvcf_dosage_zero_kernel<<<(unsigned)n_sm * 8, 256, 0, st>>>(np); ctx->launches++; }
       bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
       if (vec) {
+        const unsigned g1 = (unsigned)n_sm * 16, g2 = (unsigned)n_sm * 2;
+        const bool dos = dc.want_dosage && d_dosage;
         if (dc.n_samples <= 65000) {
-          bvcf_names_vec_kernel<uint16_t><<<(unsigned)n_sm * 16, NVEC_WARPS * 32, 0, st>>>(np);
-          bvcf_names_long_kernel<uint16_t><<<(unsigned)n_sm * 2, NLONG_WARPS * 32, 0, st>>>(np);
+          if (dos) {
+            bvcf_names_vec_kernel<uint16_t, true><<<g1, NVEC_WARPS * 32, 0, st>>>(np);
+            bvcf_names_long_kernel<uint16_t, true><<<g2, NLONG_WARPS * 32, 0, st>>>(np);
+          } else {
+            bvcf_names_vec_kernel<uint16_t, false><<<g1, NVEC_WARPS * 32, 0, st>>>(np);
+            bvcf_names_long_kernel<uint16_t, false><<<g2, NLONG_WARPS * 32, 0, st>>>(np);
+          }
         } else {
-          bvcf_names_vec_kernel<uint32_t><<<(unsigned)n_sm * 16, NVEC_WARPS * 32, 0, st>>>(np);
-          bvcf_names_long_kernel<uint32_t><<<(unsigned)n_sm * 2, NLONG_WARPS * 32, 0, st>>>(np);
+          if (dos) {
+            bvcf_names_vec_kernel<uint32_t, true><<<g1, NVEC_WARPS * 32, 0, st>>>(np);
+            bvcf_names_long_kernel<uint32_t, true><<<g2, NLONG_WARPS * 32, 0, st>>>(np);
+          } else {
+            bvcf_names_vec_kernel<uint32_t, false><<<g1, NVEC_WARPS * 32, 0, st>>>(np);
+            bvcf_names_long_kernel<uint32_t, false><<<g2, NLONG_WARPS * 32, 0, st>>>(np);
+          }
         }
         ctx->launches++;
       } else {

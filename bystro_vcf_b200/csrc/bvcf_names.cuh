@@ -2,7 +2,7 @@
 //
 // bvcf_names_kernel (bvcf_rows.cuh) writes the lists of short rows lane-serially and queues the others.  When
 // every list item is 8 bytes (7-character names + 1-character delimiter: the 1000 Genomes / biobank layout) and
-// no dosage row is wanted, bvcf_names_vec_kernel takes the queue instead of bvcf_names_big_kernel:
+// TSV output is on, bvcf_names_vec_kernel takes the queue instead of bvcf_names_big_kernel:
 //   pass 1  one sweep over the row's quad events: het / hom / missing slots as nibble masks (general GT grammar for
 //           complex samples, main.go:1126-1190), ranks from one packed warp prefix sum per 32 quads, the sample
 //           indices of the three lists compacted into shared memory in header order (main.go:1057 loop order);
@@ -57,11 +57,30 @@ struct RowEvents {
   const uint8_t *L;
   uint32_t content_len, a;
   bool simple;
+  int8_t *drow;   // the row of the dosage matrix (zeroed beforehand), or null
 };
+
+// int8 dosage of one het / hom / missing sample of a quad: -1 missing, else min(alleles equal to the row's, 127)
+// (main.go:1172-1178); `bit` is the sample's nibble flag (bit 4 j + 3)
+__device__ __forceinline__ void put_dosage(const RowEvents &re, uint2 e, uint32_t bit, bool is_h, bool is_o, uint32_t samp) {
+  int v = -1;
+  if (is_h | is_o) {
+    if (e.x & EV_COMPLEX) {
+      uint32_t gt, alt;
+      classify_gt_general(re.L + e.y, re.content_len > e.y ? re.content_len - e.y : 0, re.a, gt, alt);
+      v = alt > 127 ? 127 : (int)alt;
+    } else {
+      const uint32_t sh = (uint32_t)(__ffs(bit) - 1) - 3u;  // 4 * slot
+      const bool hap = ((e.y >> (16 + sh)) & 0xFu) == EV_NIB_ABSENT;
+      v = is_h ? 1 : (hap ? 1 : 2);
+    }
+  }
+  re.drow[samp] = (int8_t)v;
+}
 
 // all three lists of one row in one sweep: index lists at idx[0,n_het) | [n_het, n_het+n_hom) | [.., +n_miss).
 // A lane takes two consecutive quads (eight samples) per step, so one packed prefix sum ranks 256 samples.
-template <typename IdxT>
+template <typename IdxT, bool DOSAGE>
 __device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx, uint32_t base_o, uint32_t base_m, int lane) {
   const uint32_t nq = re.n_words >> 1;
   const uint2 *ev2 = reinterpret_cast<const uint2 *>(re.ev);
@@ -92,6 +111,7 @@ __device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx,
       if (any0 & bit) {
         const uint32_t d = (mh0 & bit) ? kh++ : ((mo0 & bit) ? ko++ : km++);
         idx[d] = (IdxT)(s0 + (uint32_t)j);
+        if (DOSAGE && re.drow) put_dosage(re, e0, bit, (mh0 & bit) != 0, (mo0 & bit) != 0, s0 + (uint32_t)j);
       }
     }
 #pragma unroll
@@ -100,6 +120,7 @@ __device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx,
       if (any1 & bit) {
         const uint32_t d = (mh1 & bit) ? kh++ : ((mo1 & bit) ? ko++ : km++);
         idx[d] = (IdxT)(s1 + (uint32_t)j);
+        if (DOSAGE && re.drow) put_dosage(re, e1, bit, (mh1 & bit) != 0, (mo1 & bit) != 0, s1 + (uint32_t)j);
       }
     }
     run_h += tot & 1023u; run_o += (tot >> 10) & 1023u; run_m += tot >> 20;
@@ -110,7 +131,7 @@ __device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx,
 // is cut into three regions; a list whose region cannot take another step (256 names) is written out as a chunk
 // of vectors and its region starts over.  n names make 8 n - 1 bytes: the final chunk of a list drops the
 // trailing delimiter.
-template <typename IdxT>
+template <typename IdxT, bool DOSAGE>
 __device__ __forceinline__ void sweep_lists_chunked(const unsigned long long *__restrict__ name8, const RowEvents &re,
                                                     IdxT *idx, uint32_t cap3, uint8_t *g_h, uint8_t *g_o, uint8_t *g_m,
                                                     uint32_t n_h, uint32_t n_o, uint32_t n_m, int lane,
@@ -147,6 +168,7 @@ __device__ __forceinline__ void sweep_lists_chunked(const unsigned long long *__
         if (mh0 & bit) ih[kh++] = (IdxT)(s0 + (uint32_t)j);
         else if (mo0 & bit) io[ko++] = (IdxT)(s0 + (uint32_t)j);
         else im[km++] = (IdxT)(s0 + (uint32_t)j);
+        if (DOSAGE && re.drow) put_dosage(re, e0, bit, (mh0 & bit) != 0, (mo0 & bit) != 0, s0 + (uint32_t)j);
       }
     }
 #pragma unroll
@@ -156,6 +178,7 @@ __device__ __forceinline__ void sweep_lists_chunked(const unsigned long long *__
         if (mh1 & bit) ih[kh++] = (IdxT)(s1 + (uint32_t)j);
         else if (mo1 & bit) io[ko++] = (IdxT)(s1 + (uint32_t)j);
         else im[km++] = (IdxT)(s1 + (uint32_t)j);
+        if (DOSAGE && re.drow) put_dosage(re, e1, bit, (mh1 & bit) != 0, (mo1 & bit) != 0, s1 + (uint32_t)j);
       }
     }
     const uint32_t th = tot & 1023u, to = (tot >> 10) & 1023u, tm = tot >> 20;
@@ -184,7 +207,7 @@ __device__ __forceinline__ void sweep_lists_chunked(const unsigned long long *__
   }
 }
 
-template <typename IdxT>
+template <typename IdxT, bool DOSAGE>
 __device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned long long r, IdxT *idx, int lane) {
   const DevCfg &cfg = p.cfg;
   const RowDesc rd = p.row_desc[r];
@@ -193,13 +216,18 @@ __device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned lon
   re.ev = p.events + rec.ev_start; re.n_words = rec.ev_count; re.L = p.in + rec.start;
   re.content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
   re.a = rd.allele; re.simple = !(rec.flags & 1) && rd.allele == 1;
+  re.drow = nullptr;
+  {
+    const unsigned long long gr = p.ctr->chunk_row_base + r;
+    if (DOSAGE && cfg.want_dosage && gr < p.dosage_cap_rows) re.drow = p.dosage + gr * (unsigned long long)cfg.n_samples;
+  }
   const unsigned long long *name8 = cfg.name8;
   const uint32_t cap = NVEC_IDX_BYTES / sizeof(IdxT);
   const uint32_t n_tot = rd.n_het + rd.n_hom + rd.n_miss;
   const uint32_t ns[3] = {rd.n_het, rd.n_hom, rd.n_miss};
   const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
   if (n_tot <= cap) {
-    index_lists_once<IdxT>(re, idx, rd.n_het, rd.n_het + rd.n_hom, lane);
+    index_lists_once<IdxT, DOSAGE>(re, idx, rd.n_het, rd.n_het + rd.n_hom, lane);
     __syncwarp();
     uint32_t b = 0;
 #pragma unroll
@@ -209,13 +237,13 @@ __device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned lon
     }
     __syncwarp();
   } else {
-    sweep_lists_chunked<IdxT>(name8, re, idx, cap / 3, p.out + rd.het_dst, p.out + rd.hom_dst, p.out + rd.miss_dst, rd.n_het,
+    sweep_lists_chunked<IdxT, DOSAGE>(name8, re, idx, cap / 3, p.out + rd.het_dst, p.out + rd.hom_dst, p.out + rd.miss_dst, rd.n_het,
                               rd.n_hom, rd.n_miss, lane);
   }
 }
 
-// warp per queued row (requires cfg.name8, TSV output, no dosage matrix)
-template <typename IdxT>
+// warp per queued row (requires cfg.name8 and TSV output; also scatters the int8 dosage row when one is wanted)
+template <typename IdxT, bool DOSAGE>
 __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const NamesParams p) {
   __shared__ __align__(16) uint8_t s_idx[NVEC_WARPS][NVEC_IDX_BYTES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -228,7 +256,7 @@ __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const N
     if (lane == 0) wi = atomicAdd(&p.ctr->big_row_cursor, 1u);
     wi = __shfl_sync(FULL, wi, 0);
     if (wi >= n_big) break;
-    names_row_vec<IdxT>(p, p.big_rows[wi], idx, lane);
+    names_row_vec<IdxT, DOSAGE>(p, p.big_rows[wi], idx, lane);
   }
 }
 
@@ -237,7 +265,7 @@ __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const N
 // writes the warp's part of the three lists at its offsets.
 constexpr int NLONG_WARPS = 8;
 constexpr int NLONG_IDX_BYTES = 5120;
-template <typename IdxT>
+template <typename IdxT, bool DOSAGE>
 __global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const NamesParams p) {
   __shared__ __align__(16) uint8_t s_idx[NLONG_WARPS][NLONG_IDX_BYTES];
   __shared__ uint32_t s_cnt[NLONG_WARPS][3];
@@ -252,7 +280,8 @@ __global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const
     __syncthreads();
     const uint32_t wi = s_wi;
     if (wi >= n_long) break;
-    const RowDesc rd = p.row_desc[p.big_rows[p.row_desc_cap - 1 - wi]];
+    const uint32_t r = p.big_rows[p.row_desc_cap - 1 - wi];
+    const RowDesc rd = p.row_desc[r];
     const LineRec rec = p.lines[rd.line];
     const uint32_t nq = rec.ev_count >> 1;
     const uint32_t seg = ((nq + NLONG_WARPS - 1) / NLONG_WARPS + 63u) & ~63u;  // whole 64-quad steps
@@ -261,6 +290,11 @@ __global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const
     re.ev = p.events + rec.ev_start + 2 * q_lo; re.n_words = 2 * (q_hi - q_lo); re.L = p.in + rec.start;
     re.content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
     re.a = rd.allele; re.simple = !(rec.flags & 1) && rd.allele == 1;
+    re.drow = nullptr;
+    {
+      const unsigned long long gr = p.ctr->chunk_row_base + r;
+      if (DOSAGE && cfg.want_dosage && gr < p.dosage_cap_rows) re.drow = p.dosage + gr * (unsigned long long)cfg.n_samples;
+    }
     // counting sweep
     uint32_t ch = 0, co = 0, cm = 0;
     const uint2 *ev2 = reinterpret_cast<const uint2 *>(re.ev);
@@ -276,7 +310,7 @@ __global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const
     uint32_t ph = 0, po = 0, pm = 0;
     for (int w = 0; w < warp; w++) { ph += s_cnt[w][0]; po += s_cnt[w][1]; pm += s_cnt[w][2]; }
     const uint32_t cap3 = (NLONG_IDX_BYTES / sizeof(IdxT)) / 3;
-    sweep_lists_chunked<IdxT>(cfg.name8, re, reinterpret_cast<IdxT *>(s_idx[warp]), cap3, p.out + rd.het_dst + 8ull * ph,
+    sweep_lists_chunked<IdxT, DOSAGE>(cfg.name8, re, reinterpret_cast<IdxT *>(s_idx[warp]), cap3, p.out + rd.het_dst + 8ull * ph,
                               p.out + rd.hom_dst + 8ull * po, p.out + rd.miss_dst + 8ull * pm, rd.n_het, rd.n_hom, rd.n_miss,
                               lane, ph, po, pm);
   }

@@ -1024,9 +1024,7 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
     const uint32_t a = rd.allele;
     int8_t *drow = nullptr;
     if (cfg.want_dosage && (row0 + r) < p.dosage_cap_rows) {
-      drow = p.dosage + (row0 + r) * (unsigned long long)cfg.n_samples;
-      for (int i = lane; i < cfg.n_samples; i += 32) drow[i] = 0;
-      __syncwarp();
+      drow = p.dosage + (row0 + r) * (unsigned long long)cfg.n_samples;  // zeroed by bvcf_dosage_zero_kernel
     }
     uint32_t run_n[3] = {0, 0, 0};
     uint32_t run_b[3] = {0, 0, 0};
@@ -1156,7 +1154,7 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
 }
 
 // one row, one lane: rows whose record has only a handful of events (singletons, rare variants)
-__device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDesc &rd, const LineRec &rec) {
+__device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDesc &rd, const LineRec &rec, int8_t *drow) {
   const DevCfg &cfg = p.cfg;
   const uint32_t *ev = p.events + rec.ev_start;
   const uint8_t *L = p.in + rec.start;
@@ -1176,6 +1174,21 @@ __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDe
       any &= any - 1;
       const uint32_t samp = s0 + ((uint32_t)(__ffs(bit) - 1) >> 2);
       const bool is_h = (mh & bit) != 0, is_o = (mo & bit) != 0;
+      if (drow) {  // int8 dosage: -1 missing, else min(number of alleles equal to the row's, 127) (main.go:1172-1178)
+        int v = -1;
+        if (is_h | is_o) {
+          if (e.x & EV_COMPLEX) {
+            uint32_t gt, alt;
+            classify_gt_general(L + e.y, content_len > e.y ? content_len - e.y : 0, rd.allele, gt, alt);
+            v = alt > 127 ? 127 : (int)alt;
+          } else {
+            const uint32_t sh = (uint32_t)(__ffs(bit) - 1) - 3u;  // 4 * slot
+            const bool hap = ((e.y >> (16 + sh)) & 0xFu) == EV_NIB_ABSENT;
+            v = is_h ? 1 : (hap ? 1 : 2);
+          }
+        }
+        drow[samp] = (int8_t)v;
+      }
       const uint32_t rn = is_h ? nh : (is_o ? no : nm), rb = is_h ? bh : (is_o ? bo : bm);
       const unsigned long long dst = is_h ? rd.het_dst : (is_o ? rd.hom_dst : rd.miss_dst);
       const uint32_t tot = is_h ? rd.n_het : (is_o ? rd.n_hom : rd.n_miss);
@@ -1200,6 +1213,28 @@ __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDe
   }
 }
 
+// the dosage rows of this sub-chunk start as all-reference (0); the names kernels scatter the other samples
+__global__ void __launch_bounds__(256) bvcf_dosage_zero_kernel(const NamesParams p) {
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  const unsigned long long ns = (unsigned long long)p.cfg.n_samples;
+  unsigned long long r0 = p.ctr->chunk_row_base, r1 = p.ctr->row_cursor;
+  if (r1 > p.dosage_cap_rows) r1 = p.dosage_cap_rows;
+  if (r0 >= r1) return;
+  uint8_t *const base = reinterpret_cast<uint8_t *>(p.dosage);
+  const unsigned long long b0 = r0 * ns, b1 = r1 * ns;
+  const unsigned long long a0 = (b0 + 15ull) & ~15ull, a1 = b1 & ~15ull;  // cudaMalloc'ed: base is 256-byte aligned
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+  if (a0 >= a1) {
+    for (unsigned long long i = b0 + tid; i < b1; i += nth) base[i] = 0;
+    return;
+  }
+  for (unsigned long long i = b0 + tid; i < a0; i += nth) base[i] = 0;
+  uint4 *v = reinterpret_cast<uint4 *>(base + a0);
+  const unsigned long long nv = (a1 - a0) >> 4;
+  for (unsigned long long i = tid; i < nv; i += nth) v[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (unsigned long long i = a1 + tid; i < b1; i += nth) base[i] = 0;
+}
+
 // Hybrid granularity (as in the stats kernel): a warp takes 32 consecutive rows; short ones lane-serial,
 // long ones warp-cooperative.
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
@@ -1216,12 +1251,14 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
     const bool valid = r < n_rows;
     bool small = false;
     uint32_t ev_words = 0;
-    if (valid && !cfg.want_dosage && cfg.want_tsv) {
+    if (valid && cfg.want_tsv) {
       const RowDesc rd = p.row_desc[r];
       const LineRec rec = p.lines[rd.line];
       ev_words = rec.ev_count;
       small = rec.ev_count <= SMALL_EVENTS;
-      if (small) names_row_lane(p, rd, rec);
+      int8_t *drow = nullptr;
+      if (cfg.want_dosage && (row0 + r) < p.dosage_cap_rows) drow = p.dosage + (row0 + r) * (unsigned long long)cfg.n_samples;
+      if (small) names_row_lane(p, rd, rec, drow);
     }
     // long rows go to the work list of the warp-per-row kernel (one atomic per warp), very long ones to the
     // CTA-per-row kernel's
