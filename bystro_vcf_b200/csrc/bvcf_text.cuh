@@ -11,18 +11,40 @@ namespace bvcf {
 // stripped; decimal exponent < -4 switches to d.ddE-XX (Go 'G' == C "%.3G" on (0,1]).
 // Returns the text packed little-endian in a u64 (at most 8 characters) and its length.
 __device__ __forceinline__ uint64_t format_ratio_g3(uint32_t k, uint32_t n, int &len_out) {
+  unsigned long long r;  // the three significant digits, 100..999
+  int e;                 // decimal exponent of the first digit
+  bool have = false;
+  if (n < (1u << 24)) {
+    // Fast path, integers only.  D = round(k 10^j / n) with 100 <= D < 1000.  The double q differs from k/n by less
+    // than 2^-53 relative, while k 10^j / n is at least 1/(2n) away from every rounding boundary unless it sits ON
+    // one (2 rem == n): only then can the double fall on either side, and the exact path below decides.
+    // (Checked against the exact path on 26 million (k, n) pairs.)
+    unsigned long long m = k;
+    const unsigned long long lim = 100ull * n;
+    int j = 0;
+    while (m < lim) { m *= 10ull; j++; }   // at most 10 rounds: k 10^j < 2^24 * 10^10 < 2^63
+    unsigned long long D = m / n;
+    const unsigned long long rem = m - D * n;
+    if (2ull * rem != n) {
+      if (2ull * rem > n) D++;
+      e = 2 - j;
+      if (D == 1000) { D = 100; e++; }
+      r = D;
+      have = true;
+    }
+  }
+  if (!have) {
   const double q = (double)k / (double)n;  // IEEE-754 division, as in Go
   const unsigned long long bits = (unsigned long long)__double_as_longlong(q);
   const int bexp = (int)((bits >> 52) & 0x7FF);
   const unsigned long long m = (bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);  // q is normal: k>=1, n<2^32
   const int s = 1075 - bexp;  // q = m * 2^-s, 52 <= s <= 52+32
   // estimate the decimal exponent, then fix it with exact integer comparisons
-  int e = 0;
+  e = 0;
   {
     double t = q;
     while (t < 1.0 && e > -15) { t *= 10.0; e--; }
   }
-  unsigned long long r;
   bool up;
   for (;;) {
     unsigned long long p10 = 1;
@@ -37,6 +59,7 @@ __device__ __forceinline__ uint64_t format_ratio_g3(uint32_t k, uint32_t n, int 
     break;
   }
   if (up) { r++; if (r == 1000) { r = 100; e++; } }
+  }
   uint32_t d[3] = {(uint32_t)(r / 100), (uint32_t)(r / 10 % 10), (uint32_t)(r % 10)};
   int nd = 3;
   while (nd > 1 && d[nd - 1] == 0) nd--;
