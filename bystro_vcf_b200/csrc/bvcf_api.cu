@@ -310,7 +310,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       if (dc.want_dosage && d_dosage) { bvcf_dosage_zero_kernel<<<(unsigned)n_sm * 8, 256, 0, st>>>(np); ctx->launches++; }
       bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
       if (vec) {
-        const unsigned g1 = (unsigned)n_sm * 16, g2 = (unsigned)n_sm * 2;
+        const unsigned g1 = (unsigned)n_sm * 18, g2 = (unsigned)n_sm * 2;
         const bool dos = dc.want_dosage && d_dosage;
         if (dc.n_samples <= 65000) {
           if (dos) {

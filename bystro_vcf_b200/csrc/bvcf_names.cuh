@@ -16,7 +16,7 @@
 namespace bvcf {
 
 constexpr int NVEC_WARPS = 2;
-constexpr int NVEC_IDX_BYTES = 6144;   // per-warp index buffer: 3072 samples (16-bit) / 1536 (32-bit) per sweep
+constexpr int NVEC_IDX_BYTES = 5632;   // per-warp index buffer: 2816 samples (16-bit) / 1408 (32-bit) per sweep
 
 // `n` names, given by sample index in idx[0, n) (shared memory), as list bytes [g, g + len) of the output,
 // len <= 8 n

@@ -145,7 +145,7 @@ __device__ __forceinline__ bool atoi_go(const uint8_t *p, int n, long long &out)
   for (; i < n; i++) {
     const unsigned d = (unsigned)p[i] - '0';
     if (d > 9) return false;
-    if (v > (0xFFFFFFFFFFFFFFFFull - d) / 10) return false;
+    if (v > 1844674407370955161ull || (v == 1844674407370955161ull && d > 5)) return false;  // v * 10 + d > 2^64 - 1
     v = v * 10 + d;
   }
   if (!neg && v > 0x7FFFFFFFFFFFFFFFull) return false;
