@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 CMD="python bench.py --lines $LINES --steps 2 --warmup 3 --e2e-lines 20000 --no-cpu-baseline"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_l_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:bvcf_ -s 28 -c 14 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:bvcf_ -s 30 -c 15 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
 tail -1 gpurun_out/plain_$TAG.log | cut -c1-900
 tail -3 gpurun_out/ncu_f_$TAG.log
 ls -la gpurun_out
