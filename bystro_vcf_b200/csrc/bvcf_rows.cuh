@@ -480,7 +480,11 @@ struct RowWriter {
     }
     fill = nf;
   }
-  __device__ __forceinline__ void byte(uint8_t c) { if (WRITE) packed((uint64_t)c, 1); else count++; }
+  __device__ __forceinline__ void byte(uint8_t c) {
+    if (!WRITE) { count++; return; }
+    acc |= (unsigned long long)c << (8 * fill);
+    if (++fill == 8) { store8_unaligned(g, acc); g += 8; acc = 0; fill = 0; }
+  }
   __device__ __forceinline__ void span(const uint8_t *p, int len) {
     if (!WRITE) { count += len; return; }
     for (int i = 0; i < len; i += 8) {
@@ -596,21 +600,30 @@ __device__ __forceinline__ void emit_row(const RowsParams &p, const LineRec &rec
 
   if (cfg.want_tsv) {
     // chrom (main.go:570-574)
-    if (lc.chrom_n < 4 || lc.chrom[0] != 'c') { w.byte('c'); w.byte('h'); w.byte('r'); }
+    if (lc.chrom_n < 4 || lc.chrom[0] != 'c') w.packed(0x726863ull, 3);  // "chr"
     w.span_in(lc.chrom, lc.chrom_n);
     w.byte('\t');
     if (oa.pos_verbatim) w.span_in(lc.pos, lc.pos_n); else w.dec(oa.pos_val);
-    w.byte('\t');
-    w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
-    w.byte('\t');
-    w.byte(oa.ref);
-    w.byte('\t');
-    if (oa.kind == 0) w.byte(oa.alt_c);
-    else if (oa.kind == 1) { w.byte('+'); w.span_in(oa.ins_p, oa.ins_n); }
-    else w.dec(oa.del_n);
-    w.byte('\t');
-    w.byte(lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0'));  // main.go:602-606
-    w.byte('\t');
+    if (lc.site_type != T_MULTI) {  // "\tSNP\t": the three-letter types as one piece
+      const uint8_t *tt = (const uint8_t *)TYPE_TXT[lc.site_type];
+      w.packed(0x09ull | ((uint64_t)tt[0] << 8) | ((uint64_t)tt[1] << 16) | ((uint64_t)tt[2] << 24) | (0x09ull << 32), 5);
+    } else {
+      w.byte('\t');
+      w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
+      w.byte('\t');
+    }
+    const uint8_t trtv = lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0');  // main.go:602-606
+    if (oa.kind == 0) {  // "R\tA\tt\t" as one piece
+      w.packed((uint64_t)oa.ref | (0x09ull << 8) | ((uint64_t)oa.alt_c << 16) | (0x09ull << 24) | ((uint64_t)trtv << 32) | (0x09ull << 40), 6);
+    } else {
+      w.byte(oa.ref);
+      w.byte('\t');
+      if (oa.kind == 1) { w.byte('+'); w.span_in(oa.ins_p, oa.ins_n); }
+      else w.dec(oa.del_n);
+      w.byte('\t');
+      w.byte(trtv);
+      w.byte('\t');
+    }
 
     if (cfg.n_samples == 0) {  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0"
       for (int k = 0; k < 3; k++) { w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0'); w.byte('\t'); }
