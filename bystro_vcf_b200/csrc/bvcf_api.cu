@@ -354,6 +354,13 @@ void fill_dcfg(bvcf_ctx *ctx) {
   memcpy(d.empty, ctx->empty_field.data(), ctx->empty_field.size());
   d.delim_len = (int)ctx->field_delim.size();
   memcpy(d.delim, ctx->field_delim.data(), ctx->field_delim.size());
+  {  // main.go:612-616,634-637,648-651,667 with no samples: three empty lists with ratio 0, then ac, an, sampleMaf = 0
+    std::string t;
+    for (int k = 0; k < 3; k++) t += ctx->empty_field + "\t0\t";
+    t += "0\t0\t0";
+    d.tail0_len = (int)t.size();
+    memcpy(d.tail0, t.data(), t.size());
+  }
 }
 
 Slot *find_slot(bvcf_ctx *ctx, uint64_t seq) {

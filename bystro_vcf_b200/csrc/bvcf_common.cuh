@@ -104,6 +104,8 @@ struct DevCfg {
   int empty_len;
   uint8_t delim[64];
   int delim_len;
+  uint8_t tail0[208];         // columns 7-15 of a sites-only row: "!\t0\t!\t0\t!\t0\t0\t0\t0" with the configured emptyField
+  int tail0_len;
   const uint8_t *names;       // sample names back to back
   const uint32_t *name_off;   // n_samples + 1
   int name_fixed_w;           // > 0 when every sample name has this length

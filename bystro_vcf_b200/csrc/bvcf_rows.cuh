@@ -626,8 +626,7 @@ __device__ __forceinline__ void emit_row(const RowsParams &p, const LineRec &rec
     }
 
     if (cfg.n_samples == 0) {  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0"
-      for (int k = 0; k < 3; k++) { w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0'); w.byte('\t'); }
-      w.byte('0'); w.byte('\t'); w.byte('0'); w.byte('\t'); w.byte('0');
+      w.span(cfg.tail0, cfg.tail0_len);  // composed once by the host
     } else {
       const uint32_t eff = (uint32_t)cfg.n_samples - gs.n_miss;  // main.go:563
       const uint32_t dl = (uint32_t)cfg.delim_len;
