@@ -313,8 +313,10 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
             const int jn = (nl - 3 - ws0) >> 2;
 #pragma unroll
             for (int j = 0; j < 4; j++) if (j == jn) t[j] ^= 0x03000000u & (0u - ((zone >> j) & 1u));
-          } else if (r != 0) {
-            bad_shape = true;  // short last field (r == 0: an empty last field, the field count will tell)
+          } else {
+            // r == 1, 2: a short last field; r == 0: an EMPTY last field (a tab right before the newline), one
+            // token "" that counts towards an (main.go:1143,1166): both go field by field
+            bad_shape = true;
           }
         }
         uint32_t bad = bad_digits4(t, 0xFFFFFFFFu) | (bad_shape ? 1u : 0u);

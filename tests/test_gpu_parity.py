@@ -283,3 +283,78 @@ def test_odd_bytes_in_regular_genotype_zones():
     exp = oracle_rows(vcf)
     assert got == exp
     assert len(got) > 1000
+
+
+def _fuzz_vcf(rng, n_samples, n_lines, name_w):
+    """A random VCF whose lines differ in every dimension the scan kernel's tiers care about: prefix length (the
+    field phase modulo 4 and where the 512-byte windows cut), GT shapes, FORMAT suffixes, field counts."""
+    names = [("%0*d" % (name_w, i))[-name_w:] if name_w else "s%d" % (i * 37 % 1000) for i in range(n_samples)]
+    hdr = V.HDR8 + (["FORMAT"] + names if n_samples else [])
+    gts_common = ["0|0"] * 30 + ["0|1", "1|0", "1|1", ".|.", "0|.", "2|1", "0|2", "3|3"]
+    gts_odd = ["0/0", "0/1", "1", "0", ".", "", "10|1", "1|10", "0|1|1", "1/1/1", "0|1:35", "1|1:0,3:99", "./.", "0/1|1",
+               "A|1", "1|?", "01|1", "1|", "|1", "1||1"]
+    alts = ["C", "G", "T", "C,G", "G,T,C", "AC", "ACG,AT", "<DEL>", "*", "N", "a", "C,<CN0>,G", "AT,ATT"]
+    refs = ["A", "A", "A", "AT", "ATG", "ACGT"]
+    filts = ["PASS", "PASS", "PASS", ".", "q10", "PASS;q10"]
+    recs = []
+    for i in range(n_lines):
+        info = "AC=%d;AN=%d;X=%s" % (rng.randrange(100), rng.randrange(5000), "k" * rng.randrange(0, 90))
+        ident = rng.choice([".", "rs%d" % rng.randrange(10 ** rng.randrange(1, 9))])
+        chrom = rng.choice(["1", "22", "X", "chr7", "GL000207.1"])
+        fixed = [chrom, str(rng.randrange(1, 10 ** rng.randrange(1, 9))), ident, rng.choice(refs), rng.choice(alts), "100",
+                 rng.choice(filts), info]
+        if not n_samples:
+            recs.append(fixed)
+            continue
+        mode = rng.random()
+        p_odd = 0.0 if mode < 0.5 else (0.002 if mode < 0.8 else 0.05)
+        p_alt = rng.choice([0.0, 0.001, 0.02, 0.5])
+        fmt = "GT" if rng.random() < 0.9 else "GT:DP"
+        fields = []
+        for s in range(n_samples):
+            u = rng.random()
+            if u < p_odd:
+                g = rng.choice(gts_odd)
+            elif u < p_odd + p_alt:
+                g = rng.choice(gts_common[30:])
+            else:
+                g = "0|0"
+            if fmt != "GT" and rng.random() < 0.5:
+                g += ":%d" % rng.randrange(100)
+            fields.append(g)
+        n_keep = n_samples if rng.random() < 0.97 else rng.randrange(0, n_samples + 3)  # wrong field counts vanish
+        fields = (fields + ["0|0"] * 3)[:n_keep]
+        recs.append(fixed + [fmt] + fields)
+    return V._vcf(hdr, recs)
+
+
+import os as _os
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("BVCF_FUZZ_N", "24"))))
+def test_fuzz_line_shapes_vs_oracle(seed):
+    import random
+
+    rng = random.Random(1000 + seed)
+    n_samples = rng.choice([0, 1, 3, 31, 127, 128, 129, 300, 700, 1500])
+    name_w = rng.choice([7, 7, 0, 4])  # 7-character names take the 8-byte-item kernels, the others the general ones
+    vcf = _fuzz_vcf(rng, n_samples, rng.randrange(20, 120), name_w)
+    kw = rng.choice([{}, {"keep_info": True, "keep_id": True}, {"keep_pos": True}, {"allow": None}, {"exclude": ["q10"]}])
+    assert gpu_rows(vcf, **kw) == oracle_rows(vcf, **kw)
+
+
+def test_empty_last_sample_field():
+    """A line whose last sample field is empty (a tab right before the newline) inside an otherwise regular `x|y`
+    zone: the empty token still counts one allele towards `an` (main.go:1143,1166)."""
+    ns = 300
+    hdr = V.HDR8 + ["FORMAT"] + ["Q%06d" % i for i in range(ns)]
+    recs = []
+    for i in range(8):
+        gts = ["0|0"] * ns
+        gts[5 + i] = "0|1"
+        gts[-1] = ""  # the empty last field
+        recs.append(["1", str(100 + 13 * i), ".", "A" * (1 + i % 4), "C", ".", "PASS", "X" * i, "GT"] + gts)
+    vcf = V._vcf(hdr, recs)
+    got = gpu_rows(vcf)
+    assert got == oracle_rows(vcf)
+    assert all(r[13] == str(2 * (ns - 1) + 1) for r in rows_of(got))
