@@ -358,3 +358,46 @@ def test_empty_last_sample_field():
     got = gpu_rows(vcf)
     assert got == oracle_rows(vcf)
     assert all(r[13] == str(2 * (ns - 1) + 1) for r in rows_of(got))
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("BVCF_FUZZ2_N", "16"))))
+def test_fuzz_options_dosage_chunks_vs_oracle(seed):
+    """The same random line shapes under the other axes: CRLF line ends, 64 KiB chunks through submit/collect,
+    multi-character emptyField / fieldDelimiter, the dosage matrix, diagnostics."""
+    import random
+
+    import numpy as np
+
+    from bystro_vcf_b200 import Transformer, parse_preamble, read_vcf
+    from oracle import oracle as O
+
+    rng = random.Random(5000 + seed)
+    n_samples = rng.choice([1, 5, 128, 257, 700, 1500, 3500])
+    name_w = rng.choice([7, 7, 3])
+    vcf = _fuzz_vcf(rng, n_samples, rng.randrange(30, 160), name_w)
+    if rng.random() < 0.3:
+        vcf = vcf.replace(b"\n", b"\r\n")
+    empty, delim = rng.choice([("!", ";"), ("NA", "|"), ("", ";;"), ("!", ",")])
+    okw = {"empty_field": empty, "field_delim": delim, "keep_id": rng.random() < 0.5, "keep_info": rng.random() < 0.3}
+    want_dosage = rng.random() < 0.5
+    ref = O.read_vcf(O.OracleConfig(want_dosage=want_dosage, **okw), vcf)
+    c = _cfg(keep_id=okw["keep_id"], keep_info=okw["keep_info"])
+    c.emptyField, c.fieldDelimiter = empty, delim
+    if want_dosage:
+        c.dosageMatrixOutPath = "unused.feather"
+    w, chrom, off = parse_preamble(vcf)
+    with Transformer(c, eol_width=w) as tr:
+        tr.set_header(chrom)
+        res = tr.process(vcf[off:])
+    assert res.tsv == ref.tsv
+    assert sorted(res.diags) == sorted(ref.diags)
+    if want_dosage:
+        assert res.loci == ref.loci
+        assert np.array_equal(res.dosage, ref.dosage)
+    # and the streaming driver with the smallest chunks
+    c2 = _cfg(keep_id=okw["keep_id"], keep_info=okw["keep_info"])
+    c2.emptyField, c2.fieldDelimiter = empty, delim
+    c2.chunkBytes = 1 << 16
+    out = io.BytesIO()
+    read_vcf(c2, io.BytesIO(vcf), out)
+    assert out.getvalue() == ref.tsv
