@@ -401,3 +401,39 @@ def test_fuzz_options_dosage_chunks_vs_oracle(seed):
     out = io.BytesIO()
     read_vcf(c2, io.BytesIO(vcf), out)
     assert out.getvalue() == ref.tsv
+
+
+@pytest.mark.parametrize("n_samples,dens", [(3000, 0.9), (9000, 0.5), (20000, 0.6), (20000, 0.15), (70000, 0.3)])
+def test_wide_dense_rows_name_kernels(n_samples, dens):
+    """Rows whose name lists outgrow the per-warp index buffer (chunked sweep) and whose event lists exceed 4,096 quads
+    (CTA-per-row kernel), with 16-bit (<= 65,000 samples) and 32-bit sample indices; multi-allelic and missing
+    samples mixed in; with and without the dosage matrix."""
+    import random
+
+    import numpy as np
+
+    from bystro_vcf_b200 import Transformer, parse_preamble
+    from oracle import oracle as O
+
+    rng = random.Random(n_samples + int(dens * 100))
+    hdr = V.HDR8 + ["FORMAT"] + ["W%06d" % i for i in range(n_samples)]
+    pool = ["0|1", "1|0", "1|1", "1|1", ".|.", "2|1", "0|2", "1", "1|1|0"]
+    recs = []
+    for i in range(6):
+        d = dens if i % 2 == 0 else dens / 8
+        gts = [rng.choice(pool) if rng.random() < d else "0|0" for _ in range(n_samples)]
+        recs.append(["7", str(500 + i), ".", "A", "C,G" if i % 3 == 0 else "C", ".", "PASS", ".", "GT"] + gts)
+    vcf = V._vcf(hdr, recs)
+    for want_dosage in (False, True):
+        ref = O.read_vcf(O.OracleConfig(want_dosage=want_dosage), vcf)
+        c = _cfg()
+        if want_dosage:
+            c.dosageMatrixOutPath = "unused.feather"
+        w, chrom, off = parse_preamble(vcf)
+        with Transformer(c, eol_width=w) as tr:
+            tr.set_header(chrom)
+            res = tr.process(vcf[off:])
+        assert res.tsv == ref.tsv
+        if want_dosage:
+            assert res.loci == ref.loci
+            assert np.array_equal(res.dosage, ref.dosage)
