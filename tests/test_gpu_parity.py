@@ -437,3 +437,28 @@ def test_wide_dense_rows_name_kernels(n_samples, dens):
         if want_dosage:
             assert res.loci == ref.loci
             assert np.array_equal(res.dosage, ref.dosage)
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("BVCF_FUZZ3_N", "12"))))
+def test_fuzz_resident_tiny_subchunks_vs_oracle(seed):
+    """The device-resident entry points (bvcf_resident_*) on random line shapes, cut into 64 KiB sub-chunks so that
+    lines straddle sub-chunk and range boundaries everywhere."""
+    import random
+
+    from bystro_vcf_b200 import Transformer, parse_preamble
+    from oracle import oracle as O
+
+    rng = random.Random(9000 + seed)
+    n_samples = rng.choice([0, 2, 128, 700, 1500, 4000])
+    vcf = _fuzz_vcf(rng, n_samples, rng.randrange(40, 200), 7)
+    ref = O.read_vcf(O.OracleConfig(), vcf)
+    w, chrom, off = parse_preamble(vcf)
+    body = vcf[off:]
+    with Transformer(_cfg(), eol_width=w, resident_subchunk_bytes=1 << 16) as tr:
+        tr.set_header(chrom)
+        tr.resident_alloc(len(body), max(len(body), 1 << 20))
+        tr.resident_upload(0, body)
+        stats, _ = tr.resident_run(len(body))
+        out = tr.resident_download(0, stats["out_bytes"]) if stats["out_bytes"] else b""
+    assert out == ref.tsv
+    assert stats["n_rows"] == ref.n_rows
