@@ -462,3 +462,40 @@ def test_fuzz_resident_tiny_subchunks_vs_oracle(seed):
         out = tr.resident_download(0, stats["out_bytes"]) if stats["out_bytes"] else b""
     assert out == ref.tsv
     assert stats["n_rows"] == ref.n_rows
+
+
+def test_output_and_row_capacity_retries():
+    """Outputs larger than the library's first guess: the kernels flag the overflow, the host grows the buffer and
+    re-runs the chunk (output several times the input: every ALT of a sites-only line is a row; eight rows per
+    record with samples: an 8-base MNP), through submit/collect and through the resident entry points."""
+    from bystro_vcf_b200 import Transformer, parse_preamble
+    from oracle import oracle as O
+
+    # sites-only, three rows per 30-byte line
+    recs = [["1", str(10 + i), ".", "A", "C,G,T", ".", "PASS", "."] for i in range(60000)]
+    vcf = V._vcf(V.HDR8, recs)
+    ref = O.read_vcf(O.OracleConfig(), vcf)
+    assert len(ref.tsv) > 3 * len(vcf)
+    w, chrom, off = parse_preamble(vcf)
+    body = vcf[off:]
+    with Transformer(_cfg(), eol_width=w) as tr:
+        tr.set_header(chrom)
+        res = tr.process(body)
+        assert res.retries > 0 and res.tsv == ref.tsv
+        tr.resident_alloc(len(body), 4096)  # absurdly small output region
+        tr.resident_upload(0, body)
+        stats, _ = tr.resident_run(len(body))
+        assert stats["retries"] > 0
+        assert tr.resident_download(0, stats["out_bytes"]) == ref.tsv
+    # samples + MNPs: more rows than row descriptors
+    hdr = V.HDR8 + ["FORMAT", "S1", "S2", "S3"]
+    recs = [["2", str(100 + 10 * i), ".", "ACGTACGT", "TGCATGCA", ".", "PASS", ".", "GT", "0|1", "1|1", "0|0"] for i in range(40000)]
+    vcf = V._vcf(hdr, recs)
+    ref = O.read_vcf(O.OracleConfig(), vcf)
+    assert ref.n_rows == 8 * 40000
+    w, chrom, off = parse_preamble(vcf)
+    with Transformer(_cfg(), eol_width=w) as tr:
+        tr.set_header(chrom)
+        res = tr.process(vcf[off:])
+    assert res.tsv == ref.tsv
+    assert res.retries > 0
