@@ -545,21 +545,33 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
       __syncwarp();
       int hint = 0;  // 1: window A was regular and is done, B is known not to be; 2: A is known not to be regular
       if (fast) {
-        const uint32_t so_b = (stage_off + WIN) & (RING - 1);
-        const uint4 va = lds128(ring_lane_s + stage_off);
-        const uint4 vb = lds128(ring_lane_s + so_b);
-        const uint32_t w4b = lds32(ring_base_s + ((so_b + lane * 16 + 16) & (RING - 1)));
         const uint32_t rp = st.refpat;
         const uint32_t sh = (uint32_t)st.fsr * 8u;
         const uint32_t rot = __funnelshift_l(rp, rp, sh);  // the pattern as the unaligned raw words see it
+        uint4 va, vb;
+        uint32_t w4b;
+        bool allref;
         // T1 x2: every byte of both windows (and the 4 bytes after them) repeats the reference genotype.
-        // The vote also orders these shared-memory reads before the stages are refilled.
-        const uint32_t diff = (va.x ^ rot) | (va.y ^ rot) | (va.z ^ rot) | (va.w ^ rot) | (vb.x ^ rot) | (vb.y ^ rot) |
-                              (vb.z ^ rot) | (vb.w ^ rot) | (w4b ^ rot);
-        if (__all_sync(FULL, diff == 0)) {
+        // All-reference pairs come in streaks (most of real data): the streak is a loop of its own, nothing of the
+        // warp's state but the column and allele counters moves.  The vote also orders these shared-memory reads
+        // before the stages are refilled.
+        for (;;) {
+          const uint32_t so_b = (stage_off + WIN) & (RING - 1);
+          va = lds128(ring_lane_s + stage_off);
+          vb = lds128(ring_lane_s + so_b);
+          w4b = lds32(ring_base_s + ((so_b + lane * 16 + 16) & (RING - 1)));
+          const uint32_t diff = (va.x ^ rot) | (va.y ^ rot) | (va.z ^ rot) | (va.w ^ rot) | (vb.x ^ rot) | (vb.y ^ rot) |
+                                (vb.z ^ rot) | (vb.w ^ rot) | (w4b ^ rot);
+          allref = __all_sync(FULL, diff == 0);
+          if (!allref) break;
           st.a.an_uni += 512; st.col += 256;
-          continue;
+          if (!(it + 4 < n_avail)) break;  // the next pair would be the last the loop takes: leave it to the loop
+          it += 2; stage_off = (stage_off + 2 * WIN) & (RING - 1);
+          issue_pair();
+          asm volatile("cp.async.wait_group %0;\n" ::"n"(PF_PAIRS - 1));
+          __syncwarp();
         }
+        if (allref) continue;
         // T2 x2: both windows regular -> one ordered compaction for the 256 fields
         const uint32_t w4a = lds32(ring_base_s + ((stage_off + lane * 16 + 16) & (RING - 1)));
         const uint32_t ta[4] = {__funnelshift_r(va.x, va.y, sh) ^ rp, __funnelshift_r(va.y, va.z, sh) ^ rp,
