@@ -1041,91 +1041,6 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
     uint32_t run_n[3] = {0, 0, 0};
     uint32_t run_b[3] = {0, 0, 0};
     const unsigned long long dsts[3] = {rd.het_dst, rd.hom_dst, rd.miss_dst};
-    if (cfg.name8 && cfg.want_tsv && !drow && !(rec.flags & 1) && a == 1) {
-      // ---- the common row: ALT #1 of a record whose samples only carry alleles 0/1 (or are missing), 8-byte
-      // items, no dosage.  The class is read straight off the event's code bits; ballot/popc give the rank;
-      // each lane stores its own item (alignment uniform per class). ----
-      uint8_t *const base_h = p.out + rd.het_dst, *const base_o = p.out + rd.hom_dst, *const base_m = p.out + rd.miss_dst;
-      uint32_t run_h = 0, run_o = 0, run_m = 0;
-      uint32_t off_unused;
-      uint32_t w_next = slot_load(ev, lane, rec.ev_count, off_unused);
-      for (uint32_t base = 0; base < 2 * rec.ev_count; base += 32) {
-        const uint32_t w = w_next;  // software pipelining: the next batch's words are already in flight
-        w_next = slot_load(ev, base + 32 + lane, rec.ev_count, off_unused);
-        const bool valid = !(w & EV_OFFSET_TAG);
-        const uint32_t x = (w >> 20) & 0x3FFu;  // c1 | c2 << 5
-        const bool is_m = valid && x == (EV_CODE_MISSING | (EV_CODE_MISSING << 5));
-        const bool is_o = valid && (x == (1u | (1u << 5)) || x == (1u | (EV_CODE_ABSENT << 5)));
-        const bool is_h = valid && !is_m && !is_o;
-        const uint32_t bh = __ballot_sync(FULL, is_h), bo = __ballot_sync(FULL, is_o), bm = __ballot_sync(FULL, is_m);
-        unsigned long long it = valid ? cfg.name8[w & EV_SAMPLE_MASK] : 0ull;
-        if (bh) {
-          if (is_h) {
-            const uint32_t idx = run_h + __popc(bh & lt);
-            if (idx + 1 == rd.n_het) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);
-            store8_unaligned(base_h + 8ull * idx, it);
-          }
-          run_h += __popc(bh);
-        }
-        if (bo) {
-          if (is_o) {
-            const uint32_t idx = run_o + __popc(bo & lt);
-            if (idx + 1 == rd.n_hom) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);
-            store8_unaligned(base_o + 8ull * idx, it);
-          }
-          run_o += __popc(bo);
-        }
-        if (bm) {
-          if (is_m) {
-            const uint32_t idx = run_m + __popc(bm & lt);
-            if (idx + 1 == rd.n_miss) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);
-            store8_unaligned(base_m + 8ull * idx, it);
-          }
-          run_m += __popc(bm);
-        }
-      }
-      return;
-    }
-    if (cfg.name8 && cfg.want_tsv) {
-      // ---- fast path: every list item is exactly 8 bytes (name + delimiter).  Each lane ranks its item
-      // within its class with ballot/popc and stores the 8 bytes itself with the widest aligned pieces the
-      // destination allows (2-4 stores; the alignment is uniform per class, so no divergence). ----
-      const uint32_t totals[3] = {rd.n_het, rd.n_hom, rd.n_miss};
-      uint32_t off_next;
-      uint32_t w_next = slot_load(ev, lane, rec.ev_count, off_next);
-      for (uint32_t base = 0; base < 2 * rec.ev_count; base += 32) {
-        const uint32_t k = base + lane;
-        const uint32_t w_cur = w_next, off_cur = off_next;  // software pipelining: the next batch is already in flight
-        w_next = slot_load(ev, k + 32, rec.ev_count, off_next);
-        int cls;
-        uint32_t samp, alt;
-        if (__any_sync(FULL, (w_cur & (EV_COMPLEX | EV_OFFSET_TAG)) == EV_COMPLEX)) {
-          uint32_t gtx;  // a sample in this batch needs the general GT grammar
-          cls = classify_word(w_cur, off_cur, L, content_len, a, samp, gtx, alt);
-        } else {
-          const uint32_t c1 = (w_cur >> 20) & 31, c2 = (w_cur >> 25) & 31;
-          samp = w_cur & EV_SAMPLE_MASK;
-          alt = (c1 == a) + (c2 == a);
-          const bool dip = c2 != EV_CODE_ABSENT;
-          cls = (w_cur & EV_OFFSET_TAG) ? 0 : (c1 == EV_CODE_MISSING ? 3 : (alt == 0 ? 0 : ((alt == 2 || !dip) ? 2 : 1)));
-        }
-        if (drow && !(w_cur & EV_OFFSET_TAG))
-          drow[samp] = cls == 3 ? (int8_t)-1 : (int8_t)(alt > 127 ? 127 : alt);  // main.go:1172-1178
-        unsigned long long it = cls ? cfg.name8[samp] : 0ull;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const uint32_t bal = __ballot_sync(FULL, cls == c + 1);
-          if (bal == 0) continue;  // warp-uniform
-          if (cls == c + 1) {
-            const uint32_t idx = run_n[c] + __popc(bal & lt);
-            if (idx + 1 == totals[c]) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
-            store8_unaligned(p.out + dsts[c] + 8ull * idx, it);
-          }
-          run_n[c] += __popc(bal);
-        }
-      }
-      return;
-    }
     for (uint32_t base = 0; base < 2 * rec.ev_count; base += 32) {
       uint32_t samp, gtx, alt;
       const uint32_t k = base + lane;
@@ -1292,7 +1207,8 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
   }
 }
 
-// warp per row: the rows the hybrid kernel queued
+// warp per row: the rows the hybrid kernel queued, when the list items are not fixed 8-byte pieces
+// (variable-width names or a longer delimiter; otherwise bvcf_names.cuh takes them)
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_big_kernel(const NamesParams p) {
   const int lane = threadIdx.x & 31;
   if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
