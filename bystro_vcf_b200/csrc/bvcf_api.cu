@@ -308,7 +308,8 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       const bool vec = dc.name8 && dc.want_tsv && !no_vec;
       np.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
       if (dc.want_dosage && d_dosage) { bvcf_dosage_zero_kernel<<<(unsigned)n_sm * 8, 256, 0, st>>>(np); ctx->launches++; }
-      bvcf_names_kernel<<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
+      if (dc.want_dosage && d_dosage) bvcf_names_kernel<true><<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
+      else bvcf_names_kernel<false><<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
       if (vec) {
         const unsigned g1 = (unsigned)n_sm * 18, g2 = (unsigned)n_sm * 2;
         const bool dos = dc.want_dosage && d_dosage;

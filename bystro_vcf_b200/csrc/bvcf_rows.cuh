@@ -1081,6 +1081,7 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
 }
 
 // one row, one lane: rows whose record has only a handful of events (singletons, rare variants)
+template <bool DOSAGE>
 __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDesc &rd, const LineRec &rec, int8_t *drow) {
   const DevCfg &cfg = p.cfg;
   const uint32_t *ev = p.events + rec.ev_start;
@@ -1101,7 +1102,7 @@ __device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDe
       any &= any - 1;
       const uint32_t samp = s0 + ((uint32_t)(__ffs(bit) - 1) >> 2);
       const bool is_h = (mh & bit) != 0, is_o = (mo & bit) != 0;
-      if (drow) {  // int8 dosage: -1 missing, else min(number of alleles equal to the row's, 127) (main.go:1172-1178)
+      if (DOSAGE && drow) {  // int8 dosage: -1 missing, else min(number of alleles equal to the row's, 127) (main.go:1172-1178)
         int v = -1;
         if (is_h | is_o) {
           if (e.x & EV_COMPLEX) {
@@ -1164,6 +1165,7 @@ __global__ void __launch_bounds__(256) bvcf_dosage_zero_kernel(const NamesParams
 
 // Hybrid granularity (as in the stats kernel): a warp takes 32 consecutive rows; short ones lane-serial,
 // long ones warp-cooperative.
+template <bool DOSAGE>
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
@@ -1184,8 +1186,8 @@ __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const Name
       ev_words = rec.ev_count;
       small = rec.ev_count <= SMALL_EVENTS;
       int8_t *drow = nullptr;
-      if (cfg.want_dosage && (row0 + r) < p.dosage_cap_rows) drow = p.dosage + (row0 + r) * (unsigned long long)cfg.n_samples;
-      if (small) names_row_lane(p, rd, rec, drow);
+      if (DOSAGE && cfg.want_dosage && (row0 + r) < p.dosage_cap_rows) drow = p.dosage + (row0 + r) * (unsigned long long)cfg.n_samples;
+      if (small) names_row_lane<DOSAGE>(p, rd, rec, drow);
     }
     // long rows go to the work list of the warp-per-row kernel (one atomic per warp), very long ones to the
     // CTA-per-row kernel's
