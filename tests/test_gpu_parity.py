@@ -299,6 +299,8 @@ def _fuzz_vcf(rng, n_samples, n_lines, name_w):
     recs = []
     for i in range(n_lines):
         info = "AC=%d;AN=%d;X=%s" % (rng.randrange(100), rng.randrange(5000), "k" * rng.randrange(0, 90))
+        if rng.random() < 0.05:
+            info += ";LONG=" + "z" * rng.randrange(400, 3000)  # the fixed fields span several 512-byte windows
         ident = rng.choice([".", "rs%d" % rng.randrange(10 ** rng.randrange(1, 9))])
         chrom = rng.choice(["1", "22", "X", "chr7", "GL000207.1"])
         fixed = [chrom, str(rng.randrange(1, 10 ** rng.randrange(1, 9))), ident, rng.choice(refs), rng.choice(alts), "100",
@@ -325,6 +327,8 @@ def _fuzz_vcf(rng, n_samples, n_lines, name_w):
         n_keep = n_samples if rng.random() < 0.97 else rng.randrange(0, n_samples + 3)  # wrong field counts vanish
         fields = (fields + ["0|0"] * 3)[:n_keep]
         recs.append(fixed + [fmt] + fields)
+        if rng.random() < 0.03:
+            recs.append(rng.choice([[], [""], ["1"], ["1", "5"], fixed[:5]]))  # blank and truncated lines vanish
     return V._vcf(hdr, recs)
 
 
