@@ -446,6 +446,50 @@ __device__ __forceinline__ void store8_unaligned(uint8_t *d, unsigned long long 
   }
 }
 
+// The EMIT writer's state and its two out-of-line steps.  Inlined at some fifty call sites they made the EMIT
+// kernel 147 KB of code, and the pass stalled on instruction fetch (39 % of its stall samples).  The state travels
+// by value (registers under the device ABI).
+struct WState {
+  uint8_t *g;                // address of the first pending byte
+  unsigned long long acc;    // pending bytes, little-endian
+  int fill;                  // how many (0..7)
+};
+__device__ __noinline__ WState wput(WState s, unsigned long long chars, int len) {  // len <= 8, bytes >= len zero
+  s.acc |= chars << (8 * s.fill);
+  int nf = s.fill + len;
+  if (nf >= 8) {
+    store8_unaligned(s.g, s.acc);
+    s.g += 8;
+    s.acc = s.fill ? chars >> (8 * (8 - s.fill)) : 0ull;
+    nf -= 8;
+  }
+  s.fill = nf;
+  return s;
+}
+__device__ __noinline__ WState wspan(WState s, const uint8_t *p, int len) {
+  for (int i = 0; i < len; i += 8) {
+    const int n = len - i < 8 ? len - i : 8;
+    unsigned long long v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < n) v |= (unsigned long long)p[i + k] << (8 * k);
+    s.acc |= v << (8 * s.fill);
+    int nf = s.fill + n;
+    if (nf >= 8) {
+      store8_unaligned(s.g, s.acc);
+      s.g += 8;
+      s.acc = s.fill ? v >> (8 * (8 - s.fill)) : 0ull;
+      nf -= 8;
+    }
+    s.fill = nf;
+  }
+  return s;
+}
+__device__ __noinline__ WState wflush(WState s) {
+  for (int i = 0; i < s.fill; i++) s.g[i] = (uint8_t)(s.acc >> (8 * i));
+  s.g += s.fill; s.acc = 0; s.fill = 0;
+  return s;
+}
+
 // Writer policy of emit_row: kWrite (bytes are produced), kGlobal (bytes go to the output buffer: loci and
 // RowDesc are written too).  span_in() is a span of the INPUT line (long ones may be referenced, not copied);
 // list() reserves the bytes of one sample-name list; lists_done() ends the three lists of a row.
@@ -460,40 +504,22 @@ struct RowWriter {
   unsigned long long acc;    // pending bytes, little-endian
   int fill;                  // how many (0..7); they belong at g[0..fill)
   __device__ __forceinline__ void begin(uint8_t *dst) { g = dst; acc = 0; fill = 0; }
-  __device__ __forceinline__ void flush() {
-    if (WRITE) {
-      for (int i = 0; i < fill; i++) g[i] = (uint8_t)(acc >> (8 * i));
-      g += fill; acc = 0; fill = 0;
-    }
-  }
+  __device__ __forceinline__ WState st() const { WState s; s.g = g; s.acc = acc; s.fill = fill; return s; }
+  __device__ __forceinline__ void set(const WState &s) { g = s.g; acc = s.acc; fill = s.fill; }
+  __device__ __forceinline__ void flush() { if (WRITE) set(wflush(st())); }
   __device__ __forceinline__ void finish() { flush(); }
   // up to 8 characters packed little-endian; bytes at and above len must be zero
   __device__ __forceinline__ void packed(uint64_t chars, int len) {
     if (!WRITE) { count += len; return; }
-    acc |= chars << (8 * fill);
-    int nf = fill + len;
-    if (nf >= 8) {
-      store8_unaligned(g, acc);
-      g += 8;
-      acc = fill ? chars >> (8 * (8 - fill)) : 0ull;
-      nf -= 8;
-    }
-    fill = nf;
+    set(wput(st(), chars, len));
   }
   __device__ __forceinline__ void byte(uint8_t c) {
     if (!WRITE) { count++; return; }
-    acc |= (unsigned long long)c << (8 * fill);
-    if (++fill == 8) { store8_unaligned(g, acc); g += 8; acc = 0; fill = 0; }
+    set(wput(st(), (unsigned long long)c, 1));
   }
   __device__ __forceinline__ void span(const uint8_t *p, int len) {
     if (!WRITE) { count += len; return; }
-    for (int i = 0; i < len; i += 8) {
-      const int n = len - i < 8 ? len - i : 8;
-      unsigned long long v = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) if (k < n) v |= (unsigned long long)p[i + k] << (8 * k);
-      packed(v, n);
-    }
+    set(wspan(st(), p, len));
   }
   __device__ __forceinline__ void span_in(const uint8_t *p, int len) { span(p, len); }
   __device__ __forceinline__ void dec(long long v) {
