@@ -232,9 +232,15 @@ def run_ours(args):
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
                 "algorithmic_bytes_per_step": need, "avg_ms_per_step": scan_ms}
         roof["frac"] = roof["achieved"] / peak
+        # the kernel is launched once per 16 GiB sub-chunk of the resident input: per-launch figures beside the per-step ones
+        n_launch = max(1, -(-need // (16 << 30)))
+        roof["launches_per_step"] = n_launch
+        roof["algorithmic_bytes_per_launch"] = need / n_launch
+        roof["avg_ms_per_launch"] = scan_ms / n_launch
         ratio, src = scan_traffic_ratio()
-        if ratio is not None:  # per launch (= per step here: one launch per sub-chunk), scaled from the ncu capture
-            roof["traffic"] = ratio * need
+        if ratio is not None:  # DRAM read+write bytes per launch, scaled from the committed ncu --set full capture
+            roof["traffic"] = ratio * need / n_launch
+            roof["traffic_per_step"] = ratio * need
             roof["traffic_source"] = src
         pipe = {"achieved": alg_bytes / (dev_ms / args.steps / 1e3) / 1e9, "unit": "GB/s",
                 "algorithmic_bytes_per_step": alg_bytes, "bytes_per_variant": alg_bytes / n_lines}
