@@ -76,7 +76,7 @@ struct bvcf_ctx {
   std::vector<std::string> allow, exclude;
   bool header_set = false;
   DevCfg dcfg{};
-  DevBuf d_filt_blob, d_filt_off, d_names, d_name_off, d_name8;
+  DevBuf d_filt_blob, d_filt_off, d_names, d_name_off, d_name8, d_name16;
   std::vector<Slot> slots;
   // resident path
   DevBuf r_in, r_out, r_dosage, r_loci;
@@ -305,7 +305,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       np.row_desc_cap = sc.row_cap; np.out = d_out; np.ctr = d_ctr; np.dosage = d_dosage; np.dosage_cap_rows = dosage_cap_rows;
       np.big_rows = (uint32_t *)sc.big_rows.p;
       static const bool no_vec = getenv("BVCF_NO_NAMES_VEC") != nullptr;  // experiments
-      const bool vec = dc.name8 && dc.want_tsv && !no_vec;
+      const bool vec = (dc.name8 || dc.name16) && dc.want_tsv && !no_vec;
       np.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
       if (dc.want_dosage && d_dosage) { bvcf_dosage_zero_kernel<<<(unsigned)n_sm * 8, 256, 0, st>>>(np); ctx->launches++; }
       if (dc.want_dosage && d_dosage) bvcf_names_kernel<true><<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
@@ -515,7 +515,7 @@ void bvcf_destroy(bvcf_ctx *ctx) {
     if (s.h_out) cudaFreeHost(s.h_out);
     if (s.h_dosage) cudaFreeHost(s.h_dosage);
   }
-  for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->d_name8, &ctx->r_in, &ctx->r_out,
+  for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->d_name8, &ctx->d_name16, &ctx->r_in, &ctx->r_out,
                     &ctx->r_dosage, &ctx->r_loci})
     dev_free(*b);
   scratch_free(ctx->r_sc);
@@ -563,6 +563,8 @@ int bvcf_set_header(bvcf_ctx *ctx, const char *chrom_line, size_t len) {
   ctx->dcfg.name_off = (const uint32_t *)ctx->d_name_off.p;
   ctx->dcfg.name_fixed_w = fixed_w;
   ctx->dcfg.name8 = nullptr;
+  ctx->dcfg.name16 = nullptr;
+  ctx->dcfg.item_bytes = 0;
   if (fixed_w == 7 && ctx->field_delim.size() == 1 && ns > 0) {
     std::vector<unsigned long long> n8(ns);
     for (int i = 0; i < ns; i++) {
@@ -574,6 +576,19 @@ int bvcf_set_header(bvcf_ctx *ctx, const char *chrom_line, size_t len) {
     if ((rc = dev_reserve(ctx, ctx->d_name8, n8.size() * 8))) return rc;
     CK(cudaMemcpy(ctx->d_name8.p, n8.data(), n8.size() * 8, cudaMemcpyHostToDevice));
     ctx->dcfg.name8 = (const unsigned long long *)ctx->d_name8.p;
+    ctx->dcfg.item_bytes = 8;
+  } else if (fixed_w > 0 && ns > 0 && fixed_w + (int)ctx->field_delim.size() >= 5 && fixed_w + (int)ctx->field_delim.size() <= 16) {
+    // any other fixed width: 16-byte padded items for the vector names kernels
+    const int I = fixed_w + (int)ctx->field_delim.size();
+    std::vector<uint8_t> n16((size_t)ns * 16, 0);
+    for (int i = 0; i < ns; i++) {
+      memcpy(&n16[(size_t)i * 16], &blob[(size_t)i * fixed_w], fixed_w);
+      memcpy(&n16[(size_t)i * 16 + fixed_w], ctx->field_delim.data(), ctx->field_delim.size());
+    }
+    if ((rc = dev_reserve(ctx, ctx->d_name16, n16.size()))) return rc;
+    CK(cudaMemcpy(ctx->d_name16.p, n16.data(), n16.size(), cudaMemcpyHostToDevice));
+    ctx->dcfg.name16 = (const uint4 *)ctx->d_name16.p;
+    ctx->dcfg.item_bytes = I;
   }
   ctx->header_set = true;
   return BVCF_OK;

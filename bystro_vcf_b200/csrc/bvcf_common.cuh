@@ -111,6 +111,9 @@ struct DevCfg {
   int name_fixed_w;           // > 0 when every sample name has this length
   const unsigned long long *name8;  // name + delimiter packed in 8 bytes per sample, when 7-char names and a
                                     // 1-char delimiter make every list item exactly 8 bytes; else null
+  const uint4 *name16;              // name + delimiter zero-padded to 16 bytes per sample, when all names have one
+                                    // width and an item (name + delimiter) is 5..16 bytes; else null
+  int item_bytes;                   // that item size
 };
 
 // ---- warp helpers --------------------------------------------------------------------------------

@@ -1,7 +1,8 @@
 // bvcf_names.cuh -- north-star kernel (4b), sample-name lists of the long rows as aligned 16-byte vectors.
 //
 // bvcf_names_kernel (bvcf_rows.cuh) writes the lists of short rows lane-serially and queues the others.  When
-// every list item is 8 bytes (7-character names + 1-character delimiter: the 1000 Genomes / biobank layout) and
+// every list item has one size of 5..16 bytes (fixed-width names; 7-character names + 1-character delimiter, the
+// 1000 Genomes / biobank layout, get the 8-byte fast path) and
 // TSV output is on, bvcf_names_vec_kernel takes the queue instead of bvcf_names_big_kernel:
 //   pass 1  one sweep over the row's quad events: het / hom / missing slots as nibble masks (general GT grammar for
 //           complex samples, main.go:1126-1190), ranks from one packed warp prefix sum per 32 quads, the sample
@@ -49,6 +50,65 @@ __device__ __forceinline__ void emit_name_vectors(const unsigned long long *__re
     }
   }
   for (uint32_t b = h + 16u * nvec + lane; b < len; b += 32) g[b] = (uint8_t)(name8[idx[b >> 3]] >> (8 * (b & 7u)));
+}
+
+// ---- any fixed item size -------------------------------------------------------------------------------
+// 7-character names with a 1-character delimiter are 8-byte items (name8, emit_name_vectors above).  Any other fixed
+// name width with an item of 5..16 bytes uses items zero-padded to 16 bytes: a vector is assembled from the (up to
+// four) items it overlaps with 128-bit shifts.
+struct ItemTable {
+  const unsigned long long *name8;
+  const uint4 *name16;
+  uint32_t item_bytes;    // I = name width + delimiter length
+  uint32_t delim_bytes;   // n names make n I - delim_bytes bytes
+};
+__device__ __forceinline__ ItemTable item_table(const DevCfg &cfg) {
+  ItemTable t;
+  t.name8 = cfg.name8; t.name16 = cfg.name16; t.item_bytes = (uint32_t)cfg.item_bytes; t.delim_bytes = (uint32_t)cfg.delim_len;
+  return t;
+}
+
+template <typename IdxT>
+__device__ __forceinline__ void emit_item_vectors(const uint4 *__restrict__ name16, uint32_t I, uint8_t *g, const IdxT *idx,
+                                                  uint32_t n, uint32_t len, int lane) {
+  auto item_byte = [&](uint32_t b) -> uint8_t {
+    const uint32_t k = b / I, o = b - k * I;
+    return reinterpret_cast<const uint8_t *>(name16 + idx[k])[o];
+  };
+  const uint32_t head = (16u - (uint32_t)((uintptr_t)g & 15u)) & 15u;
+  const uint32_t h = head < len ? head : len;
+  for (uint32_t b = lane; b < h; b += 32) g[b] = item_byte(b);
+  if (h == len) return;
+  const uint32_t nvec = (len - h) >> 4;
+  uint4 *gv = reinterpret_cast<uint4 *>(g + h);
+  const uint32_t q512 = 512u / I, r512 = 512u - q512 * I;  // a lane's next vector is 512 bytes on
+  uint32_t k = (h + 16u * lane) / I, o = (h + 16u * lane) - k * I;
+  for (uint32_t v = lane; v < nvec; v += 32) {
+    unsigned __int128 acc = 0;
+    uint32_t filled = 0, kk = k, oo = o;
+    while (filled < 16u) {
+      unsigned __int128 it = 0;
+      if (kk < n) {
+        const uint4 t = name16[idx[kk]];
+        it = ((unsigned __int128)(((unsigned long long)t.w << 32) | t.z) << 64) | (((unsigned long long)t.y << 32) | t.x);
+      }
+      acc |= (it >> (8u * oo)) << (8u * filled);  // the item from its byte oo on, placed after what is there
+      filled += I - oo;
+      kk++; oo = 0;
+    }
+    const unsigned long long lo = (unsigned long long)acc, hi = (unsigned long long)(acc >> 64);
+    gv[v] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    k += q512; o += r512;
+    if (o >= I) { o -= I; k++; }
+  }
+  for (uint32_t b = h + 16u * nvec + lane; b < len; b += 32) g[b] = item_byte(b);
+}
+
+// `n` names by sample index as list bytes [g, g + len), whatever the item size
+template <typename IdxT>
+__device__ __forceinline__ void emit_items(const ItemTable &t, uint8_t *g, const IdxT *idx, uint32_t n, uint32_t len, int lane) {
+  if (t.name8) emit_name_vectors<IdxT>(t.name8, g, idx, n, len, lane);
+  else emit_item_vectors<IdxT>(t.name16, t.item_bytes, g, idx, n, len, lane);
 }
 
 struct RowEvents {
@@ -132,7 +192,7 @@ __device__ __forceinline__ void index_lists_once(const RowEvents &re, IdxT *idx,
 // of vectors and its region starts over.  n names make 8 n - 1 bytes: the final chunk of a list drops the
 // trailing delimiter.
 template <typename IdxT, bool DOSAGE>
-__device__ __forceinline__ void sweep_lists_chunked(const unsigned long long *__restrict__ name8, const RowEvents &re,
+__device__ __forceinline__ void sweep_lists_chunked(const ItemTable &tab, const RowEvents &re,
                                                     IdxT *idx, uint32_t cap3, uint8_t *g_h, uint8_t *g_o, uint8_t *g_m,
                                                     uint32_t n_h, uint32_t n_o, uint32_t n_m, int lane,
                                                     uint32_t sh = 0, uint32_t so = 0, uint32_t sm = 0) {
@@ -188,18 +248,18 @@ __device__ __forceinline__ void sweep_lists_chunked(const unsigned long long *__
     if (last || fh + 256 > cap3 || fo + 256 > cap3 || fm + 256 > cap3) {
       __syncwarp();
       if (fh && (last || fh + 256 > cap3)) {
-        const uint32_t len = 8u * fh - (sh >= n_h ? 1u : 0u);
-        emit_name_vectors<IdxT>(name8, g_h, ih, fh, len, lane);
+        const uint32_t len = tab.item_bytes * fh - (sh >= n_h ? tab.delim_bytes : 0u);
+        emit_items<IdxT>(tab, g_h, ih, fh, len, lane);
         g_h += len; fh = 0;
       }
       if (fo && (last || fo + 256 > cap3)) {
-        const uint32_t len = 8u * fo - (so >= n_o ? 1u : 0u);
-        emit_name_vectors<IdxT>(name8, g_o, io, fo, len, lane);
+        const uint32_t len = tab.item_bytes * fo - (so >= n_o ? tab.delim_bytes : 0u);
+        emit_items<IdxT>(tab, g_o, io, fo, len, lane);
         g_o += len; fo = 0;
       }
       if (fm && (last || fm + 256 > cap3)) {
-        const uint32_t len = 8u * fm - (sm >= n_m ? 1u : 0u);
-        emit_name_vectors<IdxT>(name8, g_m, im, fm, len, lane);
+        const uint32_t len = tab.item_bytes * fm - (sm >= n_m ? tab.delim_bytes : 0u);
+        emit_items<IdxT>(tab, g_m, im, fm, len, lane);
         g_m += len; fm = 0;
       }
       __syncwarp();
@@ -221,7 +281,7 @@ __device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned lon
     const unsigned long long gr = p.ctr->chunk_row_base + r;
     if (DOSAGE && cfg.want_dosage && gr < p.dosage_cap_rows) re.drow = p.dosage + gr * (unsigned long long)cfg.n_samples;
   }
-  const unsigned long long *name8 = cfg.name8;
+  const ItemTable tab = item_table(cfg);
   const uint32_t cap = NVEC_IDX_BYTES / sizeof(IdxT);
   const uint32_t n_tot = rd.n_het + rd.n_hom + rd.n_miss;
   const uint32_t ns[3] = {rd.n_het, rd.n_hom, rd.n_miss};
@@ -232,12 +292,12 @@ __device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned lon
     uint32_t b = 0;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      if (ns[c]) emit_name_vectors<IdxT>(name8, p.out + dsts[c], idx + b, ns[c], 8u * ns[c] - 1u, lane);
+      if (ns[c]) emit_items<IdxT>(tab, p.out + dsts[c], idx + b, ns[c], tab.item_bytes * ns[c] - tab.delim_bytes, lane);
       b += ns[c];
     }
     __syncwarp();
   } else {
-    sweep_lists_chunked<IdxT, DOSAGE>(name8, re, idx, cap / 3, p.out + rd.het_dst, p.out + rd.hom_dst, p.out + rd.miss_dst, rd.n_het,
+    sweep_lists_chunked<IdxT, DOSAGE>(tab, re, idx, cap / 3, p.out + rd.het_dst, p.out + rd.hom_dst, p.out + rd.miss_dst, rd.n_het,
                               rd.n_hom, rd.n_miss, lane);
   }
 }
@@ -310,8 +370,10 @@ __global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const
     uint32_t ph = 0, po = 0, pm = 0;
     for (int w = 0; w < warp; w++) { ph += s_cnt[w][0]; po += s_cnt[w][1]; pm += s_cnt[w][2]; }
     const uint32_t cap3 = (NLONG_IDX_BYTES / sizeof(IdxT)) / 3;
-    sweep_lists_chunked<IdxT, DOSAGE>(cfg.name8, re, reinterpret_cast<IdxT *>(s_idx[warp]), cap3, p.out + rd.het_dst + 8ull * ph,
-                              p.out + rd.hom_dst + 8ull * po, p.out + rd.miss_dst + 8ull * pm, rd.n_het, rd.n_hom, rd.n_miss,
+    const ItemTable tab = item_table(cfg);
+    const unsigned long long I = tab.item_bytes;
+    sweep_lists_chunked<IdxT, DOSAGE>(tab, re, reinterpret_cast<IdxT *>(s_idx[warp]), cap3, p.out + rd.het_dst + I * ph,
+                              p.out + rd.hom_dst + I * po, p.out + rd.miss_dst + I * pm, rd.n_het, rd.n_hom, rd.n_miss,
                               lane, ph, po, pm);
   }
 }

@@ -407,8 +407,10 @@ def test_fuzz_options_dosage_chunks_vs_oracle(seed):
     assert out.getvalue() == ref.tsv
 
 
-@pytest.mark.parametrize("n_samples,dens", [(3000, 0.9), (9000, 0.5), (20000, 0.6), (20000, 0.15), (70000, 0.3)])
-def test_wide_dense_rows_name_kernels(n_samples, dens):
+@pytest.mark.parametrize("n_samples,dens,name_fmt", [(3000, 0.9, "W%06d"), (9000, 0.5, "W%06d"), (20000, 0.6, "W%06d"),
+                                                     (20000, 0.15, "W%06d"), (70000, 0.3, "W%06d"), (3000, 0.8, "ID%08d"),
+                                                     (20000, 0.5, "s%04d"[:6] + "x"), (9000, 0.6, "LONGNAME%07d")])
+def test_wide_dense_rows_name_kernels(n_samples, dens, name_fmt):
     """Rows whose name lists outgrow the per-warp index buffer (chunked sweep) and whose event lists exceed 4,096 quads
     (CTA-per-row kernel), with 16-bit (<= 65,000 samples) and 32-bit sample indices; multi-allelic and missing
     samples mixed in; with and without the dosage matrix."""
@@ -420,7 +422,9 @@ def test_wide_dense_rows_name_kernels(n_samples, dens):
     from oracle import oracle as O
 
     rng = random.Random(n_samples + int(dens * 100))
-    hdr = V.HDR8 + ["FORMAT"] + ["W%06d" % i for i in range(n_samples)]
+    # 7-character names: 8-byte items; 10 and 15 characters: 16-byte padded items; "s%04dx" grows from 6 to 7 characters
+    # (variable width: the general kernels)
+    hdr = V.HDR8 + ["FORMAT"] + [name_fmt % i for i in range(n_samples)]
     pool = ["0|1", "1|0", "1|1", "1|1", ".|.", "2|1", "0|2", "1", "1|1|0"]
     recs = []
     for i in range(6):
