@@ -187,46 +187,66 @@ struct StatsParams {
   uint32_t *big_recs;        // work list: records reduced by a whole warp (bvcf_line_stats_big_kernel)
 };
 
-// one event word classified against ALT numbers 1..STAT_ALLELES at once
-struct Ev3 {
-  int cls[STAT_ALLELES];
-  uint32_t alt[STAT_ALLELES];
-  uint32_t gtx, samp;
-  bool is_ev;
+// per-thread partial genotype summary of a record for ALT numbers 1..STAT_ALLELES
+struct StatAcc {
+  uint32_t n_miss, an_x, mb;
+  uint32_t n_het[STAT_ALLELES], n_hom[STAT_ALLELES], ac[STAT_ALLELES], hb[STAT_ALLELES], ob[STAT_ALLELES];
 };
-__device__ __forceinline__ void classify3w(uint32_t w, uint32_t off, const uint8_t *L,
-                                           uint32_t content_len, Ev3 &o) {
-  o.is_ev = !(w & EV_OFFSET_TAG);
-  o.samp = w & EV_SAMPLE_MASK;
-  o.gtx = 0;
-  if (o.is_ev && (w & EV_COMPLEX)) {  // general GT grammar, exact (main.go:1126-1190)
+__device__ __forceinline__ void stat_zero(StatAcc &s) {
+  s.n_miss = s.an_x = s.mb = 0;
 #pragma unroll
-    for (int a = 0; a < STAT_ALLELES; a++)
-      o.cls[a] = classify_gt_general(L + off, content_len > off ? content_len - off : 0, a + 1, o.gtx, o.alt[a]);
-  } else {
-    const uint32_t c1 = (w >> 20) & 31, c2 = (w >> 25) & 31;
-    const bool miss = c1 == EV_CODE_MISSING;
-    const uint32_t gt = c2 == EV_CODE_ABSENT ? 1 : 2;
+  for (int a = 0; a < STAT_ALLELES; a++) s.n_het[a] = s.n_hom[a] = s.ac[a] = s.hb[a] = s.ob[a] = 0;
+}
+// one quad event into the summary: nibble masks per allele number, the general GT grammar for complex samples
+// (main.go:1126-1190), name lengths only when the names are not all one width
+__device__ __forceinline__ void stat_quad(StatAcc &s, const DevCfg &cfg, bool fixed, uint2 e, const uint8_t *L, uint32_t content_len) {
+  const uint32_t s0 = (e.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
+  if (e.x & EV_COMPLEX) {
+    const uint32_t nl = fixed ? 0u : name_len(cfg, s0);
 #pragma unroll
     for (int a = 0; a < STAT_ALLELES; a++) {
-      o.alt[a] = (o.is_ev && !miss) ? (c1 == (uint32_t)(a + 1)) + (c2 == (uint32_t)(a + 1)) : 0;
-      o.cls[a] = !o.is_ev ? 0 : (miss ? 3 : (o.alt[a] == 0 ? 0 : (o.alt[a] == gt ? 2 : 1)));
+      uint32_t gt, alt;
+      const int cls = classify_gt_general(L + e.y, content_len > e.y ? content_len - e.y : 0, a + 1, gt, alt);
+      s.ac[a] += alt;
+      if (cls == 1) { s.n_het[a]++; s.hb[a] += nl; } else if (cls == 2) { s.n_hom[a]++; s.ob[a] += nl; }
+      if (a == 0) { s.an_x += gt; if (cls == 3) { s.n_miss++; s.mb += nl; } }
+    }
+    return;
+  }
+  const uint32_t dt = nib_eq(e.y, 0xEEEEEEEEu);
+  const uint32_t ms = (dt | (dt >> 16)) & 0x8888u;             // samples with a '.' token
+  const uint32_t gone = ((ms | (ms << 16)) >> 3) * 15u;        // both nibbles of those samples
+  s.n_miss += __popc(ms);
+  uint32_t mh[STAT_ALLELES], mo[STAT_ALLELES];
+#pragma unroll
+  for (int a = 0; a < STAT_ALLELES; a++) {
+    uint32_t mm;
+    quad_masks(e.x, e.y, a + 1, false, L, content_len, true, mh[a], mo[a], mm);
+    s.n_het[a] += __popc(mh[a]); s.n_hom[a] += __popc(mo[a]);
+    s.ac[a] += __popc(nib_eq(e.y, (uint32_t)(a + 1) * 0x11111111u) & ~gone);
+  }
+  if (!fixed) {
+    uint32_t any = ms;
+#pragma unroll
+    for (int a = 0; a < STAT_ALLELES; a++) any |= mh[a] | mo[a];
+    while (any) {  // at most four samples
+      const uint32_t bit = any & (0u - any);
+      any &= any - 1;
+      const uint32_t nl = name_len(cfg, s0 + ((uint32_t)(__ffs(bit) - 1) >> 2));
+      if (ms & bit) s.mb += nl;
+#pragma unroll
+      for (int a = 0; a < STAT_ALLELES; a++) {
+        if (mh[a] & bit) s.hb[a] += nl; else if (mo[a] & bit) s.ob[a] += nl;
+      }
     }
   }
-}
-
-__device__ __forceinline__ void classify3(const uint32_t *ev, uint32_t v, uint32_t n_words, const uint8_t *L,
-                                          uint32_t content_len, Ev3 &o) {
-  uint32_t off;
-  const uint32_t w = slot_load(ev, v, n_words, off);
-  classify3w(w, off, L, content_len, o);
 }
 
 constexpr uint32_t SMALL_EVENTS = 12;  // records with at most this many event words are reduced by one lane
 
 // Hybrid granularity: a warp takes 32 consecutive records.  Each lane reduces its own record when it has
-// few events (most of real data: singletons and rare variants); records with long event lists are then
-// reduced one at a time by the whole warp with ballot/popc.
+// few events (most of real data: singletons and rare variants); records with long event lists are queued for
+// the CTA-per-record kernel.
 __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams p) {
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
@@ -246,27 +266,22 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams 
     if (small) {  // ---- lane-serial ----
       const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
       const uint32_t *ev = p.events + rec.ev_start;
+      StatAcc t;
+      stat_zero(t);
+      for (uint32_t q = 0; 2 * q + 1 < rec.ev_count; q++)
+        stat_quad(t, cfg, fixed, *reinterpret_cast<const uint2 *>(ev + 2 * q), p.in + rec.start, content_len);
       LineStats s;
-      s.n_miss = 0; s.an = rec.an; s.miss_bytes = 0; s.pad = 0; s.pad2 = 0;
+      s.n_miss = t.n_miss; s.an = rec.an + t.an_x; s.pad = 0; s.pad2 = 0;
+      s.miss_bytes = fixed ? t.n_miss * cfg.name_fixed_w : t.mb;
 #pragma unroll
-      for (int a = 0; a < STAT_ALLELES; a++) { s.n_het[a] = s.n_hom[a] = s.ac[a] = s.het_bytes[a] = s.hom_bytes[a] = 0; }
-      for (uint32_t k = 0; k < 2 * rec.ev_count; k++) {
-        Ev3 e;
-        classify3(ev, k, rec.ev_count, p.in + rec.start, content_len, e);
-        if (!e.is_ev) continue;
-        const uint32_t nl = name_len(cfg, e.samp);
-        s.an += e.gtx;
-        if (e.cls[0] == 3) { s.n_miss++; s.miss_bytes += nl; }
-#pragma unroll
-        for (int a = 0; a < STAT_ALLELES; a++) {
-          s.ac[a] += e.alt[a];
-          if (e.cls[a] == 1) { s.n_het[a]++; s.het_bytes[a] += nl; }
-          else if (e.cls[a] == 2) { s.n_hom[a]++; s.hom_bytes[a] += nl; }
-        }
+      for (int a = 0; a < STAT_ALLELES; a++) {
+        s.n_het[a] = t.n_het[a]; s.n_hom[a] = t.n_hom[a]; s.ac[a] = t.ac[a];
+        s.het_bytes[a] = fixed ? t.n_het[a] * cfg.name_fixed_w : t.hb[a];
+        s.hom_bytes[a] = fixed ? t.n_hom[a] * cfg.name_fixed_w : t.ob[a];
       }
       p.stats[li] = s;
     }
-    // ---- the long ones go to the work list of the warp-per-record kernel (one atomic per warp) ----
+    // ---- the long ones go to the work list of the CTA-per-record kernel (one atomic per warp) ----
     const uint32_t big = __ballot_sync(FULL, needed && !small);
     if (big) {
       uint32_t base = 0;
@@ -278,13 +293,12 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_kernel(const StatsParams 
 }
 
 // CTA per record: the records the hybrid kernel queued (long event lists: up to 50,000 quads at biobank width);
-// the eight warps take interleaved 32-quad batches, ballot/popc and REDUX per warp, shared-memory atomics across
+// a thread takes every 256th quad, REDUX per warp, shared-memory atomics across the warps
 __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsParams p) {
   __shared__ uint32_t s_wi;
   __shared__ uint32_t s_acc[3 + 5 * STAT_ALLELES];
   const DevCfg &cfg = p.cfg;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr uint32_t NW = 8;  // warps per CTA (launch: 256 threads)
+  const int lane = threadIdx.x & 31;
   if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const uint32_t n_big = p.ctr->n_big_recs;
   const bool fixed = cfg.name_fixed_w > 0;
@@ -297,100 +311,42 @@ __global__ void __launch_bounds__(256) bvcf_line_stats_big_kernel(const StatsPar
     if (wi >= n_big) break;
     const uint32_t li = p.big_recs[wi];
     const LineRec rec = p.lines[li];
-    {
-      const uint64_t start = rec.start;
-      const uint32_t len = rec.len, an0 = rec.an, ev_start = rec.ev_start, ev_count = rec.ev_count;
-      const int l = 0;
-      const uint32_t lb = li;
-      const uint32_t content_len = len >= (uint32_t)cfg.eol_width ? len - (uint32_t)cfg.eol_width : 0;
-      const uint32_t *ev = p.events + ev_start;
-      const uint8_t *L = p.in + start;
-      uint32_t n_het[STAT_ALLELES] = {0, 0, 0}, n_hom[STAT_ALLELES] = {0, 0, 0}, ac[STAT_ALLELES] = {0, 0, 0};
-      uint32_t hb[STAT_ALLELES] = {0, 0, 0}, ob[STAT_ALLELES] = {0, 0, 0};
-      uint32_t n_miss = 0, an_x = 0, mb = 0;
-      if (fixed) {
-        // fixed-width names: no per-sample lengths are needed, so a lane takes a whole quad (four samples) and
-        // counts with nibble masks; one REDUX per counter at the end
-        const uint32_t nq = ev_count >> 1;
-        uint32_t lh[STAT_ALLELES] = {0, 0, 0}, lo_[STAT_ALLELES] = {0, 0, 0}, lm = 0;
-        for (uint32_t q = warp * 32 + lane; q < nq; q += NW * 32) {
-          const uint2 e = *reinterpret_cast<const uint2 *>(ev + 2 * q);
-          if (e.x & EV_COMPLEX) {
+    const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
+    const uint32_t *ev = p.events + rec.ev_start;
+    const uint8_t *L = p.in + rec.start;
+    const uint32_t nq = rec.ev_count >> 1;
+    StatAcc t;
+    stat_zero(t);
+    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x)
+      stat_quad(t, cfg, fixed, *reinterpret_cast<const uint2 *>(ev + 2 * q), L, content_len);
+    // warp totals -> shared memory
+    const uint32_t w_miss = __reduce_add_sync(FULL, t.n_miss), w_an = __reduce_add_sync(FULL, t.an_x), w_mb = __reduce_add_sync(FULL, t.mb);
+    uint32_t w[5 * STAT_ALLELES];
 #pragma unroll
-            for (int a = 0; a < STAT_ALLELES; a++) {
-              uint32_t gt, alt;
-              const int cls = classify_gt_general(L + e.y, content_len > e.y ? content_len - e.y : 0, a + 1, gt, alt);
-              lh[a] += cls == 1; lo_[a] += cls == 2; ac[a] += alt;
-              if (a == 0) { lm += cls == 3; an_x += gt; }
-            }
-          } else {
-            const uint32_t dt = nib_eq(e.y, 0xEEEEEEEEu);
-            const uint32_t ms = (dt | (dt >> 16)) & 0x8888u;             // samples with a '.' token
-            const uint32_t gone = ((ms | (ms << 16)) >> 3) * 15u;        // both nibbles of those samples
-            lm += __popc(ms);
+    for (int a = 0; a < STAT_ALLELES; a++) {
+      w[5 * a] = __reduce_add_sync(FULL, t.n_het[a]); w[5 * a + 1] = __reduce_add_sync(FULL, t.n_hom[a]);
+      w[5 * a + 2] = __reduce_add_sync(FULL, t.ac[a]); w[5 * a + 3] = __reduce_add_sync(FULL, t.hb[a]);
+      w[5 * a + 4] = __reduce_add_sync(FULL, t.ob[a]);
+    }
+    if (lane == 0) {
+      atomicAdd(&s_acc[0], w_miss); atomicAdd(&s_acc[1], w_an); atomicAdd(&s_acc[2], w_mb);
 #pragma unroll
-            for (int a = 0; a < STAT_ALLELES; a++) {
-              uint32_t mh, mo, mm;
-              quad_masks(e.x, e.y, a + 1, false, L, content_len, true, mh, mo, mm);
-              lh[a] += __popc(mh); lo_[a] += __popc(mo);
-              ac[a] += __popc(nib_eq(e.y, (uint32_t)(a + 1) * 0x11111111u) & ~gone);
-            }
-          }
-        }
-        n_miss = __reduce_add_sync(FULL, lm);
-#pragma unroll
-        for (int a = 0; a < STAT_ALLELES; a++) { n_het[a] = __reduce_add_sync(FULL, lh[a]); n_hom[a] = __reduce_add_sync(FULL, lo_[a]); }
-      } else {
-      uint32_t off_next;
-      uint32_t w_next = slot_load(ev, warp * 32 + lane, ev_count, off_next);
-      for (uint32_t base = warp * 32; base < 2 * ev_count; base += NW * 32) {
-        const uint32_t w_cur = w_next, off_cur = off_next;  // software pipelining: the next batch is already in flight
-        w_next = slot_load(ev, base + NW * 32 + lane, ev_count, off_next);
-        Ev3 e;
-        classify3w(w_cur, off_cur, L, content_len, e);
-        const uint32_t nl = (e.is_ev && !fixed) ? name_len(cfg, e.samp) : 0;
-        n_miss += __popc(__ballot_sync(FULL, e.cls[0] == 3));
-        if (e.cls[0] == 3) mb += nl;
-        an_x += e.gtx;
-#pragma unroll
-        for (int a = 0; a < STAT_ALLELES; a++) {
-          n_het[a] += __popc(__ballot_sync(FULL, e.cls[a] == 1));
-          n_hom[a] += __popc(__ballot_sync(FULL, e.cls[a] == 2));
-          ac[a] += e.alt[a];
-          if (e.cls[a] == 1) hb[a] += nl; else if (e.cls[a] == 2) ob[a] += nl;
-        }
-      }
-      }
-      // warp totals -> shared memory (n_miss, n_het, n_hom are warp-uniform already)
-      const uint32_t w_an = __reduce_add_sync(FULL, an_x), w_mb = __reduce_add_sync(FULL, mb);
-      uint32_t w_ac[STAT_ALLELES], w_hb[STAT_ALLELES], w_ob[STAT_ALLELES];
+      for (int k = 0; k < 5 * STAT_ALLELES; k++) atomicAdd(&s_acc[3 + k], w[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      LineStats s;
+      s.n_miss = s_acc[0]; s.pad = 0; s.pad2 = 0;
+      s.an = rec.an + s_acc[1];
+      s.miss_bytes = fixed ? s.n_miss * cfg.name_fixed_w : s_acc[2];
 #pragma unroll
       for (int a = 0; a < STAT_ALLELES; a++) {
-        w_ac[a] = __reduce_add_sync(FULL, ac[a]); w_hb[a] = __reduce_add_sync(FULL, hb[a]); w_ob[a] = __reduce_add_sync(FULL, ob[a]);
+        s.n_het[a] = s_acc[3 + 5 * a]; s.n_hom[a] = s_acc[4 + 5 * a];
+        s.ac[a] = s_acc[5 + 5 * a];
+        s.het_bytes[a] = fixed ? s.n_het[a] * cfg.name_fixed_w : s_acc[6 + 5 * a];
+        s.hom_bytes[a] = fixed ? s.n_hom[a] * cfg.name_fixed_w : s_acc[7 + 5 * a];
       }
-      if (lane == 0) {
-        atomicAdd(&s_acc[0], n_miss); atomicAdd(&s_acc[1], w_an); atomicAdd(&s_acc[2], w_mb);
-#pragma unroll
-        for (int a = 0; a < STAT_ALLELES; a++) {
-          atomicAdd(&s_acc[3 + 5 * a], n_het[a]); atomicAdd(&s_acc[4 + 5 * a], n_hom[a]); atomicAdd(&s_acc[5 + 5 * a], w_ac[a]);
-          atomicAdd(&s_acc[6 + 5 * a], w_hb[a]); atomicAdd(&s_acc[7 + 5 * a], w_ob[a]);
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        LineStats s;
-        s.n_miss = s_acc[0]; s.pad = 0; s.pad2 = 0;
-        s.an = an0 + s_acc[1];
-        s.miss_bytes = fixed ? s.n_miss * cfg.name_fixed_w : s_acc[2];
-#pragma unroll
-        for (int a = 0; a < STAT_ALLELES; a++) {
-          s.n_het[a] = s_acc[3 + 5 * a]; s.n_hom[a] = s_acc[4 + 5 * a];
-          s.ac[a] = s_acc[5 + 5 * a];
-          s.het_bytes[a] = fixed ? s.n_het[a] * cfg.name_fixed_w : s_acc[6 + 5 * a];
-          s.hom_bytes[a] = fixed ? s.n_hom[a] * cfg.name_fixed_w : s_acc[7 + 5 * a];
-        }
-        p.stats[lb + l] = s;
-      }
+      p.stats[li] = s;
     }
   }
 }
