@@ -1,16 +1,19 @@
 // bvcf_names.cuh -- north-star kernel (4b), sample-name lists of the long rows as aligned 16-byte vectors.
 //
-// bvcf_names_kernel (bvcf_rows.cuh) writes the lists of short rows lane-serially and queues the others.  When
-// every list item has one size of 5..16 bytes (fixed-width names; 7-character names + 1-character delimiter, the
-// 1000 Genomes / biobank layout, get the 8-byte fast path) and
-// TSV output is on, bvcf_names_vec_kernel takes the queue instead of bvcf_names_big_kernel:
-//   pass 1  one sweep over the row's quad events: het / hom / missing slots as nibble masks (general GT grammar for
-//           complex samples, main.go:1126-1190), ranks from one packed warp prefix sum per 32 quads, the sample
+// bvcf_names_kernel (bvcf_rows.cuh) writes the lists of short rows lane-serially and queues the others.  When every
+// list item (name + delimiter) has one size of 5..16 bytes and TSV output is on, the queues are served here instead
+// of by bvcf_names_big_kernel (7-character names + 1-character delimiter, the 1000 Genomes / biobank layout, are
+// 8-byte items with a fast path of their own):
+//   sweep   one pass over the row's quad events: het / hom / missing slots as nibble masks (general GT grammar for
+//           complex samples, main.go:1126-1190), ranks from one packed warp prefix sum per 64 quads, the sample
 //           indices of the three lists compacted into shared memory in header order (main.go:1057 loop order);
-//   pass 2  each list (main.go:617,639,653 strings.Join) leaves as aligned uint4 stores, every vector assembled
-//           from the two or three neighbouring 8-byte items it overlaps; byte stores only at the ragged ends.
-// The old kernel stored each item with 2-4 narrow unaligned stores (0.6 store sectors per clock per SM: the LSU
-// limit, not HBM).
+//           with --dosageOutput the same pass scatters the int8 dosages (main.go:1172-1178);
+//   emit    each list (main.go:617,639,653 strings.Join) leaves as aligned uint4 stores, every vector assembled
+//           from the items it overlaps; byte stores only at the ragged ends.
+//   bvcf_names_vec_kernel   warp per row (index buffer of 2,816 samples; longer lists in chunks, still one sweep)
+//   bvcf_names_long_kernel  CTA per row beyond 4,096 quads: counting sweep, prefix over the warps, chunked sweeps
+// The first-generation kernel stored each item with 2-4 narrow unaligned stores (0.6 store sectors per clock per
+// SM: the LSU limit, not HBM).
 #pragma once
 #include "bvcf_rows.cuh"
 
