@@ -4,9 +4,11 @@
 //   bvcf_scan_genotype_kernel      index + genotype events                    (north-star kernels 1+3)
 //   bvcf_prefix_* (mode 0)         per-range record counts -> bases
 //   bvcf_compact_lines_kernel      input-ordered line table
+//   bvcf_line_stats_{,big_}kernel  genotype summaries the scan could not finish inline
 //   bvcf_rows_kernel<SIZE>         FILTER + getAlleles + row sizes            (north-star kernels 2+4a)
 //   bvcf_prefix_* (mode 1)         row offsets, advances the run's output cursor
-//   bvcf_rows_kernel<EMIT>         scatter-write of the rows                  (north-star kernel 4b)
+//   bvcf_rows_kernel<EMIT>         scatter-write of the rows' fixed columns   (north-star kernel 4b)
+//   bvcf_names_*                   sample-name lists, dosage rows             (north-star kernel 4b)
 #include "../../include/bvcf.h"
 
 #include <algorithm>

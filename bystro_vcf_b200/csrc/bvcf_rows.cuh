@@ -1,19 +1,24 @@
 // bvcf_rows.cuh -- north-star kernels (2)+(4): per-line fixed-field kernel + two-pass row emitter.
 //
-//   bvcf_line_stats_kernel   warp per record: reduce the scan kernel's genotype events for ALT #1 to
-//                            het/hom/missing counts, ac, an with __ballot_sync/__popc   (main.go:1042-1194)
-//   bvcf_rows_kernel<SIZE>   thread per record: FILTER allow/exclude against a shared-memory table
-//                            (main.go:447-454), getAlleles' decision tree -- ACTG QC, multiallelic split, MNP
-//                            decomposition, padding trim + left-normalisation, site type, trTv
-//                            (main.go:723-1038, 602-606) -- and the exact size of every row it will emit
+//   bvcf_line_stats_kernel      records whose genotype summary is not complete in the scan kernel's LineRec (ALT
+//   bvcf_line_stats_big_kernel  numbers other than 1, complex GTs, variable-width names): het/hom/missing counts,
+//                               ac, an and list byte lengths for ALT numbers 1..3 from the quad events with nibble
+//                               masks (main.go:1042-1194); lane per record, CTA per record with a long event list
+//   bvcf_rows_kernel<SIZE>      thread per record: FILTER allow/exclude against a shared-memory table
+//                               (main.go:447-454), getAlleles' decision tree -- ACTG QC, multiallelic split, MNP
+//                               decomposition, padding trim + left-normalisation, site type, trTv
+//                               (main.go:723-1038, 602-606) -- and the exact size of every row it will emit
 //   (exclusive scan of the sizes: bvcf_prefix.cuh)
-//   bvcf_rows_kernel<EMIT>   same code, now writing every non-list byte of its rows at the scanned offsets
-//                            (main.go:586-695) and one RowDesc per row
-//   bvcf_names_kernel        warp per row: scatter-writes the heterozygote / homozygote / missing sample-name
-//                            lists (main.go:617,639,653 strings.Join) and the int8 dosage row (main.go:576-584)
+//   bvcf_rows_kernel<EMIT>      same code, now writing every non-list byte of its rows at the scanned offsets
+//                               (main.go:586-695) and one RowDesc per row
+//   bvcf_rows_list_kernel       both passes for the records that may yield several rows (sites-only input)
+//   bvcf_dosage_zero_kernel     the int8 dosage rows of the sub-chunk start as all-reference (main.go:576-584)
+//   bvcf_names_kernel           lane per short row: the heterozygote / homozygote / missing sample-name lists
+//                               (main.go:617,639,653 strings.Join) and the row's dosages; queues the long rows
+//   bvcf_names_big_kernel       warp per queued row, any name widths (bvcf_names.cuh takes fixed-size items)
 //
-// Rows of ALT #1 (99 % of real data) use the warp-reduced stats; other ALT numbers are reduced by the
-// record's own thread straight from the event list.
+// Rows of ALT #1..3 use the LineRec / LineStats summaries; higher ALT numbers are reduced by the record's own
+// thread straight from the event list.
 #pragma once
 #include "bvcf_common.cuh"
 #include "bvcf_text.cuh"
