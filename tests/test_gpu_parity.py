@@ -335,7 +335,10 @@ def _fuzz_vcf(rng, n_samples, n_lines, name_w):
 import os as _os
 
 
-@pytest.mark.parametrize("seed", range(int(_os.environ.get("BVCF_FUZZ_N", "24"))))
+_FUZZ_OFF = int(_os.environ.get("BVCF_FUZZ_OFFSET", "0"))
+
+
+@pytest.mark.parametrize("seed", range(_FUZZ_OFF, _FUZZ_OFF + int(_os.environ.get("BVCF_FUZZ_N", "24"))))
 def test_fuzz_line_shapes_vs_oracle(seed):
     import random
 
@@ -364,7 +367,7 @@ def test_empty_last_sample_field():
     assert all(r[13] == str(2 * (ns - 1) + 1) for r in rows_of(got))
 
 
-@pytest.mark.parametrize("seed", range(int(_os.environ.get("BVCF_FUZZ2_N", "16"))))
+@pytest.mark.parametrize("seed", range(_FUZZ_OFF, _FUZZ_OFF + int(_os.environ.get("BVCF_FUZZ2_N", "16"))))
 def test_fuzz_options_dosage_chunks_vs_oracle(seed):
     """The same random line shapes under the other axes: CRLF line ends, 64 KiB chunks through submit/collect,
     multi-character emptyField / fieldDelimiter, the dosage matrix, diagnostics."""
@@ -447,7 +450,7 @@ def test_wide_dense_rows_name_kernels(n_samples, dens, name_fmt):
             assert np.array_equal(res.dosage, ref.dosage)
 
 
-@pytest.mark.parametrize("seed", range(int(_os.environ.get("BVCF_FUZZ3_N", "12"))))
+@pytest.mark.parametrize("seed", range(_FUZZ_OFF, _FUZZ_OFF + int(_os.environ.get("BVCF_FUZZ3_N", "12"))))
 def test_fuzz_resident_tiny_subchunks_vs_oracle(seed):
     """The device-resident entry points (bvcf_resident_*) on random line shapes, cut into 64 KiB sub-chunks so that
     lines straddle sub-chunk and range boundaries everywhere."""
