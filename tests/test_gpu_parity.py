@@ -510,3 +510,66 @@ def test_output_and_row_capacity_retries():
         res = tr.process(vcf[off:])
     assert res.tsv == ref.tsv
     assert res.retries > 0
+
+
+def _fuzz_alleles_vcf(rng, n_lines, with_samples):
+    """Random REF/ALT pairs around getAlleles' decision tree (main.go:723-1038): SNPs, MNPs, insertions and deletions
+    with shared prefixes/suffixes, mixed and malformed alleles, odd POS, multi-allelic lists."""
+    B = "ACGT"
+
+    def bases(n):
+        return "".join(rng.choice(B) for _ in range(n))
+
+    def alt_of(ref):
+        u = rng.random()
+        if u < 0.25:  # SNP / MNP
+            a = list(ref)
+            for _ in range(rng.randrange(1, len(a) + 1)):
+                i = rng.randrange(len(a)); a[i] = rng.choice(B)
+            return "".join(a)
+        if u < 0.45:  # insertion after a shared prefix, maybe a shared suffix
+            k = rng.randrange(0, len(ref) + 1)
+            return ref[:k] + bases(rng.randrange(1, 6)) + ref[k:]
+        if u < 0.65 and len(ref) > 1:  # deletion
+            k = rng.randrange(1, len(ref)); m = rng.randrange(k, len(ref) + 1)
+            return ref[:k] + ref[m:] if ref[:k] + ref[m:] else ref[0]
+        if u < 0.72:
+            return bases(rng.randrange(1, 9))  # unrelated
+        if u < 0.80:
+            return rng.choice(["<DEL>", "*", ".", "N", "acgt", "A[chr1:5[", "", ref])
+        return rng.choice(B)
+
+    hdr = V.HDR8 + (["FORMAT", "S1", "S2", "S3"] if with_samples else [])
+    recs = []
+    for i in range(n_lines):
+        ref = bases(rng.choice([1, 1, 1, 2, 3, 4, 8]))
+        alts = ",".join(alt_of(ref) for _ in range(rng.choice([1, 1, 1, 2, 3, 5])))
+        odd_pos = [str(rng.randrange(1, 10 ** rng.randrange(1, 10))), "x", "+5", "-3", "007", "9223372036854775807"]
+        pos = rng.choice(odd_pos) if rng.random() < 0.1 else str(rng.randrange(1, 250000000))
+        rec = [rng.choice(["1", "chr1", "MT", "GL000207.1", "c"]), pos, rng.choice([".", "rs1;rs2"]), ref, alts, ".",
+               rng.choice(["PASS", "PASS", ".", "q10"]), "AC=1"]
+        if with_samples:
+            n_alt = alts.count(",") + 1
+            gts = ["%s|%s" % (rng.randrange(0, n_alt + 1), rng.randrange(0, n_alt + 1)) for _ in range(3)]
+            rec += ["GT"] + gts
+        recs.append(rec)
+    return V._vcf(hdr, recs)
+
+
+@pytest.mark.parametrize("seed", range(_FUZZ_OFF, _FUZZ_OFF + int(_os.environ.get("BVCF_FUZZ4_N", "12"))))
+def test_fuzz_alleles_vs_oracle(seed):
+    import random
+
+    from bystro_vcf_b200 import Transformer, parse_preamble
+    from oracle import oracle as O
+
+    rng = random.Random(77000 + seed)
+    vcf = _fuzz_alleles_vcf(rng, rng.randrange(50, 400), rng.random() < 0.5)
+    okw = {"keep_id": rng.random() < 0.5, "keep_info": rng.random() < 0.5, "keep_pos": rng.random() < 0.5}
+    ref = O.read_vcf(O.OracleConfig(**okw), vcf)
+    w, chrom, off = parse_preamble(vcf)
+    with Transformer(_cfg(**okw), eol_width=w) as tr:
+        tr.set_header(chrom)
+        res = tr.process(vcf[off:])
+    assert res.tsv == ref.tsv
+    assert sorted(res.diags) == sorted(ref.diags)
