@@ -67,7 +67,7 @@ struct Slot {
 };
 
 constexpr uint32_t LOCI_STRIDE = 64;
-constexpr uint32_t DIAG_CAP = 1u << 16;
+constexpr uint32_t DIAG_CAP0 = 1u << 16;   // first guess; grown to the count a chunk reports, then the chunk runs again
 
 }  // namespace
 
@@ -88,6 +88,8 @@ struct bvcf_ctx {
   RunCounters *r_d_ctr = nullptr, *r_h_ctr = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   double ev_factor = 0.5;  // event slice bytes per range byte
+  uint32_t diag_cap = DIAG_CAP0;   // diagnostics a chunk may report (grown on demand, never truncated)
+  uint32_t min_line_bytes = 16;    // line slots per range = range_bytes / max(H, this) + 2; halved on slot_overflow
   uint64_t launches = 0;
   std::string last_error;
   uint64_t r_last_records = 0;
@@ -149,7 +151,9 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
   uint64_t sub = std::min<uint64_t>(round_up(total_bytes + 512, sc.range_bytes), round_up(sub_limit, sc.range_bytes));
   sc.sub_bytes = sub;
   sc.n_ranges = (uint32_t)(sub / sc.range_bytes);
-  sc.slots = sc.range_bytes / (uint32_t)std::max(H, 16) + 2;
+  // a record needs at least H bytes (H - 1 tabs + the newline); with H < 16 the first guess is 16 and slot_overflow
+  // lowers it (bvcf_collect / bvcf_resident_run re-run the chunk)
+  sc.slots = sc.range_bytes / std::max<uint32_t>((uint32_t)std::max(H, 1), ctx->min_line_bytes) + 2;
   uint64_t evb = (uint64_t)(sc.range_bytes * ctx->ev_factor) + 16 * 1024;
   if (ctx->dcfg.n_samples == 0) evb = 64;
   sc.evcap_words = (uint32_t)(evb / 4) & ~1u;  // quad events are 8-byte aligned
@@ -275,7 +279,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     rp.out = d_out; rp.out_cap = out_cap; rp.ctr = d_ctr;
     rp.row_desc = (RowDesc *)sc.row_desc.p; rp.row_desc_cap = dc.n_samples > 0 ? sc.row_cap : 0;
     rp.dosage_cap_rows = dosage_cap_rows; rp.loci = d_loci; rp.loci_stride = LOCI_STRIDE;
-    rp.diags = d_diags; rp.diag_cap = DIAG_CAP;
+    rp.diags = d_diags; rp.diag_cap = ctx->diag_cap;
     rp.multi_recs = (uint32_t *)sc.multi_recs.p;
     const bool defer_multi = dc.n_samples == 0;  // see RowsParams::multi_recs
     const unsigned rgrid = (unsigned)n_sm * 16;
@@ -392,7 +396,7 @@ int slot_enqueue(bvcf_ctx *ctx, Slot &s, bool upload) {
       dos_rows = est;
     }
   }
-  if ((rc = dev_reserve(ctx, s.d_diags, (size_t)DIAG_CAP * 16))) return rc;
+  if ((rc = dev_reserve(ctx, s.d_diags, (size_t)ctx->diag_cap * 16))) return rc;
   if (upload) CK(cudaMemcpyAsync(s.d_in.p, s.h_src, len, cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemsetAsync((uint8_t *)s.d_in.p + len, '\n', buf_len - len, s.stream));
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(RunCounters), s.stream));
@@ -457,6 +461,7 @@ int bvcf_create(bvcf_ctx **out, int cuda_device, const bvcf_config *cfg) {
   for (int i = 0; i < cfg->n_allow; i++) ctx->allow.push_back(cfg->allow[i] ? cfg->allow[i] : "");
   for (int i = 0; i < cfg->n_exclude; i++) ctx->exclude.push_back(cfg->exclude[i] ? cfg->exclude[i] : "");
   if (ctx->allow.size() + ctx->exclude.size() > 64) { delete ctx; return BVCF_E_TOO_LARGE; }
+  if (const char *e = getenv("BVCF_DIAG_CAP")) ctx->diag_cap = (uint32_t)std::max(1, atoi(e));  // tests: force the grow-and-retry path
   if (ctx->cfg.n_slots <= 0) ctx->cfg.n_slots = 3;
   if (ctx->cfg.max_chunk_bytes == 0) ctx->cfg.max_chunk_bytes = 256ull << 20;
   if (ctx->cfg.resident_subchunk_bytes == 0) ctx->cfg.resident_subchunk_bytes = 16ull << 30;
@@ -632,7 +637,15 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
     CK(cudaEventSynchronize(s->done));
     const RunCounters &c = *s->h_ctr;
     bool again = false;
-    if (c.slot_overflow) return BVCF_E_TOO_LARGE;                       // cannot happen: slots cover the minimum line
+    if (c.slot_overflow) {                                              // lines shorter than assumed: more line slots
+      if (ctx->min_line_bytes <= 1) return BVCF_E_TOO_LARGE;
+      ctx->min_line_bytes /= 2;
+      s->retries++;
+      if (s->retries > 8) return BVCF_E_TOO_LARGE;
+      const int rc = slot_enqueue(ctx, *s, false);
+      if (rc) return rc;
+      continue;
+    }
     if (c.ev_overflow) {                                                // dense genotype block: more event slots
       ctx->ev_factor *= 4;
       s->retries++;
@@ -653,6 +666,7 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
       if ((rc = dev_reserve(ctx, s->d_loci, (size_t)(c.row_cursor + 64) * LOCI_STRIDE))) return rc;
       again = true;
     }
+    if (c.n_diags > ctx->diag_cap) { ctx->diag_cap = c.n_diags + c.n_diags / 4; again = true; }  // every log line or none
     if (!again) break;
     s->retries++;
     if (s->retries > 8) return BVCF_E_TOO_LARGE;
@@ -683,7 +697,7 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
     s->h_loci_raw.resize((size_t)c.row_cursor * LOCI_STRIDE);
     CK(cudaMemcpyAsync(s->h_loci_raw.data(), s->d_loci.p, s->h_loci_raw.size(), cudaMemcpyDeviceToHost, s->stream));
   }
-  const uint32_t nd = std::min<uint32_t>(c.n_diags, DIAG_CAP);
+  const uint32_t nd = c.n_diags;  // <= diag_cap: larger counts re-ran the chunk above
   if (nd) {
     s->h_diag_raw.resize((size_t)nd * 4);
     CK(cudaMemcpyAsync(s->h_diag_raw.data(), s->d_diags.p, (size_t)nd * 16, cudaMemcpyDeviceToHost, s->stream));
@@ -791,7 +805,12 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
     CK(cudaStreamSynchronize(ctx->r_stream));
     const RunCounters &c = *ctx->r_h_ctr;
     bool again = false;
-    if (c.slot_overflow) return BVCF_E_TOO_LARGE;
+    if (c.slot_overflow) {  // lines shorter than assumed: more line slots, run again
+      if (ctx->min_line_bytes <= 1) return BVCF_E_TOO_LARGE;
+      ctx->min_line_bytes /= 2;
+      if (++retries > 8) return BVCF_E_TOO_LARGE;
+      continue;
+    }
     if (c.ev_overflow) {  // dense genotype block: more event slots, run again
       ctx->ev_factor *= 4;
       if (++retries > 8) return BVCF_E_TOO_LARGE;

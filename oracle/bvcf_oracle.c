@@ -133,7 +133,7 @@ int oracle_alt_is_valid(const char *alt, size_t n) {
 /* ---------- getAlleles (main.go:723-1038) ---------- */
 
 typedef struct {
-  char pos[24];
+  char *pos; /* malloc'd: a verbatim POS field is copied whole, whatever its length (main.go:742,803) */
   char ref;
   char *alt; /* malloc'd */
   size_t alt_len;
@@ -171,7 +171,7 @@ static void al_push(allele_list *l, const char *pos, size_t pos_n, char ref, con
     l->a = (out_allele *)realloc(l->a, l->cap * sizeof(out_allele));
   }
   out_allele *o = &l->a[l->n++];
-  if (pos_n > 23) pos_n = 23;
+  o->pos = (char *)malloc(pos_n + 1);
   memcpy(o->pos, pos, pos_n);
   o->pos[pos_n] = 0;
   o->ref = ref;
@@ -190,7 +190,7 @@ static void al_push_int(allele_list *l, long long pos, char ref, long long alt, 
   al_push(l, pb, pn, ref, "", ab, an, idx);
 }
 static void al_free(allele_list *l) {
-  for (int i = 0; i < l->n; i++) free(l->a[i].alt);
+  for (int i = 0; i < l->n; i++) { free(l->a[i].alt); free(l->a[i].pos); }
   free(l->a);
   l->a = NULL;
   l->n = l->cap = 0;
@@ -340,7 +340,7 @@ int oracle_get_alleles(const char *chrom, const char *pos, const char *ref, cons
   strcpy(type_out, l.type);
   int n = l.n;
   for (int i = 0; i < n && i < cap; i++) {
-    strcpy(pos_out[i], l.a[i].pos);
+    snprintf(pos_out[i], 24, "%s", l.a[i].pos); /* unit-level API: 23 characters are plenty for the vectors */
     ref_out[i] = l.a[i].ref;
     alt_out[i] = strdup(l.a[i].alt);
     idx_out[i] = l.a[i].idx;
