@@ -153,7 +153,7 @@ def run_ours(args):
         stats, times = tr.resident_run(need)
     assert stats["n_lines"] == n_lines and stats["n_records"] == n_lines, stats
     launches0 = tr.launches
-    acc = {"scan_ms": 0.0, "compact_ms": 0.0, "stats_ms": 0.0, "size_ms": 0.0, "emit_ms": 0.0, "names_ms": 0.0, "total_ms": 0.0}
+    acc = {"scan_ms": 0.0, "compact_ms": 0.0, "stats_ms": 0.0, "rows_ms": 0.0, "names_ms": 0.0, "total_ms": 0.0}
     barrier()
     with ClockSampler(dev) as clk:
         t0 = time.perf_counter()

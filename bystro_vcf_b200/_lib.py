@@ -65,8 +65,7 @@ class CKernelTimes(C.Structure):
         ("scan_ms", C.c_float),
         ("compact_ms", C.c_float),
         ("stats_ms", C.c_float),
-        ("size_ms", C.c_float),
-        ("emit_ms", C.c_float),
+        ("rows_ms", C.c_float),
         ("names_ms", C.c_float),
         ("total_ms", C.c_float),
         ("launches", C.c_uint32),

@@ -5,10 +5,9 @@
 //   bvcf_prefix_* (mode 0)         per-range record counts -> bases
 //   bvcf_compact_lines_kernel      input-ordered line table
 //   bvcf_line_stats_{,big_}kernel  genotype summaries the scan could not finish inline
-//   bvcf_rows_kernel<SIZE>         FILTER + getAlleles + row sizes            (north-star kernels 2+4a)
-//   bvcf_prefix_* (mode 1)         row offsets, advances the run's output cursor
-//   bvcf_rows_kernel<EMIT>         scatter-write of the rows' fixed columns   (north-star kernel 4b)
-//   bvcf_names_*                   sample-name lists, dosage rows             (north-star kernel 4b)
+//   bvcf_tile_kernel               FILTER + getAlleles + row text, sizes scanned on the fly (decoupled look-back),
+//                                  rows and short name lists written in one pass  (north-star kernels 2+4)
+//   bvcf_names_{vec,long,big}_     long sample-name lists, their dosage rows  (north-star kernel 4b)
 #include "../../include/bvcf.h"
 
 #include <algorithm>
@@ -21,6 +20,7 @@
 #include "bvcf_common.cuh"
 #include "bvcf_prefix.cuh"
 #include "bvcf_rows.cuh"
+#include "bvcf_tile.cuh"
 #include "bvcf_names.cuh"
 #include "bvcf_scan.cuh"
 
@@ -39,14 +39,13 @@ struct Scratch {
   uint32_t range_bytes = 0, n_ranges = 0, slots = 0, evcap_words = 0;
   uint64_t max_records = 0;
   uint64_t row_cap = 0;       // RowDesc slots (rows one sub-chunk may emit)
-  DevBuf recs, range_nrec, range_nlines, rec_base, line_base, events, dense, line_bytes, line_rows, line_off,
-      row_off, partial, stats1, row_desc, big_recs, big_rows, multi_recs;
+  DevBuf recs, range_nrec, range_nlines, rec_base, line_base, events, dense, partial, stats1, row_desc, big_recs, tile_state;
 };
 
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
-  DevBuf d_in, d_out, d_dosage, d_loci, d_diags;
+  DevBuf d_in, d_out, d_dosage, d_loci, d_loci_off, d_diags;
   Scratch sc;
   RunCounters *d_ctr = nullptr;
   RunCounters *h_ctr = nullptr;  // pinned
@@ -54,9 +53,10 @@ struct Slot {
   size_t h_out_cap = 0;
   int8_t *h_dosage = nullptr;    // pinned
   size_t h_dosage_cap = 0;
-  std::vector<uint8_t> h_loci;
-  std::vector<uint64_t> h_loci_off;
-  std::vector<uint8_t> h_loci_raw;
+  uint8_t *h_loci = nullptr;     // pinned
+  size_t h_loci_cap = 0;
+  uint64_t *h_loci_off = nullptr;  // pinned, rows + 1
+  size_t h_loci_off_cap = 0;
   std::vector<bvcf_diag> h_diags;
   std::vector<uint32_t> h_diag_raw;
   bool busy = false;
@@ -66,7 +66,7 @@ struct Slot {
   uint32_t retries = 0;
 };
 
-constexpr uint32_t LOCI_STRIDE = 64;
+constexpr uint32_t LOCI_GUESS = 32;          // first guess of locus bytes per row; the buffer grows to what a chunk reports
 constexpr uint32_t DIAG_CAP0 = 1u << 16;   // first guess; grown to the count a chunk reports, then the chunk runs again
 
 }  // namespace
@@ -81,7 +81,7 @@ struct bvcf_ctx {
   DevBuf d_filt_blob, d_filt_off, d_names, d_name_off, d_name8, d_name16;
   std::vector<Slot> slots;
   // resident path
-  DevBuf r_in, r_out, r_dosage, r_loci;
+  DevBuf r_in, r_out, r_dosage, r_loci, r_loci_off;
   size_t r_in_bytes = 0;
   Scratch r_sc;
   cudaStream_t r_stream = nullptr;
@@ -170,29 +170,24 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
   if ((rc = dev_reserve(ctx, sc.rec_base, (size_t)sc.n_ranges * 8))) return rc;
   if ((rc = dev_reserve(ctx, sc.line_base, (size_t)sc.n_ranges * 8))) return rc;
   if ((rc = dev_reserve(ctx, sc.events, (size_t)sc.n_ranges * sc.evcap_words * 4))) return rc;
-  if ((rc = dev_reserve(ctx, sc.line_bytes, sc.max_records * 4))) return rc;
-  if ((rc = dev_reserve(ctx, sc.line_rows, sc.max_records * 4))) return rc;
-  if ((rc = dev_reserve(ctx, sc.line_off, sc.max_records * 8))) return rc;
-  if ((rc = dev_reserve(ctx, sc.row_off, sc.max_records * 8))) return rc;
   if ((rc = dev_reserve(ctx, sc.partial, 2 * PFX_BLOCKS * 8))) return rc;
-  if ((rc = dev_reserve(ctx, sc.multi_recs, sc.max_records * 4))) return rc;
+  if ((rc = dev_reserve(ctx, sc.tile_state, (sc.max_records / TILE_THREADS + 2) * 2 * sizeof(ulonglong2)))) return rc;
   if (ctx->dcfg.n_samples > 0) {
-    sc.row_cap = std::max<uint64_t>(sc.row_cap, sc.max_records + sc.max_records / 4 + 1024);
+    // rows queued for the names kernels: usually a third of the records; grown on row_overflow
+    sc.row_cap = std::max<uint64_t>(sc.row_cap, sc.max_records / 2 + 1024);
     if ((rc = dev_reserve(ctx, sc.stats1, sc.max_records * sizeof(LineStats)))) return rc;
     if ((rc = dev_reserve(ctx, sc.row_desc, sc.row_cap * sizeof(RowDesc)))) return rc;
     if ((rc = dev_reserve(ctx, sc.big_recs, sc.max_records * 4))) return rc;
-    if ((rc = dev_reserve(ctx, sc.big_rows, sc.row_cap * 4))) return rc;
   }
   return 0;
 }
 void scratch_free(Scratch &sc) {
   for (DevBuf *b : {&sc.recs, &sc.range_nrec, &sc.range_nlines, &sc.rec_base, &sc.line_base, &sc.events, &sc.dense,
-                    &sc.line_bytes, &sc.line_rows, &sc.line_off, &sc.row_off, &sc.partial, &sc.stats1, &sc.row_desc, &sc.big_recs,
-                    &sc.big_rows, &sc.multi_recs})
+                    &sc.partial, &sc.stats1, &sc.row_desc, &sc.big_recs, &sc.tile_state})
     dev_free(*b);
 }
 
-constexpr int N_STAGE_EV = 7;
+constexpr int N_STAGE_EV = 6;
 struct StageEvents {  // optional per-stage timing of one sub-chunk
   cudaEvent_t e[N_STAGE_EV];
 };
@@ -200,7 +195,8 @@ struct StageEvents {  // optional per-stage timing of one sub-chunk
 // Enqueue the whole pipeline for data lines in [0, len) of d_in.  Never synchronises.
 int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t *d_in, uint64_t len, uint64_t buf_len,
                      uint8_t *d_out, uint64_t out_cap, RunCounters *d_ctr, int8_t *d_dosage, uint64_t dosage_cap_rows,
-                     uint8_t *d_loci, uint32_t *d_diags, std::vector<StageEvents> *timing) {
+                     uint8_t *d_loci, uint64_t loci_cap, unsigned long long *d_loci_off, uint32_t *d_diags,
+                     std::vector<StageEvents> *timing) {
   const DevCfg &dc = ctx->dcfg;
   const uint64_t total_ranges = (len + sc.range_bytes - 1) / sc.range_bytes;
   int smem = SCAN_WARPS * RING;
@@ -247,7 +243,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     pp.a = sp.range_nrec; pp.b = sp.range_nlines;
     pp.out_a = (uint64_t *)sc.rec_base.p; pp.out_b = (uint64_t *)sc.line_base.p;
     pp.partial = (unsigned long long *)sc.partial.p;
-    pp.n_ptr = nullptr; pp.n_imm = nr; pp.ctr = d_ctr; pp.mode = 0; pp.out_cap = 0;
+    pp.n_ptr = nullptr; pp.n_imm = nr; pp.ctr = d_ctr;
     bvcf_prefix_reduce_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pp);
     bvcf_prefix_spine_kernel<<<1, 1024, 0, st>>>(pp);
     bvcf_prefix_scan_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pp);
@@ -271,51 +267,29 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       ctx->launches += 2;
     }
     if (se) CK(cudaEventRecord(se->e[3], st));
-    // 4. size pass (thread per record)
-    RowsParams rp{};
-    rp.in = d_in; rp.cfg = dc; rp.lines = cp.dense; rp.events = sp.events; rp.stats = (const LineStats *)sc.stats1.p;
-    rp.line_bytes = (uint32_t *)sc.line_bytes.p; rp.line_rows = (uint32_t *)sc.line_rows.p;
-    rp.line_off = (uint64_t *)sc.line_off.p; rp.row_off = (uint64_t *)sc.row_off.p;
-    rp.out = d_out; rp.out_cap = out_cap; rp.ctr = d_ctr;
-    rp.row_desc = (RowDesc *)sc.row_desc.p; rp.row_desc_cap = dc.n_samples > 0 ? sc.row_cap : 0;
-    rp.dosage_cap_rows = dosage_cap_rows; rp.loci = d_loci; rp.loci_stride = LOCI_STRIDE;
-    rp.diags = d_diags; rp.diag_cap = ctx->diag_cap;
-    rp.multi_recs = (uint32_t *)sc.multi_recs.p;
-    const bool defer_multi = dc.n_samples == 0;  // see RowsParams::multi_recs
-    const unsigned rgrid = (unsigned)n_sm * 16;
-    if (defer_multi) bvcf_rows_kernel<false, true><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
-    else bvcf_rows_kernel<false, false><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
-    if (defer_multi) bvcf_rows_list_kernel<false><<<(unsigned)n_sm * 8, ROWS_THREADS, 0, st>>>(rp);  // the queued multi-row records
-    // 5. row offsets
-    PrefixParams pq{};
-    pq.a = rp.line_bytes; pq.b = rp.line_rows; pq.out_a = (uint64_t *)sc.line_off.p; pq.out_b = (uint64_t *)sc.row_off.p;
-    pq.partial = (unsigned long long *)sc.partial.p;
-    pq.n_ptr = &d_ctr->chunk_records; pq.n_imm = 0; pq.ctr = d_ctr; pq.mode = 1; pq.out_cap = out_cap;
-    pq.row_cap = dc.n_samples > 0 ? sc.row_cap : ~0ull;
-    bvcf_prefix_reduce_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pq);
-    bvcf_prefix_spine_kernel<<<1, 1024, 0, st>>>(pq);
-    bvcf_prefix_scan_kernel<<<PFX_BLOCKS, PFX_THREADS, 0, st>>>(pq);
-    ctx->launches += defer_multi ? 5 : 4;
+    // 4. rows: FILTER + getAlleles + row text + short name lists, one pass (tile of 128 records per CTA)
+    static const bool no_vec = getenv("BVCF_NO_NAMES_VEC") != nullptr;  // experiments
+    const bool vec = (dc.name8 || dc.name16) && dc.want_tsv && !no_vec && dc.n_samples > 0;
+    TileParams tp{};
+    tp.in = d_in; tp.cfg = dc; tp.lines = cp.dense; tp.events = sp.events; tp.stats = (const LineStats *)sc.stats1.p;
+    tp.out = d_out; tp.out_cap = out_cap; tp.ctr = d_ctr;
+    tp.tile_state = (ulonglong2 *)sc.tile_state.p;
+    tp.row_desc = (RowDesc *)sc.row_desc.p; tp.row_desc_cap = dc.n_samples > 0 ? sc.row_cap : 0;
+    tp.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
+    tp.dosage = d_dosage; tp.dosage_cap_rows = dosage_cap_rows;
+    tp.loci = d_loci; tp.loci_cap = loci_cap; tp.loci_off = d_loci_off;
+    tp.diag.diags = d_diags; tp.diag.cap = ctx->diag_cap; tp.diag.ctr = d_ctr;
+    CK(cudaMemsetAsync(sc.tile_state.p, 0, ((size_t)sc.max_records / TILE_THREADS + 2) * 2 * sizeof(ulonglong2), st));
+    bvcf_tile_kernel<<<(unsigned)n_sm * 4, TILE_THREADS, 0, st>>>(tp);
+    ctx->launches++;
     if (se) CK(cudaEventRecord(se->e[4], st));
-    // 6. emit pass: every non-list byte + one RowDesc per row
-    if (defer_multi) bvcf_rows_kernel<true, true><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
-    else bvcf_rows_kernel<true, false><<<rgrid, ROWS_THREADS, 0, st>>>(rp);
-    if (defer_multi) bvcf_rows_list_kernel<true><<<(unsigned)n_sm * 8, ROWS_THREADS, 0, st>>>(rp);
-    ctx->launches += defer_multi ? 2 : 1;
-    if (se) CK(cudaEventRecord(se->e[5], st));
-    // 7. sample-name lists + dosage rows: short rows lane-serially, the queued long rows by a warp each --
-    // as aligned vectors when every list item is 8 bytes and no dosage row is wanted (bvcf_names.cuh)
+    // 5. long sample-name lists + their dosage rows: a warp per queued row -- as aligned vectors when every list
+    // item has one size of 5..16 bytes (bvcf_names.cuh) -- and a CTA per row beyond 4,096 quads
     if (dc.n_samples > 0) {
       NamesParams np{};
       np.in = d_in; np.cfg = dc; np.lines = cp.dense; np.events = sp.events; np.row_desc = (const RowDesc *)sc.row_desc.p;
       np.row_desc_cap = sc.row_cap; np.out = d_out; np.ctr = d_ctr; np.dosage = d_dosage; np.dosage_cap_rows = dosage_cap_rows;
-      np.big_rows = (uint32_t *)sc.big_rows.p;
-      static const bool no_vec = getenv("BVCF_NO_NAMES_VEC") != nullptr;  // experiments
-      const bool vec = (dc.name8 || dc.name16) && dc.want_tsv && !no_vec;
-      np.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
-      if (dc.want_dosage && d_dosage) { bvcf_dosage_zero_kernel<<<(unsigned)n_sm * 8, 256, 0, st>>>(np); ctx->launches++; }
-      if (dc.want_dosage && d_dosage) bvcf_names_kernel<true><<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
-      else bvcf_names_kernel<false><<<wgrid, NAMES_WARPS * 32, 0, st>>>(np);
+      np.long_words = tp.long_words;
       if (vec) {
         const unsigned g1 = (unsigned)n_sm * 18, g2 = (unsigned)n_sm * 2;
         const bool dos = dc.want_dosage && d_dosage;
@@ -336,13 +310,13 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
             bvcf_names_long_kernel<uint32_t, false><<<g2, NLONG_WARPS * 32, 0, st>>>(np);
           }
         }
-        ctx->launches++;
+        ctx->launches += 2;
       } else {
         bvcf_names_big_kernel<<<wgrid * 4, NAMES_WARPS * 32, 0, st>>>(np);
+        ctx->launches++;
       }
-      ctx->launches += 2;
     }
-    if (se) CK(cudaEventRecord(se->e[6], st));
+    if (se) CK(cudaEventRecord(se->e[5], st));
   }
   CK(cudaGetLastError());
   return 0;
@@ -388,11 +362,12 @@ int slot_enqueue(bvcf_ctx *ctx, Slot &s, bool upload) {
   const DevCfg &dc = ctx->dcfg;
   uint64_t dos_rows = 0;
   if (dc.want_dosage && dc.n_samples > 0) {
-    dos_rows = s.d_dosage.cap / (uint64_t)dc.n_samples;
+    dos_rows = std::min<uint64_t>(s.d_dosage.cap / (uint64_t)dc.n_samples, s.d_loci_off.cap / 8);
     if (dos_rows == 0) {
       const uint64_t est = std::max<uint64_t>(len / std::max(1, dc.H) * 2, 1024);
       if ((rc = dev_reserve(ctx, s.d_dosage, est * dc.n_samples))) return rc;
-      if ((rc = dev_reserve(ctx, s.d_loci, est * LOCI_STRIDE))) return rc;
+      if ((rc = dev_reserve(ctx, s.d_loci_off, est * 8))) return rc;
+      if ((rc = dev_reserve(ctx, s.d_loci, est * LOCI_GUESS))) return rc;
       dos_rows = est;
     }
   }
@@ -401,8 +376,8 @@ int slot_enqueue(bvcf_ctx *ctx, Slot &s, bool upload) {
   CK(cudaMemsetAsync((uint8_t *)s.d_in.p + len, '\n', buf_len - len, s.stream));
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(RunCounters), s.stream));
   rc = enqueue_pipeline(ctx, s.sc, s.stream, (const uint8_t *)s.d_in.p, len, buf_len, (uint8_t *)s.d_out.p, s.d_out.cap,
-                        s.d_ctr, (int8_t *)s.d_dosage.p, dos_rows, (uint8_t *)s.d_loci.p, (uint32_t *)s.d_diags.p,
-                        nullptr);
+                        s.d_ctr, (int8_t *)s.d_dosage.p, dos_rows, (uint8_t *)s.d_loci.p, s.d_loci.cap,
+                        (unsigned long long *)s.d_loci_off.p, (uint32_t *)s.d_diags.p, nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(RunCounters), cudaMemcpyDeviceToHost, s.stream));
   CK(cudaEventRecord(s.done, s.stream));
@@ -515,15 +490,17 @@ void bvcf_destroy(bvcf_ctx *ctx) {
   for (auto &s : ctx->slots) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
-    for (DevBuf *b : {&s.d_in, &s.d_out, &s.d_dosage, &s.d_loci, &s.d_diags}) dev_free(*b);
+    for (DevBuf *b : {&s.d_in, &s.d_out, &s.d_dosage, &s.d_loci, &s.d_loci_off, &s.d_diags}) dev_free(*b);
     scratch_free(s.sc);
     if (s.d_ctr) cudaFree(s.d_ctr);
     if (s.h_ctr) cudaFreeHost(s.h_ctr);
     if (s.h_out) cudaFreeHost(s.h_out);
     if (s.h_dosage) cudaFreeHost(s.h_dosage);
+    if (s.h_loci) cudaFreeHost(s.h_loci);
+    if (s.h_loci_off) cudaFreeHost(s.h_loci_off);
   }
   for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->d_name8, &ctx->d_name16, &ctx->r_in, &ctx->r_out,
-                    &ctx->r_dosage, &ctx->r_loci})
+                    &ctx->r_dosage, &ctx->r_loci, &ctx->r_loci_off})
     dev_free(*b);
   scratch_free(ctx->r_sc);
   if (ctx->r_stream) cudaStreamDestroy(ctx->r_stream);
@@ -660,11 +637,18 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
       if (rc) return rc;
       again = true;
     }
-    if (dc.want_dosage && dc.n_samples > 0 && c.row_cursor * (uint64_t)dc.n_samples > s->d_dosage.cap) {
-      int rc = dev_reserve(ctx, s->d_dosage, (size_t)(c.row_cursor + 64) * dc.n_samples);
-      if (rc) return rc;
-      if ((rc = dev_reserve(ctx, s->d_loci, (size_t)(c.row_cursor + 64) * LOCI_STRIDE))) return rc;
-      again = true;
+    if (dc.want_dosage && dc.n_samples > 0) {  // dosage rows, locus offsets and locus bytes grow to what the chunk reported
+      if (c.row_cursor * (uint64_t)dc.n_samples > s->d_dosage.cap || c.row_cursor * 8 > s->d_loci_off.cap) {
+        int rc = dev_reserve(ctx, s->d_dosage, (size_t)(c.row_cursor + 64) * dc.n_samples);
+        if (rc) return rc;
+        if ((rc = dev_reserve(ctx, s->d_loci_off, (size_t)(c.row_cursor + 64) * 8))) return rc;
+        again = true;
+      }
+      if (c.loci_cursor > s->d_loci.cap) {
+        int rc = dev_reserve(ctx, s->d_loci, (size_t)(c.loci_cursor + c.loci_cursor / 8 + 4096));
+        if (rc) return rc;
+        again = true;
+      }
     }
     if (c.n_diags > ctx->diag_cap) { ctx->diag_cap = c.n_diags + c.n_diags / 4; again = true; }  // every log line or none
     if (!again) break;
@@ -694,8 +678,22 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
       s->h_dosage_cap = nb + nb / 4;
     }
     CK(cudaMemcpyAsync(s->h_dosage, s->d_dosage.p, nb, cudaMemcpyDeviceToHost, s->stream));
-    s->h_loci_raw.resize((size_t)c.row_cursor * LOCI_STRIDE);
-    CK(cudaMemcpyAsync(s->h_loci_raw.data(), s->d_loci.p, s->h_loci_raw.size(), cudaMemcpyDeviceToHost, s->stream));
+    if (c.loci_cursor > s->h_loci_cap) {
+      if (s->h_loci) cudaFreeHost(s->h_loci);
+      s->h_loci = nullptr; s->h_loci_cap = 0;
+      const size_t cap = (size_t)(c.loci_cursor + c.loci_cursor / 4 + 4096);
+      CK(cudaMallocHost(&s->h_loci, cap));
+      s->h_loci_cap = cap;
+    }
+    if (c.row_cursor + 1 > s->h_loci_off_cap) {
+      if (s->h_loci_off) cudaFreeHost(s->h_loci_off);
+      s->h_loci_off = nullptr; s->h_loci_off_cap = 0;
+      const size_t cap = (size_t)(c.row_cursor + c.row_cursor / 4 + 64);
+      CK(cudaMallocHost(&s->h_loci_off, cap * 8));
+      s->h_loci_off_cap = cap;
+    }
+    CK(cudaMemcpyAsync(s->h_loci, s->d_loci.p, c.loci_cursor, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_loci_off, s->d_loci_off.p, c.row_cursor * 8, cudaMemcpyDeviceToHost, s->stream));
   }
   const uint32_t nd = c.n_diags;  // <= diag_cap: larger counts re-ran the chunk above
   if (nd) {
@@ -709,18 +707,11 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
     memset(dosage, 0, sizeof(*dosage));
     dosage->n_samples = (uint32_t)dc.n_samples;
     if (dos && c.row_cursor) {
-      s->h_loci.clear();
-      s->h_loci_off.assign(1, 0);
-      for (uint64_t r = 0; r < c.row_cursor; r++) {
-        const char *p = (const char *)s->h_loci_raw.data() + r * LOCI_STRIDE;
-        const size_t n = strnlen(p, LOCI_STRIDE);
-        s->h_loci.insert(s->h_loci.end(), p, p + n);
-        s->h_loci_off.push_back(s->h_loci.size());
-      }
+      s->h_loci_off[c.row_cursor] = c.loci_cursor;  // rows are packed in row order: row r ends where row r + 1 starts
       dosage->n_rows = c.row_cursor;
       dosage->dosage = s->h_dosage;
-      dosage->loci = s->h_loci.data();
-      dosage->loci_off = s->h_loci_off.data();
+      dosage->loci = s->h_loci;
+      dosage->loci_off = s->h_loci_off;
     }
   }
   s->h_diags.clear();
@@ -792,14 +783,16 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
     const uint64_t buf_len = std::min<uint64_t>((ctx->r_in.cap - IN_SLACK) / 1024 * 1024, round_up(len, 1024) + 2048);
     CK(cudaMemsetAsync(ctx->r_d_ctr, 0, sizeof(RunCounters), ctx->r_stream));
     uint64_t dos_rows = 0;
-    if (dc.want_dosage && dc.n_samples > 0) dos_rows = ctx->r_dosage.cap / (uint64_t)dc.n_samples;
+    if (dc.want_dosage && dc.n_samples > 0)
+      dos_rows = std::min<uint64_t>(ctx->r_dosage.cap / (uint64_t)dc.n_samples, ctx->r_loci_off.cap / 8);
     for (auto &t : timing)
       for (auto e : t.e) ctx->ev_pool.push_back(e);
     timing.clear();
     launches0 = ctx->launches;
     rc = enqueue_pipeline(ctx, ctx->r_sc, ctx->r_stream, (const uint8_t *)ctx->r_in.p, len, buf_len,
                           (uint8_t *)ctx->r_out.p, ctx->r_out.cap, ctx->r_d_ctr, (int8_t *)ctx->r_dosage.p, dos_rows,
-                          (uint8_t *)ctx->r_loci.p, nullptr, times ? &timing : nullptr);
+                          (uint8_t *)ctx->r_loci.p, ctx->r_loci.cap, (unsigned long long *)ctx->r_loci_off.p, nullptr,
+                          times ? &timing : nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->r_h_ctr, ctx->r_d_ctr, sizeof(RunCounters), cudaMemcpyDeviceToHost, ctx->r_stream));
     CK(cudaStreamSynchronize(ctx->r_stream));
@@ -821,10 +814,16 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       if ((rc = dev_reserve(ctx, ctx->r_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096)))) return rc;
       again = true;
     }
-    if (dc.want_dosage && dc.n_samples > 0 && c.row_cursor * (uint64_t)dc.n_samples > ctx->r_dosage.cap) {
-      if ((rc = dev_reserve(ctx, ctx->r_dosage, (size_t)(c.row_cursor + 64) * dc.n_samples))) return rc;
-      if ((rc = dev_reserve(ctx, ctx->r_loci, (size_t)(c.row_cursor + 64) * LOCI_STRIDE))) return rc;
-      again = true;
+    if (dc.want_dosage && dc.n_samples > 0) {
+      if (c.row_cursor * (uint64_t)dc.n_samples > ctx->r_dosage.cap || c.row_cursor * 8 > ctx->r_loci_off.cap) {
+        if ((rc = dev_reserve(ctx, ctx->r_dosage, (size_t)(c.row_cursor + 64) * dc.n_samples))) return rc;
+        if ((rc = dev_reserve(ctx, ctx->r_loci_off, (size_t)(c.row_cursor + 64) * 8))) return rc;
+        again = true;
+      }
+      if (c.loci_cursor > ctx->r_loci.cap) {
+        if ((rc = dev_reserve(ctx, ctx->r_loci, (size_t)(c.loci_cursor + c.loci_cursor / 8 + 4096)))) return rc;
+        again = true;
+      }
     }
     if (!again) break;
     if (++retries > 8) return BVCF_E_TOO_LARGE;
@@ -843,9 +842,8 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       cudaEventElapsedTime(&ms, t.e[0], t.e[1]); times->scan_ms += ms;
       cudaEventElapsedTime(&ms, t.e[1], t.e[2]); times->compact_ms += ms;
       cudaEventElapsedTime(&ms, t.e[2], t.e[3]); times->stats_ms += ms;
-      cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->size_ms += ms;
-      cudaEventElapsedTime(&ms, t.e[4], t.e[5]); times->emit_ms += ms;
-      cudaEventElapsedTime(&ms, t.e[5], t.e[6]); times->names_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->rows_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[4], t.e[5]); times->names_ms += ms;
     }
     if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[N_STAGE_EV - 1]);
     times->launches = (uint32_t)(ctx->launches - launches0);  // of the last (successful) attempt

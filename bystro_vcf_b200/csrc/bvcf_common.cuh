@@ -68,25 +68,27 @@ __device__ __forceinline__ uint32_t ev_slot_word(uint32_t h, uint32_t pl, int j)
 struct RunCounters {
   unsigned long long out_cursor;   // bytes of TSV written so far (device-side running offset)
   unsigned long long row_cursor;   // rows written so far
+  unsigned long long loci_cursor;  // bytes of locus strings written so far (dosage output)
   unsigned long long n_lines;      // all newline-terminated lines
   unsigned long long n_records;    // lines with the right field count
+  unsigned long long chunk_out_base;   // out_cursor before this sub-chunk (set by the prefix spine, mode 0)
+  unsigned long long chunk_row_base;
+  unsigned long long chunk_loci_base;
+  unsigned long long chunk_line_base;  // n_lines before this sub-chunk (diagnostic line numbers)
   unsigned int ev_overflow;        // a range ran out of event slots
   unsigned int slot_overflow;      // a range ran out of line slots
   unsigned int out_overflow;       // output region too small
+  unsigned int row_overflow;       // a sub-chunk queued more rows for the names kernels than RowDesc slots
   unsigned int n_diags;
-  unsigned int row_overflow;       // a sub-chunk emitted more rows than RowDesc slots
-  unsigned int n_big_recs;         // work list of the stats kernel: records with long event lists (per sub-chunk)
-  unsigned int n_big_rows;         // work list of the names kernel: rows with long event lists (per sub-chunk)
-  unsigned int big_row_cursor;     // next entry of the names work list to be taken (dynamic scheduling)
-  unsigned long long chunk_out_base;  // out_cursor before this sub-chunk (set by the scan-finalize kernel)
-  unsigned long long chunk_row_base;
-  unsigned long long chunk_line_base; // n_lines before this sub-chunk (diagnostic line numbers)
   unsigned int chunk_records;      // records in the current sub-chunk (device-side n for grid-stride kernels)
+  unsigned int n_big_recs;         // work list of the stats kernel: records with long event lists (per sub-chunk)
   unsigned int big_rec_cursor;     // next entry of the stats work list to be taken
-  unsigned int n_multi_recs;       // work list of bvcf_rows_list_kernel: records that may yield several rows
+  unsigned int tile_ticket;        // bvcf_tile_kernel: next tile of 128 records to be taken (per sub-chunk)
+  unsigned int n_desc;             // RowDesc entries handed out so far, both lists (per sub-chunk)
+  unsigned int n_big_rows;         // names work list: rows written by a warp each (per sub-chunk)
+  unsigned int big_row_cursor;     // next entry to be taken (dynamic scheduling)
   unsigned int n_long_rows;        // rows with very long event lists: written by a whole CTA (bvcf_names_long_kernel)
   unsigned int long_row_cursor;
-  unsigned int pad1;
 };
 
 // ---- configuration as the kernels see it ---------------------------------------------------------

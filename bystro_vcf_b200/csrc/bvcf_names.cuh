@@ -1,6 +1,6 @@
 // bvcf_names.cuh -- north-star kernel (4b), sample-name lists of the long rows as aligned 16-byte vectors.
 //
-// bvcf_names_kernel (bvcf_rows.cuh) writes the lists of short rows lane-serially and queues the others.  When every
+// bvcf_tile_kernel (bvcf_tile.cuh) writes the lists of short rows itself and queues the others.  When every
 // list item (name + delimiter) has one size of 5..16 bytes and TSV output is on, the queues are served here instead
 // of by bvcf_names_big_kernel (7-character names + 1-character delimiter, the 1000 Genomes / biobank layout, are
 // 8-byte items with a fast path of their own):
@@ -271,9 +271,8 @@ __device__ __forceinline__ void sweep_lists_chunked(const ItemTable &tab, const 
 }
 
 template <typename IdxT, bool DOSAGE>
-__device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned long long r, IdxT *idx, int lane) {
+__device__ __forceinline__ void names_row_vec(const NamesParams &p, const RowDesc &rd, IdxT *idx, int lane) {
   const DevCfg &cfg = p.cfg;
-  const RowDesc rd = p.row_desc[r];
   const LineRec rec = p.lines[rd.line];
   RowEvents re;
   re.ev = p.events + rec.ev_start; re.n_words = rec.ev_count; re.L = p.in + rec.start;
@@ -281,7 +280,7 @@ __device__ __forceinline__ void names_row_vec(const NamesParams &p, unsigned lon
   re.a = rd.allele; re.simple = !(rec.flags & 1) && rd.allele == 1;
   re.drow = nullptr;
   {
-    const unsigned long long gr = p.ctr->chunk_row_base + r;
+    const unsigned long long gr = p.ctr->chunk_row_base + rd.row;
     if (DOSAGE && cfg.want_dosage && gr < p.dosage_cap_rows) re.drow = p.dosage + gr * (unsigned long long)cfg.n_samples;
   }
   const ItemTable tab = item_table(cfg);
@@ -310,7 +309,7 @@ template <typename IdxT, bool DOSAGE>
 __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const NamesParams p) {
   __shared__ __align__(16) uint8_t s_idx[NVEC_WARPS][NVEC_IDX_BYTES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow | p.ctr->row_overflow) return;
   const uint32_t n_big = p.ctr->n_big_rows;
   IdxT *idx = reinterpret_cast<IdxT *>(s_idx[warp]);
   // rows differ by three orders of magnitude in size: warps take the next queued row from a shared cursor
@@ -319,7 +318,7 @@ __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const N
     if (lane == 0) wi = atomicAdd(&p.ctr->big_row_cursor, 1u);
     wi = __shfl_sync(FULL, wi, 0);
     if (wi >= n_big) break;
-    names_row_vec<IdxT, DOSAGE>(p, p.big_rows[wi], idx, lane);
+    names_row_vec<IdxT, DOSAGE>(p, p.row_desc[wi], idx, lane);
   }
 }
 
@@ -334,7 +333,7 @@ __global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const
   __shared__ uint32_t s_cnt[NLONG_WARPS][3];
   __shared__ uint32_t s_wi;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow | p.ctr->row_overflow) return;
   const DevCfg &cfg = p.cfg;
   const uint32_t n_long = p.ctr->n_long_rows;
   for (;;) {
@@ -343,8 +342,7 @@ __global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const
     __syncthreads();
     const uint32_t wi = s_wi;
     if (wi >= n_long) break;
-    const uint32_t r = p.big_rows[p.row_desc_cap - 1 - wi];
-    const RowDesc rd = p.row_desc[r];
+    const RowDesc rd = p.row_desc[p.row_desc_cap - 1 - wi];
     const LineRec rec = p.lines[rd.line];
     const uint32_t nq = rec.ev_count >> 1;
     const uint32_t seg = ((nq + NLONG_WARPS - 1) / NLONG_WARPS + 63u) & ~63u;  // whole 64-quad steps
@@ -355,7 +353,7 @@ __global__ void __launch_bounds__(NLONG_WARPS * 32) bvcf_names_long_kernel(const
     re.a = rd.allele; re.simple = !(rec.flags & 1) && rd.allele == 1;
     re.drow = nullptr;
     {
-      const unsigned long long gr = p.ctr->chunk_row_base + r;
+      const unsigned long long gr = p.ctr->chunk_row_base + rd.row;
       if (DOSAGE && cfg.want_dosage && gr < p.dosage_cap_rows) re.drow = p.dosage + gr * (unsigned long long)cfg.n_samples;
     }
     // counting sweep

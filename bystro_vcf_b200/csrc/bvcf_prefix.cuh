@@ -19,9 +19,6 @@ struct PrefixParams {
   const unsigned int *n_ptr;    // element count in device memory, or null
   uint32_t n_imm;               // used when n_ptr == null
   RunCounters *ctr;
-  int mode;                     // 0: range counts (a=records, b=lines)   1: row sizes (a=bytes, b=rows)
-  unsigned long long out_cap;   // mode 1: capacity of the output region
-  unsigned long long row_cap;   // mode 1: RowDesc slots per sub-chunk
 };
 
 __device__ __forceinline__ uint32_t pfx_n(const PrefixParams &p) { return p.n_ptr ? *p.n_ptr : p.n_imm; }
@@ -80,26 +77,18 @@ __global__ void __launch_bounds__(1024) bvcf_prefix_spine_kernel(const PrefixPar
   }
   if (t == 1023) {
     RunCounters *c = p.ctr;
-    if (p.mode == 0) {
-      c->chunk_records = (unsigned int)sa[t];
-      c->chunk_line_base = c->n_lines;
-      c->n_big_recs = 0;
-      c->big_rec_cursor = 0;
-      c->n_multi_recs = 0;
-      c->n_records += sa[t];
-      c->n_lines += sb[t];
-    } else if (!(c->ev_overflow | c->slot_overflow)) {  // sizes are garbage after a scratch overflow: leave the cursors
-      c->n_big_rows = 0;
-      c->big_row_cursor = 0;
-      c->n_long_rows = 0;
-      c->long_row_cursor = 0;
-      c->chunk_out_base = c->out_cursor;
-      c->chunk_row_base = c->row_cursor;
-      c->out_cursor += sa[t];
-      c->row_cursor += sb[t];
-      if (c->out_cursor > p.out_cap) c->out_overflow = 1;
-      if (sb[t] > p.row_cap) c->row_overflow = 1;
-    }
+    // per-range counts of one sub-chunk: publish the record count, start the sub-chunk's cursors and work lists
+    c->chunk_records = (unsigned int)sa[t];
+    c->chunk_line_base = c->n_lines;
+    c->n_records += sa[t];
+    c->n_lines += sb[t];
+    c->n_big_recs = 0; c->big_rec_cursor = 0;
+    c->tile_ticket = 0; c->n_desc = 0;
+    c->n_big_rows = 0; c->big_row_cursor = 0;
+    c->n_long_rows = 0; c->long_row_cursor = 0;
+    c->chunk_out_base = c->out_cursor;
+    c->chunk_row_base = c->row_cursor;
+    c->chunk_loci_base = c->loci_cursor;
   }
 }
 

@@ -1,34 +1,24 @@
-// bvcf_rows.cuh -- north-star kernels (2)+(4): per-line fixed-field kernel + two-pass row emitter.
+// bvcf_rows.cuh -- north-star kernels (2)+(3b): what the per-record code shares.
 //
 //   bvcf_line_stats_kernel      records whose genotype summary is not complete in the scan kernel's LineRec (ALT
 //   bvcf_line_stats_big_kernel  numbers other than 1, complex GTs, variable-width names): het/hom/missing counts,
 //                               ac, an and list byte lengths for ALT numbers 1..3 from the quad events with nibble
 //                               masks (main.go:1042-1194); lane per record, CTA per record with a long event list
-//   bvcf_rows_kernel<SIZE>      thread per record: FILTER allow/exclude against a shared-memory table
-//                               (main.go:447-454), getAlleles' decision tree -- ACTG QC, multiallelic split, MNP
-//                               decomposition, padding trim + left-normalisation, site type, trTv
-//                               (main.go:723-1038, 602-606) -- and the exact size of every row it will emit
-//   (exclusive scan of the sizes: bvcf_prefix.cuh)
-//   bvcf_rows_kernel<EMIT>      same code, now writing every non-list byte of its rows at the scanned offsets
-//                               (main.go:586-695) and one RowDesc per row
-//   bvcf_rows_list_kernel       both passes for the records that may yield several rows (sites-only input)
-//   bvcf_dosage_zero_kernel     the int8 dosage rows of the sub-chunk start as all-reference (main.go:576-584)
-//   bvcf_names_kernel           lane per short row: the heterozygote / homozygote / missing sample-name lists
-//                               (main.go:617,639,653 strings.Join) and the row's dosages; queues the long rows
+//   AlleleGen / gen_next        getAlleles' decision tree as a resumable generator -- ACTG QC, multiallelic split,
+//                               MNP decomposition, padding trim + left-normalisation, site type (main.go:723-1038)
 //   bvcf_names_big_kernel       warp per queued row, any name widths (bvcf_names.cuh takes fixed-size items)
 //
-// Rows of ALT #1..3 use the LineRec / LineStats summaries; higher ALT numbers are reduced by the record's own
-// thread straight from the event list.
+// The rows themselves are composed and written by bvcf_tile_kernel (bvcf_tile.cuh).  Rows of ALT #1..3 use the
+// LineRec / LineStats summaries; higher ALT numbers are reduced by the record's own thread straight from the event
+// list.
 #pragma once
 #include "bvcf_common.cuh"
 #include "bvcf_text.cuh"
 
 namespace bvcf {
 
-constexpr int ROWS_THREADS = 128;
 constexpr int NAMES_WARPS = 2;   // small CTAs: rows differ wildly in size, a finished warp must not pin the others' slots
 constexpr int FILT_SMEM = 1024;      // FILTER table bytes kept in shared memory
-constexpr uint32_t ROW_STAGE_BYTES = 6144;  // per-warp staging of 32 sample-less rows (EMIT pass)
 
 // genotype summary of one (record, ALT number)
 struct GtStats {
@@ -44,42 +34,22 @@ struct __align__(16) LineStats {
   uint32_t pad2;
 };
 
-// one emitted row, for the names kernel
+// one emitted row whose sample-name lists (and dosage row) are left to the names kernels: rows of records with
+// more than SMALL_EVENTS event words.  bvcf_tile_kernel appends them to a work list (ordinary rows from the front
+// of the array, rows beyond NamesParams::long_words event words from its end).
 struct __align__(16) RowDesc {
   uint32_t line;        // record index in the dense line table
   uint32_t allele;      // ALT number (altIdx + 1)
   unsigned long long het_dst, hom_dst, miss_dst;  // absolute byte offsets of the three lists in the output
-  uint32_t n_het, n_hom, n_miss, pad;             // list lengths (names)
+  uint32_t n_het, n_hom, n_miss;                  // list lengths (names)
+  uint32_t row;                                   // row number within the sub-chunk (its dosage row)
 };
 
-struct RowsParams {
-  const uint8_t *in;
-  DevCfg cfg;
-  const LineRec *lines;      // dense, input order
-  const uint32_t *events;    // sub-chunk event buffer
-  const LineStats *stats;    // per record, ALT #1..3 (null when there are no samples)
-  uint32_t *line_bytes;      // SIZE out
-  uint32_t *line_rows;       // SIZE out
-  const uint64_t *line_off;  // EMIT in: exclusive prefix of line_bytes
-  const uint64_t *row_off;   // EMIT in: exclusive prefix of line_rows
-  uint8_t *out;
-  unsigned long long out_cap;
+// diagnostics (main.go:730-986 log.Printf sites): 4 words each -- line_lo, line_hi, alt_no, code
+struct DiagSink {
+  uint32_t *diags;
+  uint32_t cap;
   RunCounters *ctr;
-  RowDesc *row_desc;         // EMIT out, indexed by the row number within the sub-chunk
-  unsigned long long row_desc_cap;
-  // dosage matrix (main.go:576-584)
-  unsigned long long dosage_cap_rows;
-  uint8_t *loci;             // rows x loci_stride, NUL padded
-  uint32_t loci_stride;
-  // diagnostics (main.go:730-986 log.Printf sites)
-  uint32_t *diags;           // 4 words each: line_lo, line_hi, alt_no, code
-  uint32_t diag_cap;
-  // DEFER kernels: records that can yield several rows (comma in ALT, equal-length REF/ALT longer than one base) are
-  // queued by the SIZE pass and handled by bvcf_rows_list_kernel in both passes, so that the main kernels call
-  // emit_row once per warp instead of once per row of their widest record.  Pays off for sites-only input (cheap
-  // rows, many multi-allelic lines: -17 % on C3); with samples such records are rare and a short list kernel is a
-  // serial tail, so the host leaves it off there.
-  uint32_t *multi_recs;
 };
 
 // site types (bystro-utils parse.Snp/Ins/Del/Mnp/Multi)
@@ -378,136 +348,6 @@ __device__ __noinline__ GtStats reduce_events_thread(const DevCfg &cfg, const Li
   return s;
 }
 
-// ---- row writer: counts in the SIZE pass, byte stores in the EMIT pass --------------------------------
-// 8 bytes to an arbitrarily aligned address with the widest naturally aligned pieces (2-4 stores)
-__device__ __forceinline__ void store8_unaligned(uint8_t *d, unsigned long long v) {
-  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-  switch ((uintptr_t)d & 3u) {
-    case 0:
-      *reinterpret_cast<uint32_t *>(d) = lo;
-      *reinterpret_cast<uint32_t *>(d + 4) = hi;
-      break;
-    case 2:
-      *reinterpret_cast<uint16_t *>(d) = (uint16_t)lo;
-      *reinterpret_cast<uint32_t *>(d + 2) = (uint32_t)(v >> 16);
-      *reinterpret_cast<uint16_t *>(d + 6) = (uint16_t)(hi >> 16);
-      break;
-    case 1:
-      d[0] = (uint8_t)lo;
-      *reinterpret_cast<uint16_t *>(d + 1) = (uint16_t)(lo >> 8);
-      *reinterpret_cast<uint32_t *>(d + 3) = (uint32_t)(v >> 24);
-      d[7] = (uint8_t)(hi >> 24);
-      break;
-    default:
-      d[0] = (uint8_t)lo;
-      *reinterpret_cast<uint32_t *>(d + 1) = (uint32_t)(v >> 8);
-      *reinterpret_cast<uint16_t *>(d + 5) = (uint16_t)(hi >> 8);
-      d[7] = (uint8_t)(hi >> 24);
-      break;
-  }
-}
-
-// The EMIT writer's state and its two out-of-line steps.  Inlined at some fifty call sites they made the EMIT
-// kernel 147 KB of code, and the pass stalled on instruction fetch (39 % of its stall samples).  The state travels
-// by value (registers under the device ABI).
-struct WState {
-  uint8_t *g;                // address of the first pending byte
-  unsigned long long acc;    // pending bytes, little-endian
-  int fill;                  // how many (0..7)
-};
-__device__ __noinline__ WState wput(WState s, unsigned long long chars, int len) {  // len <= 8, bytes >= len zero
-  s.acc |= chars << (8 * s.fill);
-  int nf = s.fill + len;
-  if (nf >= 8) {
-    store8_unaligned(s.g, s.acc);
-    s.g += 8;
-    s.acc = s.fill ? chars >> (8 * (8 - s.fill)) : 0ull;
-    nf -= 8;
-  }
-  s.fill = nf;
-  return s;
-}
-__device__ __noinline__ WState wspan(WState s, const uint8_t *p, int len) {
-  for (int i = 0; i < len; i += 8) {
-    const int n = len - i < 8 ? len - i : 8;
-    unsigned long long v = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) if (k < n) v |= (unsigned long long)p[i + k] << (8 * k);
-    s.acc |= v << (8 * s.fill);
-    int nf = s.fill + n;
-    if (nf >= 8) {
-      store8_unaligned(s.g, s.acc);
-      s.g += 8;
-      s.acc = s.fill ? v >> (8 * (8 - s.fill)) : 0ull;
-      nf -= 8;
-    }
-    s.fill = nf;
-  }
-  return s;
-}
-__device__ __noinline__ WState wflush(WState s) {
-  for (int i = 0; i < s.fill; i++) s.g[i] = (uint8_t)(s.acc >> (8 * i));
-  s.g += s.fill; s.acc = 0; s.fill = 0;
-  return s;
-}
-
-// Writer policy of emit_row: kWrite (bytes are produced), kGlobal (bytes go to the output buffer: loci and
-// RowDesc are written too).  span_in() is a span of the INPUT line (long ones may be referenced, not copied);
-// list() reserves the bytes of one sample-name list; lists_done() ends the three lists of a row.
-template <bool WRITE>
-struct RowWriter {
-  static constexpr bool kWrite = WRITE, kGlobal = WRITE;
-  uint8_t *g;                // global cursor (EMIT)
-  unsigned long long count;  // bytes (SIZE)
-  const uint8_t *out0;       // output base (EMIT): list destinations are offsets from it
-  // EMIT: bytes gather in a 64-bit register and leave eight at a time (2-4 aligned stores instead of 8 byte
-  // stores: every store of a thread is a transaction of its own, the pass was bound by them)
-  unsigned long long acc;    // pending bytes, little-endian
-  int fill;                  // how many (0..7); they belong at g[0..fill)
-  __device__ __forceinline__ void begin(uint8_t *dst) { g = dst; acc = 0; fill = 0; }
-  __device__ __forceinline__ WState st() const { WState s; s.g = g; s.acc = acc; s.fill = fill; return s; }
-  __device__ __forceinline__ void set(const WState &s) { g = s.g; acc = s.acc; fill = s.fill; }
-  __device__ __forceinline__ void flush() { if (WRITE) set(wflush(st())); }
-  __device__ __forceinline__ void finish() { flush(); }
-  // up to 8 characters packed little-endian; bytes at and above len must be zero
-  __device__ __forceinline__ void packed(uint64_t chars, int len) {
-    if (!WRITE) { count += len; return; }
-    set(wput(st(), chars, len));
-  }
-  __device__ __forceinline__ void byte(uint8_t c) {
-    if (!WRITE) { count++; return; }
-    set(wput(st(), (unsigned long long)c, 1));
-  }
-  __device__ __forceinline__ void span(const uint8_t *p, int len) {
-    if (!WRITE) { count += len; return; }
-    set(wspan(st(), p, len));
-  }
-  __device__ __forceinline__ void span_in(const uint8_t *p, int len) { span(p, len); }
-  __device__ __forceinline__ void dec(long long v) {
-    if (!WRITE) {
-      count += (v < 0 ? 1 : 0) + dec_len(v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v);
-      return;
-    }
-    unsigned long long lo, hi;
-    const int len = itoa_pack(v, lo, hi);  // registers, no byte buffer in local memory
-    if (len >= 0) {
-      packed(lo, len < 8 ? len : 8);
-      if (len > 8) packed(hi, len - 8);
-    } else {
-      uint8_t buf[24];
-      const int l2 = itoa_dec(v, buf);
-      for (int i = 0; i < l2; i++) byte(buf[i]);
-    }
-  }
-  __device__ __forceinline__ void skip(unsigned long long len) { if (WRITE) { flush(); g += len; } else count += len; }
-  __device__ __forceinline__ unsigned long long list(int, uint32_t, unsigned long long bytes, uint32_t) {
-    if (WRITE) flush();
-    const unsigned long long d = WRITE ? (unsigned long long)(g - out0) : 0ull;
-    skip(bytes);  // filled by the names kernel
-    return d;
-  }
-  __device__ __forceinline__ void lists_done(uint32_t) {}
-};
 
 // ---- one output allele of getAlleles ------------------------------------------------------------
 struct OutAllele {
@@ -531,129 +371,11 @@ struct LineCtx {
   uint32_t li;
 };
 
-template <class W>
-__device__ __forceinline__ void emit_row(const RowsParams &p, const LineRec &rec, const LineCtx &lc, const OutAllele &oa,
-                                      GtStats &gs, int &gs_idx, W &w, uint32_t &n_rows,
-                                      unsigned long long row_base) {
-  constexpr bool WRITE = W::kGlobal;
-  const DevCfg &cfg = p.cfg;
-  const uint32_t a = (uint32_t)oa.alt_idx + 1;
-  if (cfg.n_samples > 0) {
-    if (gs_idx != oa.alt_idx) {  // MNP bases share their ALT index: reduce once (main.go:865-868)
-      if (cfg.name_fixed_w > 0 && !(rec.flags & 1)) {
-        // the scan kernel's inline summary is complete: only ALT #1 occurs among the samples
-        gs.n_het = a == 1 ? rec.n_het1 : 0; gs.n_hom = a == 1 ? rec.n_hom1 : 0; gs.ac = a == 1 ? rec.ac1 : 0;
-        gs.n_miss = rec.n_miss; gs.an = rec.an;
-        gs.het_bytes = gs.n_het * cfg.name_fixed_w; gs.hom_bytes = gs.n_hom * cfg.name_fixed_w;
-        gs.miss_bytes = gs.n_miss * cfg.name_fixed_w;
-      } else if (a <= (uint32_t)STAT_ALLELES) {
-        const LineStats &ls = p.stats[lc.li];
-        gs.n_het = ls.n_het[a - 1]; gs.n_hom = ls.n_hom[a - 1]; gs.ac = ls.ac[a - 1];
-        gs.het_bytes = ls.het_bytes[a - 1]; gs.hom_bytes = ls.hom_bytes[a - 1];
-        gs.n_miss = ls.n_miss; gs.an = ls.an; gs.miss_bytes = ls.miss_bytes;
-      } else {
-        gs = reduce_events_thread(cfg, rec, p.events + rec.ev_start, lc.L, lc.content_len, a);
-      }
-      gs_idx = oa.alt_idx;
-    }
-    if (gs.ac == 0) return;  // main.go:558
-  }
-  const uint32_t row_id = n_rows++;
-  const unsigned long long r = row_base + row_id;  // row number within the sub-chunk
 
-  if (WRITE && cfg.want_dosage && cfg.n_samples > 0) {  // locus "chrom:pos:ref:alt" main.go:577
-    const unsigned long long gr = p.ctr->chunk_row_base + r;
-    if (gr < p.dosage_cap_rows) {
-      uint8_t *lo = p.loci + gr * (unsigned long long)p.loci_stride;
-      uint32_t n = 0;
-      const uint32_t cap = p.loci_stride - 1;
-      auto put = [&](uint8_t c) { if (n < cap) lo[n] = c; n++; };
-      if (lc.chrom_n < 4 || lc.chrom[0] != 'c') { put('c'); put('h'); put('r'); }
-      for (int i = 0; i < lc.chrom_n; i++) put(lc.chrom[i]);
-      put(':');
-      if (oa.pos_verbatim) { for (int i = 0; i < lc.pos_n; i++) put(lc.pos[i]); }
-      else { uint8_t b[24]; const int l = itoa_dec(oa.pos_val, b); for (int i = 0; i < l; i++) put(b[i]); }
-      put(':'); put(oa.ref); put(':');
-      if (oa.kind == 0) put(oa.alt_c);
-      else if (oa.kind == 1) { put('+'); for (int i = 0; i < oa.ins_n; i++) put(oa.ins_p[i]); }
-      else { uint8_t b[24]; const int l = itoa_dec(oa.del_n, b); for (int i = 0; i < l; i++) put(b[i]); }
-      lo[n < cap ? n : cap] = 0;
-    }
-  }
-  RowDesc rd;
-  rd.line = lc.li; rd.allele = a;
-  rd.het_dst = rd.hom_dst = rd.miss_dst = ~0ull;
-  rd.n_het = rd.n_hom = rd.n_miss = 0; rd.pad = 0;
-
-  if (cfg.want_tsv) {
-    // chrom (main.go:570-574)
-    if (lc.chrom_n < 4 || lc.chrom[0] != 'c') w.packed(0x726863ull, 3);  // "chr"
-    w.span_in(lc.chrom, lc.chrom_n);
-    w.byte('\t');
-    if (oa.pos_verbatim) w.span_in(lc.pos, lc.pos_n); else w.dec(oa.pos_val);
-    if (lc.site_type != T_MULTI) {  // "\tSNP\t": the three-letter types as one piece
-      const uint8_t *tt = (const uint8_t *)TYPE_TXT[lc.site_type];
-      w.packed(0x09ull | ((uint64_t)tt[0] << 8) | ((uint64_t)tt[1] << 16) | ((uint64_t)tt[2] << 24) | (0x09ull << 32), 5);
-    } else {
-      w.byte('\t');
-      w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
-      w.byte('\t');
-    }
-    const uint8_t trtv = lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0');  // main.go:602-606
-    if (oa.kind == 0) {  // "R\tA\tt\t" as one piece
-      w.packed((uint64_t)oa.ref | (0x09ull << 8) | ((uint64_t)oa.alt_c << 16) | (0x09ull << 24) | ((uint64_t)trtv << 32) | (0x09ull << 40), 6);
-    } else {
-      w.byte(oa.ref);
-      w.byte('\t');
-      if (oa.kind == 1) { w.byte('+'); w.span_in(oa.ins_p, oa.ins_n); }
-      else w.dec(oa.del_n);
-      w.byte('\t');
-      w.byte(trtv);
-      w.byte('\t');
-    }
-
-    if (cfg.n_samples == 0) {  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0"
-      w.span(cfg.tail0, cfg.tail0_len);  // composed once by the host
-    } else {
-      const uint32_t eff = (uint32_t)cfg.n_samples - gs.n_miss;  // main.go:563
-      const uint32_t dl = (uint32_t)cfg.delim_len;
-      const uint32_t cnts[3] = {gs.n_het, gs.n_hom, gs.n_miss};
-      const uint32_t nb[3] = {gs.het_bytes, gs.hom_bytes, gs.miss_bytes};
-      const uint32_t den[3] = {eff, eff, (uint32_t)cfg.n_samples};
-      unsigned long long dsts[3] = {~0ull, ~0ull, ~0ull};
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        if (cnts[k] == 0) {
-          w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0');
-        } else {
-          dsts[k] = w.list(k, cnts[k], (unsigned long long)nb[k] + (unsigned long long)(cnts[k] - 1) * dl, a);
-          w.byte('\t');
-          int fl;
-          const uint64_t ft = format_ratio_g3(cnts[k], den[k], fl);
-          w.packed(ft, fl);
-        }
-        w.byte('\t');
-      }
-      w.lists_done(a);
-      rd.het_dst = dsts[0]; rd.hom_dst = dsts[1]; rd.miss_dst = dsts[2];
-      rd.n_het = gs.n_het; rd.n_hom = gs.n_hom; rd.n_miss = gs.n_miss;
-      w.dec(gs.ac); w.byte('\t');
-      w.dec(gs.an); w.byte('\t');
-      if (gs.ac == 0) w.byte('0');
-      else { int fl; const uint64_t ft = format_ratio_g3(gs.ac, gs.an, fl); w.packed(ft, fl); }
-    }
-    if (cfg.keep_pos) { w.byte('\t'); w.span_in(lc.pos, lc.pos_n); }
-    if (cfg.keep_id) { w.byte('\t'); w.span_in(lc.id, lc.id_n); }
-    if (cfg.keep_info) { w.byte('\t'); w.dec(oa.alt_idx); w.byte('\t'); w.span_in(lc.info, lc.info_n); }
-    w.byte('\n');
-  }
-  if (WRITE && cfg.n_samples > 0 && r < p.row_desc_cap) p.row_desc[r] = rd;
-}
-
-__device__ __forceinline__ void push_diag(const RowsParams &p, unsigned long long line_no, int alt_no, int code) {
+__device__ __forceinline__ void push_diag(const DiagSink &p, unsigned long long line_no, int alt_no, int code) {
   if (!p.diags) return;
   const uint32_t i = atomicAdd(&p.ctr->n_diags, 1u);
-  if (i < p.diag_cap) {
+  if (i < p.cap) {
     p.diags[4 * i] = (uint32_t)line_no;
     p.diags[4 * i + 1] = (uint32_t)(line_no >> 32);
     p.diags[4 * i + 2] = (uint32_t)alt_no;
@@ -674,7 +396,7 @@ struct AlleleGen {
   bool pos_ok, last, done;
 };
 
-__device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const RowsParams &p, unsigned long long line_no,
+__device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const DiagSink &p, unsigned long long line_no,
                                           bool diag) {
   bool same = g.alt_n == g.ref_n;
   for (int i = 0; same && i < g.alt_n; i++) same = g.alt[i] == g.ref[i];
@@ -699,7 +421,7 @@ __device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const RowsP
   }
 }
 
-__device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const RowsParams &p, unsigned long long line_no,
+__device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const DiagSink &p, unsigned long long line_no,
                                          bool diag) {
   const uint8_t *ref = g.ref;
   const int ref_n = g.ref_n;
@@ -796,234 +518,40 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Rows
   }
 }
 
-// ---- one record: field index, linePasses, getAlleles, one emit_row per output allele ------------------
-// DEFER: return true, doing nothing, when the record may yield more than one row.
-template <class W, bool DEFER>
-__device__ __forceinline__ bool process_record(const RowsParams &p, uint32_t li, const LineRec &rec, W &w,
-                                               const uint8_t *s_filt, const uint32_t *s_filt_off, uint32_t &n_rows,
-                                               unsigned long long row_base, bool diag) {
-  const DevCfg &cfg = p.cfg;
-  const int n_filt = cfg.n_allow + cfg.n_excl;
-  const uint8_t *L = p.in + rec.start;
-  const uint32_t n = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;  // main.go:535
-  // ---- first eight/nine tabs (strings.Split, main.go:535) ----
-  const int need = cfg.H - 1 < 9 ? cfg.H - 1 : 9;
-  uint32_t t[9];
-  int found = need;
-  bool far = false;  // a tab beyond 64 KiB from the line start: the scan kernel could not record it
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-    t[k] = rec.tab[k];
-    far = far || (k < need && t[k] == 0xFFFFu);
-  }
-  if (far) {
-    found = 0;
-    for (uint32_t i = 0; i < n && found < need; i++)
-      if (L[i] == '\t') {
-#pragma unroll
-        for (int k = 0; k < 9; k++) if (k == found) t[k] = i;  // static indexing keeps t[] in registers
-        found++;
-      }
-  }
-  bool pass = found >= need;  // always true for scan-kernel records; defensive
-#pragma unroll
-  for (int k = 0; k < 9; k++) if (k >= found) t[k] = n;
-  LineCtx lc;
-  lc.L = L; lc.content_len = n; lc.li = li;
-  lc.chrom = L; lc.chrom_n = (int)t[0];
-  lc.pos = L + t[0] + 1; lc.pos_n = (int)(t[1] - t[0] - 1);
-  lc.id = L + t[1] + 1; lc.id_n = (int)(t[2] - t[1] - 1);
-  const uint8_t *ref = L + t[2] + 1; const int ref_n = (int)(t[3] - t[2] - 1);
-  const uint8_t *alt = L + t[3] + 1; const int alt_n = (int)(t[4] - t[3] - 1);
-  const uint8_t *filt = L + t[5] + 1; const int filt_n = (int)(t[6] - t[5] - 1);
-  lc.info = L + t[6] + 1; lc.info_n = (int)(t[7] - t[6] - 1);
-  lc.multi = false; lc.site_type = T_SNP;
-
-  // ---- linePasses (main.go:447-454): exact whole-field match against the shared-memory table ----
-  if (pass && (!cfg.allow_all || cfg.n_excl > 0)) {
-    bool in_allow = false, in_excl = false;
-    for (int k = 0; k < n_filt; k++) {
-      const uint32_t o = s_filt_off[k], ln = s_filt_off[k + 1] - o;
-      bool eq = (int)ln == filt_n;
-      for (int i = 0; eq && i < filt_n; i++) eq = s_filt[o + i] == filt[i];
-      if (eq) { if (k < cfg.n_allow) in_allow = true; else in_excl = true; }
-    }
-    if (!cfg.allow_all && !in_allow) pass = false;
-    if (in_excl) pass = false;
-  }
-
-  // ---- getAlleles (main.go:723-1038) as a resumable generator: one converged emit_row call site ----
-  {
-    AlleleGen g;
-    g.ref = ref; g.alt = alt; g.ref_n = ref_n; g.alt_n = alt_n;
-    g.s = 0; g.alt_idx = 0; g.mnp_i = -1; g.ta = alt; g.tn = 0; g.last = false;
-    g.done = !(pass && ref_n > 0 && alt_n > 0);
-    g.ipos = 0;
-    g.pos_ok = g.done ? false : atoi_go(lc.pos, lc.pos_n, g.ipos);
-    const unsigned long long line_no = p.ctr->chunk_line_base + rec.ord;
-    if (!g.done) gen_begin(g, lc, p, line_no, diag);
-    GtStats gs;
-    int gs_idx = -1;
-    OutAllele oa;
-    oa.ins_p = nullptr; oa.ins_n = 0; oa.del_n = 0; oa.pos_val = 0;
-    if (DEFER) {
-      if (!g.done && (lc.multi || (alt_n == ref_n && ref_n > 1))) return true;
-      if (gen_next(g, oa, p, line_no, diag)) emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);  // at most one row
-    } else {
-      while (gen_next(g, oa, p, line_no, diag)) emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, n_rows, row_base);
-    }
-  }
-  return false;
-}
-
-// ---- thread per record, grid-stride, record count read from device memory ----------------------------
-template <bool WRITE, bool DEFER>
-__global__ void __launch_bounds__(ROWS_THREADS, WRITE ? 4 : 5) bvcf_rows_kernel(const __grid_constant__ RowsParams p) {
-  __shared__ uint8_t s_filt[FILT_SMEM];
-  __shared__ uint32_t s_filt_off[65];
-  __shared__ __align__(16) uint8_t s_rowstage[WRITE ? ROWS_THREADS / 32 : 1][WRITE ? ROW_STAGE_BYTES : 16];
-  const DevCfg &cfg = p.cfg;
-  // FILTER allow/exclude table -> shared memory
-  const int n_filt = cfg.n_allow + cfg.n_excl;
-  for (int i = threadIdx.x; i < cfg.filt_bytes && i < FILT_SMEM; i += blockDim.x) s_filt[i] = cfg.filt_blob[i];
-  for (int i = threadIdx.x; i <= n_filt && i < 65; i += blockDim.x) s_filt_off[i] = cfg.filt_off[i];
-  __syncthreads();
-  if (WRITE && p.ctr->out_overflow) return;
-  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;  // the host grows the scratch and re-runs the chunk
-  const uint32_t n_rec = p.ctr->chunk_records;
-  const unsigned long long out_base = p.ctr->chunk_out_base;
-  const uint32_t total_threads = gridDim.x * blockDim.x;
-
-  const int lane = threadIdx.x & 31;
-  uint8_t *stage = s_rowstage[threadIdx.x >> 5];
-  for (uint32_t li_base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); li_base < n_rec; li_base += total_threads) {
-    const uint32_t li = li_base + lane;
-    const bool valid = li < n_rec;
-    // Without sample lists the rows of 32 consecutive records are one contiguous span of the output: compose
-    // them in shared memory and copy the span out with aligned 16-byte stores instead of byte stores.
-    bool staged = false;
-    unsigned long long span_base = 0;
-    uint32_t span = 0, my_rel = 0, mis = 0;
-    if (WRITE && cfg.n_samples == 0) {
-      const unsigned long long off = valid ? p.line_off[li] : 0;
-      const unsigned long long end = valid ? off + p.line_bytes[li] : 0;
-      span_base = __shfl_sync(FULL, off, 0);
-      const uint32_t last = n_rec - li_base > 32 ? 31 : n_rec - li_base - 1;
-      const unsigned long long span64 = __shfl_sync(FULL, end, last) - span_base;
-      mis = (uint32_t)((uintptr_t)(p.out + out_base + span_base) & 15u);
-      staged = span64 + mis <= ROW_STAGE_BYTES;
-      span = (uint32_t)span64;
-      my_rel = (uint32_t)(off - span_base);
-    }
-    bool deferred = false;
-    if (valid) {
-    const LineRec rec = p.lines[li];
-
-    RowWriter<WRITE> w;
-    w.count = 0;
-    w.out0 = p.out;
-    w.begin(WRITE ? (staged ? stage + mis + my_rel : p.out + out_base + p.line_off[li]) : nullptr);
-    uint32_t n_rows = 0;
-    const unsigned long long row_base = WRITE ? p.row_off[li] : 0;  // row number within the sub-chunk
-
-    deferred = process_record<RowWriter<WRITE>, DEFER>(p, li, rec, w, s_filt, s_filt_off, n_rows, row_base, !WRITE);
-    w.finish();
-    if (!WRITE && !deferred) {
-      p.line_bytes[li] = (uint32_t)w.count;
-      p.line_rows[li] = n_rows;
-    }
-    }  // valid
-    if (!WRITE && DEFER) {  // queue the multi-row records (one atomic per warp)
-      const uint32_t dm = __ballot_sync(FULL, deferred);
-      if (dm) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&p.ctr->n_multi_recs, (unsigned int)__popc(dm));
-        base = __shfl_sync(FULL, base, 0);
-        if (deferred) p.multi_recs[base + __popc(dm & ((1u << lane) - 1u))] = li;
-      }
-    }
-    if (WRITE && staged) {
-      __syncwarp();
-      uint8_t *gb = p.out + out_base + span_base;
-      const uint8_t *sb = stage + mis;
-      const uint32_t head = span < ((16u - mis) & 15u) ? span : ((16u - mis) & 15u);
-      for (uint32_t i = lane; i < head; i += 32) gb[i] = sb[i];
-      const uint32_t nvec = (span - head) >> 4;
-      for (uint32_t v = lane; v < nvec; v += 32)
-        *reinterpret_cast<uint4 *>(gb + head + 16 * v) = *reinterpret_cast<const uint4 *>(sb + head + 16 * v);
-      for (uint32_t i = head + 16 * nvec + lane; i < span; i += 32) gb[i] = sb[i];
-      __syncwarp();
-    }
-  }
-}
-
-// the queued multi-row records, thread per record, both passes
-template <bool WRITE>
-__global__ void __launch_bounds__(ROWS_THREADS) bvcf_rows_list_kernel(const __grid_constant__ RowsParams p) {
-  __shared__ uint8_t s_filt[FILT_SMEM];
-  __shared__ uint32_t s_filt_off[65];
-  const DevCfg &cfg = p.cfg;
-  const int n_filt = cfg.n_allow + cfg.n_excl;
-  for (int i = threadIdx.x; i < cfg.filt_bytes && i < FILT_SMEM; i += blockDim.x) s_filt[i] = cfg.filt_blob[i];
-  for (int i = threadIdx.x; i <= n_filt && i < 65; i += blockDim.x) s_filt_off[i] = cfg.filt_off[i];
-  __syncthreads();
-  if (WRITE && p.ctr->out_overflow) return;
-  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
-  const uint32_t n = p.ctr->n_multi_recs;
-  const unsigned long long out_base = p.ctr->chunk_out_base;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t li = p.multi_recs[i];
-    const LineRec rec = p.lines[li];
-    RowWriter<WRITE> w;
-    w.count = 0;
-    w.out0 = p.out;
-    w.begin(WRITE ? p.out + out_base + p.line_off[li] : nullptr);
-    uint32_t n_rows = 0;
-    const unsigned long long row_base = WRITE ? p.row_off[li] : 0;
-    process_record<RowWriter<WRITE>, false>(p, li, rec, w, s_filt, s_filt_off, n_rows, row_base, !WRITE);
-    w.finish();
-    if (!WRITE) {
-      p.line_bytes[li] = (uint32_t)w.count;
-      p.line_rows[li] = n_rows;
-    }
-  }
-}
-
 // ---- warp per row: sample-name lists + dosage row ----------------------------------------------------
 struct NamesParams {
   const uint8_t *in;
   DevCfg cfg;
   const LineRec *lines;
   const uint32_t *events;
+  // the work list bvcf_tile_kernel filled: entries [0, ctr->n_big_rows) are rows written by a warp each
+  // (bvcf_names_vec_kernel / bvcf_names_big_kernel); rows with more than long_words event words sit at the END of
+  // the array, entries [row_desc_cap - ctr->n_long_rows, row_desc_cap), for bvcf_names_long_kernel (a CTA per row)
   const RowDesc *row_desc;
   unsigned long long row_desc_cap;
   uint8_t *out;
   RunCounters *ctr;
-  int8_t *dosage;
+  int8_t *dosage;            // zeroed by bvcf_tile_kernel
   unsigned long long dosage_cap_rows;
-  uint32_t *big_rows;        // work list: rows written by a whole warp (bvcf_names_big_kernel / _vec_)
-  // rows with more than long_words event words are queued from the END of big_rows (row_desc_cap entries) for
-  // bvcf_names_long_kernel, a CTA per row; 0: no such kernel follows
-  uint32_t long_words;
+  uint32_t long_words;       // 0: no CTA-per-row kernel follows
 };
 
 // one row, whole warp: ballot/popc ranks, ordered scatter of the names (and the dosage row)
-__device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned long long r, unsigned long long row0,
+__device__ __forceinline__ void names_row_warp(const NamesParams &p, const RowDesc &rd, unsigned long long row0,
                                                int lane) {
   const DevCfg &cfg = p.cfg;
   const uint32_t dl = (uint32_t)cfg.delim_len;
   const bool fixed = cfg.name_fixed_w > 0;
   const uint32_t lt = (1u << lane) - 1u;
   {
-    const RowDesc rd = p.row_desc[r];
     const LineRec rec = p.lines[rd.line];
     const uint32_t *ev = p.events + rec.ev_start;
     const uint8_t *L = p.in + rec.start;
     const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
     const uint32_t a = rd.allele;
     int8_t *drow = nullptr;
-    if (cfg.want_dosage && (row0 + r) < p.dosage_cap_rows) {
-      drow = p.dosage + (row0 + r) * (unsigned long long)cfg.n_samples;  // zeroed by bvcf_dosage_zero_kernel
+    if (cfg.want_dosage && p.dosage && (row0 + rd.row) < p.dosage_cap_rows) {
+      drow = p.dosage + (row0 + rd.row) * (unsigned long long)cfg.n_samples;  // zeroed by bvcf_tile_kernel
     }
     uint32_t run_n[3] = {0, 0, 0};
     uint32_t run_b[3] = {0, 0, 0};
@@ -1067,145 +595,17 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, unsigned lo
   }
 }
 
-// one row, one lane: rows whose record has only a handful of events (singletons, rare variants)
-template <bool DOSAGE>
-__device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDesc &rd, const LineRec &rec, int8_t *drow) {
-  const DevCfg &cfg = p.cfg;
-  const uint32_t *ev = p.events + rec.ev_start;
-  const uint8_t *L = p.in + rec.start;
-  const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
-  const uint32_t dl = (uint32_t)cfg.delim_len;
-  const bool simple = !(rec.flags & 1) && rd.allele == 1;
-  // per-class cursors in scalars (a runtime-indexed array would live in local memory)
-  uint32_t nh = 0, no = 0, nm = 0, bh = 0, bo = 0, bm = 0;
-  for (uint32_t q = 0; 2 * q + 1 < rec.ev_count; q++) {
-    const uint2 e = *reinterpret_cast<const uint2 *>(ev + 2 * q);
-    uint32_t mh, mo, mm;
-    quad_masks(e.x, e.y, rd.allele, simple, L, content_len, true, mh, mo, mm);
-    const uint32_t s0 = (e.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
-    uint32_t any = mh | mo | mm;
-    while (any) {
-      const uint32_t bit = any & (0u - any);
-      any &= any - 1;
-      const uint32_t samp = s0 + ((uint32_t)(__ffs(bit) - 1) >> 2);
-      const bool is_h = (mh & bit) != 0, is_o = (mo & bit) != 0;
-      if (DOSAGE && drow) {  // int8 dosage: -1 missing, else min(number of alleles equal to the row's, 127) (main.go:1172-1178)
-        int v = -1;
-        if (is_h | is_o) {
-          if (e.x & EV_COMPLEX) {
-            uint32_t gt, alt;
-            classify_gt_general(L + e.y, content_len > e.y ? content_len - e.y : 0, rd.allele, gt, alt);
-            v = alt > 127 ? 127 : (int)alt;
-          } else {
-            const uint32_t sh = (uint32_t)(__ffs(bit) - 1) - 3u;  // 4 * slot
-            const bool hap = ((e.y >> (16 + sh)) & 0xFu) == EV_NIB_ABSENT;
-            v = is_h ? 1 : (hap ? 1 : 2);
-          }
-        }
-        drow[samp] = (int8_t)v;
-      }
-      const uint32_t rn = is_h ? nh : (is_o ? no : nm), rb = is_h ? bh : (is_o ? bo : bm);
-      const unsigned long long dst = is_h ? rd.het_dst : (is_o ? rd.hom_dst : rd.miss_dst);
-      const uint32_t tot = is_h ? rd.n_het : (is_o ? rd.n_hom : rd.n_miss);
-      uint8_t *d = p.out + dst + rb;
-      uint32_t adv = 0;
-      if (rn > 0) {
-        for (uint32_t i = 0; i < dl; i++) d[i] = cfg.delim[i];
-        d += dl; adv = dl;
-      }
-      const uint32_t nl = name_len(cfg, samp);
-      if (cfg.name8) {
-        unsigned long long it = cfg.name8[samp];
-        if (rn + 1 == tot) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
-        store8_unaligned(d, it);
-      } else {
-        const uint8_t *src = name_ptr(cfg, samp);
-        for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
-      }
-      adv += nl;
-      if (is_h) { nh++; bh += adv; } else if (is_o) { no++; bo += adv; } else { nm++; bm += adv; }
-    }
-  }
-}
 
-// the dosage rows of this sub-chunk start as all-reference (0); the names kernels scatter the other samples
-__global__ void __launch_bounds__(256) bvcf_dosage_zero_kernel(const NamesParams p) {
-  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
-  const unsigned long long ns = (unsigned long long)p.cfg.n_samples;
-  unsigned long long r0 = p.ctr->chunk_row_base, r1 = p.ctr->row_cursor;
-  if (r1 > p.dosage_cap_rows) r1 = p.dosage_cap_rows;
-  if (r0 >= r1) return;
-  uint8_t *const base = reinterpret_cast<uint8_t *>(p.dosage);
-  const unsigned long long b0 = r0 * ns, b1 = r1 * ns;
-  const unsigned long long a0 = (b0 + 15ull) & ~15ull, a1 = b1 & ~15ull;  // cudaMalloc'ed: base is 256-byte aligned
-  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
-  if (a0 >= a1) {
-    for (unsigned long long i = b0 + tid; i < b1; i += nth) base[i] = 0;
-    return;
-  }
-  for (unsigned long long i = b0 + tid; i < a0; i += nth) base[i] = 0;
-  uint4 *v = reinterpret_cast<uint4 *>(base + a0);
-  const unsigned long long nv = (a1 - a0) >> 4;
-  for (unsigned long long i = tid; i < nv; i += nth) v[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (unsigned long long i = a1 + tid; i < b1; i += nth) base[i] = 0;
-}
-
-// Hybrid granularity (as in the stats kernel): a warp takes 32 consecutive rows; short ones lane-serial,
-// long ones warp-cooperative.
-template <bool DOSAGE>
-__global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_kernel(const NamesParams p) {
-  const DevCfg &cfg = p.cfg;
-  const int lane = threadIdx.x & 31;
-  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
-  const unsigned long long row0 = p.ctr->chunk_row_base;
-  unsigned long long n_rows = p.ctr->row_cursor - row0;  // rows of this sub-chunk
-  if (n_rows > p.row_desc_cap) n_rows = p.row_desc_cap;
-  const unsigned long long total_warps = (unsigned long long)gridDim.x * NAMES_WARPS;
-  for (unsigned long long rb = ((unsigned long long)blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5)) * 32; rb < n_rows;
-       rb += total_warps * 32) {
-    const unsigned long long r = rb + lane;
-    const bool valid = r < n_rows;
-    bool small = false;
-    uint32_t ev_words = 0;
-    if (valid && cfg.want_tsv) {
-      const RowDesc rd = p.row_desc[r];
-      const LineRec rec = p.lines[rd.line];
-      ev_words = rec.ev_count;
-      small = rec.ev_count <= SMALL_EVENTS;
-      int8_t *drow = nullptr;
-      if (DOSAGE && cfg.want_dosage && (row0 + r) < p.dosage_cap_rows) drow = p.dosage + (row0 + r) * (unsigned long long)cfg.n_samples;
-      if (small) names_row_lane<DOSAGE>(p, rd, rec, drow);
-    }
-    // long rows go to the work list of the warp-per-row kernel (one atomic per warp), very long ones to the
-    // CTA-per-row kernel's
-    const bool very = valid && !small && p.long_words && ev_words > p.long_words;
-    const uint32_t big = __ballot_sync(FULL, valid && !small && !very);
-    if (big) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&p.ctr->n_big_rows, (unsigned int)__popc(big));
-      base = __shfl_sync(FULL, base, 0);
-      if (valid && !small && !very) p.big_rows[base + __popc(big & ((1u << lane) - 1u))] = (uint32_t)r;
-    }
-    const uint32_t vm = __ballot_sync(FULL, very);
-    if (vm) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&p.ctr->n_long_rows, (unsigned int)__popc(vm));
-      base = __shfl_sync(FULL, base, 0);
-      if (very) p.big_rows[p.row_desc_cap - 1 - (base + __popc(vm & ((1u << lane) - 1u)))] = (uint32_t)r;
-    }
-  }
-}
-
-// warp per row: the rows the hybrid kernel queued, when the list items are not fixed 8-byte pieces
+// warp per row: the rows bvcf_tile_kernel queued, when the list items are not fixed 8-byte pieces
 // (variable-width names or a longer delimiter; otherwise bvcf_names.cuh takes them)
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_big_kernel(const NamesParams p) {
   const int lane = threadIdx.x & 31;
-  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow | p.ctr->row_overflow) return;
   const unsigned long long row0 = p.ctr->chunk_row_base;
-  const uint32_t n_big = p.ctr->n_big_rows;
+  const uint32_t n_big = p.ctr->n_big_rows, n_long = p.ctr->n_long_rows;
   const uint32_t total_warps = gridDim.x * NAMES_WARPS;
-  for (uint32_t wi = blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5); wi < n_big; wi += total_warps)
-    names_row_warp(p, p.big_rows[wi], row0, lane);
+  for (uint32_t wi = blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5); wi < n_big + n_long; wi += total_warps)
+    names_row_warp(p, wi < n_big ? p.row_desc[wi] : p.row_desc[p.row_desc_cap - 1 - (wi - n_big)], row0, lane);
 }
 
 }  // namespace bvcf

@@ -374,6 +374,20 @@ def parse_preamble(data: bytes):
         p = e + 1
 
 
+def chunk_line_locus(block, line_no: int):
+    """CHROM and POS text of data line `line_no` (0-based) of a chunk: what the reference's log lines start with
+    (main.go:730-986 "%s:%s ...")."""
+    p = 0
+    for _ in range(line_no):
+        p = block.find(b"\n", p) + 1
+        if p <= 0:
+            return "?", "?"
+    f = bytes(block[p:block.find(b"\n", p)]).split(b"\t", 2)
+    if len(f) < 2:
+        return "?", "?"
+    return f[0].decode("latin-1"), f[1].decode("latin-1")
+
+
 def write_sample_list(config: Config, chrom_line: bytes, normalize: bool = True) -> None:
     """writeSampleListIfWanted / makeSampleList main.go:398-445"""
     if not config.sampleListPath:
@@ -390,7 +404,8 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
     """readVcf (main.go:241-396) on the GPU: header discovery on the host, every data line on the device.
 
     reader/writer are binary file objects (the reference's *bufio.Reader / *bufio.Writer).  Rows are
-    written in input order.  The TSV header line is NOT written here (main() does that, main.go:199)."""
+    written in input order.  The TSV header line is NOT written here (main() does that, main.go:199).
+    diag_sink(text, line_no, alt_no, code) receives the reference's log.Printf line for every skipped allele."""
     chunk_bytes = max(int(config.chunkBytes), 1 << 16)
     head = reader.read(1 << 20)
     while True:  # make sure the whole preamble (meta lines + #CHROM line) is in `head`
@@ -413,7 +428,11 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
         tr.set_header(chrom_line)
         if not config.noOut:
             write_sample_list(config, chrom_line, config.normalizeHeader)
-        if config.dosageMatrixOutPath:
+        n_samples_hdr = max(len(chrom_line.split(b"\t")) - 9, 0)
+        if config.dosageMatrixOutPath and n_samples_hdr == 0:
+            # main.go:308-318: no samples -> an empty dosage file, and no dosage work
+            open(config.dosageMatrixOutPath, "wb").close()
+        elif config.dosageMatrixOutPath:
             from .dosage import DosageWriter  # Arrow IPC framing
 
             names = [s.replace(b".", b"_") if config.normalizeHeader else s for s in chrom_line.split(b"\t")[9:]]
@@ -426,14 +445,15 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
             nonlocal seq_out
             while seq_out < upto:
                 res = tr.collect(seq_out)
-                pending.pop(seq_out, None)
+                block_of_seq = pending.pop(seq_out, b"")
                 if writer is not None and not config.noOut:
                     writer.write(res.tsv)
                 if arrow is not None and res.dosage is not None:
                     arrow.write(res.loci, res.dosage)
-                if diag_sink is not None:
-                    for d in res.diags:
-                        diag_sink(totals["n_lines"] + d[0], d[1], d[2])
+                if diag_sink is not None and res.diags:
+                    for ln, alt_no, code in res.diags:
+                        chrom, pos = chunk_line_locus(block_of_seq, ln)
+                        diag_sink(format_diag(chrom, pos, alt_no, code), totals["n_lines"] + ln, alt_no, code)
                 totals["n_lines"] += res.n_lines
                 totals["n_records"] += res.n_records
                 totals["n_rows"] += res.n_rows

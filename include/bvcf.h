@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BVCF_ABI_VERSION 1
+#define BVCF_ABI_VERSION 2
 
 typedef struct bvcf_ctx bvcf_ctx;
 
@@ -101,9 +101,9 @@ typedef struct {
   float scan_ms;     /* bvcf_scan_genotype_kernel: newline/tab index + per-sample GT classify  (north-star kernels 1+3) */
   float compact_ms;  /* line-table compaction + prefix sums */
   float stats_ms;    /* bvcf_line_stats_kernel: het/hom/missing/ac/an per record (kernel 3, reduction half) */
-  float size_ms;     /* bvcf_rows_kernel<size>: FILTER + getAlleles + row sizing (kernels 2+4a) + offset scan */
-  float emit_ms;     /* bvcf_rows_kernel<emit>: fixed columns of every row (kernel 4b) */
-  float names_ms;    /* bvcf_names_kernel: sample-name lists + dosage rows (kernel 4b) */
+  float rows_ms;     /* bvcf_tile_kernel: FILTER + getAlleles + row text, offsets by decoupled look-back, rows and short
+                        sample-name lists written in one pass (kernels 2+4) */
+  float names_ms;    /* bvcf_names_{vec,long,big}_kernel: long sample-name lists + their dosage rows (kernel 4b) */
   float total_ms;    /* first launch to last launch, whole run */
   uint32_t launches; /* kernels launched */
 } bvcf_kernel_times;

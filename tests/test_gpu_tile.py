@@ -1,0 +1,139 @@
+"""bvcf_tile_kernel's corners vs the CPU oracle, through the C ABI: variable-size locus strings, the slow path
+(records that do not fit the shared-memory arena), capacity retries of the diagnostics buffer and the line
+slots, INFO spans appended at copy-out, many tiles (decoupled look-back)."""
+import io
+import random
+
+import pytest
+
+import ref_vectors as V
+from test_gpu_parity import _cfg, gpu_rows, oracle_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def _process(vcf, cfg, **tr_kw):
+    from bystro_vcf_b200 import Transformer, parse_preamble
+
+    w, chrom, off = parse_preamble(vcf)
+    with Transformer(cfg, eol_width=w, **tr_kw) as tr:
+        tr.set_header(chrom)
+        return tr.process(vcf[off:])
+
+
+def _hdr(n):
+    return V.HDR8 + ["FORMAT"] + ["S%04d_ab" % i for i in range(n)]
+
+
+def test_dosage_locus_longer_than_63_bytes():
+    """"chrom:pos:ref:+INS" keys used to live in 64-byte slots.  A 200-bp insertion, a 300-bp padded
+    insertion, a long contig name and a 150-bp deletion: loci, dosages and rows all match (main.go:577)."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    rng = random.Random(5)
+    ins200 = "A" + "".join(rng.choice("ACGT") for _ in range(200))
+    pad = "".join(rng.choice("ACGT") for _ in range(40))
+    ins300 = pad + "".join(rng.choice("ACGT") for _ in range(300))
+    contig = "GL000207.1_some_very_long_unplaced_scaffold_name_that_goes_on_and_on_0123456789"
+    n = 12
+    gts = ["0|1", "1|1", "0|0", ".|.", "1|0", "0|0", "0|0", "1", "0|0", "0/1", "0|0", "1|1"]
+    recs = [["1", "1000", "rs1", "A", ins200, ".", "PASS", "DP=1", "GT"] + gts,
+            [contig, "123456789", "rs2", pad, ins300, ".", "PASS", "DP=2", "GT"] + gts,
+            ["chr7", "55", "rs3", "G" + "T" * 150, "G", ".", "PASS", "DP=3", "GT"] + gts,
+            [contig, "77", "rs4", "A", "C," + ins200 + ",G", ".", "PASS", "DP=4", "GT"] + ["1|2", "2|3", "0|3"] + gts[3:]]
+    vcf = V._vcf(_hdr(n), recs)
+    ref = O.read_vcf(O.OracleConfig(want_dosage=True, keep_id=True, keep_info=True), vcf)
+    assert max(len(x) for x in ref.loci) > 300
+    c = _cfg(keep_id=True, keep_info=True)
+    c.dosageMatrixOutPath = "unused.feather"
+    res = _process(vcf, c)
+    assert res.tsv == ref.tsv
+    assert res.loci == ref.loci
+    assert np.array_equal(res.dosage, ref.dosage)
+
+
+@pytest.mark.parametrize("with_samples", [False, True])
+def test_slow_path_records(with_samples):
+    """Records whose rows do not fit the tile's arena -- a 3,000-base insertion, a 70-base MNP (70 rows), a 40-ALT
+    site, a 5,000-character ID -- next to ordinary ones, with and without samples, keepId/keepInfo/keepPos on."""
+    rng = random.Random(11)
+    seq = lambda k: "".join(rng.choice("ACGT") for _ in range(k))
+    n = 9 if with_samples else 0
+    hdr = _hdr(n) if with_samples else V.HDR8
+    tail = lambda: (["GT"] + [rng.choice(["0|0", "0|1", "1|1", "1|0", ".|.", "2|1", "0|2"]) for _ in range(n)]) if with_samples else []
+    recs = []
+    for i in range(400):
+        k = i % 8
+        pos = str(1000 + 7 * i)
+        if k == 0:
+            recs.append(["1", pos, "rs%d" % i, "A", "A" + seq(3000), ".", "PASS", "X=%d" % i] + tail())
+        elif k == 1:
+            r = seq(70)
+            a = "".join({"A": "C", "C": "G", "G": "T", "T": "A"}[ch] for ch in r)
+            recs.append(["2", pos, ".", r, a, ".", "PASS", "MNP"] + tail())
+        elif k == 2:
+            recs.append(["3", pos, ".", "A", ",".join(rng.choice(["C", "G", "T", "AT", "ACC"]) for _ in range(40)), ".", "PASS",
+                         "M"] + tail())
+        elif k == 3:
+            recs.append(["4", pos, "r" * 5000, "G", "T", ".", "PASS", "ID"] + tail())
+        else:
+            recs.append(["5", pos, "rs%d" % i, "C", "T", ".", "PASS", "DP=%d" % i] + tail())
+    vcf = V._vcf(hdr, recs)
+    for kw in (dict(), dict(keep_id=True, keep_info=True, keep_pos=True)):
+        assert gpu_rows(vcf, **kw) == oracle_rows(vcf, **kw)
+
+
+def test_long_info_spans_appended_at_copy_out():
+    """--keepInfo with INFO fields from 0 to 9,000 bytes: the span is copied from the input line after the staged row"""
+    rng = random.Random(3)
+    n = 5
+    recs = []
+    for i in range(700):
+        ln = rng.choice([0, 1, 7, 8, 9, 15, 16, 17, 100, 1000, 9000])
+        info = "".join(rng.choice("ABCdef=;0123") for _ in range(ln)) if ln else ""
+        gts = [rng.choice(["0|0", "0|1", "1|1"]) for _ in range(n)]
+        recs.append(["1", str(100 + i), "rs%d" % i, "A", "G", ".", "PASS", info, "GT"] + gts)
+    vcf = V._vcf(_hdr(n), recs)
+    assert gpu_rows(vcf, keep_info=True) == oracle_rows(vcf, keep_info=True)
+    assert gpu_rows(vcf, keep_info=True, keep_id=True) == oracle_rows(vcf, keep_info=True, keep_id=True)
+
+
+def test_diagnostics_beyond_first_capacity(monkeypatch):
+    """diagnostics past the buffer's capacity used to be dropped; now the buffer grows and the chunk runs again"""
+    from oracle import oracle as O
+
+    monkeypatch.setenv("BVCF_DIAG_CAP", "16")
+    recs = [["1", str(5 + i), ".", "A", "<DEL>" if i % 2 else "A", ".", "PASS", "."] for i in range(500)]
+    vcf = V._vcf(V.HDR8, recs)
+    ref = O.read_vcf(O.OracleConfig(), vcf)
+    res = _process(vcf, _cfg())
+    assert res.retries > 0
+    assert sorted(res.diags) == sorted(ref.diags) and len(ref.diags) == 500
+    assert res.tsv == ref.tsv
+
+
+def test_short_lines_grow_the_line_slots():
+    """with 8 <= H < 16 and lines shorter than 16 bytes the per-range line slots ran out and the chunk failed"""
+    recs = [["1", str(i % 10), "", "A", "C", "", ".", ""] for i in range(40000)]  # 12-byte lines
+    vcf = V._vcf(V.HDR8, recs)
+    exp = oracle_rows(vcf)
+    res = _process(vcf, _cfg())
+    assert res.retries > 0
+    assert res.tsv == exp and res.n_rows == 40000
+
+
+def test_many_tiles_look_back(chr1_fixture):
+    """1,000+ tiles of 128 records with very different sizes: every tile's offset comes from the look-back chain"""
+    from oracle import oracle as O
+
+    rng = random.Random(17)
+    n = 40
+    recs = []
+    for i in range(150000):
+        dense = i % 97 == 0
+        gts = [rng.choice(["0|1", "1|1", "1|0"]) if dense or rng.random() < 0.02 else "0|0" for _ in range(n)]
+        recs.append(["1", str(10 + i), ".", "A", "G", ".", "PASS", ".", "GT"] + gts)
+    vcf = V._vcf(_hdr(n), recs)
+    assert gpu_rows(vcf) == oracle_rows(vcf)

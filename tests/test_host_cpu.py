@@ -57,7 +57,7 @@ def test_c_abi_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for s in declared:
         assert hasattr(L, s), s
-    assert L.bvcf_abi_version() == 1
+    assert L.bvcf_abi_version() == 2
     assert L.bvcf_strerror(0) == b"ok" and b"newline" in L.bvcf_strerror(-4)
 
 
