@@ -5,8 +5,10 @@
 //   bvcf_prefix_* (mode 0)         per-range record counts -> bases
 //   bvcf_compact_lines_kernel      input-ordered line table
 //   bvcf_line_stats_{,big_}kernel  genotype summaries the scan could not finish inline
-//   bvcf_tile_kernel               FILTER + getAlleles + row text, sizes scanned on the fly (decoupled look-back),
-//                                  rows and short name lists written in one pass  (north-star kernels 2+4)
+//   bvcf_compose_kernel            FILTER + getAlleles + row text + short name lists, staged per tile of 32 records
+//   bvcf_tile_{reduce,spine,offsets}  tile totals -> output offsets, cursors            (north-star kernels 2+4)
+//   bvcf_copyout_kernel            rows to the output with aligned stores, loci, RowDesc work lists
+//   bvcf_slow_rows_kernel          the few records that do not fit a tile's arena
 //   bvcf_names_{vec,long,big}_     long sample-name lists, their dosage rows  (north-star kernel 4b)
 #include "../../include/bvcf.h"
 
@@ -39,7 +41,10 @@ struct Scratch {
   uint32_t range_bytes = 0, n_ranges = 0, slots = 0, evcap_words = 0;
   uint64_t max_records = 0;
   uint64_t row_cap = 0;       // RowDesc slots (rows one sub-chunk may emit)
-  DevBuf recs, range_nrec, range_nlines, rec_base, line_base, events, dense, partial, stats1, row_desc, big_recs, tile_state;
+  DevBuf recs, range_nrec, range_nlines, rec_base, line_base, events, dense, partial, stats1, row_desc, big_recs, tile_agg,
+      tile_base, tile_partial, tile_scratch, slow;
+  uint64_t scratch_cap = 0;   // bytes of tile blocks (grown on scratch_overflow)
+  uint32_t slow_cap = 0;      // slow-path list entries (grown on slow_overflow)
 };
 
 struct Slot {
@@ -171,7 +176,15 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
   if ((rc = dev_reserve(ctx, sc.line_base, (size_t)sc.n_ranges * 8))) return rc;
   if ((rc = dev_reserve(ctx, sc.events, (size_t)sc.n_ranges * sc.evcap_words * 4))) return rc;
   if ((rc = dev_reserve(ctx, sc.partial, 2 * PFX_BLOCKS * 8))) return rc;
-  if ((rc = dev_reserve(ctx, sc.tile_state, (sc.max_records / TILE_THREADS + 2) * 2 * sizeof(ulonglong2)))) return rc;
+  const uint64_t max_tiles = sc.max_records / TILE_THREADS + 2;
+  if ((rc = dev_reserve(ctx, sc.tile_agg, max_tiles * sizeof(TileAgg)))) return rc;
+  if ((rc = dev_reserve(ctx, sc.tile_base, max_tiles * sizeof(TileBase)))) return rc;
+  if ((rc = dev_reserve(ctx, sc.tile_partial, (size_t)TSCAN_BLOCKS * 5 * 8))) return rc;
+  // a tile's block: 1 KiB of per-record sizes, 32 bytes per row, the staged text (about 110 bytes per row)
+  sc.scratch_cap = std::max<uint64_t>(sc.scratch_cap, std::min<uint64_t>(total_bytes / 8 + (8ull << 20), sc.max_records * 224ull + (1ull << 20)));
+  if ((rc = dev_reserve(ctx, sc.tile_scratch, sc.scratch_cap + 64))) return rc;  // the copy-out reads whole words
+  sc.slow_cap = std::max<uint32_t>(sc.slow_cap, 1u << 16);
+  if ((rc = dev_reserve(ctx, sc.slow, (size_t)sc.slow_cap * sizeof(SlowRec)))) return rc;
   if (ctx->dcfg.n_samples > 0) {
     // rows queued for the names kernels: usually a third of the records; grown on row_overflow
     sc.row_cap = std::max<uint64_t>(sc.row_cap, sc.max_records / 2 + 1024);
@@ -183,7 +196,8 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
 }
 void scratch_free(Scratch &sc) {
   for (DevBuf *b : {&sc.recs, &sc.range_nrec, &sc.range_nlines, &sc.rec_base, &sc.line_base, &sc.events, &sc.dense,
-                    &sc.partial, &sc.stats1, &sc.row_desc, &sc.big_recs, &sc.tile_state})
+                    &sc.partial, &sc.stats1, &sc.row_desc, &sc.big_recs, &sc.tile_agg, &sc.tile_base, &sc.tile_partial,
+                    &sc.tile_scratch, &sc.slow})
     dev_free(*b);
 }
 
@@ -273,15 +287,23 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     TileParams tp{};
     tp.in = d_in; tp.cfg = dc; tp.lines = cp.dense; tp.events = sp.events; tp.stats = (const LineStats *)sc.stats1.p;
     tp.out = d_out; tp.out_cap = out_cap; tp.ctr = d_ctr;
-    tp.tile_state = (ulonglong2 *)sc.tile_state.p;
+    tp.tile_agg = (TileAgg *)sc.tile_agg.p; tp.tile_base = (TileBase *)sc.tile_base.p;
+    tp.tile_partial = (unsigned long long *)sc.tile_partial.p;
+    tp.scratch = (uint8_t *)sc.tile_scratch.p; tp.scratch_cap = sc.scratch_cap;
+    tp.slow = (SlowRec *)sc.slow.p; tp.slow_cap = sc.slow_cap;
     tp.row_desc = (RowDesc *)sc.row_desc.p; tp.row_desc_cap = dc.n_samples > 0 ? sc.row_cap : 0;
     tp.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
     tp.dosage = d_dosage; tp.dosage_cap_rows = dosage_cap_rows;
     tp.loci = d_loci; tp.loci_cap = loci_cap; tp.loci_off = d_loci_off;
     tp.diag.diags = d_diags; tp.diag.cap = ctx->diag_cap; tp.diag.ctr = d_ctr;
-    CK(cudaMemsetAsync(sc.tile_state.p, 0, ((size_t)sc.max_records / TILE_THREADS + 2) * 2 * sizeof(ulonglong2), st));
-    bvcf_tile_kernel<<<(unsigned)n_sm * 4, TILE_THREADS, 0, st>>>(tp);
-    ctx->launches++;
+    cudaFuncSetAttribute(bvcf_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
+    bvcf_compose_kernel<<<(unsigned)n_sm * 4, TILE_WARPS * 32, TILE_SMEM, st>>>(tp);
+    bvcf_tile_reduce_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);
+    bvcf_tile_spine_kernel<<<1, 32, 0, st>>>(tp);
+    bvcf_tile_offsets_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);
+    bvcf_copyout_kernel<<<(unsigned)n_sm * 16, TILE_WARPS * 32, 0, st>>>(tp);
+    bvcf_slow_rows_kernel<<<(unsigned)n_sm, 64, 0, st>>>(tp);
+    ctx->launches += 6;
     if (se) CK(cudaEventRecord(se->e[4], st));
     // 5. long sample-name lists + their dosage rows: a warp per queued row -- as aligned vectors when every list
     // item has one size of 5..16 bytes (bvcf_names.cuh) -- and a CTA per row beyond 4,096 quads
@@ -651,6 +673,8 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
       }
     }
     if (c.n_diags > ctx->diag_cap) { ctx->diag_cap = c.n_diags + c.n_diags / 4; again = true; }  // every log line or none
+    if (c.scratch_overflow) { s->sc.scratch_cap = c.scratch_cursor + c.scratch_cursor / 4 + (1ull << 20); again = true; }
+    if (c.slow_overflow) { s->sc.slow_cap = c.n_slow + c.n_slow / 4 + 1024; again = true; }
     if (!again) break;
     s->retries++;
     if (s->retries > 8) return BVCF_E_TOO_LARGE;
@@ -810,6 +834,8 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       continue;
     }
     if (c.row_overflow) { ctx->r_sc.row_cap = ctx->r_sc.row_cap * 4 + c.row_cursor; again = true; }
+    if (c.scratch_overflow) { ctx->r_sc.scratch_cap = c.scratch_cursor + c.scratch_cursor / 4 + (1ull << 20); again = true; }
+    if (c.slow_overflow) { ctx->r_sc.slow_cap = c.n_slow + c.n_slow / 4 + 1024; again = true; }
     if (c.out_overflow) {
       if ((rc = dev_reserve(ctx, ctx->r_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096)))) return rc;
       again = true;

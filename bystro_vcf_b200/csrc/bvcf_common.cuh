@@ -75,6 +75,7 @@ struct RunCounters {
   unsigned long long chunk_row_base;
   unsigned long long chunk_loci_base;
   unsigned long long chunk_line_base;  // n_lines before this sub-chunk (diagnostic line numbers)
+  unsigned long long scratch_cursor;   // bytes of tile blocks in the scratch buffer (per sub-chunk)
   unsigned int ev_overflow;        // a range ran out of event slots
   unsigned int slot_overflow;      // a range ran out of line slots
   unsigned int out_overflow;       // output region too small
@@ -83,8 +84,12 @@ struct RunCounters {
   unsigned int chunk_records;      // records in the current sub-chunk (device-side n for grid-stride kernels)
   unsigned int n_big_recs;         // work list of the stats kernel: records with long event lists (per sub-chunk)
   unsigned int big_rec_cursor;     // next entry of the stats work list to be taken
-  unsigned int tile_ticket;        // bvcf_tile_kernel: next tile of 128 records to be taken (per sub-chunk)
-  unsigned int n_desc;             // RowDesc entries handed out so far, both lists (per sub-chunk)
+  unsigned int tile_ticket;        // bvcf_compose_kernel: next tile of 32 records to be taken (per sub-chunk)
+  unsigned int tile_ticket2;       // bvcf_copyout_kernel: the same
+  unsigned int n_slow;             // slow-path records of the sub-chunk (bvcf_slow_rows_kernel's work list)
+  unsigned int scratch_overflow;   // the tile blocks did not fit the scratch buffer
+  unsigned int slow_overflow;      // more slow-path records than list entries
+  unsigned int pad0;
   unsigned int n_big_rows;         // names work list: rows written by a warp each (per sub-chunk)
   unsigned int big_row_cursor;     // next entry to be taken (dynamic scheduling)
   unsigned int n_long_rows;        // rows with very long event lists: written by a whole CTA (bvcf_names_long_kernel)

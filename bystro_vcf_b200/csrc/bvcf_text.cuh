@@ -10,30 +10,78 @@ namespace bvcf {
 // digits, ties to even, with 128-bit integer arithmetic: D = round(m * 10^(2-e) / 2^-x).  Trailing zeros are
 // stripped; decimal exponent < -4 switches to d.ddE-XX (Go 'G' == C "%.3G" on (0,1]).
 // Returns the text packed little-endian in a u64 (at most 8 characters) and its length.
-__device__ __forceinline__ uint64_t format_ratio_g3(uint32_t k, uint32_t n, int &len_out) {
-  unsigned long long r;  // the three significant digits, 100..999
-  int e;                 // decimal exponent of the first digit
-  bool have = false;
+__device__ const unsigned long long BVCF_P10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull,
+    100000000ull, 1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
+    100000000000000ull, 1000000000000000ull, 10000000000000000ull, 100000000000000000ull, 1000000000000000000ull,
+    10000000000000000000ull};
+
+// the text of three significant digits r (100..999) with decimal exponent e (value = r / 100 * 10^e, e <= 0)
+__device__ __forceinline__ uint64_t g3_text(uint32_t r, int e, int &len_out) {
+  const uint32_t d0 = r / 100u, r2 = r - d0 * 100u, d1 = r2 / 10u, d2 = r2 - d1 * 10u;
+  const int nd = d2 ? 3 : (d1 ? 2 : 1);  // trailing zeros are stripped
+  if (e < -4) {  // %E style: d[.dd]E-XX
+    uint64_t out = '0' + d0;
+    int len = 1;
+    if (nd > 1) {
+      out |= (uint64_t)'.' << 8 | (uint64_t)('0' + d1) << 16;
+      len = 3;
+      if (nd > 2) { out |= (uint64_t)('0' + d2) << 24; len = 4; }
+    }
+    const uint32_t ae = (uint32_t)(-e), t = ae / 10u;
+    out |= ((uint64_t)'E' | (uint64_t)'-' << 8 | (uint64_t)('0' + t) << 16 | (uint64_t)('0' + (ae - t * 10u)) << 24) << (8 * len);
+    len_out = len + 4;
+    return out;
+  }
+  if (e >= 0) {  // only q == 1 (or rounds to 1): d[.dd]
+    uint64_t out = '0' + d0;
+    int len = 1;
+    if (nd > 1) {
+      out |= (uint64_t)'.' << 8 | (uint64_t)('0' + d1) << 16;
+      len = 3;
+      if (nd > 2) { out |= (uint64_t)('0' + d2) << 24; len = 4; }
+    }
+    len_out = len;
+    return out;
+  }
+  // 0.[000]ddd: "0." + (-e - 1) zeros + the digits
+  const int z = -e - 1;  // 0..3
+  const uint64_t digits = (uint64_t)('0' + d0) | (uint64_t)('0' + d1) << 8 | (uint64_t)('0' + d2) << 16;
+  const uint64_t keep = nd == 3 ? 0xFFFFFFull : (nd == 2 ? 0xFFFFull : 0xFFull);
+  const uint64_t pre = 0x3030303030302E30ull & ((1ull << (8 * (2 + z))) - 1ull);  // "0.000000" cut to 2 + z characters
+  len_out = 2 + z + nd;
+  return pre | (digits & keep) << (8 * (2 + z));
+}
+
+// (out of line: four call sites per row composer, and the exact path is a few hundred instructions of 128-bit
+// arithmetic -- inlined they pushed the compose kernel past the instruction cache)
+__device__ __noinline__ uint64_t format_ratio_g3(uint32_t k, uint32_t n, int &len_out) {
   if (n < (1u << 24)) {
     // Fast path, integers only.  D = round(k 10^j / n) with 100 <= D < 1000.  The double q differs from k/n by less
     // than 2^-53 relative, while k 10^j / n is at least 1/(2n) away from every rounding boundary unless it sits ON
     // one (2 rem == n): only then can the double fall on either side, and the exact path below decides.
     // (Checked against the exact path on 26 million (k, n) pairs.)
-    unsigned long long m = k;
+    // j and D are first guessed in single precision, then made exact with 64-bit integer comparisons: no 64-bit
+    // division, no digit loop.
+    const float qf = __fdividef((float)k, (float)n);
+    int j = 2 + (qf < 1.0f) + (qf < 0.1f) + (qf < 0.01f) + (qf < 0.001f) + (qf < 1e-4f) + (qf < 1e-5f) + (qf < 1e-6f) + (qf < 1e-7f);
+    unsigned long long m = (unsigned long long)k * BVCF_P10[j];   // k 10^j < 2^24 * 10^10 < 2^63
     const unsigned long long lim = 100ull * n;
-    int j = 0;
-    while (m < lim) { m *= 10ull; j++; }   // at most 10 rounds: k 10^j < 2^24 * 10^10 < 2^63
-    unsigned long long D = m / n;
-    const unsigned long long rem = m - D * n;
-    if (2ull * rem != n) {
-      if (2ull * rem > n) D++;
-      e = 2 - j;
+    while (m < lim) { m *= 10ull; j++; }                          // the guess may be one off at a power of ten
+    while (m >= 10ull * lim) { j--; m = (unsigned long long)k * BVCF_P10[j]; }
+    unsigned long long D = (unsigned long long)(__fdividef((float)m, (float)n));  // within a few units of m / n
+    if (D > 999ull) D = 999ull;
+    long long rem = (long long)m - (long long)(D * n);
+    while (rem < 0) { D--; rem += n; }
+    while (rem >= (long long)n) { D++; rem -= n; }
+    if (2ull * (unsigned long long)rem != n) {
+      if (2ull * (unsigned long long)rem > n) D++;
+      int e = 2 - j;
       if (D == 1000) { D = 100; e++; }
-      r = D;
-      have = true;
+      return g3_text((uint32_t)D, e, len_out);
     }
   }
-  if (!have) {
+  unsigned long long r;  // the three significant digits, 100..999
+  int e;                 // decimal exponent of the first digit
   const double q = (double)k / (double)n;  // IEEE-754 division, as in Go
   const unsigned long long bits = (unsigned long long)__double_as_longlong(q);
   const int bexp = (int)((bits >> 52) & 0x7FF);
@@ -59,29 +107,7 @@ __device__ __forceinline__ uint64_t format_ratio_g3(uint32_t k, uint32_t n, int 
     break;
   }
   if (up) { r++; if (r == 1000) { r = 100; e++; } }
-  }
-  uint32_t d[3] = {(uint32_t)(r / 100), (uint32_t)(r / 10 % 10), (uint32_t)(r % 10)};
-  int nd = 3;
-  while (nd > 1 && d[nd - 1] == 0) nd--;
-  uint64_t out = 0;
-  int len = 0;
-  auto put = [&](uint32_t c) { out |= (uint64_t)c << (8 * len); len++; };
-  if (e < -4) {  // %E style
-    put('0' + d[0]);
-    if (nd > 1) { put('.'); for (int i = 1; i < nd; i++) put('0' + d[i]); }
-    put('E'); put('-');
-    const int ae = -e;
-    put('0' + ae / 10); put('0' + ae % 10);
-  } else if (e >= 0) {  // only q == 1 (or rounds to 1)
-    put('0' + d[0]);
-    if (nd > 1) { put('.'); for (int i = 1; i < nd; i++) put('0' + d[i]); }
-  } else {
-    put('0'); put('.');
-    for (int i = 0; i < -e - 1; i++) put('0');
-    for (int i = 0; i < nd; i++) put('0' + d[i]);
-  }
-  len_out = len;
-  return out;
+  return g3_text((uint32_t)r, e, len_out);
 }
 
 // ---- strconv.Itoa -----------------------------------------------------------------------------
@@ -108,7 +134,7 @@ __device__ __forceinline__ int dec_len(unsigned long long u) {
 }
 // strconv.Itoa without a byte buffer: the text of v packed little-endian in (lo, hi), at most 16 characters.
 // Returns the length, or -1 when the text is longer (callers fall back to itoa_dec).
-__device__ __forceinline__ int itoa_pack(long long v, unsigned long long &lo, unsigned long long &hi) {
+__device__ __noinline__ int itoa_pack(long long v, unsigned long long &lo, unsigned long long &hi) {
   unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
   if (u >= 1000000000000000ull) return -1;
   lo = 0; hi = 0;

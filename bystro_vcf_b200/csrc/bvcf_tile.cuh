@@ -1,33 +1,85 @@
-// bvcf_tile.cuh -- north-star kernels (2)+(4) in ONE pass: the per-line fixed-field kernel and the row emitter.
+// bvcf_tile.cuh -- north-star kernels (2)+(4): the per-line fixed-field kernel and the row emitter, generator run ONCE.
 //
-// bvcf_tile_kernel: a CTA takes tiles of 128 consecutive records (dynamic ticket), one thread per record.
-//   A  compose   FILTER allow/exclude against a shared-memory table (main.go:447-454), getAlleles (main.go:723-1038,
-//                the generator of bvcf_rows.cuh), genotype summary lookup, ac == 0 skip (main.go:558), and the TEXT of
-//                every row (main.go:586-695) composed with byte stores into a shared-memory arena: fixed columns,
-//                float text, and -- for records with at most SMALL_EVENTS event words -- the sample-name lists too
-//                (main.go:617,639,653), so that such a row is one contiguous string.  Long lists stay holes.
-//   B  offsets   block scan of the records' output bytes / rows / locus bytes, then a decoupled look-back over
-//                the tiles before this one (128-bit descriptors: flag | bytes, rows) gives the tile's place in the
-//                output: no size pass, no separate prefix kernels, the getAlleles generator runs once.
-//   C  copy-out  every thread copies its rows from the arena to the output with aligned 8-byte stores (funnel-
-//                shifted shared-memory words), appends the INFO span straight from the input line, writes locus
-//                strings + the small rows' dosages (main.go:576-584), and queues the rows with holes for the names
-//                kernels (bvcf_names.cuh) as RowDesc entries.
-// Records that do not fit the arena (very long alleles / IDs, dozens of rows per record) take the slow path: sized in
-// A by the same code with stores switched off, written in C by their own thread straight to global memory.
+// Tiles of 32 consecutive records, a warp per tile, one thread per record, no ordering between tiles anywhere:
+//   bvcf_compose_kernel   FILTER allow/exclude against a shared-memory table (main.go:447-454), getAlleles
+//                         (main.go:723-1038, the generator of bvcf_rows.cuh), genotype summary lookup, ac == 0 skip
+//                         (main.go:558), and the TEXT of every row (main.go:586-695) composed with byte stores into a
+//                         shared-memory arena: fixed columns, float text, and -- for records with at most
+//                         SMALL_EVENTS event words -- the sample-name lists too (main.go:617,639,653), so that such a
+//                         row is one contiguous string.  Long lists stay holes.  The tile's arena, row table and
+//                         per-record sizes leave as one compact block of a global scratch buffer (coalesced 16-byte
+//                         stores) next to the tile's totals: bytes, rows, locus bytes, queued rows.
+//   bvcf_tile_{reduce,spine,offsets}_kernel   exclusive scan of the tile totals -> every tile's place in the output,
+//                         in the locus buffer and in the RowDesc work lists; advances the run's cursors.
+//   bvcf_copyout_kernel   pulls a tile's block back into shared memory and lets every thread copy its rows to the
+//                         output with aligned 8-byte stores (funnel-shifted shared-memory words); appends the INFO span
+//                         straight from the input line, writes locus strings + the small rows' dosages
+//                         (main.go:576-584), queues the rows with holes for the names kernels (bvcf_names.cuh).
+//   bvcf_slow_rows_kernel records that did not fit the arena (very long alleles / IDs, dozens of rows per record):
+//                         sized by the compose kernel with the stores switched off, written here by one thread each
+//                         straight to global memory.
 //
 // Replaces round 1's bvcf_rows_kernel<SIZE> + 3 prefix kernels + bvcf_rows_kernel<EMIT> + bvcf_names_kernel
-// (+ bvcf_rows_list_kernel x2, bvcf_dosage_zero_kernel): the SIZE/EMIT pair ran the generator twice and spent 60 % of
-// its instructions in an 8-byte register writer with unaligned global stores.
+// (+ bvcf_rows_list_kernel x2, bvcf_dosage_zero_kernel): that pair ran the generator twice and spent 60 % of its
+// instructions in an 8-byte register writer with unaligned global stores.  A single-kernel version with a decoupled
+// look-back between the tiles was measured first and dropped: with thousands of tiles in flight every wave waited
+// for its slowest tile's compose phase (45 % of the issued instructions were look-back polls).
 #pragma once
 #include "bvcf_rows.cuh"
 
 namespace bvcf {
 
-constexpr int TILE_THREADS = 128;          // records per tile, one thread each
-constexpr uint32_t TILE_ARENA = 32768;     // staging bytes per CTA
-constexpr uint32_t TILE_ROWS = 256;        // staged rows per tile; thread t's first row is rows[t]
+constexpr int TILE_THREADS = 32;           // records per tile, one thread each: a tile is a warp's
+constexpr int TILE_WARPS = 4;              // warps (independent tiles) per CTA
+constexpr uint32_t TILE_ARENA = 10240;     // staging bytes per warp
+constexpr uint32_t TILE_ROWS = 64;         // staged rows per tile; lane l's first row is rows[l]
 constexpr uint32_t ROW_NONE = 0xFFFFu;
+
+// one staged row (shared memory, then the tile's scratch block)
+struct __align__(16) TRow {
+  uint32_t hole_len[3];   // bytes of the het / hom / missing list when it is NOT staged (filled by the names kernels)
+  uint16_t hole_pos[3];   // where the hole sits in the staged string (staged bytes before it)
+  uint16_t soff;          // arena offset of the staged string: TSV bytes, the locus, then (queued rows) three counts
+  uint16_t slen;          // staged TSV bytes
+  uint16_t loc_len;       // staged locus bytes
+  uint16_t next;          // next row of the same record, ROW_NONE at the end
+  uint16_t allele;        // ALT number
+  uint16_t flags;         // bit 0: the INFO span and the EOL follow the staged bytes; bit 1: queue a RowDesc
+  uint16_t pad;
+};
+static_assert(sizeof(TRow) == 32, "TRow layout");
+
+// what one record contributes to its tile (scratch block, one per lane)
+struct __align__(16) LaneRec {
+  unsigned long long bytes;   // TSV bytes of all its rows
+  uint32_t rows, loci;        // rows, locus bytes
+  uint32_t n_desc;            // RowDesc entries it will queue
+  uint16_t first;             // its first staged row (chain through TRow::next)
+  uint16_t flags;             // bit 0: slow path (nothing staged, the sizes are still exact); bit 1: its rows go to the long list
+  uint32_t info_off, info_n;  // INFO span of its line (offset from the line start)
+};
+static_assert(sizeof(LaneRec) == 32, "LaneRec layout");
+
+// a tile's totals (compose kernel) and where its scratch block is
+struct __align__(16) TileAgg {
+  unsigned long long bytes;
+  unsigned long long scratch_off;     // byte offset of the block in the scratch buffer
+  uint32_t rows, loci, n_big, n_long;
+  uint32_t arena_used, n_trows;       // block layout: 32 LaneRec, n_trows TRow, arena_used bytes (16-byte padded)
+  uint32_t pad[2];
+};
+static_assert(sizeof(TileAgg) == 48, "TileAgg layout");
+// exclusive prefix of the totals over the tiles before this one (tile offsets kernels)
+struct __align__(16) TileBase {
+  unsigned long long bytes, loci;
+  uint32_t rows, n_big, n_long, pad;
+};
+static_assert(sizeof(TileBase) == 32, "TileBase layout");
+// a slow-path record with its place in the outputs (copy-out kernel -> slow rows kernel)
+struct __align__(16) SlowRec {
+  unsigned long long out_off, loci_off;
+  uint32_t li, row, desc, flags;      // flags bit 0: RowDesc slots are available, bit 1: long list
+};
 
 struct TileParams {
   const uint8_t *in;
@@ -38,7 +90,13 @@ struct TileParams {
   uint8_t *out;
   unsigned long long out_cap;
   RunCounters *ctr;
-  ulonglong2 *tile_state;      // two descriptors per tile (zeroed before the launch): {flag | bytes, rows}, {flag | locus bytes, 0}
+  TileAgg *tile_agg;           // per tile
+  TileBase *tile_base;         // per tile
+  unsigned long long *tile_partial;  // TSCAN_BLOCKS x 5
+  uint8_t *scratch;            // tile blocks
+  unsigned long long scratch_cap;
+  SlowRec *slow;               // slow-path records of the sub-chunk
+  uint32_t slow_cap;
   RowDesc *row_desc;           // work list for the names kernels (see RowDesc)
   unsigned long long row_desc_cap;
   uint32_t long_words;         // rows of records with more event words go to the END of row_desc (CTA-per-row kernel); 0: none
@@ -51,61 +109,44 @@ struct TileParams {
   DiagSink diag;
 };
 
-// one staged row (shared memory)
-struct __align__(16) TRow {
-  uint32_t hole_len[3];   // bytes of the het / hom / missing list when it is NOT staged (filled by the names kernels)
-  uint32_t cnt[3];        // names per list
-  uint16_t hole_pos[3];   // where the hole sits in the staged string (staged bytes before it)
-  uint16_t soff;          // arena offset of the staged string: TSV bytes, then the locus
-  uint16_t slen;          // staged TSV bytes
-  uint16_t loc_len;       // staged locus bytes
-  uint16_t next;          // next row of the same record, ROW_NONE at the end
-  uint16_t allele;        // ALT number
-  uint16_t flags;         // bit 0: the INFO span and the EOL follow the staged bytes; bit 1: queue a RowDesc
-  uint16_t pad[3];
-};
-static_assert(sizeof(TRow) == 48, "TRow layout");
-
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t tl_lds8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
-  return v;
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
+// up to 7 bytes of v (little-endian) to g, widest naturally aligned pieces first where the address allows
+__device__ __forceinline__ void store_head(uint8_t *&g, unsigned long long &v, uint32_t &n, uint32_t &moved) {
+  // bytes up to the next 8-byte boundary of g (at most n)
+  moved = 0;
+  if (((uintptr_t)g & 1u) && n >= 1) { *g = (uint8_t)v; v >>= 8; g += 1; n -= 1; moved += 1; }
+  if (((uintptr_t)g & 2u) && n >= 2) { *reinterpret_cast<uint16_t *>(g) = (uint16_t)v; v >>= 16; g += 2; n -= 2; moved += 2; }
+  if (((uintptr_t)g & 4u) && n >= 4) { *reinterpret_cast<uint32_t *>(g) = (uint32_t)v; v >>= 32; g += 4; n -= 4; moved += 4; }
 }
-__device__ __forceinline__ uint32_t tl_lds32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
-  return v;
+__device__ __forceinline__ void store_tail(uint8_t *g, unsigned long long v, uint32_t n) {  // n < 8, g 8-byte aligned or n small
+  if (n & 4u) { *reinterpret_cast<uint32_t *>(g) = (uint32_t)v; v >>= 32; g += 4; }
+  if (n & 2u) { *reinterpret_cast<uint16_t *>(g) = (uint16_t)v; v >>= 16; g += 2; }
+  if (n & 1u) *g = (uint8_t)v;
 }
-__device__ __forceinline__ void st_state(ulonglong2 *p, unsigned long long x, unsigned long long y) {
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};\n" ::"l"(p), "l"(x), "l"(y) : "memory");
-}
-__device__ __forceinline__ ulonglong2 ld_state(const ulonglong2 *p) {
-  ulonglong2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-  return v;
+// eight bytes from global memory at any alignment (three aligned words, funnel-shifted); reads up to 11 bytes past s
+__device__ __forceinline__ unsigned long long ldg64_unaligned(const uint8_t *s) {
+  const uint32_t sh = (uint32_t)((uintptr_t)s & 3u) * 8u;
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
+  const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+  return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
 }
 
-// n bytes from shared memory (address sa, any alignment) to global memory (any alignment): byte stores up to the
-// first 8-byte boundary of the destination, then aligned 8-byte stores of funnel-shifted shared-memory words.
-// May read up to 11 bytes past the source (the arena is padded).
-__device__ __forceinline__ void copy_s2g(uint8_t *g, uint32_t sa, uint32_t n) {
-  while (n && ((uintptr_t)g & 7u)) { *g++ = (uint8_t)tl_lds8(sa++); n--; }
-  if (n >= 8) {
-    const uint32_t sh = (sa & 3u) * 8u;
-    uint32_t wa = sa & ~3u;
-    uint32_t w0 = tl_lds32(wa);
-    do {
-      const uint32_t w1 = tl_lds32(wa + 4), w2 = tl_lds32(wa + 8);
-      *reinterpret_cast<uint2 *>(g) = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
-      w0 = w2; wa += 8; g += 8; sa += 8; n -= 8;
-    } while (n >= 8);
-  }
-  while (n) { *g++ = (uint8_t)tl_lds8(sa++); n--; }
-}
-// the same from global memory (a span of the input line; the input region is padded, so whole words may be read)
+// n bytes from global memory (a tile's scratch block, a span of the input line: both padded, so whole words may be
+// read) to global memory, any alignments: at most three narrow stores up to the first 8-byte boundary of the
+// destination, aligned 8-byte stores of funnel-shifted source words, at most three narrow stores at the end.
 __device__ __forceinline__ void copy_g2g(uint8_t *g, const uint8_t *s, uint32_t n) {
-  while (n && ((uintptr_t)g & 7u)) { *g++ = *s++; n--; }
+  if (n == 0) return;
+  if ((uintptr_t)g & 7u) {
+    unsigned long long v = ldg64_unaligned(s);
+    if (n < 8 && (((uintptr_t)g & 7u) + n) <= 8u) {  // the whole piece sits inside one 8-byte word of the destination
+      for (uint32_t i = 0; i < n; i++) g[i] = (uint8_t)(v >> (8 * i));
+      return;
+    }
+    uint32_t moved;
+    store_head(g, v, n, moved);
+    s += moved;
+  }
   if (n >= 8) {
     const uint32_t sh = (uint32_t)((uintptr_t)s & 3u) * 8u;
     const uint32_t *wp = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
@@ -116,7 +157,7 @@ __device__ __forceinline__ void copy_g2g(uint8_t *g, const uint8_t *s, uint32_t 
       w0 = w2; wp += 2; g += 8; s += 8; n -= 8;
     } while (n >= 8);
   }
-  while (n) { *g++ = *s++; n--; }
+  if (n) store_tail(g, ldg64_unaligned(s), n);
 }
 
 // ---- byte sinks of the row composer ---------------------------------------------------------------------
@@ -128,8 +169,11 @@ struct StageWriter {
   __device__ __forceinline__ void byte(uint32_t c) { if (stg) sts8(a, c); a++; }
   __device__ __forceinline__ void packed(unsigned long long chars, int len) {  // len <= 8 characters, little-endian
     if (stg) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) if (k < len) sts8(a + k, (uint32_t)(chars >> (8 * k)) & 0xFFu);
+      // a rolled loop on purpose: unrolled and inlined at some thirty call sites this was 7,000 instructions of a
+      // kernel that stalled on instruction fetch
+      uint32_t lo = (uint32_t)chars, hi = (uint32_t)(chars >> 32);
+#pragma unroll 1
+      for (int k = 0; k < len; k++) { sts8(a + k, lo & 0xFFu); lo = __funnelshift_r(lo, hi, 8); hi >>= 8; }
     }
     a += len;
   }
@@ -329,7 +373,8 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
         if (!big) need += lb[0] + lb[1] + lb[2];
       }
       if (want_locus) need += 8u + (uint32_t)lc.chrom_n + pos_b + alt_b;
-      ri = ro.first == ROW_NONE ? threadIdx.x : atomicAdd(sh.rows_cur, 1u);
+      if (big) need += 16u;  // three counts, 4-byte aligned
+      ri = ro.first == ROW_NONE ? (threadIdx.x & 31u) : atomicAdd(sh.rows_cur, 1u);
       const uint32_t off = atomicAdd(sh.arena_cur, (need + 15u) & ~15u);
       if (ri >= TILE_ROWS || off + need > TILE_ARENA) {
         ro.failed = true; ro.first = ROW_NONE;  // the whole record takes the slow path; keep sizing
@@ -460,7 +505,10 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
     if (big) ro.n_desc++;
     if (row) {
       row->hole_len[0] = hlen[0]; row->hole_len[1] = hlen[1]; row->hole_len[2] = hlen[2];
-      row->cnt[0] = cnts[0]; row->cnt[1] = cnts[1]; row->cnt[2] = cnts[2];
+      if (big) {  // the names per list travel behind the staged bytes (RowDesc needs them at copy-out)
+        const uint32_t ca = (w.a + 3u) & ~3u;
+        sts32(ca, cnts[0]); sts32(ca + 4, cnts[1]); sts32(ca + 8, cnts[2]);
+      }
       row->hole_pos[0] = (uint16_t)hpos[0]; row->hole_pos[1] = (uint16_t)hpos[1]; row->hole_pos[2] = (uint16_t)hpos[2];
       row->soff = (uint16_t)(a0 - sh.arena_s); row->slen = (uint16_t)slen; row->loc_len = (uint16_t)loc_len;
       row->next = (uint16_t)ROW_NONE; row->allele = (uint16_t)a;
@@ -559,251 +607,391 @@ __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, co
   while (gen_next(g, oa, p.diag, line_no, diag)) tile_emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, ro, sh, so);
 }
 
-// inclusive scan of v over the CTA's 128 threads (4 warps); total returned in `total`
-__device__ __forceinline__ unsigned long long block_scan64(unsigned long long v, unsigned long long *s_w, unsigned long long &total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// inclusive scan of v over the warp; the total in `total`
+__device__ __forceinline__ unsigned long long warp_scan64(unsigned long long v, unsigned long long &total, int lane) {
   unsigned long long x = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const unsigned long long t = __shfl_up_sync(FULL, x, d);
     if (lane >= d) x += t;
   }
-  if (lane == 31) s_w[warp] = x;
-  __syncthreads();
-  unsigned long long off = 0, tot = 0;
-#pragma unroll
-  for (int k = 0; k < TILE_THREADS / 32; k++) {
-    const unsigned long long wv = s_w[k];
-    if (k < warp) off += wv;
-    tot += wv;
-  }
-  __syncthreads();
-  total = tot;
-  return x + off;
+  total = __shfl_sync(FULL, x, 31);
+  return x;
 }
 
-// decoupled look-back over descriptor q (0: bytes + rows, 1: locus bytes) of the tiles before `tile`; one warp.
-// Publishes this tile's aggregate, then its inclusive prefix.  Returns the exclusive prefix.
-constexpr unsigned long long TS_AGG = 1ull << 62, TS_PFX = 2ull << 62, TS_VAL = (1ull << 62) - 1ull;
-__device__ __forceinline__ void tile_lookback(ulonglong2 *state, uint32_t tile, int q, unsigned long long agg_x,
-                                              unsigned long long agg_y, unsigned long long &ex_x, unsigned long long &ex_y, int lane) {
-  ex_x = 0; ex_y = 0;
-  if (tile == 0) {
-    if (lane == 0) st_state(&state[q], TS_PFX | agg_x, agg_y);
-    return;
-  }
-  if (lane == 0) st_state(&state[2ull * tile + q], TS_AGG | agg_x, agg_y);
-  long long j = (long long)tile - 1;
-  for (;;) {
-    const long long idx = j - lane;
-    ulonglong2 v;
-    v.x = TS_PFX; v.y = 0;  // before the first tile: an inclusive prefix of nothing
-    if (idx >= 0) {
-      do { v = ld_state(&state[2ull * (unsigned long long)idx + q]); } while ((v.x >> 62) == 0);  // that tile is running: it took its ticket before ours
-    }
-    const uint32_t pm = __ballot_sync(FULL, (v.x >> 62) == 2ull);
-    const int cut = pm ? __ffs(pm) - 1 : 31;  // the nearest tile that already knows its inclusive prefix
-    ex_x += warp_sum64(lane <= cut ? (v.x & TS_VAL) : 0ull);
-    ex_y += warp_sum64(lane <= cut ? v.y : 0ull);
-    if (pm) break;
-    j -= 32;
-  }
-  if (lane == 0) st_state(&state[2ull * tile + q], TS_PFX | (ex_x + agg_x), ex_y + agg_y);
-}
+constexpr uint32_t TILE_SMEM_WARP = TILE_ARENA + 16 + TILE_ROWS * (uint32_t)sizeof(TRow);   // arena (+ padding) and row table
+constexpr uint32_t TILE_SMEM = TILE_WARPS * TILE_SMEM_WARP;
+constexpr uint32_t TILE_BLOCK_HDR = 32u * (uint32_t)sizeof(LaneRec);
 
-__global__ void __launch_bounds__(TILE_THREADS, 4) bvcf_tile_kernel(const __grid_constant__ TileParams p) {
-  __shared__ __align__(16) uint8_t s_arena[TILE_ARENA + 16];
-  __shared__ TRow s_rows[TILE_ROWS];
+// ---- compose ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_WARPS * 32, 4) bvcf_compose_kernel(const __grid_constant__ TileParams p) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
   __shared__ uint8_t s_filt[FILT_SMEM];
   __shared__ uint32_t s_filt_off[65];
-  __shared__ unsigned long long s_w[TILE_THREADS / 32];
-  __shared__ unsigned long long s_base[4];   // tile bases: bytes, rows, locus bytes
-  __shared__ uint32_t s_cur[2];              // arena bytes in use, next free row descriptor
-  __shared__ uint32_t s_misc[4];             // tile ticket, big_base, long_base, desc_ok
+  __shared__ uint32_t s_cur[TILE_WARPS][2];   // per warp: arena bytes in use, next free row descriptor
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // FILTER allow/exclude table -> shared memory
   const int n_filt = cfg.n_allow + cfg.n_excl;
   for (int i = threadIdx.x; i < cfg.filt_bytes && i < FILT_SMEM; i += blockDim.x) s_filt[i] = cfg.filt_blob[i];
   for (int i = threadIdx.x; i <= n_filt && i < 65; i += blockDim.x) s_filt_off[i] = cfg.filt_off[i];
+  __syncthreads();  // the only CTA barrier: from here on every warp is on its own
   if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;  // the host grows the scratch and re-runs the chunk
   const uint32_t n_rec = p.ctr->chunk_records;
   const uint32_t n_tiles = (n_rec + TILE_THREADS - 1) / TILE_THREADS;
-  const unsigned long long out_base = p.ctr->chunk_out_base, row0 = p.ctr->chunk_row_base, loci0 = p.ctr->chunk_loci_base;
   const bool has_samples = cfg.n_samples > 0;
-  const bool want_locus = cfg.want_dosage && has_samples;
+  uint8_t *const my_smem = s_dyn + (size_t)warp * TILE_SMEM_WARP;
+  TRow *const s_rows = reinterpret_cast<TRow *>(my_smem + TILE_ARENA + 16);
   TileShared sh;
-  sh.arena_s = (uint32_t)__cvta_generic_to_shared(s_arena);
+  sh.arena_s = (uint32_t)__cvta_generic_to_shared(my_smem);
   sh.rows = s_rows;
-  sh.arena_cur = &s_cur[0];
-  sh.rows_cur = &s_cur[1];
+  sh.arena_cur = &s_cur[warp][0];
+  sh.rows_cur = &s_cur[warp][1];
 
   for (;;) {
-    __syncthreads();  // the previous tile is done with the arena
-    if (threadIdx.x == 0) {
-      s_misc[0] = atomicAdd(&p.ctr->tile_ticket, 1u);
-      s_cur[0] = 0; s_cur[1] = TILE_THREADS;
+    uint32_t tile = 0;
+    if (lane == 0) {
+      tile = atomicAdd(&p.ctr->tile_ticket, 1u);
+      s_cur[warp][0] = 0; s_cur[warp][1] = TILE_THREADS;
     }
-    __syncthreads();
-    const uint32_t tile = s_misc[0];
+    tile = __shfl_sync(FULL, tile, 0);  // also orders the cursor reset before the lanes' allocations
     if (tile >= n_tiles) break;
-    const uint32_t li = tile * TILE_THREADS + threadIdx.x;
+    const uint32_t li = tile * TILE_THREADS + lane;
     const bool valid = li < n_rec;
 
-    // ---- A: compose ----
     RecOut ro;
     ro.bytes = 0; ro.rows = 0; ro.loci = 0; ro.n_desc = 0; ro.first = ROW_NONE; ro.last = ROW_NONE; ro.failed = false;
     SlowOut so;
     so.row = 0; so.loci_off = 0; so.desc = 0; so.is_long = false; so.desc_ok = false; so.big_base = 0; so.long_base = 0;
-    LineRec rec;
-    rec.start = 0; rec.len = 0; rec.an = 0; rec.ev_start = 0; rec.ev_count = 0; rec.ord = 0; rec.flags = 0;
-    rec.n_het1 = rec.n_hom1 = rec.n_miss = rec.ac1 = 0;
     const uint8_t *info_p = nullptr;
-    uint32_t info_n = 0;
+    uint32_t info_n = 0, info_off = 0, ev_count = 0;
     if (valid) {
-      rec = p.lines[li];
+      const LineRec rec = p.lines[li];
+      ev_count = rec.ev_count;
       StageWriter w;
       w.a = 0; w.stg = false;
       tile_record<StageWriter>(p, li, rec, w, ro, sh, so, s_filt, s_filt_off, true, info_p, info_n);
+      info_off = (uint32_t)(info_p - (p.in + rec.start));
     }
-    const bool is_long = p.long_words && rec.ev_count > p.long_words;
+    const bool is_long = p.long_words && ev_count > p.long_words;
     if (ro.failed && has_samples) ro.n_desc = ro.rows;
+    __syncwarp();  // every lane's staged bytes and row descriptors are in shared memory
 
-    // ---- B: offsets within the tile, then the tile's place in the output ----
-    unsigned long long tot_b, tot_rl, tot_d;
-    const unsigned long long in_b = block_scan64(ro.bytes, s_w, tot_b);
-    const unsigned long long in_rl = block_scan64((unsigned long long)ro.rows | ((unsigned long long)ro.loci << 32), s_w, tot_rl);
-    const unsigned long long my_d = is_long ? ((unsigned long long)ro.n_desc << 32) : (unsigned long long)ro.n_desc;
-    const unsigned long long in_d = block_scan64(my_d, s_w, tot_d);
-    const uint32_t tile_rows = (uint32_t)tot_rl, tile_loci = (uint32_t)(tot_rl >> 32);
-    const uint32_t tile_big = (uint32_t)tot_d, tile_long = (uint32_t)(tot_d >> 32);
-    if (warp == 0) {
-      unsigned long long ex_b, ex_r;
-      tile_lookback(p.tile_state, tile, 0, tot_b, tile_rows, ex_b, ex_r, lane);
-      if (lane == 0) {
-        s_base[0] = ex_b; s_base[1] = ex_r;
-        if (tile == n_tiles - 1) {  // the sub-chunk's totals
-          p.ctr->out_cursor = out_base + ex_b + tot_b;
-          p.ctr->row_cursor = row0 + ex_r + tile_rows;
-          if (out_base + ex_b + tot_b > p.out_cap) p.ctr->out_overflow = 1;
-        }
-      }
-    } else if (warp == 1) {
-      if (want_locus) {
-        unsigned long long ex_l, ex_0;
-        tile_lookback(p.tile_state, tile, 1, tile_loci, 0ull, ex_l, ex_0, lane);
-        if (lane == 0) {
-          s_base[2] = ex_l;
-          if (tile == n_tiles - 1) p.ctr->loci_cursor = loci0 + ex_l + tile_loci;
-        }
-      } else if (lane == 0) {
-        s_base[2] = 0;
-      }
-    } else if (warp == 2 && lane == 0) {
-      // RowDesc slots for this tile's queued rows: ordinary rows from the front, long ones from the end
-      uint32_t ok = 1, bb = 0, lb = 0;
-      const uint32_t tot = tile_big + tile_long;
-      if (tot) {
-        const uint32_t d0 = atomicAdd(&p.ctr->n_desc, tot);
-        if ((unsigned long long)d0 + tot > p.row_desc_cap) { p.ctr->row_overflow = 1; ok = 0; }
-        else {
-          if (tile_big) bb = atomicAdd(&p.ctr->n_big_rows, tile_big);
-          if (tile_long) lb = atomicAdd(&p.ctr->n_long_rows, tile_long);
-        }
-      }
-      s_misc[1] = bb; s_misc[2] = lb; s_misc[3] = ok;
+    // ---- the tile's totals and its scratch block: 32 LaneRec | n_trows TRow | arena_used bytes ----
+    const unsigned long long tot_b = warp_sum64(ro.bytes);
+    const uint32_t tot_rows = __reduce_add_sync(FULL, ro.rows), tot_loci = __reduce_add_sync(FULL, ro.loci);
+    const uint32_t tot_big = __reduce_add_sync(FULL, is_long ? 0u : ro.n_desc), tot_long = __reduce_add_sync(FULL, is_long ? ro.n_desc : 0u);
+    uint32_t arena_used = s_cur[warp][0], n_trows = s_cur[warp][1];
+    if (arena_used > TILE_ARENA) arena_used = TILE_ARENA;   // failed allocations moved the cursor past the end
+    if (n_trows > TILE_ROWS) n_trows = TILE_ROWS;
+    arena_used = (arena_used + 15u) & ~15u;
+    const uint32_t block_bytes = TILE_BLOCK_HDR + n_trows * (uint32_t)sizeof(TRow) + arena_used;
+    unsigned long long soff = 0;
+    if (lane == 0) soff = atomicAdd(reinterpret_cast<unsigned long long *>(&p.ctr->scratch_cursor), (unsigned long long)block_bytes);
+    soff = __shfl_sync(FULL, soff, 0);
+    const bool fits = soff + block_bytes <= p.scratch_cap;  // else: the host grows the scratch buffer and re-runs the chunk
+    if (lane == 0) {
+      TileAgg ag;
+      ag.bytes = tot_b; ag.scratch_off = soff; ag.rows = tot_rows; ag.loci = tot_loci; ag.n_big = tot_big; ag.n_long = tot_long;
+      ag.arena_used = arena_used; ag.n_trows = n_trows; ag.pad[0] = ag.pad[1] = 0;
+      p.tile_agg[tile] = ag;
+      if (!fits) p.ctr->scratch_overflow = 1;
+    }
+    if (fits) {
+      uint8_t *blk = p.scratch + soff;
+      LaneRec lr;
+      lr.bytes = ro.bytes; lr.rows = ro.rows; lr.loci = ro.loci; lr.n_desc = ro.n_desc;
+      lr.first = (uint16_t)ro.first; lr.flags = (uint16_t)((ro.failed ? 1u : 0u) | (is_long ? 2u : 0u));
+      lr.info_off = info_off; lr.info_n = info_n;
+      reinterpret_cast<LaneRec *>(blk)[lane] = lr;
+      uint4 *dst = reinterpret_cast<uint4 *>(blk + TILE_BLOCK_HDR);
+      const uint4 *rsrc = reinterpret_cast<const uint4 *>(s_rows);
+      const uint32_t nrv = n_trows * (uint32_t)(sizeof(TRow) / 16);
+      for (uint32_t i = lane; i < nrv; i += 32) dst[i] = rsrc[i];
+      dst += nrv;
+      const uint4 *asrc = reinterpret_cast<const uint4 *>(my_smem);
+      const uint32_t nav = arena_used >> 4;
+      for (uint32_t i = lane; i < nav; i += 32) dst[i] = asrc[i];
+    }
+    __syncwarp();  // every lane is done with the arena before the next tile's cursor reset
+  }
+}
+
+// ---- tile offsets: exclusive scan of the tile totals (five quantities) over the sub-chunk's tiles ------------
+constexpr int TSCAN_BLOCKS = 148, TSCAN_THREADS = 256;
+struct Tot5 {
+  unsigned long long bytes, loci, rows, big, lng;
+};
+__device__ __forceinline__ Tot5 tot5_of(const TileAgg &a) {
+  Tot5 t;
+  t.bytes = a.bytes; t.loci = a.loci; t.rows = a.rows; t.big = a.n_big; t.lng = a.n_long;
+  return t;
+}
+__device__ __forceinline__ void tscan_span(uint32_t n_tiles, uint32_t &lo, uint32_t &hi) {
+  const uint32_t span = (n_tiles + TSCAN_BLOCKS - 1) / TSCAN_BLOCKS;
+  const unsigned long long l = (unsigned long long)blockIdx.x * span;
+  lo = l > n_tiles ? n_tiles : (uint32_t)l;
+  hi = l + span > n_tiles ? n_tiles : (uint32_t)(l + span);
+}
+__global__ void __launch_bounds__(TSCAN_THREADS) bvcf_tile_reduce_kernel(const __grid_constant__ TileParams p) {
+  __shared__ unsigned long long s_w[5][TSCAN_THREADS / 32];
+  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  const uint32_t n_tiles = (p.ctr->chunk_records + TILE_THREADS - 1) / TILE_THREADS;
+  uint32_t lo, hi;
+  tscan_span(n_tiles, lo, hi);
+  unsigned long long s[5] = {0, 0, 0, 0, 0};
+  for (uint32_t t = lo + threadIdx.x; t < hi; t += TSCAN_THREADS) {
+    const Tot5 v = tot5_of(p.tile_agg[t]);
+    s[0] += v.bytes; s[1] += v.loci; s[2] += v.rows; s[3] += v.big; s[4] += v.lng;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const unsigned long long w = warp_sum64(s[k]);
+    if ((threadIdx.x & 31) == 0) s_w[k][threadIdx.x >> 5] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    unsigned long long t = 0;
+    for (int i = 0; i < TSCAN_THREADS / 32; i++) t += s_w[threadIdx.x][i];
+    p.tile_partial[5 * blockIdx.x + threadIdx.x] = t;
+  }
+}
+// one warp: exclusive scan of the TSCAN_BLOCKS span totals; advances the run's cursors, raises the capacity flags
+__global__ void __launch_bounds__(32) bvcf_tile_spine_kernel(const __grid_constant__ TileParams p) {
+  RunCounters *c = p.ctr;
+  if (c->ev_overflow | c->slot_overflow) return;
+  const int lane = threadIdx.x;
+  unsigned long long run[5] = {0, 0, 0, 0, 0};
+  for (int base = 0; base < TSCAN_BLOCKS; base += 32) {
+    const int b = base + lane;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const unsigned long long v = b < TSCAN_BLOCKS ? p.tile_partial[5 * b + k] : 0ull;
+      unsigned long long tot;
+      const unsigned long long inc = warp_scan64(v, tot, lane);
+      if (b < TSCAN_BLOCKS) p.tile_partial[5 * b + k] = run[k] + inc - v;
+      run[k] += tot;
+    }
+  }
+  if (lane == 0) {
+    c->out_cursor = c->chunk_out_base + run[0];
+    c->loci_cursor = c->chunk_loci_base + run[1];
+    c->row_cursor = c->chunk_row_base + run[2];
+    c->n_big_rows = (unsigned int)run[3];
+    c->n_long_rows = (unsigned int)run[4];
+    if (c->out_cursor > p.out_cap) c->out_overflow = 1;
+    if (run[3] + run[4] > p.row_desc_cap) c->row_overflow = 1;
+  }
+}
+__global__ void __launch_bounds__(TSCAN_THREADS) bvcf_tile_offsets_kernel(const __grid_constant__ TileParams p) {
+  __shared__ unsigned long long s_w[5][TSCAN_THREADS / 32];
+  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  const uint32_t n_tiles = (p.ctr->chunk_records + TILE_THREADS - 1) / TILE_THREADS;
+  uint32_t lo, hi;
+  tscan_span(n_tiles, lo, hi);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long run[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) run[k] = p.tile_partial[5 * blockIdx.x + k];
+  for (uint32_t base = lo; base < hi; base += TSCAN_THREADS) {
+    const uint32_t t = base + threadIdx.x;
+    Tot5 v;
+    v.bytes = v.loci = v.rows = v.big = v.lng = 0;
+    if (t < hi) v = tot5_of(p.tile_agg[t]);
+    const unsigned long long in[5] = {v.bytes, v.loci, v.rows, v.big, v.lng};
+    unsigned long long inc[5], wt[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) inc[k] = warp_scan64(in[k], wt[k], lane);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) s_w[k][warp] = wt[k];
     }
     __syncthreads();
-    const unsigned long long tile_b0 = s_base[0], tile_r0 = s_base[1], tile_l0 = s_base[2];
-    const bool out_ok = out_base + tile_b0 + tot_b <= p.out_cap;  // else: flagged by the last tile, the host re-runs the chunk
-    const bool desc_ok = s_misc[3] != 0;
-    const uint32_t big_base = s_misc[1], long_base = s_misc[2];
+    unsigned long long ex[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      unsigned long long off = 0, tot = 0;
+#pragma unroll
+      for (int i = 0; i < TSCAN_THREADS / 32; i++) {
+        const unsigned long long wv = s_w[k][i];
+        if (i < warp) off += wv;
+        tot += wv;
+      }
+      ex[k] = run[k] + off + inc[k] - in[k];
+      run[k] += tot;
+    }
+    if (t < hi) {
+      TileBase b;
+      b.bytes = ex[0]; b.loci = ex[1]; b.rows = (uint32_t)ex[2]; b.n_big = (uint32_t)ex[3]; b.n_long = (uint32_t)ex[4]; b.pad = 0;
+      p.tile_base[t] = b;
+    }
+  }
+}
 
-    // ---- C: copy-out ----
+// ---- copy-out -----------------------------------------------------------------------------------------------
+// No shared memory and few registers: the staged bytes are read straight from the tile's scratch block (L2), so the
+// kernel runs at full occupancy and hides those latencies with warps instead.
+__device__ __forceinline__ TRow ld_trow(const uint8_t *p) {
+  const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
+  TRow t;
+  t.hole_len[0] = a.x; t.hole_len[1] = a.y; t.hole_len[2] = a.z;
+  t.hole_pos[0] = (uint16_t)a.w; t.hole_pos[1] = (uint16_t)(a.w >> 16);
+  t.hole_pos[2] = (uint16_t)b.x; t.soff = (uint16_t)(b.x >> 16);
+  t.slen = (uint16_t)b.y; t.loc_len = (uint16_t)(b.y >> 16);
+  t.next = (uint16_t)b.z; t.allele = (uint16_t)(b.z >> 16);
+  t.flags = (uint16_t)b.w; t.pad = 0;
+  return t;
+}
+__global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const __grid_constant__ TileParams p) {
+  const DevCfg &cfg = p.cfg;
+  const int lane = threadIdx.x & 31;
+  const RunCounters *c = p.ctr;
+  // any capacity miss: the host grows the buffer and re-runs the chunk
+  if (c->ev_overflow | c->slot_overflow | c->out_overflow | c->row_overflow | c->scratch_overflow) return;
+  const uint32_t n_rec = c->chunk_records;
+  const uint32_t n_tiles = (n_rec + TILE_THREADS - 1) / TILE_THREADS;
+  const unsigned long long out_base = c->chunk_out_base, row0 = c->chunk_row_base, loci0 = c->chunk_loci_base;
+  const bool has_samples = cfg.n_samples > 0;
+  const bool want_locus = cfg.want_dosage && has_samples;
+
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(&p.ctr->tile_ticket2, 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    if (tile >= n_tiles) break;
+    const TileAgg ag = p.tile_agg[tile];
+    const TileBase tb = p.tile_base[tile];
+    const uint8_t *blk = p.scratch + ag.scratch_off;
+    const LaneRec lr = reinterpret_cast<const LaneRec *>(blk)[lane];
+    const uint8_t *rows_g = blk + TILE_BLOCK_HDR;
+    const uint8_t *arena_g = rows_g + (size_t)ag.n_trows * sizeof(TRow);
+    const uint32_t li = tile * TILE_THREADS + lane;
+    const bool failed = lr.flags & 1u, is_long = (lr.flags & 2u) != 0;
+    unsigned long long tot;
+    const unsigned long long in_b = warp_scan64(lr.bytes, tot, lane);
+    const unsigned long long in_rl = warp_scan64((unsigned long long)lr.rows | ((unsigned long long)lr.loci << 32), tot, lane);
+    const unsigned long long in_d = warp_scan64(is_long ? ((unsigned long long)lr.n_desc << 32) : (unsigned long long)lr.n_desc, tot, lane);
+
     // this tile's dosage rows start as all-reference (0); the small rows' samples are scattered below, the queued
     // rows' by the names kernels
-    if (want_locus && p.dosage && tile_rows) {
+    if (want_locus && p.dosage && ag.rows) {
       const unsigned long long ns = (unsigned long long)cfg.n_samples;
-      unsigned long long r_lo = row0 + tile_r0, r_hi = r_lo + tile_rows;
+      unsigned long long r_lo = row0 + tb.rows, r_hi = r_lo + ag.rows;
       if (r_hi > p.dosage_cap_rows) r_hi = p.dosage_cap_rows;
       if (r_lo < r_hi) {
         uint8_t *const base = reinterpret_cast<uint8_t *>(p.dosage);
         const unsigned long long b0 = r_lo * ns, b1 = r_hi * ns;
         const unsigned long long a0 = (b0 + 15ull) & ~15ull, a1 = b1 & ~15ull;  // cudaMalloc'ed: base is 256-byte aligned
         if (a0 >= a1) {
-          for (unsigned long long i = b0 + threadIdx.x; i < b1; i += TILE_THREADS) base[i] = 0;
+          for (unsigned long long i = b0 + lane; i < b1; i += 32) base[i] = 0;
         } else {
-          for (unsigned long long i = b0 + threadIdx.x; i < a0; i += TILE_THREADS) base[i] = 0;
+          for (unsigned long long i = b0 + lane; i < a0; i += 32) base[i] = 0;
           uint4 *v = reinterpret_cast<uint4 *>(base + a0);
           const unsigned long long nv = (a1 - a0) >> 4;
-          for (unsigned long long i = threadIdx.x; i < nv; i += TILE_THREADS) v[i] = make_uint4(0u, 0u, 0u, 0u);
-          for (unsigned long long i = a1 + threadIdx.x; i < b1; i += TILE_THREADS) base[i] = 0;
+          for (unsigned long long i = lane; i < nv; i += 32) v[i] = make_uint4(0u, 0u, 0u, 0u);
+          for (unsigned long long i = a1 + lane; i < b1; i += 32) base[i] = 0;
         }
       }
-      __syncthreads();
+      __syncwarp();
     }
-    if (valid && ro.rows) {
-      unsigned long long off = out_base + tile_b0 + (in_b - ro.bytes);           // first output byte of this record
-      unsigned long long r = tile_r0 + ((uint32_t)in_rl - ro.rows);              // its first row within the sub-chunk
-      unsigned long long lo = loci0 + tile_l0 + ((uint32_t)(in_rl >> 32) - ro.loci);
-      uint32_t d_ord = is_long ? (uint32_t)(in_d >> 32) - ro.n_desc : (uint32_t)in_d - ro.n_desc;
-      if (!ro.failed) {
-        for (uint32_t ri = ro.first; ri != ROW_NONE;) {
-          const TRow t = s_rows[ri];
-          const uint32_t sa = sh.arena_s + t.soff;
+    if (li < n_rec && lr.rows) {
+      unsigned long long off = out_base + tb.bytes + (in_b - lr.bytes);           // first output byte of this record
+      unsigned long long r = (unsigned long long)tb.rows + ((uint32_t)in_rl - lr.rows);  // its first row within the sub-chunk
+      unsigned long long lo = loci0 + tb.loci + ((uint32_t)(in_rl >> 32) - lr.loci);
+      uint32_t d_ord = is_long ? tb.n_long + ((uint32_t)(in_d >> 32) - lr.n_desc) : tb.n_big + ((uint32_t)in_d - lr.n_desc);
+      if (!failed) {
+        const uint8_t *line = nullptr;
+        for (uint32_t ri = lr.first; ri != ROW_NONE;) {
+          const TRow t = ld_trow(rows_g + (size_t)ri * sizeof(TRow));
+          const uint8_t *sa = arena_g + t.soff;
           unsigned long long dsts[3] = {~0ull, ~0ull, ~0ull};
           unsigned long long row_bytes = t.slen;
-          if (out_ok) {
+          {
             uint8_t *g = p.out + off;
             uint32_t pos = 0;
+            if (t.hole_len[0] | t.hole_len[1] | t.hole_len[2]) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-              if (t.hole_len[k]) {
-                copy_s2g(g, sa + pos, t.hole_pos[k] - pos);
-                g += t.hole_pos[k] - pos;
-                pos = t.hole_pos[k];
-                dsts[k] = (unsigned long long)(g - p.out);
-                g += t.hole_len[k];
+              for (int k = 0; k < 3; k++) {
+                if (t.hole_len[k]) {
+                  copy_g2g(g, sa + pos, t.hole_pos[k] - pos);
+                  g += t.hole_pos[k] - pos;
+                  pos = t.hole_pos[k];
+                  dsts[k] = (unsigned long long)(g - p.out);
+                  g += t.hole_len[k];
+                }
               }
             }
-            copy_s2g(g, sa + pos, t.slen - pos);
+            copy_g2g(g, sa + pos, t.slen - pos);
             g += t.slen - pos;
             if (t.flags & 1u) {  // INFO straight from the input line, then the EOL (main.go:684-692)
-              copy_g2g(g, info_p, info_n);
-              g[info_n] = '\n';
+              if (!line) line = p.in + p.lines[li].start;
+              copy_g2g(g, line + lr.info_off, lr.info_n);
+              g[lr.info_n] = '\n';
             }
           }
-          row_bytes += (unsigned long long)t.hole_len[0] + t.hole_len[1] + t.hole_len[2] + ((t.flags & 1u) ? info_n + 1u : 0u);
+          row_bytes += (unsigned long long)t.hole_len[0] + t.hole_len[1] + t.hole_len[2] + ((t.flags & 1u) ? lr.info_n + 1u : 0u);
           const unsigned long long gr = row0 + r;
-          if (want_locus && out_ok && gr < p.dosage_cap_rows) {
-            if (lo + t.loc_len <= p.loci_cap) copy_s2g(p.loci + lo, sa + t.slen, t.loc_len);
+          if (want_locus && gr < p.dosage_cap_rows) {
+            if (lo + t.loc_len <= p.loci_cap) copy_g2g(p.loci + lo, sa + t.slen, t.loc_len);
             p.loci_off[gr] = lo;
-            if (!(t.flags & 2u) && p.dosage) small_dosage(p, rec, t.allele, p.dosage + gr * (unsigned long long)cfg.n_samples);
+            if (!(t.flags & 2u) && p.dosage) small_dosage(p, p.lines[li], t.allele, p.dosage + gr * (unsigned long long)cfg.n_samples);
           }
           if (t.flags & 2u) {
-            if (desc_ok) {
-              RowDesc rd;
-              rd.line = li; rd.allele = t.allele;
-              rd.het_dst = dsts[0]; rd.hom_dst = dsts[1]; rd.miss_dst = dsts[2];
-              rd.n_het = t.cnt[0]; rd.n_hom = t.cnt[1]; rd.n_miss = t.cnt[2];
-              rd.row = (uint32_t)r;
-              queue_row_desc(p, is_long, d_ord, big_base, long_base, rd);
-            }
+            const uint32_t *cnt = reinterpret_cast<const uint32_t *>(arena_g + ((t.soff + t.slen + t.loc_len + 3u) & ~3u));
+            RowDesc rd;
+            rd.line = li; rd.allele = t.allele;
+            rd.het_dst = dsts[0]; rd.hom_dst = dsts[1]; rd.miss_dst = dsts[2];
+            rd.n_het = cnt[0]; rd.n_hom = cnt[1]; rd.n_miss = cnt[2];
+            rd.row = (uint32_t)r;
+            queue_row_desc(p, is_long, d_ord, 0u, 0u, rd);
             d_ord++;
           }
           off += row_bytes; r++; lo += t.loc_len;
           ri = t.next;
         }
       } else {
-        // slow path: run the record again, bytes straight to global memory
-        GlobalWriter gw;
-        gw.g = p.out + off; gw.on = out_ok;
-        so.row = r; so.loci_off = lo; so.desc = d_ord; so.is_long = is_long; so.desc_ok = desc_ok;
-        so.big_base = big_base; so.long_base = long_base;
-        RecOut dummy = ro;
-        tile_record<GlobalWriter>(p, li, rec, gw, dummy, sh, so, s_filt, s_filt_off, false, info_p, info_n);
+        // slow path: the record is written by bvcf_slow_rows_kernel at these places
+        const uint32_t k = atomicAdd(&p.ctr->n_slow, 1u);
+        if (k < p.slow_cap) {
+          SlowRec sr;
+          sr.out_off = off; sr.loci_off = lo; sr.li = li; sr.row = (uint32_t)r; sr.desc = d_ord; sr.flags = 1u | (is_long ? 2u : 0u);
+          p.slow[k] = sr;
+        }
       }
     }
+  }
+}
+
+// ---- slow path: one thread per record, bytes straight to global memory --------------------------------------
+__global__ void __launch_bounds__(64) bvcf_slow_rows_kernel(const __grid_constant__ TileParams p) {
+  __shared__ uint8_t s_filt[FILT_SMEM];
+  __shared__ uint32_t s_filt_off[65];
+  const DevCfg &cfg = p.cfg;
+  const int n_filt = cfg.n_allow + cfg.n_excl;
+  for (int i = threadIdx.x; i < cfg.filt_bytes && i < FILT_SMEM; i += blockDim.x) s_filt[i] = cfg.filt_blob[i];
+  for (int i = threadIdx.x; i <= n_filt && i < 65; i += blockDim.x) s_filt_off[i] = cfg.filt_off[i];
+  __syncthreads();
+  const RunCounters *c = p.ctr;
+  if (c->ev_overflow | c->slot_overflow | c->out_overflow | c->row_overflow | c->scratch_overflow) return;
+  uint32_t n = c->n_slow;
+  if (n > p.slow_cap) n = p.slow_cap;  // flagged below; the host re-runs the chunk with a larger list
+  if (blockIdx.x == 0 && threadIdx.x == 0 && c->n_slow > p.slow_cap) p.ctr->slow_overflow = 1;
+  TileShared sh;
+  sh.arena_s = 0; sh.rows = nullptr; sh.arena_cur = nullptr; sh.rows_cur = nullptr;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const SlowRec sr = p.slow[i];
+    const LineRec rec = p.lines[sr.li];
+    GlobalWriter gw;
+    gw.g = p.out + sr.out_off; gw.on = true;
+    SlowOut so;
+    so.row = sr.row; so.loci_off = sr.loci_off; so.desc = sr.desc; so.is_long = (sr.flags & 2u) != 0; so.desc_ok = true;
+    so.big_base = 0; so.long_base = 0;
+    RecOut ro;
+    ro.bytes = 0; ro.rows = 0; ro.loci = 0; ro.n_desc = 0; ro.first = ROW_NONE; ro.last = ROW_NONE; ro.failed = true;
+    const uint8_t *info_p;
+    uint32_t info_n;
+    tile_record<GlobalWriter>(p, sr.li, rec, gw, ro, sh, so, s_filt, s_filt_off, false, info_p, info_n);
   }
 }
 

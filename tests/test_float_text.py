@@ -34,35 +34,60 @@ SRC = textwrap.dedent(r"""
       if (up) { r++; if (r == 1000) { r = 100; e++; } }
       *r_out = r; *e_out = e;
     }
-    /* fast path: bvcf_text.cuh, the `n < 2^24` branch; 0 = falls back */
-    static int fast(uint32_t k, uint32_t n, uint64_t *r_out, int *e_out) {
+    /* fast path: bvcf_text.cuh, the `n < 2^24` branch; 0 = falls back.  j and D are guessed in single precision and
+       made exact with integer comparisons; `dj`, `dd` perturb the guesses the way a sloppy divide (__fdividef) could */
+    static const uint64_t P10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull,
+        100000000ull, 1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
+        100000000000000ull, 1000000000000000ull, 10000000000000000ull, 100000000000000000ull, 1000000000000000000ull,
+        10000000000000000000ull};
+    static int fast(uint32_t k, uint32_t n, uint64_t *r_out, int *e_out, int dj, int dd) {
       if (n >= (1u << 24)) return 0;
-      uint64_t m = k; int j = 0; const uint64_t lim = 100ull * n;
-      while (m < lim) { m *= 10; j++; }
-      uint64_t D = m / n, rem = m - D * n;
-      if (2 * rem == n) return 0;
-      if (2 * rem > n) D++;
+      const float qf = (float)k / (float)n;
+      int j = 2 + (qf < 1.0f) + (qf < 0.1f) + (qf < 0.01f) + (qf < 0.001f) + (qf < 1e-4f) + (qf < 1e-5f) + (qf < 1e-6f) + (qf < 1e-7f);
+      j += dj; if (j < 0) j = 0; if (j > 10) j = 10;
+      uint64_t m = (uint64_t)k * P10[j];
+      const uint64_t lim = 100ull * n;
+      while (m < lim) { m *= 10ull; j++; }
+      while (m >= 10ull * lim) { j--; m = (uint64_t)k * P10[j]; }
+      uint64_t D = (uint64_t)((float)m / (float)n);
+      D = (int64_t)D + dd < 0 ? 0 : D + dd;
+      if (D > 999ull) D = 999ull;
+      long long rem = (long long)m - (long long)(D * n);
+      while (rem < 0) { D--; rem += n; }
+      while (rem >= (long long)n) { D++; rem -= n; }
+      if (2ull * (uint64_t)rem == n) return 0;
+      if (2ull * (uint64_t)rem > n) D++;
       int e = 2 - j;
       if (D == 1000) { D = 100; e++; }
       *r_out = D; *e_out = e; return 1;
     }
-    /* digits + exponent -> text, as the device does */
-    static void text(uint64_t r, int e, char *out) {
-      int d[3] = {(int)(r / 100), (int)(r / 10 % 10), (int)(r % 10)}, nd = 3, len = 0;
-      while (nd > 1 && d[nd - 1] == 0) nd--;
-      if (e < -4) {
-        out[len++] = '0' + d[0];
-        if (nd > 1) { out[len++] = '.'; for (int i = 1; i < nd; i++) out[len++] = '0' + d[i]; }
-        out[len++] = 'E'; out[len++] = '-'; out[len++] = '0' + (-e) / 10; out[len++] = '0' + (-e) % 10;
-      } else if (e >= 0) {
-        out[len++] = '0' + d[0];
-        if (nd > 1) { out[len++] = '.'; for (int i = 1; i < nd; i++) out[len++] = '0' + d[i]; }
+    /* digits + exponent -> text, as the device does (g3_text: packed little-endian in a u64) */
+    static void text(uint64_t r64, int e, char *outc) {
+      const uint32_t r = (uint32_t)r64;
+      const uint32_t d0 = r / 100u, r2 = r - d0 * 100u, d1 = r2 / 10u, d2 = r2 - d1 * 10u;
+      const int nd = d2 ? 3 : (d1 ? 2 : 1);
+      uint64_t out; int len;
+      if (e < -4 || e >= 0) {
+        out = '0' + d0; len = 1;
+        if (nd > 1) {
+          out |= (uint64_t)'.' << 8 | (uint64_t)('0' + d1) << 16; len = 3;
+          if (nd > 2) { out |= (uint64_t)('0' + d2) << 24; len = 4; }
+        }
+        if (e < -4) {
+          const uint32_t ae = (uint32_t)(-e), t = ae / 10u;
+          out |= ((uint64_t)'E' | (uint64_t)'-' << 8 | (uint64_t)('0' + t) << 16 | (uint64_t)('0' + (ae - t * 10u)) << 24) << (8 * len);
+          len += 4;
+        }
       } else {
-        out[len++] = '0'; out[len++] = '.';
-        for (int i = 0; i < -e - 1; i++) out[len++] = '0';
-        for (int i = 0; i < nd; i++) out[len++] = '0' + d[i];
+        const int z = -e - 1;
+        const uint64_t digits = (uint64_t)('0' + d0) | (uint64_t)('0' + d1) << 8 | (uint64_t)('0' + d2) << 16;
+        const uint64_t keep = nd == 3 ? 0xFFFFFFull : (nd == 2 ? 0xFFFFull : 0xFFull);
+        const uint64_t pre = 0x3030303030302E30ull & ((1ull << (8 * (2 + z))) - 1ull);
+        len = 2 + z + nd;
+        out = pre | (digits & keep) << (8 * (2 + z));
       }
-      out[len] = 0;
+      for (int i = 0; i < len; i++) outc[i] = (char)(out >> (8 * i));
+      outc[len] = 0;
     }
     int main(void) {
       const uint32_t ns[] = {5008, 2504, 400000, 399996, 3, 6, 7, 10, 16, 1000, 4096, 65535, 1u << 20, 16777215, 16777216, 50000000};
@@ -75,8 +100,14 @@ SRC = textwrap.dedent(r"""
           uint64_t r; int e;
           exact(k, n, &r, &e); text(r, e, a);
           if (strcmp(a, want)) { if (bad++ < 5) printf("exact %u/%u: %s != %s\n", k, n, a, want); }
-          if (fast(k, n, &r, &e)) { text(r, e, b); if (strcmp(b, want)) { if (bad++ < 5) printf("fast %u/%u: %s != %s\n", k, n, b, want); } }
+          if (fast(k, n, &r, &e, 0, 0)) { text(r, e, b); if (strcmp(b, want)) { if (bad++ < 5) printf("fast %u/%u: %s != %s\n", k, n, b, want); } }
           else { fb++; if (n < (1u << 24)) ties++; }
+          /* the guesses may be off: the integer corrections must make up for it */
+          static const int pert[4][2] = {{-1, -3}, {1, 3}, {-2, 2}, {2, -2}};
+          for (int pi = 0; pi < 4; pi++) {
+            uint64_t r2; int e2;
+            if (fast(k, n, &r2, &e2, pert[pi][0], pert[pi][1])) { text(r2, e2, b); if (strcmp(b, want)) { if (bad++ < 5) printf("fast' %u/%u: %s != %s\n", k, n, b, want); } }
+          }
           n_checked++;
         }
       }
@@ -104,6 +135,8 @@ def test_c_restatement_matches_device_source():
     """the constants the proof rests on are the ones in the CUDA source"""
     here = os.path.dirname(os.path.abspath(__file__))
     cu = open(os.path.join(here, "..", "bystro_vcf_b200", "csrc", "bvcf_text.cuh")).read()
-    for needle in ("if (n < (1u << 24))", "const unsigned long long lim = 100ull * n;", "if (2ull * rem != n)", "if (2ull * rem > n) D++;",
-                   "if (D == 1000) { D = 100; e++; }"):
+    for needle in ("if (n < (1u << 24))", "const unsigned long long lim = 100ull * n;", "if (2ull * (unsigned long long)rem != n)",
+                   "if (2ull * (unsigned long long)rem > n) D++;", "if (D == 1000) { D = 100; e++; }",
+                   "while (rem < 0) { D--; rem += n; }", "while (rem >= (long long)n) { D++; rem -= n; }",
+                   "0x3030303030302E30ull"):
         assert needle in cu, needle
