@@ -55,15 +55,45 @@ def build(force: bool = False, verbose: bool = False) -> None:
         subprocess.check_call(cmd)
 
 
+def _arrow_paths():
+    """include dir, library dir and library file of the Arrow C++ that ships inside the pyarrow wheel, or None"""
+    try:
+        import pyarrow
+    except Exception:
+        return None
+    inc = pyarrow.get_include()
+    for d in pyarrow.get_library_dirs():
+        for f in sorted(os.listdir(d)):
+            if f.startswith("libarrow.so."):
+                return inc, d, f
+    return None
+
+
 def build_host(force: bool = False) -> str:
-    """g++ build of the C++ host binary (the reference's main()/readVcf over the C ABI)."""
+    """g++ build of the C++ host binary (the reference's main()/readVcf over the C ABI).  The Arrow IPC writer of
+    --dosageOutput links the libarrow of the pyarrow wheel; without pyarrow the binary is built with -DBVCF_NO_ARROW."""
     bindir = os.path.join(HERE, "bin")
     os.makedirs(bindir, exist_ok=True)
     out = os.path.join(bindir, "bystro-vcf-b200")
     src = os.path.join(CSRC, "bvcf_host.cpp")
+    asrc = os.path.join(CSRC, "bvcf_arrow.cpp")
     lib = os.path.join(LIBDIR, "libbvcf.so")
-    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(lib)):
-        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", out, src, "-L", LIBDIR, "-lbvcf", "-Wl,-rpath,$ORIGIN/../lib"]
+    deps = [src, asrc, lib, os.path.join(CSRC, "bvcf_arrow.h"), os.path.join(ROOT, "include", "bvcf.h")]
+    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        arrow = _arrow_paths()
+        objs, extra = [], []
+        if arrow:
+            inc, libdir, libfile = arrow
+            aobj = os.path.join(bindir, "bvcf_arrow.o")
+            cmd = ["g++", "-O2", "-std=c++20", "-Wall", "-c", "-I", inc, "-o", aobj, asrc]
+            print("[build]", " ".join(cmd), file=sys.stderr)
+            subprocess.check_call(cmd)
+            objs.append(aobj)
+            extra = ["-L", libdir, "-l:" + libfile, "-Wl,-rpath," + libdir]
+        else:
+            extra = ["-DBVCF_NO_ARROW"]
+        cmd = (["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", out, src] + objs +
+               ["-L", LIBDIR, "-lbvcf", "-Wl,-rpath,$ORIGIN/../lib"] + extra)
         print("[build]", " ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
     return out

@@ -296,8 +296,18 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     tp.dosage = d_dosage; tp.dosage_cap_rows = dosage_cap_rows;
     tp.loci = d_loci; tp.loci_cap = loci_cap; tp.loci_off = d_loci_off;
     tp.diag.diags = d_diags; tp.diag.cap = ctx->diag_cap; tp.diag.ctr = d_ctr;
-    cudaFuncSetAttribute(bvcf_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
-    bvcf_compose_kernel<<<(unsigned)n_sm * 4, TILE_WARPS * 32, TILE_SMEM, st>>>(tp);
+    {
+      static const int variant = getenv("BVCF_COMPOSE_VARIANT") ? atoi(getenv("BVCF_COMPOSE_VARIANT")) : 4;  // experiments
+      auto launch = [&](auto kern, uint32_t arena, int minb) {
+        const uint32_t smem = TILE_WARPS * tile_smem_warp(arena);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)n_sm * minb, TILE_WARPS * 32, smem, st>>>(tp);
+      };
+      if (variant == 5) launch(bvcf_compose_kernel<5, 8192>, 8192, 5);
+      else if (variant == 6) launch(bvcf_compose_kernel<6, 7168>, 7168, 6);
+      else if (variant == 8) launch(bvcf_compose_kernel<8, 5120>, 5120, 8);
+      else launch(bvcf_compose_kernel<4, 10240>, 10240, 4);
+    }
     bvcf_tile_reduce_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);
     bvcf_tile_spine_kernel<<<1, 32, 0, st>>>(tp);
     bvcf_tile_offsets_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);

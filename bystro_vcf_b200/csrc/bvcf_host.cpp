@@ -1,8 +1,14 @@
 // bvcf_host.cpp -- `bystro-vcf-b200`: the reference's main()/readVcf (main.go:134-396) as a C++ host over the
 // libbvcf C ABI.  Same flags, same stdin/stdout contract, so it drops into
 //     pigz -d -c in.vcf.gz | bystro-vcf-b200 --keepId --keepInfo | pigz -c > out.gz
-// The per-line work happens on the GPU(s); this file only finds the header, cuts newline-aligned chunks into
-// pinned buffers, keeps n_slots chunks in flight per GPU and writes the rows back in input order.
+// The per-line work happens on the GPU(s).  Threads mirror the reference's producer + worker pool
+// (main.go:345-380) with GPUs as the workers:
+//   reader     finds newline-aligned chunk boundaries; stdin is read straight into pinned buffers, a regular
+//              --in file is memory-mapped and only the boundaries are computed here;
+//   GPU worker one per GPU (chunk k goes to GPU k mod N): stages its chunks into its own pinned ring (parallel
+//              memcpy out of the mapping), keeps n_slots chunks in flight on its context, and -- when it is chunk
+//              k's turn -- writes the rows, appends the dosage batch to the Arrow file and logs the diagnostics,
+//              so everything leaves in input order while the other GPUs keep working.
 // (The reference is Go; no Go toolchain exists in this image, so the host is C++ -- see INTEGRATION.md for
 // the equivalent cgo binding.)
 #include <cerrno>
@@ -10,13 +16,24 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "../../include/bvcf.h"
+#ifndef BVCF_NO_ARROW
+#include "bvcf_arrow.h"
+#endif
 
 namespace {
 
@@ -28,6 +45,7 @@ struct Config {  // main.go:63-80
   std::vector<std::string> allowed, excluded;
   // not in the reference
   int gpus = 1;
+  std::vector<int> devices;  // --devices a,b,...: CUDA device of each worker (a device may be listed twice); default 0..gpus-1
   size_t chunkBytes = 64u << 20;
 };
 
@@ -66,7 +84,7 @@ Config setup(int argc, char **argv) {  // main.go:82-126
   struct BF { const char *name; bool *dst; };
   const BF bf[] = {{"noOut", &c.noOut}, {"keepId", &c.keepID}, {"keepQual", &c.keepQual}, {"keepPos", &c.keepPos},
                    {"keepInfo", &c.keepInfo}};
-  std::string gpus, chunk;
+  std::string gpus, chunk, devices;
   for (int i = 1; i < argc; i++) {
     std::string s = argv[i];
     if (s.size() < 2 || s[0] != '-') break;
@@ -90,6 +108,7 @@ Config setup(int argc, char **argv) {  // main.go:82-126
       if (name == x.name) dst = x.dst;
     if (name == "gpus") dst = &gpus;          // extension: number of GPUs to use
     if (name == "chunkBytes") dst = &chunk;   // extension: host chunk size
+    if (name == "devices") dst = &devices;    // extension: explicit CUDA device per worker
     if (!dst) fatal("flag provided but not defined: -" + name);
     if (!has_val) {
       if (++i >= argc) fatal("flag needs an argument: -" + name);
@@ -102,6 +121,10 @@ Config setup(int argc, char **argv) {  // main.go:82-126
   if (!exclude.empty()) c.excluded = split_trim(exclude);             // main.go:117-123
   if (!gpus.empty()) c.gpus = std::max(1, atoi(gpus.c_str()));
   if (!chunk.empty()) c.chunkBytes = std::max<size_t>(1 << 16, strtoull(chunk.c_str(), nullptr, 10));
+  if (!devices.empty()) {
+    for (auto &d : split_trim(devices)) c.devices.push_back(atoi(d.c_str()));
+    c.gpus = (int)c.devices.size();
+  }
   return c;
 }
 
@@ -163,11 +186,74 @@ void log_diags(const uint8_t *chunk, size_t len, const bvcf_diag *d, size_t n) {
   }
 }
 
-struct InFlight {
-  uint64_t seq;
-  int gpu;
-  uint8_t *buf;
-  size_t len;
+struct Chunk {
+  uint64_t seq = 0;
+  uint8_t *buf = nullptr;        // pinned buffer holding the chunk (filled by the reader, or by the worker from `src`)
+  const uint8_t *src = nullptr;  // memory-mapped input: where the chunk's bytes are
+  size_t len = 0;
+};
+
+// bounded FIFO between the reader and one GPU worker
+class ChunkQueue {
+ public:
+  explicit ChunkQueue(size_t cap) : cap_(cap) {}
+  void push(const Chunk &c) {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return q_.size() < cap_; });
+    q_.push_back(c);
+    cv_.notify_all();
+  }
+  void close() {
+    std::lock_guard<std::mutex> l(m_);
+    closed_ = true;
+    cv_.notify_all();
+  }
+  // 1: got a chunk, 0: nothing right now (only when !block), -1: closed and drained
+  int pop(Chunk &c, bool block) {
+    std::unique_lock<std::mutex> l(m_);
+    if (block) cv_.wait(l, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return closed_ ? -1 : 0;
+    c = q_.front();
+    q_.pop_front();
+    cv_.notify_all();
+    return 1;
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<Chunk> q_;
+  size_t cap_;
+  bool closed_ = false;
+};
+
+// a GPU's pinned staging buffers
+class BufferPool {
+ public:
+  void add(uint8_t *b) { std::lock_guard<std::mutex> l(m_); free_.push_back(b); all_.push_back(b); }
+  uint8_t *take() {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return !free_.empty(); });
+    uint8_t *b = free_.back();
+    free_.pop_back();
+    return b;
+  }
+  void give(uint8_t *b) { std::lock_guard<std::mutex> l(m_); free_.push_back(b); cv_.notify_all(); }
+  ~BufferPool() { for (auto b : all_) bvcf_host_free(b); }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::vector<uint8_t *> free_, all_;
+};
+
+// whose turn it is to write (chunk order == input order)
+struct Turnstile {
+  std::mutex m;
+  std::condition_variable cv;
+  uint64_t next = 0;
+  void wait_for(uint64_t seq) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return next == seq; }); }
+  void done() { std::lock_guard<std::mutex> l(m); next++; cv.notify_all(); }
 };
 
 }  // namespace
@@ -176,11 +262,16 @@ int main(int argc, char **argv) {
   Config config = setup(argc, argv);
   int in_fd = 0;
   if (!config.inPath.empty() && (in_fd = open(config.inPath.c_str(), O_RDONLY)) < 0) fatal(config.inPath + ": " + strerror(errno));
+  // main.go:150-156 re-points os.Stderr at the file, which Go's `log` never looks at again; what the flag evidently
+  // means is honoured here: diagnostics are appended to it
   if (!config.errPath.empty() && !freopen(config.errPath.c_str(), "a", stderr)) fatal(config.errPath + ": " + strerror(errno));
   if (config.noOut && !config.outPath.empty()) fatal("Cannot specify --noOut and --out");                 // main.go:160
   if (config.noOut && config.dosageMatrixOutPath.empty()) fatal("When specifying --noOut, must specify --dosageOutput");  // :164
+#ifdef BVCF_NO_ARROW
   if (!config.dosageMatrixOutPath.empty())
-    fatal("--dosageOutput: the Arrow IPC writer lives in the Python host (python -m bystro_vcf_b200); this binary writes the TSV");
+    fatal("--dosageOutput: this binary was built without libarrow (pyarrow was not found at build time); "
+          "python -m bystro_vcf_b200 writes the Arrow file");
+#endif
   int out_fd = 1;
   if (!config.noOut && !config.outPath.empty() &&
       (out_fd = open(config.outPath.c_str(), O_WRONLY | O_CREAT, 0644)) < 0)  // no O_TRUNC, like main.go:172
@@ -190,21 +281,41 @@ int main(int argc, char **argv) {
     write_all(out_fd, (const uint8_t *)h.data(), h.size());
   }
 
+  // ---- input: a regular file is memory-mapped, anything else (pipes) is read ----
+  const uint8_t *map = nullptr;
+  size_t map_len = 0;
+  {
+    struct stat sb;
+    if (in_fd != 0 && fstat(in_fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+      void *m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, in_fd, 0);
+      if (m != MAP_FAILED) {
+        map = (const uint8_t *)m;
+        map_len = (size_t)sb.st_size;
+        madvise(m, map_len, MADV_SEQUENTIAL);
+      }
+    }
+  }
+
   // ---- preamble (main.go:250-294): EOL, ##fileformat check, #CHROM line ----
-  std::vector<uint8_t> head;
+  std::vector<uint8_t> head;  // pipe input: what has been read so far
   size_t data_off = 0;
   int eol_width = 1;
   std::string chrom_line;
   bool eof = false;
   for (bool found = false; !found;) {
-    const size_t old = head.size();
-    head.resize(old + (1 << 20));
-    ssize_t r = read(in_fd, head.data() + old, 1 << 20);
-    if (r < 0) fatal(std::string("read: ") + strerror(errno));
-    head.resize(old + (size_t)r);
-    if (r == 0) eof = true;
-    const uint8_t *p = head.data();
-    const size_t n = head.size();
+    const uint8_t *p;
+    size_t n;
+    if (map) {
+      p = map; n = map_len; eof = true;
+    } else {
+      const size_t old = head.size();
+      head.resize(old + (1 << 20));
+      ssize_t r = read(in_fd, head.data() + old, 1 << 20);
+      if (r < 0) fatal(std::string("read: ") + strerror(errno));
+      head.resize(old + (size_t)r);
+      if (r == 0) eof = true;
+      p = head.data(); n = head.size();
+    }
     const uint8_t *nl = (const uint8_t *)memchr(p, '\n', n);
     if (!nl) { if (eof) fatal("Not a VCF file"); continue; }
     size_t first_end = nl - p;
@@ -226,9 +337,8 @@ int main(int argc, char **argv) {
     }
     if (!found && eof) fatal("No header found");  // main.go:293
   }
-  if (!config.sampleListPath.empty() && !config.noOut) {  // main.go:398-445
-    FILE *f = fopen(config.sampleListPath.c_str(), "w");
-    if (!f) fatal("Couldn't write sample list file");
+  std::vector<std::string> sample_names;
+  {
     int field = 0;
     size_t s = 0;
     for (size_t i = 0; i <= chrom_line.size(); i++)
@@ -236,12 +346,36 @@ int main(int argc, char **argv) {
         if (field >= 9) {
           std::string nm = chrom_line.substr(s, i - s);
           for (auto &ch : nm) if (ch == '.') ch = '_';  // parse.NormalizeHeader
-          fprintf(f, "%s\n", nm.c_str());
+          sample_names.push_back(nm);
         }
         field++; s = i + 1;
       }
+  }
+  if (!config.sampleListPath.empty() && !config.noOut) {  // main.go:398-445
+    FILE *f = fopen(config.sampleListPath.c_str(), "w");
+    if (!f) fatal("Couldn't write sample list file");
+    for (auto &nm : sample_names) fprintf(f, "%s\n", nm.c_str());
     fclose(f);
   }
+  bool want_dosage = !config.dosageMatrixOutPath.empty();
+#ifndef BVCF_NO_ARROW
+  bvcf_arrow_writer *arrow = nullptr;
+  if (want_dosage) {
+    if (sample_names.empty()) {  // main.go:308-318
+      fprintf(stderr, "No samples found in VCF file; writing empty dosage matrix file\n");
+      FILE *f = fopen(config.dosageMatrixOutPath.c_str(), "w");
+      if (!f) fatal(config.dosageMatrixOutPath + ": " + strerror(errno));
+      fclose(f);
+      want_dosage = false;
+    } else {
+      std::vector<const char *> nm;
+      for (auto &s : sample_names) nm.push_back(s.c_str());
+      char err[512];
+      arrow = bvcf_arrow_open(config.dosageMatrixOutPath.c_str(), nm.data(), (uint32_t)nm.size(), err, sizeof err);
+      if (!arrow) fatal(std::string("dosage output: ") + err);
+    }
+  }
+#endif
 
   // ---- one context per GPU ----
   std::vector<const char *> allow_c, excl_c;
@@ -251,7 +385,7 @@ int main(int argc, char **argv) {
   bc.empty_field = config.emptyField.c_str();
   bc.field_delim = config.fieldDelimiter.c_str();
   bc.keep_id = config.keepID; bc.keep_info = config.keepInfo; bc.keep_pos = config.keepPos;
-  bc.want_tsv = !config.noOut; bc.want_dosage = 0;
+  bc.want_tsv = !config.noOut; bc.want_dosage = want_dosage;
   bc.allow = allow_c.data(); bc.n_allow = config.allowAll ? -1 : (int)allow_c.size();
   bc.exclude = excl_c.data(); bc.n_exclude = (int)excl_c.size();
   bc.eol_width = eol_width; bc.normalize_dots = 1;
@@ -259,76 +393,138 @@ int main(int argc, char **argv) {
   bc.n_slots = n_slots;
   const size_t cap = 2 * config.chunkBytes + (64u << 20);  // a chunk grows until it holds a newline
   bc.max_chunk_bytes = cap;
-  std::vector<bvcf_ctx *> ctxs(config.gpus, nullptr);
-  for (int g = 0; g < config.gpus; g++) {
-    int rc = bvcf_create(&ctxs[g], g, &bc);
+  const int n_gpu = config.gpus;
+  std::vector<bvcf_ctx *> ctxs(n_gpu, nullptr);
+  std::vector<BufferPool> pools(n_gpu);
+  std::vector<std::unique_ptr<ChunkQueue>> queues;
+  for (int g = 0; g < n_gpu; g++) {
+    int rc = bvcf_create(&ctxs[g], config.devices.empty() ? g : config.devices[g], &bc);
     if (rc) fatal(std::string("bvcf_create(gpu ") + std::to_string(g) + "): " + bvcf_strerror(rc) + " -- a CUDA device is required, there is no CPU fallback");
     rc = bvcf_set_header(ctxs[g], chrom_line.data(), chrom_line.size());
     if (rc) fatal(std::string("bvcf_set_header: ") + bvcf_strerror(rc));
+    for (int k = 0; k < n_slots + 2; k++) {
+      uint8_t *b = nullptr;
+      if (bvcf_host_alloc((void **)&b, cap)) fatal("bvcf_host_alloc failed");
+      pools[g].add(b);
+    }
+    queues.emplace_back(new ChunkQueue(n_slots + 1));
   }
 
-  // ---- chunk loop: pinned ring, n_slots chunks in flight per GPU, rows written in seq order ----
-  const size_t ring_n = (size_t)config.gpus * n_slots + 1;
-  std::vector<uint8_t *> ring(ring_n, nullptr);
-  for (auto &b : ring)
-    if (bvcf_host_alloc((void **)&b, cap)) fatal("bvcf_host_alloc failed");
-  std::vector<InFlight> q;  // FIFO
-  auto collect_one = [&]() {
-    InFlight f = q.front();
-    q.erase(q.begin());
-    const uint8_t *tsv; size_t n; const bvcf_diag *dg; size_t nd;
-    int rc = bvcf_collect(ctxs[f.gpu], f.seq, &tsv, &n, nullptr, &dg, &nd, nullptr);
-    if (rc) fatal(std::string("bvcf_collect: ") + bvcf_strerror(rc) + " " + bvcf_last_error(ctxs[f.gpu]));
-    if (!config.noOut) write_all(out_fd, tsv, n);
-    log_diags(f.buf, f.len, dg, nd);
-    bvcf_release(ctxs[f.gpu], f.seq);
+  // ---- GPU workers ----
+  Turnstile turn;
+  std::mutex fatal_m;
+  auto worker = [&](int g) {
+    bvcf_ctx *ctx = ctxs[g];
+    std::deque<Chunk> inflight;
+    bool closed = false;
+    for (;;) {
+      while (!closed && (int)inflight.size() < n_slots) {
+        Chunk c;
+        const int got = queues[g]->pop(c, /*block=*/inflight.empty());
+        if (got < 0) { closed = true; break; }
+        if (got == 0) break;
+        if (c.src) {  // memory-mapped input: this thread stages its own chunk (N GPUs, N copies in parallel)
+          c.buf = pools[g].take();
+          memcpy(c.buf, c.src, c.len);
+        }
+        const int rc = bvcf_submit(ctx, c.seq, c.buf, c.len);
+        if (rc) { std::lock_guard<std::mutex> l(fatal_m); fatal(std::string("bvcf_submit: ") + bvcf_strerror(rc) + " " + bvcf_last_error(ctx)); }
+        inflight.push_back(c);
+      }
+      if (inflight.empty()) {
+        if (closed) break;
+        continue;
+      }
+      const Chunk c = inflight.front();
+      inflight.pop_front();
+      const uint8_t *tsv; size_t n; const bvcf_diag *dg; size_t nd;
+      bvcf_dosage_batch dos;
+      const int rc = bvcf_collect(ctx, c.seq, &tsv, &n, &dos, &dg, &nd, nullptr);
+      if (rc) { std::lock_guard<std::mutex> l(fatal_m); fatal(std::string("bvcf_collect: ") + bvcf_strerror(rc) + " " + bvcf_last_error(ctx)); }
+      turn.wait_for(c.seq);  // input order
+      if (!config.noOut) write_all(out_fd, tsv, n);
+#ifndef BVCF_NO_ARROW
+      if (arrow && dos.n_rows && bvcf_arrow_write(arrow, dos.n_rows, dos.dosage, dos.loci, dos.loci_off))
+        fatal(std::string("dosage output: ") + bvcf_arrow_error(arrow));
+#endif
+      log_diags(c.buf, c.len, dg, nd);
+      turn.done();
+      bvcf_release(ctx, c.seq);
+      pools[g].give(c.buf);
+    }
   };
+  std::vector<std::thread> threads;
+  for (int g = 0; g < n_gpu; g++) threads.emplace_back(worker, g);
+
+  // ---- reader: newline-aligned chunks, chunk k to GPU k mod N ----
   uint64_t seq = 0;
-  size_t slot = 0;
-  size_t fill = head.size() - data_off;  // bytes already in the current buffer
-  if (fill > cap) fatal("header buffer larger than a chunk");
-  memcpy(ring[0], head.data() + data_off, fill);
-  head.clear(); head.shrink_to_fit();
-  while (!eof || fill) {
-    uint8_t *buf = ring[slot];
-    // fill up to chunkBytes (keep reading past it only if no newline has been seen yet)
-    while (!eof && fill < config.chunkBytes) {
-      ssize_t r = read(in_fd, buf + fill, std::min(cap - fill, config.chunkBytes - fill));
-      if (r < 0) { if (errno == EINTR) continue; fatal(std::string("read: ") + strerror(errno)); }
-      if (r == 0) { eof = true; break; }
-      fill += (size_t)r;
+  if (map) {
+    size_t p = data_off;
+    // an unterminated last line is dropped (main.go:354-357)
+    size_t end = map_len;
+    {
+      const uint8_t *last = end > p ? (const uint8_t *)memrchr(map + p, '\n', end - p) : nullptr;
+      end = last ? (size_t)(last - map) + 1 : p;
     }
-    const uint8_t *last_nl = (const uint8_t *)memrchr(buf, '\n', fill);
-    if (!last_nl) {
-      if (eof) break;  // an unterminated last line is dropped (main.go:354-357)
-      if (fill >= cap) fatal("a single line exceeds the chunk capacity; raise --chunkBytes");
-      ssize_t r = read(in_fd, buf + fill, cap - fill);
-      if (r <= 0) { eof = true; continue; }
-      fill += (size_t)r;
-      continue;
+    while (p < end) {
+      size_t q = std::min(p + config.chunkBytes, end);
+      if (q < end) {
+        const uint8_t *nl = (const uint8_t *)memrchr(map + p, '\n', q - p);
+        if (!nl) {  // a line longer than a chunk: extend to its end
+          nl = (const uint8_t *)memchr(map + q, '\n', end - q);
+          if (!nl) break;
+        }
+        q = (size_t)(nl - map) + 1;
+      }
+      if (q - p > cap) fatal("a single line exceeds the chunk capacity; raise --chunkBytes");
+      Chunk c;
+      c.seq = seq; c.src = map + p; c.len = q - p;
+      queues[seq % n_gpu]->push(c);
+      seq++;
+      p = q;
     }
-    const size_t cut = (last_nl - buf) + 1;
-    const size_t next = (slot + 1) % ring_n;
-    // the next ring buffer may still belong to an in-flight chunk: drain until it is free
-    while (q.size() >= ring_n - 1) collect_one();
-    memcpy(ring[next], buf + cut, fill - cut);  // carry the partial line
-    const int gpu = (int)(seq % config.gpus);
-    size_t on_gpu = 0;
-    for (auto &f : q) on_gpu += f.gpu == gpu;
-    while (on_gpu >= (size_t)n_slots) {  // FIFO order keeps the output ordered
-      on_gpu -= q.front().gpu == gpu;
-      collect_one();
+  } else {
+    uint8_t *buf = pools[0].take();
+    size_t fill = head.size() - data_off;  // bytes already in the current buffer
+    if (fill > cap) fatal("header buffer larger than a chunk");
+    memcpy(buf, head.data() + data_off, fill);
+    head.clear(); head.shrink_to_fit();
+    while (!eof || fill) {
+      while (!eof && fill < config.chunkBytes) {
+        ssize_t r = read(in_fd, buf + fill, std::min(cap - fill, config.chunkBytes - fill));
+        if (r < 0) { if (errno == EINTR) continue; fatal(std::string("read: ") + strerror(errno)); }
+        if (r == 0) { eof = true; break; }
+        fill += (size_t)r;
+      }
+      const uint8_t *last_nl = fill ? (const uint8_t *)memrchr(buf, '\n', fill) : nullptr;
+      if (!last_nl) {
+        if (eof) break;  // an unterminated last line is dropped (main.go:354-357)
+        if (fill >= cap) fatal("a single line exceeds the chunk capacity; raise --chunkBytes");
+        ssize_t r = read(in_fd, buf + fill, cap - fill);
+        if (r <= 0) { eof = true; continue; }
+        fill += (size_t)r;
+        continue;
+      }
+      const size_t cut = (last_nl - buf) + 1;
+      uint8_t *next = pools[(seq + 1) % n_gpu].take();  // the next chunk's buffer comes from its GPU's ring
+      memcpy(next, buf + cut, fill - cut);              // carry the partial line
+      Chunk c;
+      c.seq = seq; c.buf = buf; c.len = cut;
+      queues[seq % n_gpu]->push(c);
+      seq++;
+      fill -= cut;
+      buf = next;
     }
-    int rc = bvcf_submit(ctxs[gpu], seq, buf, cut);
-    if (rc) fatal(std::string("bvcf_submit: ") + bvcf_strerror(rc));
-    q.push_back({seq, gpu, buf, cut});
-    seq++;
-    fill -= cut;
-    slot = next;
+    pools[seq % n_gpu].give(buf);
   }
-  while (!q.empty()) collect_one();
-  for (auto &b : ring) bvcf_host_free(b);
+  for (auto &q : queues) q->close();
+  for (auto &t : threads) t.join();
+  int rc_exit = 0;
+#ifndef BVCF_NO_ARROW
+  if (arrow && bvcf_arrow_close(arrow)) rc_exit = 1;
+#endif
   for (auto c : ctxs) bvcf_destroy(c);
+  if (map) munmap((void *)map, map_len);
   if (out_fd != 1) close(out_fd);
-  return 0;
+  return rc_exit;
 }

@@ -31,8 +31,7 @@ namespace bvcf {
 
 constexpr int TILE_THREADS = 32;           // records per tile, one thread each: a tile is a warp's
 constexpr int TILE_WARPS = 4;              // warps (independent tiles) per CTA
-constexpr uint32_t TILE_ARENA = 10240;     // staging bytes per warp
-constexpr uint32_t TILE_ROWS = 64;         // staged rows per tile; lane l's first row is rows[l]
+constexpr uint32_t TILE_ROWS = 48;         // staged rows per tile; lane l's first row is rows[l]
 constexpr uint32_t ROW_NONE = 0xFFFFu;
 
 // one staged row (shared memory, then the tile's scratch block)
@@ -222,6 +221,7 @@ struct RecOut {
 };
 struct TileShared {
   uint32_t arena_s;           // shared-memory address of the arena
+  uint32_t arena_cap;         // its size
   TRow *rows;
   uint32_t *arena_cur, *rows_cur;
 };
@@ -376,7 +376,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
       if (big) need += 16u;  // three counts, 4-byte aligned
       ri = ro.first == ROW_NONE ? (threadIdx.x & 31u) : atomicAdd(sh.rows_cur, 1u);
       const uint32_t off = atomicAdd(sh.arena_cur, (need + 15u) & ~15u);
-      if (ri >= TILE_ROWS || off + need > TILE_ARENA) {
+      if (ri >= TILE_ROWS || off + need > sh.arena_cap) {
         ro.failed = true; ro.first = ROW_NONE;  // the whole record takes the slow path; keep sizing
       } else {
         row = &sh.rows[ri];
@@ -619,12 +619,15 @@ __device__ __forceinline__ unsigned long long warp_scan64(unsigned long long v, 
   return x;
 }
 
-constexpr uint32_t TILE_SMEM_WARP = TILE_ARENA + 16 + TILE_ROWS * (uint32_t)sizeof(TRow);   // arena (+ padding) and row table
-constexpr uint32_t TILE_SMEM = TILE_WARPS * TILE_SMEM_WARP;
+// shared memory per warp: arena (+ padding) and row table
+__host__ __device__ constexpr uint32_t tile_smem_warp(uint32_t arena) { return arena + 16 + TILE_ROWS * (uint32_t)sizeof(TRow); }
 constexpr uint32_t TILE_BLOCK_HDR = 32u * (uint32_t)sizeof(LaneRec);
 
 // ---- compose ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_WARPS * 32, 4) bvcf_compose_kernel(const __grid_constant__ TileParams p) {
+// MINB resident CTAs per SM (sets the register budget), ARENA staging bytes per warp
+template <int MINB, uint32_t ARENA>
+__global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(const __grid_constant__ TileParams p) {
+  constexpr uint32_t TILE_ARENA = ARENA, TILE_SMEM_WARP = tile_smem_warp(ARENA);
   extern __shared__ __align__(16) uint8_t s_dyn[];
   __shared__ uint8_t s_filt[FILT_SMEM];
   __shared__ uint32_t s_filt_off[65];
@@ -644,6 +647,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 4) bvcf_compose_kernel(const 
   TRow *const s_rows = reinterpret_cast<TRow *>(my_smem + TILE_ARENA + 16);
   TileShared sh;
   sh.arena_s = (uint32_t)__cvta_generic_to_shared(my_smem);
+  sh.arena_cap = TILE_ARENA;
   sh.rows = s_rows;
   sh.arena_cur = &s_cur[warp][0];
   sh.rows_cur = &s_cur[warp][1];
@@ -978,7 +982,7 @@ __global__ void __launch_bounds__(64) bvcf_slow_rows_kernel(const __grid_constan
   if (n > p.slow_cap) n = p.slow_cap;  // flagged below; the host re-runs the chunk with a larger list
   if (blockIdx.x == 0 && threadIdx.x == 0 && c->n_slow > p.slow_cap) p.ctr->slow_overflow = 1;
   TileShared sh;
-  sh.arena_s = 0; sh.rows = nullptr; sh.arena_cur = nullptr; sh.rows_cur = nullptr;
+  sh.arena_s = 0; sh.arena_cap = 0; sh.rows = nullptr; sh.arena_cur = nullptr; sh.rows_cur = nullptr;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const SlowRec sr = p.slow[i];
     const LineRec rec = p.lines[sr.li];

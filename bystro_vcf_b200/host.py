@@ -388,6 +388,40 @@ def chunk_line_locus(block, line_no: int):
     return f[0].decode("latin-1"), f[1].decode("latin-1")
 
 
+class PinnedRing:
+    """n pinned host buffers (bvcf_host_alloc) with writable views: chunks are read or copied into them so that
+    bvcf_submit's H2D copy is a true asynchronous DMA."""
+
+    def __init__(self, n: int, cap: int):
+        self.cap = cap
+        self.ptrs = []
+        self.views = []
+        L = _lib.lib()
+        for _ in range(n):
+            p = C.c_void_p()
+            check(L.bvcf_host_alloc(C.byref(p), cap), None, "bvcf_host_alloc")
+            self.ptrs.append(p.value)
+            self.views.append(memoryview((C.c_char * cap).from_address(p.value)).cast("B"))
+        libc = C.CDLL(None)
+        libc.memrchr.restype = C.c_void_p
+        libc.memrchr.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+        self._memrchr = libc.memrchr
+
+    def last_newline(self, i: int, n: int) -> int:
+        """length of the longest newline-terminated prefix of buffer i's first n bytes, or -1"""
+        if n <= 0:
+            return -1
+        r = self._memrchr(self.ptrs[i], 10, n)
+        return -1 if not r else r - self.ptrs[i] + 1
+
+    def close(self):
+        L = _lib.lib()
+        self.views = []
+        for p in self.ptrs:
+            L.bvcf_host_free(p)
+        self.ptrs = []
+
+
 def write_sample_list(config: Config, chrom_line: bytes, normalize: bool = True) -> None:
     """writeSampleListIfWanted / makeSampleList main.go:398-445"""
     if not config.sampleListPath:
@@ -437,20 +471,24 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
 
             names = [s.replace(b".", b"_") if config.normalizeHeader else s for s in chrom_line.split(b"\t")[9:]]
             arrow = DosageWriter(config.dosageMatrixOutPath, names)
-        carry = head[off:]
+        # chunks are staged in pinned host buffers (bvcf_host_alloc) and read into them directly: a pageable source
+        # would make the driver bounce every H2D copy through its own staging buffer
+        cap = 2 * chunk_bytes + (64 << 20) if transformer is None else max(2 * chunk_bytes, 1 << 20)
+        ring = PinnedRing(tr.n_slots + 1, cap)
         seq_in = seq_out = 0
-        pending = {}
+        pending = {}  # seq -> (address, length) of the chunk while it is in flight
 
         def drain(upto: int):
             nonlocal seq_out
             while seq_out < upto:
                 res = tr.collect(seq_out)
-                block_of_seq = pending.pop(seq_out, b"")
+                addr, blen = pending.pop(seq_out, (0, 0))
                 if writer is not None and not config.noOut:
                     writer.write(res.tsv)
                 if arrow is not None and res.dosage is not None:
                     arrow.write(res.loci, res.dosage)
                 if diag_sink is not None and res.diags:
+                    block_of_seq = C.string_at(addr, blen)
                     for ln, alt_no, code in res.diags:
                         chrom, pos = chunk_line_locus(block_of_seq, ln)
                         diag_sink(format_diag(chrom, pos, alt_no, code), totals["n_lines"] + ln, alt_no, code)
@@ -460,31 +498,45 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
                 totals["out_bytes"] += len(res.tsv)
                 seq_out += 1
 
-        eof = False
-        while not eof:
-            data = reader.read(chunk_bytes)
-            if not data:
-                eof = True
-                block = carry
-                carry = b""
-                cut = block.rfind(b"\n")
-                block = block[:cut + 1]  # an unterminated last line is dropped (main.go:354-357)
-            else:
-                block = carry + data if carry else data
-                cut = block.rfind(b"\n")
+        try:
+            slot = 0
+            fill = len(head) - off  # bytes waiting in the current buffer
+            if fill > cap:
+                raise BvcfError("the VCF preamble does not fit a chunk buffer; raise chunkBytes")
+            C.memmove(ring.ptrs[0], head[off:], fill)
+            eof = False
+            while not eof or fill:
+                view = ring.views[slot]
+                while not eof and fill < chunk_bytes:
+                    n = reader.readinto(view[fill:min(cap, chunk_bytes)])
+                    if not n:
+                        eof = True
+                        break
+                    fill += n
+                cut = ring.last_newline(slot, fill)
                 if cut < 0:
-                    carry = block
+                    if eof:
+                        break  # an unterminated last line is dropped (main.go:354-357)
+                    if fill >= cap:
+                        raise BvcfError("a single line exceeds the chunk capacity; raise chunkBytes")
+                    n = reader.readinto(view[fill:cap])
+                    if not n:
+                        eof = True
+                    fill += n or 0
                     continue
-                carry = block[cut + 1:]
-                block = block[:cut + 1]
-            if block:
+                nxt = (slot + 1) % len(ring.ptrs)
                 if seq_in - seq_out >= tr.n_slots:
-                    drain(seq_out + 1)
-                pending[seq_in] = block
-                tr.submit(seq_in, block)
-                totals["in_bytes"] += len(block)
+                    drain(seq_out + 1)  # frees the next ring buffer too (n_slots + 1 buffers, n_slots in flight)
+                C.memmove(ring.ptrs[nxt], ring.ptrs[slot] + cut, fill - cut)  # carry the partial line
+                pending[seq_in] = (ring.ptrs[slot], cut)
+                tr.submit(seq_in, (ring.ptrs[slot], cut))
+                totals["in_bytes"] += cut
                 seq_in += 1
-        drain(seq_in)
+                fill -= cut
+                slot = nxt
+            drain(seq_in)
+        finally:
+            ring.close()
     finally:
         if arrow is not None:
             arrow.close()

@@ -64,3 +64,154 @@ def test_cpp_cli_not_a_vcf():
     p = subprocess.run([BIN], input=b"hello\nworld\n", stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=ROOT)
     assert p.returncode == 1 and b"Not a VCF file" in p.stderr
     assert p.stdout.decode().rstrip("\n").split("\t") == V.BASE_HEADER  # header is printed first (main.go:199)
+
+
+def test_python_cli_log_lines_match_reference_formats(tmp_path):
+    """the Python CLI used to print "line N ALT #k msg"; now the reference's formats, and --err is honoured"""
+    recs = [["1", "5", ".", "A", "A", ".", "PASS", "."], ["1", "6", ".", "A", "<DEL>", ".", "PASS", "."],
+            ["1", "10", ".", "TAGCTT", "TAC,T", ".", "PASS", "."], ["1", "y", ".", "AT", "A,ATT", ".", "PASS", "."]]
+    vcf = V._vcf(V.HDR8, recs)
+    errp = tmp_path / "err.log"
+    out, err = _run([sys.executable, "-m", "bystro_vcf_b200", "--err", str(errp)], vcf)
+    assert sorted(errp.read_text().strip().split("\n")) == sorted(
+        ["1:5 : REF == ALT", "1:6 ALT #1 ALT not ACTG", "1:10 ALT#1 Mixed indel/snp sites not supported", "1:y Invalid POS"])
+
+
+def _tiled(chr1_fixture, tiles, first_mb=12):
+    """header + the first `first_mb` MB of the fixture's data lines, `tiles` times over"""
+    from bystro_vcf_b200 import parse_preamble
+
+    _, _, off = parse_preamble(chr1_fixture)
+    body = chr1_fixture[off:off + (first_mb << 20)].rsplit(b"\n", 1)[0] + b"\n"
+    return chr1_fixture[:off] + body * tiles
+
+
+def _devices():
+    """two workers: two GPUs when the box has them, the same GPU twice otherwise"""
+    import torch
+
+    return [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+
+
+@pytest.mark.parametrize("host", ["cpp-mmap", "cpp-pipe", "python"])
+def test_multi_gpu_hosts_match_single(chr1_fixture, tmp_path, host):
+    """the multi-GPU product hosts (chunk k -> GPU k mod N, rows written in input order) give the
+    single-GPU bytes: C++ binary with a memory-mapped --in file and with a pipe, shard.read_vcf_multi."""
+    import io
+
+    from bystro_vcf_b200 import Config, read_vcf
+    from bystro_vcf_b200.shard import read_vcf_multi
+
+    vcf = _tiled(chr1_fixture, 8)
+    c = Config()
+    c.allowedFilters = {"PASS": True, ".": True}
+    c.keepID = c.keepInfo = True
+    c.chunkBytes = 7 << 20
+    single = io.BytesIO()
+    st = read_vcf(c, io.BytesIO(vcf), single)
+    devs = _devices()
+    if host == "python":
+        out = io.BytesIO()
+        st2 = read_vcf_multi(c, vcf, out, devs)
+        assert st2["n_rows"] == st["n_rows"] and st2["n_chunks"] > 8
+        got = out.getvalue()
+    else:
+        flags = ["--keepId", "--keepInfo", "--chunkBytes", str(7 << 20), "--devices", ",".join(map(str, devs))]
+        if host == "cpp-mmap":
+            inp = tmp_path / "in.vcf"
+            inp.write_bytes(vcf)
+            raw, _ = _run([BIN, "--in", str(inp)] + flags, b"")
+        else:
+            raw, _ = _run([BIN] + flags, vcf)
+        got = raw.partition(b"\n")[2]
+    assert hashlib.md5(got).hexdigest() == hashlib.md5(single.getvalue()).hexdigest()
+    assert len(got) == st["out_bytes"]
+
+
+@pytest.mark.parametrize("host", ["cpp", "python-multi"])
+def test_dosage_output_file_from_the_hosts(chr1_fixture, tmp_path, host):
+    """--dosageOutput in the drop-in binary (libarrow of the pyarrow wheel) and on the multi-GPU
+    Python path: an Arrow IPC file, zstd, `locus` + one non-nullable int8 column per sample, batches of at most 5,000
+    rows, read back like main_test.go:2947-2976 and compared with the oracle's matrix."""
+    import numpy as np
+    import pyarrow as pa
+
+    from oracle import oracle as O
+
+    vcf = _tiled(chr1_fixture, 6, first_mb=20)  # ~11,800 rows: three batches
+    ref = O.read_vcf(O.OracleConfig(want_dosage=True), vcf)
+    path = tmp_path / "dosage.feather"
+    devs = _devices()
+    if host == "cpp":
+        raw, _ = _run([BIN, "--dosageOutput", str(path), "--chunkBytes", str(16 << 20), "--devices", ",".join(map(str, devs))], vcf)
+        assert raw.partition(b"\n")[2] == ref.tsv
+    else:
+        import io
+
+        from bystro_vcf_b200 import Config
+        from bystro_vcf_b200.shard import read_vcf_multi
+
+        c = Config()
+        c.allowedFilters = {"PASS": True, ".": True}
+        c.dosageMatrixOutPath = str(path)
+        c.chunkBytes = 16 << 20
+        out = io.BytesIO()
+        read_vcf_multi(c, vcf, out, devs)
+        assert out.getvalue() == ref.tsv
+    rd = pa.ipc.open_file(str(path))
+    assert rd.schema.names[0] == "locus" and len(rd.schema.names) == 2505
+    assert all(not f.nullable for f in rd.schema) and rd.schema.field(1).type == pa.int8()
+    assert rd.num_record_batches >= 3 and all(rd.get_batch(i).num_rows <= 5000 for i in range(rd.num_record_batches))
+    tab = rd.read_all()
+    assert [x.encode() for x in tab.column(0).to_pylist()] == ref.loci
+    mat = np.stack([tab.column(j + 1).to_numpy() for j in range(2504)], axis=1)
+    assert np.array_equal(mat, ref.dosage)
+
+
+def test_cpp_cli_noout_dosage_only_and_sample_list(chr1_fixture, tmp_path):
+    """--noOut with --dosageOutput (main.go:160-166), no samples -> empty dosage file (main.go:308-318)"""
+    import pyarrow as pa
+
+    vcf = _tiled(chr1_fixture, 1, first_mb=6)
+    path = tmp_path / "d.feather"
+    raw, _ = _run([BIN, "--noOut", "--dosageOutput", str(path)], vcf)
+    assert raw == b""
+    assert pa.ipc.open_file(str(path)).read_all().num_rows > 500
+    sites = V._vcf(V.HDR8, [["1", "5", ".", "A", "G", ".", "PASS", "."]])
+    p2 = tmp_path / "e.feather"
+    raw, err = _run([BIN, "--dosageOutput", str(p2)], sites)
+    assert p2.read_bytes() == b"" and raw.count(b"\n") == 2 and "No samples found" in err
+
+
+def test_file_to_file_wall_clock(chr1_fixture, tmp_path):
+    """the whole main.go:134-217 contract timed around the binary -- file in (tmpfs when there is one),
+    file out, read + staging + H2D + kernels + D2H + write; the number is printed for the log."""
+    import time
+
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else str(tmp_path)
+    inp, outp = os.path.join(d, "bvcf_f2f_in.vcf"), os.path.join(d, "bvcf_f2f_out.tsv")
+    vcf = _tiled(chr1_fixture, 10, first_mb=100)  # ~1 GB
+    try:
+        with open(inp, "wb") as f:
+            f.write(vcf)
+        if os.path.exists(outp):
+            os.remove(outp)
+        t0 = time.perf_counter()
+        _run([BIN, "--in", inp, "--out", outp], b"")
+        dt = time.perf_counter() - t0
+        n_lines = vcf.count(b"\n")
+        print("file->file: %.2f GB in %.2f s = %.2f GB/s, %.2f M variants/s (context creation included)"
+              % (len(vcf) / 1e9, dt, len(vcf) / 1e9 / dt, n_lines / 1e6 / dt))
+        from bystro_vcf_b200 import parse_preamble
+
+        _, _, off = parse_preamble(vcf)
+        one = oracle_body = None
+        from oracle import oracle as O
+
+        one = O.read_vcf(O.OracleConfig(), vcf[:off] + vcf[off:off + (100 << 20)].rsplit(b"\n", 1)[0] + b"\n").tsv
+        got = open(outp, "rb").read().partition(b"\n")[2]
+        assert got == one * 10
+    finally:
+        for p in (inp, outp):
+            if os.path.exists(p):
+                os.remove(p)
