@@ -69,6 +69,8 @@ class CKernelTimes(C.Structure):
         ("names_ms", C.c_float),
         ("total_ms", C.c_float),
         ("launches", C.c_uint32),
+        ("compose_ms", C.c_float),
+        ("copyout_ms", C.c_float),
     ]
 
 

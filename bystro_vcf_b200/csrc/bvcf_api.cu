@@ -201,7 +201,7 @@ void scratch_free(Scratch &sc) {
     dev_free(*b);
 }
 
-constexpr int N_STAGE_EV = 6;
+constexpr int N_STAGE_EV = 8;  // 0..5 stage boundaries, 6..7 inside the rows stage (compose | offsets | copy-out)
 struct StageEvents {  // optional per-stage timing of one sub-chunk
   cudaEvent_t e[N_STAGE_EV];
 };
@@ -297,21 +297,31 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     tp.loci = d_loci; tp.loci_cap = loci_cap; tp.loci_off = d_loci_off;
     tp.diag.diags = d_diags; tp.diag.cap = ctx->diag_cap; tp.diag.ctr = d_ctr;
     {
-      static const int variant = getenv("BVCF_COMPOSE_VARIANT") ? atoi(getenv("BVCF_COMPOSE_VARIANT")) : 4;  // experiments
-      auto launch = [&](auto kern, uint32_t arena, int minb) {
-        const uint32_t smem = TILE_WARPS * tile_smem_warp(arena);
+      auto launch = [&](auto kern, uint32_t arena, uint32_t rows, int minb) {
+        const uint32_t smem = TILE_WARPS * tile_smem_warp(arena, rows);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<(unsigned)n_sm * minb, TILE_WARPS * 32, smem, st>>>(tp);
       };
-      if (variant == 5) launch(bvcf_compose_kernel<5, 8192>, 8192, 5);
-      else if (variant == 6) launch(bvcf_compose_kernel<6, 7168>, 7168, 6);
-      else if (variant == 8) launch(bvcf_compose_kernel<8, 5120>, 5120, 8);
-      else launch(bvcf_compose_kernel<4, 10240>, 10240, 4);
+      // (5, 6 and 8 resident CTAs per SM were measured too: the spills of a 96 / 80 / 64-register build cost more than
+      // the extra warps hide -- rows 0.42 -> 0.51 / 0.52 / 0.55 ms on 600,000 chr1-shape variants)
+      // L2 prefetch of the next tile's lines / scratch block: measured, no gain (compose 0.323 -> 0.329 ms, copy-out
+      // 0.116 -> 0.124 ms on 600,000 chr1-shape variants: the waits are dependent L1/L2 hits, not DRAM), so off
+      static const int pf = getenv("BVCF_PREFETCH") ? atoi(getenv("BVCF_PREFETCH")) : 0;  // experiments: bit 0 compose, bit 1 copy-out
+      if (dc.n_samples == 0) {
+        if (pf & 1) launch(bvcf_compose_kernel<4, 8192, 160, true>, 8192, 160, 4);
+        else launch(bvcf_compose_kernel<4, 8192, 160, false>, 8192, 160, 4);
+      } else {
+        if (pf & 1) launch(bvcf_compose_kernel<4, 10240, 48, true>, 10240, 48, 4);
+        else launch(bvcf_compose_kernel<4, 10240, 48, false>, 10240, 48, 4);
+      }
+      if (se) CK(cudaEventRecord(se->e[6], st));
+      bvcf_tile_reduce_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);
+      bvcf_tile_spine_kernel<<<1, 32, 0, st>>>(tp);
+      bvcf_tile_offsets_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);
+      if (se) CK(cudaEventRecord(se->e[7], st));
+      if (pf & 2) bvcf_copyout_kernel<true><<<(unsigned)n_sm * 16, TILE_WARPS * 32, 0, st>>>(tp);
+      else bvcf_copyout_kernel<false><<<(unsigned)n_sm * 16, TILE_WARPS * 32, 0, st>>>(tp);
     }
-    bvcf_tile_reduce_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);
-    bvcf_tile_spine_kernel<<<1, 32, 0, st>>>(tp);
-    bvcf_tile_offsets_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);
-    bvcf_copyout_kernel<<<(unsigned)n_sm * 16, TILE_WARPS * 32, 0, st>>>(tp);
     bvcf_slow_rows_kernel<<<(unsigned)n_sm, 64, 0, st>>>(tp);
     ctx->launches += 6;
     if (se) CK(cudaEventRecord(se->e[4], st));
@@ -880,8 +890,10 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       cudaEventElapsedTime(&ms, t.e[2], t.e[3]); times->stats_ms += ms;
       cudaEventElapsedTime(&ms, t.e[3], t.e[4]); times->rows_ms += ms;
       cudaEventElapsedTime(&ms, t.e[4], t.e[5]); times->names_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[3], t.e[6]); times->compose_ms += ms;
+      cudaEventElapsedTime(&ms, t.e[7], t.e[4]); times->copyout_ms += ms;
     }
-    if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[N_STAGE_EV - 1]);
+    if (!timing.empty()) cudaEventElapsedTime(&times->total_ms, timing.front().e[0], timing.back().e[5]);
     times->launches = (uint32_t)(ctx->launches - launches0);  // of the last (successful) attempt
     for (auto &t : timing)
       for (auto e : t.e) ctx->ev_pool.push_back(e);

@@ -31,7 +31,7 @@ namespace bvcf {
 
 constexpr int TILE_THREADS = 32;           // records per tile, one thread each: a tile is a warp's
 constexpr int TILE_WARPS = 4;              // warps (independent tiles) per CTA
-constexpr uint32_t TILE_ROWS = 48;         // staged rows per tile; lane l's first row is rows[l]
+constexpr uint32_t TILE_ROWS_MAX = 160;    // most staged rows per tile any kernel variant allows; lane l's first row is rows[l]
 constexpr uint32_t ROW_NONE = 0xFFFFu;
 
 // one staged row (shared memory, then the tile's scratch block)
@@ -222,6 +222,7 @@ struct RecOut {
 struct TileShared {
   uint32_t arena_s;           // shared-memory address of the arena
   uint32_t arena_cap;         // its size
+  uint32_t rows_cap;          // row descriptors
   TRow *rows;
   uint32_t *arena_cur, *rows_cur;
 };
@@ -376,7 +377,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
       if (big) need += 16u;  // three counts, 4-byte aligned
       ri = ro.first == ROW_NONE ? (threadIdx.x & 31u) : atomicAdd(sh.rows_cur, 1u);
       const uint32_t off = atomicAdd(sh.arena_cur, (need + 15u) & ~15u);
-      if (ri >= TILE_ROWS || off + need > sh.arena_cap) {
+      if (ri >= sh.rows_cap || off + need > sh.arena_cap) {
         ro.failed = true; ro.first = ROW_NONE;  // the whole record takes the slow path; keep sizing
       } else {
         row = &sh.rows[ri];
@@ -620,14 +621,17 @@ __device__ __forceinline__ unsigned long long warp_scan64(unsigned long long v, 
 }
 
 // shared memory per warp: arena (+ padding) and row table
-__host__ __device__ constexpr uint32_t tile_smem_warp(uint32_t arena) { return arena + 16 + TILE_ROWS * (uint32_t)sizeof(TRow); }
+__host__ __device__ constexpr uint32_t tile_smem_warp(uint32_t arena, uint32_t rows) { return arena + 16 + rows * (uint32_t)sizeof(TRow); }
 constexpr uint32_t TILE_BLOCK_HDR = 32u * (uint32_t)sizeof(LaneRec);
 
 // ---- compose ------------------------------------------------------------------------------------------------
-// MINB resident CTAs per SM (sets the register budget), ARENA staging bytes per warp
-template <int MINB, uint32_t ARENA>
+// MINB resident CTAs per SM (sets the register budget), ARENA staging bytes and ROWS row descriptors per warp.
+// Records with samples give about one row each (wide text: 10 KiB, 48 rows); sites-only input gives 1.6 short rows per
+// record at BASELINE's 30 % multi-allelic / MNP mix (8 KiB, 160 rows).
+template <int MINB, uint32_t ARENA, uint32_t ROWS, bool PREFETCH>
 __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(const __grid_constant__ TileParams p) {
-  constexpr uint32_t TILE_ARENA = ARENA, TILE_SMEM_WARP = tile_smem_warp(ARENA);
+  constexpr uint32_t TILE_ARENA = ARENA, TILE_ROWS = ROWS, TILE_SMEM_WARP = tile_smem_warp(ARENA, ROWS);
+  static_assert(ROWS <= TILE_ROWS_MAX && ROWS >= TILE_THREADS, "row table size");
   extern __shared__ __align__(16) uint8_t s_dyn[];
   __shared__ uint8_t s_filt[FILT_SMEM];
   __shared__ uint32_t s_filt_off[65];
@@ -648,18 +652,52 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
   TileShared sh;
   sh.arena_s = (uint32_t)__cvta_generic_to_shared(my_smem);
   sh.arena_cap = TILE_ARENA;
+  sh.rows_cap = TILE_ROWS;
   sh.rows = s_rows;
   sh.arena_cur = &s_cur[warp][0];
   sh.rows_cur = &s_cur[warp][1];
 
-  for (;;) {
-    uint32_t tile = 0;
-    if (lane == 0) {
-      tile = atomicAdd(&p.ctr->tile_ticket, 1u);
-      s_cur[warp][0] = 0; s_cur[warp][1] = TILE_THREADS;
+  // Tiles are taken with a fixed stride so that a warp knows its next two tiles: the record of the tile after next is
+  // loaded (its line start, its event list) while this tile is composed, and the first bytes of the next tile's lines
+  // and events are pulled into L2.  The lines were last touched by the scan kernel gigabytes ago: without this every
+  // thread waits for DRAM two or three times in a row at the start of its record.
+  auto rec_head = [&](uint32_t t, unsigned long long &start, uint32_t &ev_start) {
+    const uint32_t i = t * TILE_THREADS + lane;
+    start = ~0ull; ev_start = 0;
+    if (t < n_tiles && i < n_rec) {
+      const uint4 a = reinterpret_cast<const uint4 *>(p.lines + i)[0], b = reinterpret_cast<const uint4 *>(p.lines + i)[1];
+      start = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
+      ev_start = b.x;
     }
-    tile = __shfl_sync(FULL, tile, 0);  // also orders the cursor reset before the lanes' allocations
-    if (tile >= n_tiles) break;
+  };
+  auto pull = [&](unsigned long long start, uint32_t ev_start) {
+    if (start != ~0ull) {
+      const uint8_t *l = p.in + start;
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(l));
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(l + 128));
+      if (has_samples) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.events + ev_start));
+    }
+  };
+  // Tiles are handed out by a ticket counter (rows differ a lot in cost), two tickets ahead, so that a warp knows its
+  // next two tiles: the record of the tile after next is loaded (line start, event list) while this tile is composed,
+  // and the first bytes of the next tile's lines and events are pulled into L2.  The lines were last touched by the
+  // scan kernel gigabytes ago: without this every thread waits for DRAM two or three times at the start of its record.
+  auto ticket = [&]() {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&p.ctr->tile_ticket, 1u);
+    return __shfl_sync(FULL, t, 0);
+  };
+  uint32_t tile = ticket(), tile_n1 = ticket(), tile_n2;
+  unsigned long long nx_start;  // line start / event list of this lane's record in the NEXT tile
+  uint32_t nx_ev;
+  if (PREFETCH) rec_head(tile_n1, nx_start, nx_ev); else { nx_start = ~0ull; nx_ev = 0; }
+  for (; tile < n_tiles; tile = tile_n1, tile_n1 = tile_n2) {
+    if (lane == 0) { s_cur[warp][0] = 0; s_cur[warp][1] = TILE_THREADS; }
+    tile_n2 = ticket();  // also orders the cursor reset before the lanes' allocations
+    if (PREFETCH) {
+      pull(nx_start, nx_ev);
+      rec_head(tile_n2, nx_start, nx_ev);  // consumed one iteration from now
+    }
     const uint32_t li = tile * TILE_THREADS + lane;
     const bool valid = li < n_rec;
 
@@ -847,6 +885,7 @@ __device__ __forceinline__ TRow ld_trow(const uint8_t *p) {
   t.flags = (uint16_t)b.w; t.pad = 0;
   return t;
 }
+template <bool PREFETCH>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const __grid_constant__ TileParams p) {
   const DevCfg &cfg = p.cfg;
   const int lane = threadIdx.x & 31;
@@ -859,12 +898,26 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
   const bool has_samples = cfg.n_samples > 0;
   const bool want_locus = cfg.want_dosage && has_samples;
 
-  for (;;) {
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(&p.ctr->tile_ticket2, 1u);
-    tile = __shfl_sync(FULL, tile, 0);
-    if (tile >= n_tiles) break;
-    const TileAgg ag = p.tile_agg[tile];
+  // tiles by ticket, one ahead: the next tile's totals are loaded while this one is copied, and its whole scratch
+  // block is pulled into L2 (the dependent chain totals -> block -> row table -> staged bytes would otherwise be four
+  // DRAM round trips per tile)
+  auto ticket = [&]() {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&p.ctr->tile_ticket2, 1u);
+    return __shfl_sync(FULL, t, 0);
+  };
+  uint32_t tile = ticket(), tile_n1 = ticket();
+  TileAgg ag_next;
+  ag_next.bytes = 0; ag_next.scratch_off = 0; ag_next.rows = ag_next.loci = ag_next.n_big = ag_next.n_long = 0;
+  ag_next.arena_used = ag_next.n_trows = 0;
+  if (tile < n_tiles) ag_next = p.tile_agg[tile];
+  for (; tile < n_tiles; tile = tile_n1, tile_n1 = ticket()) {
+    const TileAgg ag = ag_next;
+    const bool more = tile_n1 < n_tiles;
+    if (more) {
+      ag_next = p.tile_agg[tile_n1];  // consumed further down, after this tile's own loads
+      if (PREFETCH) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.tile_base + tile_n1));
+    }
     const TileBase tb = p.tile_base[tile];
     const uint8_t *blk = p.scratch + ag.scratch_off;
     const LaneRec lr = reinterpret_cast<const LaneRec *>(blk)[lane];
@@ -876,6 +929,11 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
     const unsigned long long in_b = warp_scan64(lr.bytes, tot, lane);
     const unsigned long long in_rl = warp_scan64((unsigned long long)lr.rows | ((unsigned long long)lr.loci << 32), tot, lane);
     const unsigned long long in_d = warp_scan64(is_long ? ((unsigned long long)lr.n_desc << 32) : (unsigned long long)lr.n_desc, tot, lane);
+    if (PREFETCH && more) {  // the next tile's block into L2
+      const uint8_t *nb = p.scratch + ag_next.scratch_off;
+      const uint32_t nbytes = TILE_BLOCK_HDR + ag_next.n_trows * (uint32_t)sizeof(TRow) + ag_next.arena_used;
+      for (uint32_t o = lane * 128u; o < nbytes; o += 32u * 128u) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(nb + o));
+    }
 
     // this tile's dosage rows start as all-reference (0); the small rows' samples are scattered below, the queued
     // rows' by the names kernels
@@ -982,7 +1040,7 @@ __global__ void __launch_bounds__(64) bvcf_slow_rows_kernel(const __grid_constan
   if (n > p.slow_cap) n = p.slow_cap;  // flagged below; the host re-runs the chunk with a larger list
   if (blockIdx.x == 0 && threadIdx.x == 0 && c->n_slow > p.slow_cap) p.ctr->slow_overflow = 1;
   TileShared sh;
-  sh.arena_s = 0; sh.arena_cap = 0; sh.rows = nullptr; sh.arena_cur = nullptr; sh.rows_cur = nullptr;
+  sh.arena_s = 0; sh.arena_cap = 0; sh.rows_cap = 0; sh.rows = nullptr; sh.arena_cur = nullptr; sh.rows_cur = nullptr;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const SlowRec sr = p.slow[i];
     const LineRec rec = p.lines[sr.li];

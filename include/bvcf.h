@@ -106,6 +106,8 @@ typedef struct {
   float names_ms;    /* bvcf_names_{vec,long,big}_kernel: long sample-name lists + their dosage rows (kernel 4b) */
   float total_ms;    /* first launch to last launch, whole run */
   uint32_t launches; /* kernels launched */
+  float compose_ms;  /* inside rows_ms: bvcf_compose_kernel */
+  float copyout_ms;  /* inside rows_ms: the copy-out and slow-path kernels (the rest of rows_ms is the tile-offset scan) */
 } bvcf_kernel_times;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
