@@ -179,7 +179,7 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
   const uint64_t max_tiles = sc.max_records / TILE_THREADS + 2;
   if ((rc = dev_reserve(ctx, sc.tile_agg, max_tiles * sizeof(TileAgg)))) return rc;
   if ((rc = dev_reserve(ctx, sc.tile_base, max_tiles * sizeof(TileBase)))) return rc;
-  if ((rc = dev_reserve(ctx, sc.tile_partial, (size_t)TSCAN_BLOCKS * 5 * 8))) return rc;
+  if ((rc = dev_reserve(ctx, sc.tile_partial, (size_t)TSCAN_BLOCKS * TQ * 8))) return rc;
   // a tile's block: 1 KiB of per-record sizes, 32 bytes per row, the staged text (about 110 bytes per row)
   sc.scratch_cap = std::max<uint64_t>(sc.scratch_cap, std::min<uint64_t>(total_bytes / 8 + (8ull << 20), sc.max_records * 224ull + (1ull << 20)));
   if ((rc = dev_reserve(ctx, sc.tile_scratch, sc.scratch_cap + 64))) return rc;  // the copy-out reads whole words
@@ -293,6 +293,11 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     tp.slow = (SlowRec *)sc.slow.p; tp.slow_cap = sc.slow_cap;
     tp.row_desc = (RowDesc *)sc.row_desc.p; tp.row_desc_cap = dc.n_samples > 0 ? sc.row_cap : 0;
     tp.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
+    {
+      static const int mid_q = getenv("BVCF_MID_QUADS") ? atoi(getenv("BVCF_MID_QUADS")) : 64;  // experiments
+      tp.mid_words = (dc.want_tsv && dc.n_samples > 0) ? 2u * (uint32_t)std::max(mid_q, 0) : 0u;  // rows up to 64 quads: a lane per row
+      if (!vec) tp.mid_words = 0;  // names_big_kernel serves every list
+    }
     tp.dosage = d_dosage; tp.dosage_cap_rows = dosage_cap_rows;
     tp.loci = d_loci; tp.loci_cap = loci_cap; tp.loci_off = d_loci_off;
     tp.diag.diags = d_diags; tp.diag.cap = ctx->diag_cap; tp.diag.ctr = d_ctr;
@@ -335,6 +340,11 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       if (vec) {
         const unsigned g1 = (unsigned)n_sm * 18, g2 = (unsigned)n_sm * 2;
         const bool dos = dc.want_dosage && d_dosage;
+        if (tp.mid_words) {
+          if (dos) bvcf_names_mid_kernel<true><<<(unsigned)n_sm * 16, 128, 0, st>>>(np);
+          else bvcf_names_mid_kernel<false><<<(unsigned)n_sm * 16, 128, 0, st>>>(np);
+          ctx->launches++;
+        }
         if (dc.n_samples <= 65000) {
           if (dos) {
             bvcf_names_vec_kernel<uint16_t, true><<<g1, NVEC_WARPS * 32, 0, st>>>(np);

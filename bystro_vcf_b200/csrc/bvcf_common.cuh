@@ -89,7 +89,7 @@ struct RunCounters {
   unsigned int n_slow;             // slow-path records of the sub-chunk (bvcf_slow_rows_kernel's work list)
   unsigned int scratch_overflow;   // the tile blocks did not fit the scratch buffer
   unsigned int slow_overflow;      // more slow-path records than list entries
-  unsigned int pad0;
+  unsigned int n_mid_rows;         // names work list: rows written by one lane each (bvcf_names_mid_kernel)
   unsigned int n_big_rows;         // names work list: rows written by a warp each (per sub-chunk)
   unsigned int big_row_cursor;     // next entry to be taken (dynamic scheduling)
   unsigned int n_long_rows;        // rows with very long event lists: written by a whole CTA (bvcf_names_long_kernel)

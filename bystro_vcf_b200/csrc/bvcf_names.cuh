@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const N
   __shared__ __align__(16) uint8_t s_idx[NVEC_WARPS][NVEC_IDX_BYTES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow | p.ctr->row_overflow) return;
-  const uint32_t n_big = p.ctr->n_big_rows;
+  const uint32_t n_mid = p.ctr->n_mid_rows, n_big = p.ctr->n_big_rows;  // this kernel's rows follow the mid list
   IdxT *idx = reinterpret_cast<IdxT *>(s_idx[warp]);
   // rows differ by three orders of magnitude in size: warps take the next queued row from a shared cursor
   for (;;) {
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(NVEC_WARPS * 32) bvcf_names_vec_kernel(const N
     if (lane == 0) wi = atomicAdd(&p.ctr->big_row_cursor, 1u);
     wi = __shfl_sync(FULL, wi, 0);
     if (wi >= n_big) break;
-    names_row_vec<IdxT, DOSAGE>(p, p.row_desc[wi], idx, lane);
+    names_row_vec<IdxT, DOSAGE>(p, p.row_desc[n_mid + wi], idx, lane);
   }
 }
 

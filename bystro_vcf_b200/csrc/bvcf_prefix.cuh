@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(1024) bvcf_prefix_spine_kernel(const PrefixPar
     c->n_lines += sb[t];
     c->n_big_recs = 0; c->big_rec_cursor = 0;
     c->tile_ticket = 0; c->tile_ticket2 = 0; c->n_slow = 0; c->scratch_cursor = 0;
-    c->n_big_rows = 0; c->big_row_cursor = 0;
+    c->n_mid_rows = 0; c->n_big_rows = 0; c->big_row_cursor = 0;
     c->n_long_rows = 0; c->long_row_cursor = 0;
     c->chunk_out_base = c->out_cursor;
     c->chunk_row_base = c->row_cursor;

@@ -524,14 +524,16 @@ struct NamesParams {
   DevCfg cfg;
   const LineRec *lines;
   const uint32_t *events;
-  // the work list bvcf_tile_kernel filled: entries [0, ctr->n_big_rows) are rows written by a warp each
-  // (bvcf_names_vec_kernel / bvcf_names_big_kernel); rows with more than long_words event words sit at the END of
-  // the array, entries [row_desc_cap - ctr->n_long_rows, row_desc_cap), for bvcf_names_long_kernel (a CTA per row)
+  // the work lists bvcf_copyout_kernel filled: entries [0, ctr->n_mid_rows) are rows written by a lane each
+  // (bvcf_names_mid_kernel), the next ctr->n_big_rows entries rows written by a warp each (bvcf_names_vec_kernel);
+  // rows with more than long_words event words sit at the END of the array, entries [row_desc_cap -
+  // ctr->n_long_rows, row_desc_cap), for bvcf_names_long_kernel (a CTA per row).  bvcf_names_big_kernel serves all
+  // three lists when the names are not fixed-size items.
   const RowDesc *row_desc;
   unsigned long long row_desc_cap;
   uint8_t *out;
   RunCounters *ctr;
-  int8_t *dosage;            // zeroed by bvcf_tile_kernel
+  int8_t *dosage;            // zeroed by bvcf_copyout_kernel
   unsigned long long dosage_cap_rows;
   uint32_t long_words;       // 0: no CTA-per-row kernel follows
 };
@@ -596,13 +598,120 @@ __device__ __forceinline__ void names_row_warp(const NamesParams &p, const RowDe
 }
 
 
+// 8 bytes to an arbitrarily aligned address with the widest naturally aligned pieces (2-4 stores)
+__device__ __forceinline__ void store8_unaligned(uint8_t *d, unsigned long long v) {
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  switch ((uintptr_t)d & 3u) {
+    case 0:
+      *reinterpret_cast<uint32_t *>(d) = lo;
+      *reinterpret_cast<uint32_t *>(d + 4) = hi;
+      break;
+    case 2:
+      *reinterpret_cast<uint16_t *>(d) = (uint16_t)lo;
+      *reinterpret_cast<uint32_t *>(d + 2) = (uint32_t)(v >> 16);
+      *reinterpret_cast<uint16_t *>(d + 6) = (uint16_t)(hi >> 16);
+      break;
+    case 1:
+      d[0] = (uint8_t)lo;
+      *reinterpret_cast<uint16_t *>(d + 1) = (uint16_t)(lo >> 8);
+      *reinterpret_cast<uint32_t *>(d + 3) = (uint32_t)(v >> 24);
+      d[7] = (uint8_t)(hi >> 24);
+      break;
+    default:
+      d[0] = (uint8_t)lo;
+      *reinterpret_cast<uint32_t *>(d + 1) = (uint32_t)(v >> 8);
+      *reinterpret_cast<uint16_t *>(d + 5) = (uint16_t)(hi >> 8);
+      d[7] = (uint8_t)(hi >> 24);
+      break;
+  }
+}
+
+// one row, one lane: rows whose record has a moderate number of events (up to TileParams::mid_words).  A warp per
+// such row spent some 1,000 instructions on a list of a dozen names (a sweep step, three emit calls, 31 idle lanes).
+template <bool DOSAGE>
+__device__ __forceinline__ void names_row_lane(const NamesParams &p, const RowDesc &rd, const LineRec &rec, int8_t *drow) {
+  const DevCfg &cfg = p.cfg;
+  const uint32_t *ev = p.events + rec.ev_start;
+  const uint8_t *L = p.in + rec.start;
+  const uint32_t content_len = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;
+  const uint32_t dl = (uint32_t)cfg.delim_len;
+  const bool simple = !(rec.flags & 1) && rd.allele == 1;
+  // per-class cursors in scalars (a runtime-indexed array would live in local memory)
+  uint32_t nh = 0, no = 0, nm = 0, bh = 0, bo = 0, bm = 0;
+  for (uint32_t q = 0; 2 * q + 1 < rec.ev_count; q++) {
+    const uint2 e = *reinterpret_cast<const uint2 *>(ev + 2 * q);
+    uint32_t mh, mo, mm;
+    quad_masks(e.x, e.y, rd.allele, simple, L, content_len, true, mh, mo, mm);
+    const uint32_t s0 = (e.x & EV_SAMPLE_MASK) - EV_BASE_BIAS;
+    uint32_t any = mh | mo | mm;
+    while (any) {
+      const uint32_t bit = any & (0u - any);
+      any &= any - 1;
+      const uint32_t samp = s0 + ((uint32_t)(__ffs(bit) - 1) >> 2);
+      const bool is_h = (mh & bit) != 0, is_o = (mo & bit) != 0;
+      if (DOSAGE && drow) {  // int8 dosage: -1 missing, else min(number of alleles equal to the row's, 127) (main.go:1172-1178)
+        int v = -1;
+        if (is_h | is_o) {
+          if (e.x & EV_COMPLEX) {
+            uint32_t gt, alt;
+            classify_gt_general(L + e.y, content_len > e.y ? content_len - e.y : 0, rd.allele, gt, alt);
+            v = alt > 127 ? 127 : (int)alt;
+          } else {
+            const uint32_t sh = (uint32_t)(__ffs(bit) - 1) - 3u;  // 4 * slot
+            const bool hap = ((e.y >> (16 + sh)) & 0xFu) == EV_NIB_ABSENT;
+            v = is_h ? 1 : (hap ? 1 : 2);
+          }
+        }
+        drow[samp] = (int8_t)v;
+      }
+      const uint32_t rn = is_h ? nh : (is_o ? no : nm), rb = is_h ? bh : (is_o ? bo : bm);
+      const unsigned long long dst = is_h ? rd.het_dst : (is_o ? rd.hom_dst : rd.miss_dst);
+      const uint32_t tot = is_h ? rd.n_het : (is_o ? rd.n_hom : rd.n_miss);
+      uint8_t *d = p.out + dst + rb;
+      uint32_t adv = 0;
+      if (rn > 0) {
+        for (uint32_t i = 0; i < dl; i++) d[i] = cfg.delim[i];
+        d += dl; adv = dl;
+      }
+      const uint32_t nl = name_len(cfg, samp);
+      if (cfg.name8) {
+        unsigned long long it = cfg.name8[samp];
+        if (rn + 1 == tot) it = (it & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)'\t' << 56);  // after the last name
+        store8_unaligned(d, it);
+      } else {
+        const uint8_t *src = name_ptr(cfg, samp);
+        for (uint32_t i = 0; i < nl; i++) d[i] = src[i];
+      }
+      adv += nl;
+      if (is_h) { nh++; bh += adv; } else if (is_o) { no++; bo += adv; } else { nm++; bm += adv; }
+    }
+  }
+}
+
+// lane per row: the mid list (TSV output only)
+template <bool DOSAGE>
+__global__ void __launch_bounds__(128) bvcf_names_mid_kernel(const NamesParams p) {
+  const DevCfg &cfg = p.cfg;
+  if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow | p.ctr->row_overflow | p.ctr->scratch_overflow) return;
+  const unsigned long long row0 = p.ctr->chunk_row_base;
+  const uint32_t n_mid = p.ctr->n_mid_rows;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_mid; r += gridDim.x * blockDim.x) {
+    const RowDesc rd = p.row_desc[r];
+    const LineRec rec = p.lines[rd.line];
+    int8_t *drow = nullptr;
+    if (DOSAGE && cfg.want_dosage && p.dosage && (row0 + rd.row) < p.dosage_cap_rows)
+      drow = p.dosage + (row0 + rd.row) * (unsigned long long)cfg.n_samples;
+    names_row_lane<DOSAGE>(p, rd, rec, drow);
+  }
+}
+
 // warp per row: the rows bvcf_tile_kernel queued, when the list items are not fixed 8-byte pieces
 // (variable-width names or a longer delimiter; otherwise bvcf_names.cuh takes them)
 __global__ void __launch_bounds__(NAMES_WARPS * 32) bvcf_names_big_kernel(const NamesParams p) {
   const int lane = threadIdx.x & 31;
   if (p.ctr->out_overflow | p.ctr->ev_overflow | p.ctr->slot_overflow | p.ctr->row_overflow) return;
   const unsigned long long row0 = p.ctr->chunk_row_base;
-  const uint32_t n_big = p.ctr->n_big_rows, n_long = p.ctr->n_long_rows;
+  const uint32_t n_big = p.ctr->n_mid_rows + p.ctr->n_big_rows, n_long = p.ctr->n_long_rows;
   const uint32_t total_warps = gridDim.x * NAMES_WARPS;
   for (uint32_t wi = blockIdx.x * NAMES_WARPS + (threadIdx.x >> 5); wi < n_big + n_long; wi += total_warps)
     names_row_warp(p, wi < n_big ? p.row_desc[wi] : p.row_desc[p.row_desc_cap - 1 - (wi - n_big)], row0, lane);

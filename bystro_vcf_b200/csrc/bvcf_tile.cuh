@@ -54,7 +54,7 @@ struct __align__(16) LaneRec {
   uint32_t rows, loci;        // rows, locus bytes
   uint32_t n_desc;            // RowDesc entries it will queue
   uint16_t first;             // its first staged row (chain through TRow::next)
-  uint16_t flags;             // bit 0: slow path (nothing staged, the sizes are still exact); bit 1: its rows go to the long list
+  uint16_t flags;             // bit 0: slow path (nothing staged, the sizes are still exact); bits 1-2: work list of its queued rows
   uint32_t info_off, info_n;  // INFO span of its line (offset from the line start)
 };
 static_assert(sizeof(LaneRec) == 32, "LaneRec layout");
@@ -65,19 +65,19 @@ struct __align__(16) TileAgg {
   unsigned long long scratch_off;     // byte offset of the block in the scratch buffer
   uint32_t rows, loci, n_big, n_long;
   uint32_t arena_used, n_trows;       // block layout: 32 LaneRec, n_trows TRow, arena_used bytes (16-byte padded)
-  uint32_t pad[2];
+  uint32_t n_mid, pad;
 };
 static_assert(sizeof(TileAgg) == 48, "TileAgg layout");
 // exclusive prefix of the totals over the tiles before this one (tile offsets kernels)
 struct __align__(16) TileBase {
   unsigned long long bytes, loci;
-  uint32_t rows, n_big, n_long, pad;
+  uint32_t rows, n_big, n_long, n_mid;
 };
 static_assert(sizeof(TileBase) == 32, "TileBase layout");
 // a slow-path record with its place in the outputs (copy-out kernel -> slow rows kernel)
 struct __align__(16) SlowRec {
   unsigned long long out_off, loci_off;
-  uint32_t li, row, desc, flags;      // flags bit 0: RowDesc slots are available, bit 1: long list
+  uint32_t li, row, desc, flags;      // flags bit 0: RowDesc slots are available, bits 1-2: work list
 };
 
 struct TileParams {
@@ -98,7 +98,10 @@ struct TileParams {
   uint32_t slow_cap;
   RowDesc *row_desc;           // work list for the names kernels (see RowDesc)
   unsigned long long row_desc_cap;
-  uint32_t long_words;         // rows of records with more event words go to the END of row_desc (CTA-per-row kernel); 0: none
+  // queued rows by the event words of their record: up to mid_words -> the lane-per-row names kernel (entries from
+  // the front of row_desc), more than long_words -> the CTA-per-row kernel (entries from the END of row_desc), the
+  // rest -> the warp-per-row kernel (entries after the mid ones); 0: no such class
+  uint32_t mid_words, long_words;
   // dosage matrix (main.go:576-584)
   int8_t *dosage;              // rows x n_samples
   unsigned long long dosage_cap_rows;
@@ -231,14 +234,19 @@ struct SlowOut {
   unsigned long long row;       // next row number within the sub-chunk
   unsigned long long loci_off;  // next locus byte (absolute in `loci`)
   uint32_t desc;                // next RowDesc ordinal of this record's list
-  bool is_long, desc_ok;
-  uint32_t big_base, long_base;
+  int cls;                      // 0 mid, 1 big, 2 long (see TileParams::mid_words)
+  bool desc_ok;
 };
 
-__device__ __forceinline__ void queue_row_desc(const TileParams &p, bool is_long, uint32_t ord, uint32_t big_base, uint32_t long_base,
-                                               const RowDesc &rd) {
-  const unsigned long long slot = is_long ? p.row_desc_cap - 1ull - (long_base + ord) : (unsigned long long)big_base + ord;
+// entry `ord` of work list `cls`: mid rows from the front, big rows after ALL the mid rows of the sub-chunk (their
+// count is final once the tile spine kernel has run), long rows from the end
+__device__ __forceinline__ void queue_row_desc(const TileParams &p, int cls, uint32_t ord, const RowDesc &rd) {
+  const unsigned long long slot = cls == 2 ? p.row_desc_cap - 1ull - ord : (cls == 1 ? (unsigned long long)p.ctr->n_mid_rows + ord : ord);
   p.row_desc[slot] = rd;
+}
+__device__ __forceinline__ int row_class(const TileParams &p, uint32_t ev_count) {
+  if (p.long_words && ev_count > p.long_words) return 2;
+  return (p.mid_words && ev_count <= p.mid_words) ? 0 : 1;
 }
 
 // the names of a short record's row into the staged lists (main.go:617,639,653 strings.Join): one walk over the
@@ -526,7 +534,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
         rd.het_dst = dsts[0]; rd.hom_dst = dsts[1]; rd.miss_dst = dsts[2];
         rd.n_het = cnts[0]; rd.n_hom = cnts[1]; rd.n_miss = cnts[2];
         rd.row = (uint32_t)so.row;
-        queue_row_desc(p, so.is_long, so.desc, so.big_base, so.long_base, rd);
+        queue_row_desc(p, so.cls, so.desc, rd);
       }
       so.desc++;
     }
@@ -704,7 +712,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
     RecOut ro;
     ro.bytes = 0; ro.rows = 0; ro.loci = 0; ro.n_desc = 0; ro.first = ROW_NONE; ro.last = ROW_NONE; ro.failed = false;
     SlowOut so;
-    so.row = 0; so.loci_off = 0; so.desc = 0; so.is_long = false; so.desc_ok = false; so.big_base = 0; so.long_base = 0;
+    so.row = 0; so.loci_off = 0; so.desc = 0; so.cls = 1; so.desc_ok = false;
     const uint8_t *info_p = nullptr;
     uint32_t info_n = 0, info_off = 0, ev_count = 0;
     if (valid) {
@@ -715,14 +723,15 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
       tile_record<StageWriter>(p, li, rec, w, ro, sh, so, s_filt, s_filt_off, true, info_p, info_n);
       info_off = (uint32_t)(info_p - (p.in + rec.start));
     }
-    const bool is_long = p.long_words && ev_count > p.long_words;
+    const int cls = row_class(p, ev_count);
     if (ro.failed && has_samples) ro.n_desc = ro.rows;
     __syncwarp();  // every lane's staged bytes and row descriptors are in shared memory
 
     // ---- the tile's totals and its scratch block: 32 LaneRec | n_trows TRow | arena_used bytes ----
     const unsigned long long tot_b = warp_sum64(ro.bytes);
     const uint32_t tot_rows = __reduce_add_sync(FULL, ro.rows), tot_loci = __reduce_add_sync(FULL, ro.loci);
-    const uint32_t tot_big = __reduce_add_sync(FULL, is_long ? 0u : ro.n_desc), tot_long = __reduce_add_sync(FULL, is_long ? ro.n_desc : 0u);
+    const uint32_t tot_mid = __reduce_add_sync(FULL, cls == 0 ? ro.n_desc : 0u), tot_big = __reduce_add_sync(FULL, cls == 1 ? ro.n_desc : 0u),
+                   tot_long = __reduce_add_sync(FULL, cls == 2 ? ro.n_desc : 0u);
     uint32_t arena_used = s_cur[warp][0], n_trows = s_cur[warp][1];
     if (arena_used > TILE_ARENA) arena_used = TILE_ARENA;   // failed allocations moved the cursor past the end
     if (n_trows > TILE_ROWS) n_trows = TILE_ROWS;
@@ -735,7 +744,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
     if (lane == 0) {
       TileAgg ag;
       ag.bytes = tot_b; ag.scratch_off = soff; ag.rows = tot_rows; ag.loci = tot_loci; ag.n_big = tot_big; ag.n_long = tot_long;
-      ag.arena_used = arena_used; ag.n_trows = n_trows; ag.pad[0] = ag.pad[1] = 0;
+      ag.arena_used = arena_used; ag.n_trows = n_trows; ag.n_mid = tot_mid; ag.pad = 0;
       p.tile_agg[tile] = ag;
       if (!fits) p.ctr->scratch_overflow = 1;
     }
@@ -743,7 +752,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
       uint8_t *blk = p.scratch + soff;
       LaneRec lr;
       lr.bytes = ro.bytes; lr.rows = ro.rows; lr.loci = ro.loci; lr.n_desc = ro.n_desc;
-      lr.first = (uint16_t)ro.first; lr.flags = (uint16_t)((ro.failed ? 1u : 0u) | (is_long ? 2u : 0u));
+      lr.first = (uint16_t)ro.first; lr.flags = (uint16_t)((ro.failed ? 1u : 0u) | ((uint32_t)cls << 1));
       lr.info_off = info_off; lr.info_n = info_n;
       reinterpret_cast<LaneRec *>(blk)[lane] = lr;
       uint4 *dst = reinterpret_cast<uint4 *>(blk + TILE_BLOCK_HDR);
@@ -761,13 +770,9 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
 
 // ---- tile offsets: exclusive scan of the tile totals (five quantities) over the sub-chunk's tiles ------------
 constexpr int TSCAN_BLOCKS = 148, TSCAN_THREADS = 256;
-struct Tot5 {
-  unsigned long long bytes, loci, rows, big, lng;
-};
-__device__ __forceinline__ Tot5 tot5_of(const TileAgg &a) {
-  Tot5 t;
-  t.bytes = a.bytes; t.loci = a.loci; t.rows = a.rows; t.big = a.n_big; t.lng = a.n_long;
-  return t;
+constexpr int TQ = 6;  // quantities scanned: bytes, locus bytes, rows, mid / big / long queued rows
+__device__ __forceinline__ void tot_of(const TileAgg &a, unsigned long long v[TQ]) {
+  v[0] = a.bytes; v[1] = a.loci; v[2] = a.rows; v[3] = a.n_big; v[4] = a.n_long; v[5] = a.n_mid;
 }
 __device__ __forceinline__ void tscan_span(uint32_t n_tiles, uint32_t &lo, uint32_t &hi) {
   const uint32_t span = (n_tiles + TSCAN_BLOCKS - 1) / TSCAN_BLOCKS;
@@ -776,26 +781,28 @@ __device__ __forceinline__ void tscan_span(uint32_t n_tiles, uint32_t &lo, uint3
   hi = l + span > n_tiles ? n_tiles : (uint32_t)(l + span);
 }
 __global__ void __launch_bounds__(TSCAN_THREADS) bvcf_tile_reduce_kernel(const __grid_constant__ TileParams p) {
-  __shared__ unsigned long long s_w[5][TSCAN_THREADS / 32];
+  __shared__ unsigned long long s_w[TQ][TSCAN_THREADS / 32];
   if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const uint32_t n_tiles = (p.ctr->chunk_records + TILE_THREADS - 1) / TILE_THREADS;
   uint32_t lo, hi;
   tscan_span(n_tiles, lo, hi);
-  unsigned long long s[5] = {0, 0, 0, 0, 0};
+  unsigned long long s[TQ] = {0, 0, 0, 0, 0, 0};
   for (uint32_t t = lo + threadIdx.x; t < hi; t += TSCAN_THREADS) {
-    const Tot5 v = tot5_of(p.tile_agg[t]);
-    s[0] += v.bytes; s[1] += v.loci; s[2] += v.rows; s[3] += v.big; s[4] += v.lng;
+    unsigned long long v[TQ];
+    tot_of(p.tile_agg[t], v);
+#pragma unroll
+    for (int k = 0; k < TQ; k++) s[k] += v[k];
   }
 #pragma unroll
-  for (int k = 0; k < 5; k++) {
+  for (int k = 0; k < TQ; k++) {
     const unsigned long long w = warp_sum64(s[k]);
     if ((threadIdx.x & 31) == 0) s_w[k][threadIdx.x >> 5] = w;
   }
   __syncthreads();
-  if (threadIdx.x < 5) {
+  if (threadIdx.x < TQ) {
     unsigned long long t = 0;
     for (int i = 0; i < TSCAN_THREADS / 32; i++) t += s_w[threadIdx.x][i];
-    p.tile_partial[5 * blockIdx.x + threadIdx.x] = t;
+    p.tile_partial[TQ * blockIdx.x + threadIdx.x] = t;
   }
 }
 // one warp: exclusive scan of the TSCAN_BLOCKS span totals; advances the run's cursors, raises the capacity flags
@@ -803,15 +810,15 @@ __global__ void __launch_bounds__(32) bvcf_tile_spine_kernel(const __grid_consta
   RunCounters *c = p.ctr;
   if (c->ev_overflow | c->slot_overflow) return;
   const int lane = threadIdx.x;
-  unsigned long long run[5] = {0, 0, 0, 0, 0};
+  unsigned long long run[TQ] = {0, 0, 0, 0, 0, 0};
   for (int base = 0; base < TSCAN_BLOCKS; base += 32) {
     const int b = base + lane;
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-      const unsigned long long v = b < TSCAN_BLOCKS ? p.tile_partial[5 * b + k] : 0ull;
+    for (int k = 0; k < TQ; k++) {
+      const unsigned long long v = b < TSCAN_BLOCKS ? p.tile_partial[TQ * b + k] : 0ull;
       unsigned long long tot;
       const unsigned long long inc = warp_scan64(v, tot, lane);
-      if (b < TSCAN_BLOCKS) p.tile_partial[5 * b + k] = run[k] + inc - v;
+      if (b < TSCAN_BLOCKS) p.tile_partial[TQ * b + k] = run[k] + inc - v;
       run[k] += tot;
     }
   }
@@ -821,38 +828,37 @@ __global__ void __launch_bounds__(32) bvcf_tile_spine_kernel(const __grid_consta
     c->row_cursor = c->chunk_row_base + run[2];
     c->n_big_rows = (unsigned int)run[3];
     c->n_long_rows = (unsigned int)run[4];
+    c->n_mid_rows = (unsigned int)run[5];
     if (c->out_cursor > p.out_cap) c->out_overflow = 1;
-    if (run[3] + run[4] > p.row_desc_cap) c->row_overflow = 1;
+    if (run[3] + run[4] + run[5] > p.row_desc_cap) c->row_overflow = 1;
   }
 }
 __global__ void __launch_bounds__(TSCAN_THREADS) bvcf_tile_offsets_kernel(const __grid_constant__ TileParams p) {
-  __shared__ unsigned long long s_w[5][TSCAN_THREADS / 32];
+  __shared__ unsigned long long s_w[TQ][TSCAN_THREADS / 32];
   if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
   const uint32_t n_tiles = (p.ctr->chunk_records + TILE_THREADS - 1) / TILE_THREADS;
   uint32_t lo, hi;
   tscan_span(n_tiles, lo, hi);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long run[5];
+  unsigned long long run[TQ];
 #pragma unroll
-  for (int k = 0; k < 5; k++) run[k] = p.tile_partial[5 * blockIdx.x + k];
+  for (int k = 0; k < TQ; k++) run[k] = p.tile_partial[TQ * blockIdx.x + k];
   for (uint32_t base = lo; base < hi; base += TSCAN_THREADS) {
     const uint32_t t = base + threadIdx.x;
-    Tot5 v;
-    v.bytes = v.loci = v.rows = v.big = v.lng = 0;
-    if (t < hi) v = tot5_of(p.tile_agg[t]);
-    const unsigned long long in[5] = {v.bytes, v.loci, v.rows, v.big, v.lng};
-    unsigned long long inc[5], wt[5];
+    unsigned long long in[TQ] = {0, 0, 0, 0, 0, 0};
+    if (t < hi) tot_of(p.tile_agg[t], in);
+    unsigned long long inc[TQ], wt[TQ];
 #pragma unroll
-    for (int k = 0; k < 5; k++) inc[k] = warp_scan64(in[k], wt[k], lane);
+    for (int k = 0; k < TQ; k++) inc[k] = warp_scan64(in[k], wt[k], lane);
     __syncthreads();
     if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < 5; k++) s_w[k][warp] = wt[k];
+      for (int k = 0; k < TQ; k++) s_w[k][warp] = wt[k];
     }
     __syncthreads();
-    unsigned long long ex[5];
+    unsigned long long ex[TQ];
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < TQ; k++) {
       unsigned long long off = 0, tot = 0;
 #pragma unroll
       for (int i = 0; i < TSCAN_THREADS / 32; i++) {
@@ -865,7 +871,8 @@ __global__ void __launch_bounds__(TSCAN_THREADS) bvcf_tile_offsets_kernel(const 
     }
     if (t < hi) {
       TileBase b;
-      b.bytes = ex[0]; b.loci = ex[1]; b.rows = (uint32_t)ex[2]; b.n_big = (uint32_t)ex[3]; b.n_long = (uint32_t)ex[4]; b.pad = 0;
+      b.bytes = ex[0]; b.loci = ex[1]; b.rows = (uint32_t)ex[2]; b.n_big = (uint32_t)ex[3]; b.n_long = (uint32_t)ex[4];
+      b.n_mid = (uint32_t)ex[5];
       p.tile_base[t] = b;
     }
   }
@@ -924,11 +931,13 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
     const uint8_t *rows_g = blk + TILE_BLOCK_HDR;
     const uint8_t *arena_g = rows_g + (size_t)ag.n_trows * sizeof(TRow);
     const uint32_t li = tile * TILE_THREADS + lane;
-    const bool failed = lr.flags & 1u, is_long = (lr.flags & 2u) != 0;
+    const bool failed = lr.flags & 1u;
+    const int cls = (int)((lr.flags >> 1) & 3u);
     unsigned long long tot;
     const unsigned long long in_b = warp_scan64(lr.bytes, tot, lane);
     const unsigned long long in_rl = warp_scan64((unsigned long long)lr.rows | ((unsigned long long)lr.loci << 32), tot, lane);
-    const unsigned long long in_d = warp_scan64(is_long ? ((unsigned long long)lr.n_desc << 32) : (unsigned long long)lr.n_desc, tot, lane);
+    const unsigned long long in_d = warp_scan64(cls == 1 ? ((unsigned long long)lr.n_desc << 32) : (cls == 0 ? (unsigned long long)lr.n_desc : 0ull), tot, lane);
+    const unsigned long long in_l = warp_scan64(cls == 2 ? (unsigned long long)lr.n_desc : 0ull, tot, lane);
     if (PREFETCH && more) {  // the next tile's block into L2
       const uint8_t *nb = p.scratch + ag_next.scratch_off;
       const uint32_t nbytes = TILE_BLOCK_HDR + ag_next.n_trows * (uint32_t)sizeof(TRow) + ag_next.arena_used;
@@ -961,7 +970,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
       unsigned long long off = out_base + tb.bytes + (in_b - lr.bytes);           // first output byte of this record
       unsigned long long r = (unsigned long long)tb.rows + ((uint32_t)in_rl - lr.rows);  // its first row within the sub-chunk
       unsigned long long lo = loci0 + tb.loci + ((uint32_t)(in_rl >> 32) - lr.loci);
-      uint32_t d_ord = is_long ? tb.n_long + ((uint32_t)(in_d >> 32) - lr.n_desc) : tb.n_big + ((uint32_t)in_d - lr.n_desc);
+      uint32_t d_ord = cls == 2 ? tb.n_long + ((uint32_t)in_l - lr.n_desc)
+                                : (cls == 1 ? tb.n_big + ((uint32_t)(in_d >> 32) - lr.n_desc) : tb.n_mid + ((uint32_t)in_d - lr.n_desc));
       if (!failed) {
         const uint8_t *line = nullptr;
         for (uint32_t ri = lr.first; ri != ROW_NONE;) {
@@ -1006,7 +1016,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
             rd.het_dst = dsts[0]; rd.hom_dst = dsts[1]; rd.miss_dst = dsts[2];
             rd.n_het = cnt[0]; rd.n_hom = cnt[1]; rd.n_miss = cnt[2];
             rd.row = (uint32_t)r;
-            queue_row_desc(p, is_long, d_ord, 0u, 0u, rd);
+            queue_row_desc(p, cls, d_ord, rd);
             d_ord++;
           }
           off += row_bytes; r++; lo += t.loc_len;
@@ -1017,7 +1027,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
         const uint32_t k = atomicAdd(&p.ctr->n_slow, 1u);
         if (k < p.slow_cap) {
           SlowRec sr;
-          sr.out_off = off; sr.loci_off = lo; sr.li = li; sr.row = (uint32_t)r; sr.desc = d_ord; sr.flags = 1u | (is_long ? 2u : 0u);
+          sr.out_off = off; sr.loci_off = lo; sr.li = li; sr.row = (uint32_t)r; sr.desc = d_ord; sr.flags = 1u | ((uint32_t)cls << 1);
           p.slow[k] = sr;
         }
       }
@@ -1047,8 +1057,7 @@ __global__ void __launch_bounds__(64) bvcf_slow_rows_kernel(const __grid_constan
     GlobalWriter gw;
     gw.g = p.out + sr.out_off; gw.on = true;
     SlowOut so;
-    so.row = sr.row; so.loci_off = sr.loci_off; so.desc = sr.desc; so.is_long = (sr.flags & 2u) != 0; so.desc_ok = true;
-    so.big_base = 0; so.long_base = 0;
+    so.row = sr.row; so.loci_off = sr.loci_off; so.desc = sr.desc; so.cls = (int)((sr.flags >> 1) & 3u); so.desc_ok = true;
     RecOut ro;
     ro.bytes = 0; ro.rows = 0; ro.loci = 0; ro.n_desc = 0; ro.first = ROW_NONE; ro.last = ROW_NONE; ro.failed = true;
     const uint8_t *info_p;
