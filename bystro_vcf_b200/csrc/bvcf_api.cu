@@ -294,8 +294,11 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     tp.row_desc = (RowDesc *)sc.row_desc.p; tp.row_desc_cap = dc.n_samples > 0 ? sc.row_cap : 0;
     tp.long_words = vec ? 8192u : 0u;  // rows beyond 4,096 quads: a CTA per row
     {
-      static const int mid_q = getenv("BVCF_MID_QUADS") ? atoi(getenv("BVCF_MID_QUADS")) : 64;  // experiments
-      tp.mid_words = (dc.want_tsv && dc.n_samples > 0) ? 2u * (uint32_t)std::max(mid_q, 0) : 0u;  // rows up to 64 quads: a lane per row
+      // rows of up to 16 quads: a lane per row.  Measured on 600,000 chr1-shape variants (names stage): no mid class
+      // 0.349 ms, 16 quads 0.345, 32 quads 0.359, 64 quads 0.408, 128 quads 0.49 -- a lane's own event list and its
+      // scattered 8-byte stores cost more than the idle lanes of a warp-per-row sweep once rows hold a few dozen names
+      static const int mid_q = getenv("BVCF_MID_QUADS") ? atoi(getenv("BVCF_MID_QUADS")) : 16;  // experiments
+      tp.mid_words = (dc.want_tsv && dc.n_samples > 0) ? 2u * (uint32_t)std::max(mid_q, 0) : 0u;
       if (!vec) tp.mid_words = 0;  // names_big_kernel serves every list
     }
     tp.dosage = d_dosage; tp.dosage_cap_rows = dosage_cap_rows;
