@@ -79,7 +79,8 @@ SYMBOLS = [
     "bvcf_create", "bvcf_destroy", "bvcf_header_line", "bvcf_set_header", "bvcf_host_alloc", "bvcf_host_free",
     "bvcf_submit", "bvcf_collect", "bvcf_release", "bvcf_resident_alloc", "bvcf_resident_upload",
     "bvcf_resident_run", "bvcf_resident_download", "bvcf_resident_peek", "bvcf_resident_line_index", "bvcf_strerror",
-    "bvcf_last_error", "bvcf_abi_version", "bvcf_launch_count",
+    "bvcf_last_error", "bvcf_abi_version", "bvcf_launch_count", "bvcf_resident_run_at", "bvcf_resident_inflate_bgzf",
+    "bvcf_bgzf_text_bytes",
 ]
 
 _lib = None
@@ -121,6 +122,12 @@ def lib():
     L.bvcf_resident_upload.argtypes = [vp, sz, vp, sz]
     L.bvcf_resident_run.restype = C.c_int
     L.bvcf_resident_run.argtypes = [vp, sz, C.POINTER(CChunkStats), C.POINTER(CKernelTimes)]
+    L.bvcf_resident_run_at.restype = C.c_int
+    L.bvcf_resident_run_at.argtypes = [vp, sz, sz, C.POINTER(CChunkStats), C.POINTER(CKernelTimes)]
+    L.bvcf_resident_inflate_bgzf.restype = C.c_int
+    L.bvcf_resident_inflate_bgzf.argtypes = [vp, vp, sz, sz, C.POINTER(sz)]
+    L.bvcf_bgzf_text_bytes.restype = C.c_int
+    L.bvcf_bgzf_text_bytes.argtypes = [vp, sz, C.POINTER(u64), C.POINTER(u64)]
     L.bvcf_resident_download.restype = C.c_int
     L.bvcf_resident_download.argtypes = [vp, sz, vp, sz]
     L.bvcf_resident_peek.restype = C.c_int

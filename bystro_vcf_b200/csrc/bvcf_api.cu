@@ -25,6 +25,7 @@
 #include "bvcf_tile.cuh"
 #include "bvcf_names.cuh"
 #include "bvcf_scan.cuh"
+#include "bvcf_inflate.cuh"
 
 using namespace bvcf;
 
@@ -86,7 +87,8 @@ struct bvcf_ctx {
   DevBuf d_filt_blob, d_filt_off, d_names, d_name_off, d_name8, d_name16;
   std::vector<Slot> slots;
   // resident path
-  DevBuf r_in, r_out, r_dosage, r_loci, r_loci_off;
+  DevBuf r_in, r_out, r_dosage, r_loci, r_loci_off, r_comp, r_blocks;
+  uint32_t *r_d_bad = nullptr;
   size_t r_in_bytes = 0;
   Scratch r_sc;
   cudaStream_t r_stream = nullptr;
@@ -207,12 +209,14 @@ struct StageEvents {  // optional per-stage timing of one sub-chunk
 };
 
 // Enqueue the whole pipeline for data lines in [0, len) of d_in.  Never synchronises.
-int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t *d_in, uint64_t len, uint64_t buf_len,
+int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t *d_in, uint64_t begin, uint64_t len, uint64_t buf_len,
                      uint8_t *d_out, uint64_t out_cap, RunCounters *d_ctr, int8_t *d_dosage, uint64_t dosage_cap_rows,
                      uint8_t *d_loci, uint64_t loci_cap, unsigned long long *d_loci_off, uint32_t *d_diags,
                      std::vector<StageEvents> *timing) {
   const DevCfg &dc = ctx->dcfg;
-  const uint64_t total_ranges = (len + sc.range_bytes - 1) / sc.range_bytes;
+  // data lines live in [begin, len); ranges tile the region from begin rounded down to 512 bytes
+  const uint64_t a0 = begin & ~511ull;
+  const uint64_t total_ranges = (len - a0 + sc.range_bytes - 1) / sc.range_bytes;
   int smem = SCAN_WARPS * RING;
   if (const char *e = getenv("BVCF_SCAN_SMEM_KB")) smem = std::max(smem, atoi(e) * 1024);  // experiments: cap CTAs/SM
   cudaFuncSetAttribute(bvcf_scan_genotype_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -239,7 +243,7 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     }
     // 1. scan: index + genotype events
     ScanParams sp{};
-    sp.in = d_in; sp.begin = 0; sp.end = len; sp.buf_len = buf_len; sp.a0 = 0;
+    sp.in = d_in; sp.begin = begin; sp.end = len; sp.buf_len = buf_len; sp.a0 = a0;
     sp.range_bytes = sc.range_bytes; sp.r0 = (uint32_t)r0; sp.n_ranges = nr;
     sp.slots_per_range = sc.slots; sp.evcap_words = sc.evcap_words;
     sp.recs = (LineRec *)sc.recs.p; sp.range_nrec = (uint32_t *)sc.range_nrec.p;
@@ -430,7 +434,7 @@ int slot_enqueue(bvcf_ctx *ctx, Slot &s, bool upload) {
   if (upload) CK(cudaMemcpyAsync(s.d_in.p, s.h_src, len, cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemsetAsync((uint8_t *)s.d_in.p + len, '\n', buf_len - len, s.stream));
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(RunCounters), s.stream));
-  rc = enqueue_pipeline(ctx, s.sc, s.stream, (const uint8_t *)s.d_in.p, len, buf_len, (uint8_t *)s.d_out.p, s.d_out.cap,
+  rc = enqueue_pipeline(ctx, s.sc, s.stream, (const uint8_t *)s.d_in.p, 0, len, buf_len, (uint8_t *)s.d_out.p, s.d_out.cap,
                         s.d_ctr, (int8_t *)s.d_dosage.p, dos_rows, (uint8_t *)s.d_loci.p, s.d_loci.cap,
                         (unsigned long long *)s.d_loci_off.p, (uint32_t *)s.d_diags.p, nullptr);
   if (rc) return rc;
@@ -555,11 +559,12 @@ void bvcf_destroy(bvcf_ctx *ctx) {
     if (s.h_loci_off) cudaFreeHost(s.h_loci_off);
   }
   for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->d_name8, &ctx->d_name16, &ctx->r_in, &ctx->r_out,
-                    &ctx->r_dosage, &ctx->r_loci, &ctx->r_loci_off})
+                    &ctx->r_dosage, &ctx->r_loci, &ctx->r_loci_off, &ctx->r_comp, &ctx->r_blocks})
     dev_free(*b);
   scratch_free(ctx->r_sc);
   if (ctx->r_stream) cudaStreamDestroy(ctx->r_stream);
   if (ctx->r_d_ctr) cudaFree(ctx->r_d_ctr);
+  if (ctx->r_d_bad) cudaFree(ctx->r_d_bad);
   if (ctx->r_h_ctr) cudaFreeHost(ctx->r_h_ctr);
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
@@ -825,9 +830,13 @@ int bvcf_resident_upload(bvcf_ctx *ctx, size_t offset, const void *host, size_t 
 }
 
 int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_kernel_times *times) {
+  return bvcf_resident_run_at(ctx, 0, len, stats, times);
+}
+
+int bvcf_resident_run_at(bvcf_ctx *ctx, size_t begin, size_t len, bvcf_chunk_stats *stats, bvcf_kernel_times *times) {
   if (!ctx) return BVCF_E_ARG;
   if (!ctx->header_set) return BVCF_E_STATE;
-  if (len > ctx->r_in_bytes) return BVCF_E_ARG;
+  if (len > ctx->r_in_bytes || begin > len) return BVCF_E_ARG;
   cudaSetDevice(ctx->device);
   const DevCfg &dc = ctx->dcfg;
   uint32_t retries = 0;
@@ -835,7 +844,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
   std::vector<StageEvents> timing;
   for (;;) {
     int rc;
-    if ((rc = scratch_reserve(ctx, ctx->r_sc, len, ctx->cfg.resident_subchunk_bytes))) return rc;
+    if ((rc = scratch_reserve(ctx, ctx->r_sc, len - (begin & ~511ull), ctx->cfg.resident_subchunk_bytes))) return rc;
     // the bytes after `len` must not look like data: pad (idempotent)
     const uint64_t buf_len = std::min<uint64_t>((ctx->r_in.cap - IN_SLACK) / 1024 * 1024, round_up(len, 1024) + 2048);
     CK(cudaMemsetAsync(ctx->r_d_ctr, 0, sizeof(RunCounters), ctx->r_stream));
@@ -846,7 +855,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
       for (auto e : t.e) ctx->ev_pool.push_back(e);
     timing.clear();
     launches0 = ctx->launches;
-    rc = enqueue_pipeline(ctx, ctx->r_sc, ctx->r_stream, (const uint8_t *)ctx->r_in.p, len, buf_len,
+    rc = enqueue_pipeline(ctx, ctx->r_sc, ctx->r_stream, (const uint8_t *)ctx->r_in.p, begin, len, buf_len,
                           (uint8_t *)ctx->r_out.p, ctx->r_out.cap, ctx->r_d_ctr, (int8_t *)ctx->r_dosage.p, dos_rows,
                           (uint8_t *)ctx->r_loci.p, ctx->r_loci.cap, (unsigned long long *)ctx->r_loci_off.p, nullptr,
                           times ? &timing : nullptr);
@@ -892,7 +901,7 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
   ctx->r_last_len = len;
   if (stats) {
     stats->n_lines = c.n_lines; stats->n_records = c.n_records; stats->n_rows = c.row_cursor;
-    stats->in_bytes = len; stats->out_bytes = c.out_cursor; stats->retries = retries;
+    stats->in_bytes = len - begin; stats->out_bytes = c.out_cursor; stats->retries = retries;
   }
   if (times) {
     memset(times, 0, sizeof(*times));
@@ -911,6 +920,74 @@ int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_k
     for (auto &t : timing)
       for (auto e : t.e) ctx->ev_pool.push_back(e);
   }
+  return BVCF_OK;
+}
+
+// ---- bgzf input ------------------------------------------------------------------------------
+// walk the gzip members of a bgzf buffer (RFC 1952 header with the "BC" extra subfield of the SAM spec 4.1)
+static int bgzf_walk(const uint8_t *c, size_t n, std::vector<InflateBlock> *blocks, uint64_t *text_bytes) {
+  size_t p = 0;
+  uint64_t out = 0;
+  while (p < n) {
+    if (n - p < 18 || c[p] != 0x1f || c[p + 1] != 0x8b || c[p + 2] != 8 || !(c[p + 3] & 4)) return BVCF_E_ARG;
+    const size_t xlen = (size_t)c[p + 10] | ((size_t)c[p + 11] << 8);
+    if (n - p < 12 + xlen) return BVCF_E_ARG;
+    size_t bsize = 0;
+    for (size_t q = p + 12; q + 4 <= p + 12 + xlen;) {
+      const size_t slen = (size_t)c[q + 2] | ((size_t)c[q + 3] << 8);
+      if (c[q] == 'B' && c[q + 1] == 'C' && slen == 2 && q + 6 <= p + 12 + xlen) bsize = ((size_t)c[q + 4] | ((size_t)c[q + 5] << 8)) + 1;
+      q += 4 + slen;
+    }
+    if (bsize < 12 + xlen + 8 || n - p < bsize) return BVCF_E_ARG;  // not bgzf, or a truncated last block
+    const uint32_t isize = (uint32_t)c[p + bsize - 4] | ((uint32_t)c[p + bsize - 3] << 8) | ((uint32_t)c[p + bsize - 2] << 16) |
+                           ((uint32_t)c[p + bsize - 1] << 24);
+    if (isize && blocks) {
+      InflateBlock b;
+      b.in_off = p + 12 + xlen; b.in_len = (uint32_t)(bsize - 12 - xlen - 8); b.out_off = out; b.out_len = isize;
+      blocks->push_back(b);
+    }
+    out += isize;
+    p += bsize;
+  }
+  if (text_bytes) *text_bytes = out;
+  return BVCF_OK;
+}
+
+int bvcf_bgzf_text_bytes(const void *comp, size_t comp_len, uint64_t *text_bytes, uint64_t *n_blocks) {
+  if (!comp || !text_bytes) return BVCF_E_ARG;
+  std::vector<InflateBlock> blocks;
+  const int rc = bgzf_walk((const uint8_t *)comp, comp_len, &blocks, text_bytes);
+  if (n_blocks) *n_blocks = blocks.size();
+  return rc;
+}
+
+int bvcf_resident_inflate_bgzf(bvcf_ctx *ctx, const void *comp, size_t comp_len, size_t dst_offset, size_t *text_bytes) {
+  if (!ctx || !comp) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  std::vector<InflateBlock> blocks;
+  uint64_t total = 0;
+  int rc = bgzf_walk((const uint8_t *)comp, comp_len, &blocks, &total);
+  if (rc) return rc;
+  if (dst_offset + total > ctx->r_in_bytes) return BVCF_E_ARG;
+  if (text_bytes) *text_bytes = (size_t)total;
+  if (blocks.empty()) return BVCF_OK;
+  if (blocks.size() >= (1ull << 32)) return BVCF_E_TOO_LARGE;
+  for (auto &b : blocks) b.out_off += dst_offset;
+  if ((rc = dev_reserve(ctx, ctx->r_comp, comp_len + 16))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->r_blocks, blocks.size() * sizeof(InflateBlock)))) return rc;
+  if (!ctx->r_d_bad) CK(cudaMalloc(&ctx->r_d_bad, 4));
+  CK(cudaMemcpyAsync(ctx->r_comp.p, comp, comp_len, cudaMemcpyHostToDevice, ctx->r_stream));  // the compressed bytes cross PCIe
+  CK(cudaMemcpyAsync(ctx->r_blocks.p, blocks.data(), blocks.size() * sizeof(InflateBlock), cudaMemcpyHostToDevice, ctx->r_stream));
+  CK(cudaMemsetAsync(ctx->r_d_bad, 0, 4, ctx->r_stream));
+  InflateParams ip{};
+  ip.comp = (const uint8_t *)ctx->r_comp.p; ip.out = (uint8_t *)ctx->r_in.p; ip.blocks = (const InflateBlock *)ctx->r_blocks.p;
+  ip.n_blocks = (uint32_t)blocks.size(); ip.n_bad = ctx->r_d_bad;
+  bvcf_inflate_kernel<<<(ip.n_blocks + 63) / 64, 64, 0, ctx->r_stream>>>(ip);
+  ctx->launches++;
+  uint32_t bad = 0;
+  CK(cudaMemcpyAsync(&bad, ctx->r_d_bad, 4, cudaMemcpyDeviceToHost, ctx->r_stream));
+  CK(cudaStreamSynchronize(ctx->r_stream));
+  if (bad) { ctx->last_error = std::to_string(bad) + " bgzf block(s) did not inflate to their ISIZE"; return BVCF_E_ARG; }
   return BVCF_OK;
 }
 

@@ -296,9 +296,24 @@ class Transformer:
                 C.cast(C.c_char_p(data), C.c_void_p).value
         check(self._L.bvcf_resident_upload(self._ctx, offset, addr, n), self._ctx, "bvcf_resident_upload")
 
-    def resident_run(self, length: int, want_times: bool = True):
+    def resident_inflate_bgzf(self, comp, dst_offset: int = 0) -> int:
+        """bgzf blocks (bytes-like or (address, length), pinned for full PCIe speed) -> text in the resident input
+        region at dst_offset, inflated on the GPU.  Returns the number of text bytes."""
+        if isinstance(comp, tuple):
+            addr, n = comp
+        else:
+            n = len(comp)
+            comp = bytes(comp) if not isinstance(comp, bytes) else comp
+            self._keep_comp = comp
+            addr = C.cast(C.c_char_p(comp), C.c_void_p).value
+        out = C.c_size_t()
+        check(self._L.bvcf_resident_inflate_bgzf(self._ctx, addr, n, dst_offset, C.byref(out)), self._ctx,
+              "bvcf_resident_inflate_bgzf")
+        return out.value
+
+    def resident_run(self, length: int, want_times: bool = True, begin: int = 0):
         st, kt = CChunkStats(), CKernelTimes()
-        check(self._L.bvcf_resident_run(self._ctx, length, C.byref(st), C.byref(kt) if want_times else None), self._ctx,
+        check(self._L.bvcf_resident_run_at(self._ctx, begin, length, C.byref(st), C.byref(kt) if want_times else None), self._ctx,
               "bvcf_resident_run")
         stats = {k: getattr(st, k) for k, _ in CChunkStats._fields_}
         times = {k: getattr(kt, k) for k, _ in CKernelTimes._fields_}
@@ -433,6 +448,93 @@ def write_sample_list(config: Config, chrom_line: bytes, normalize: bool = True)
                 fh.write((s.replace(b".", b"_") if normalize else s) + b"\n")
 
 
+def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Optional[BinaryIO], batch_text: int = 512 << 20) -> dict:
+    """readVcf (main.go:241-396) for bgzf input: groups of whole blocks are uploaded COMPRESSED and inflated on the GPU
+    straight into the resident input region; the transform runs there; only rows come back.  Replaces the `pigz -d -c |`
+    in front of the reference (README.md:10).  Rows only: the dosage matrix and the diagnostics of skipped alleles are
+    not produced on this path yet."""
+    from . import bgzf
+
+    if config.dosageMatrixOutPath:
+        raise BvcfError("--dosageOutput with bgzf input is not supported: decompress first (bgzip -dc | ...)")
+    buf = bytearray(head)
+    eof = False
+
+    def fill(n: int):
+        nonlocal eof
+        while not eof and len(buf) < n:
+            more = reader.read(max(n - len(buf), 8 << 20))
+            if not more:
+                eof = True
+            else:
+                buf.extend(more)
+
+    # ---- preamble: inflate the first blocks on the host until the #CHROM line is in sight ----
+    want = 1 << 20
+    while True:
+        fill(want)
+        text0 = bgzf.inflate_host(buf, want * 4)
+        try:
+            width, chrom_line, data_off = parse_preamble(text0)
+            break
+        except NotAVcfError as e:
+            if (str(e) == "Not a VCF file" and re.search(rb"[\r\n]", text0)) or eof:
+                raise
+            want *= 4
+    totals = {"n_lines": 0, "n_records": 0, "n_rows": 0, "out_bytes": 0, "in_bytes": 0, "compressed_bytes": 0}
+    if not config.noOut:
+        write_sample_list(config, chrom_line, config.normalizeHeader)
+    max_line = 8 << 20  # room for the carried partial line
+    with Transformer(config, eol_width=width) as tr:
+        tr.set_header(chrom_line)
+        tr.resident_alloc(batch_text + max_line + (1 << 20), batch_text // 4 + (64 << 20))
+        carry = b""
+        begin = data_off  # the first group holds the meta lines and the header: they are skipped on the device
+        while True:
+            # ---- a group of whole blocks worth about batch_text bytes of text ----
+            p = text = 0
+            while text < batch_text:
+                fill(p + (1 << 16) + 18)
+                bs = bgzf.block_size(buf, p)
+                if bs == 0 or p + bs > len(buf):
+                    if not eof:
+                        fill(p + max(bs, 1 << 16) + 18)
+                        continue
+                    break
+                text += int.from_bytes(buf[p + bs - 4:p + bs], "little")
+                p += bs
+            if p == 0:
+                break
+            group = bytes(buf[:p])
+            del buf[:p]
+            if carry:
+                tr.resident_upload(0, carry)
+            n_text = tr.resident_inflate_bgzf(group, len(carry))
+            total = len(carry) + n_text
+            totals["compressed_bytes"] += len(group)
+            # ---- the longest newline-terminated prefix; what follows it is carried into the next group ----
+            tail_n = min(total - begin, max_line)
+            tail = tr.resident_peek(total - tail_n, tail_n) if tail_n > 0 else b""
+            k = tail.rfind(b"\n")
+            if k < 0:
+                if tail_n == total - begin:  # no complete line in this group at all
+                    carry = carry + tr.resident_peek(len(carry), n_text) if begin == 0 else tr.resident_peek(begin, total - begin)
+                    begin = 0
+                    continue
+                raise BvcfError("a single line exceeds %d bytes" % max_line)
+            end = total - tail_n + k + 1
+            stats, _ = tr.resident_run(end, want_times=False, begin=begin)
+            if writer is not None and not config.noOut and stats["out_bytes"]:
+                writer.write(tr.resident_download(0, stats["out_bytes"]))
+            for key in ("n_lines", "n_records", "n_rows", "out_bytes"):
+                totals[key] += stats[key]
+            totals["in_bytes"] += end - begin
+            carry = tail[k + 1:]
+            begin = 0
+        # an unterminated last line (carry) is dropped (main.go:354-357)
+    return totals
+
+
 def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], transformer: Optional[Transformer] = None,
              diag_sink=None) -> dict:
     """readVcf (main.go:241-396) on the GPU: header discovery on the host, every data line on the device.
@@ -442,6 +544,12 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
     diag_sink(text, line_no, alt_no, code) receives the reference's log.Printf line for every skipped allele."""
     chunk_bytes = max(int(config.chunkBytes), 1 << 16)
     head = reader.read(1 << 20)
+    from . import bgzf
+
+    if bgzf.is_bgzf(head):  # .vcf.gz: the compressed bytes go to the GPU, which inflates them (SURVEY 8f-3)
+        if transformer is not None:
+            raise BvcfError("read_vcf: pass no transformer for bgzf input")
+        return _read_vcf_bgzf(config, head, reader, writer)
     while True:  # make sure the whole preamble (meta lines + #CHROM line) is in `head`
         try:
             width, chrom_line, off = parse_preamble(head)

@@ -151,6 +151,18 @@ int bvcf_resident_upload(bvcf_ctx *ctx, size_t offset, const void *host, size_t 
 /* Run the whole pipeline over data lines in [0, len) of the resident region (must end with '\n').
  * No host<->device traffic except a few counters at the end. */
 int bvcf_resident_run(bvcf_ctx *ctx, size_t len, bvcf_chunk_stats *stats, bvcf_kernel_times *times);
+/* The same over data lines in [begin, len): what comes before `begin` (meta lines, the #CHROM line of a file that was
+ * inflated whole) is not looked at.  `begin` must be the first byte of a line. */
+int bvcf_resident_run_at(bvcf_ctx *ctx, size_t begin, size_t len, bvcf_chunk_stats *stats, bvcf_kernel_times *times);
+
+/* bgzf-compressed input (bgzip / htslib .vcf.gz; upstream of main.go:192 the reference pipes through `pigz -d -c`,
+ * README.md:10,46): only the COMPRESSED bytes cross PCIe, the DEFLATE blocks are inflated on the GPU (one thread per
+ * 64 KiB block) straight into the resident input region at `dst_offset`.  `comp` must hold whole bgzf blocks.
+ * text_bytes receives the uncompressed size.  BVCF_E_ARG: not bgzf, corrupt, or larger than the region. */
+int bvcf_resident_inflate_bgzf(bvcf_ctx *ctx, const void *comp, size_t comp_len, size_t dst_offset, size_t *text_bytes);
+/* Host only: the uncompressed size (sum of ISIZE) and block count of a bgzf buffer of whole blocks. */
+int bvcf_bgzf_text_bytes(const void *comp, size_t comp_len, uint64_t *text_bytes, uint64_t *n_blocks);
+
 /* Copy `len` output bytes starting at `offset` back to the host. */
 int bvcf_resident_download(bvcf_ctx *ctx, size_t offset, void *host, size_t len);
 /* Copy `len` bytes of the resident INPUT region back to the host (device-generated workloads). */

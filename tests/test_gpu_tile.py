@@ -137,3 +137,86 @@ def test_many_tiles_look_back(chr1_fixture):
         recs.append(["1", str(10 + i), ".", "A", "G", ".", "PASS", ".", "GT"] + gts)
     vcf = V._vcf(_hdr(n), recs)
     assert gpu_rows(vcf) == oracle_rows(vcf)
+
+
+# ---- bgzf input: DEFLATE inflated on the GPU -------------------------------------------------
+def _inflate_on_gpu(comp: bytes, n_text: int) -> bytes:
+    from bystro_vcf_b200 import Transformer
+
+    with Transformer(_cfg()) as tr:
+        tr.set_header(b"#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO")
+        tr.resident_alloc(max(n_text, 1), 4096)
+        got = tr.resident_inflate_bgzf(comp)
+        assert got == n_text
+        return tr.resident_peek(0, n_text) if n_text else b""
+
+
+@pytest.mark.parametrize("kind", ["dynamic", "fixed", "stored", "mixed-levels"])
+def test_gpu_inflate_block_types(kind):
+    """stored, fixed-Huffman and dynamic-Huffman DEFLATE blocks, matches at every distance / length class, literals of
+    all 256 byte values, blocks from 1 byte to the 65,280-byte bgzf maximum: byte-identical to zlib on the host"""
+    import zlib
+
+    from bystro_vcf_b200 import bgzf
+
+    rng = random.Random(29)
+    parts = [bytes(rng.randrange(256) for _ in range(70000)),                      # literals, all byte values
+             b"0|0\t" * 50000,                                                     # distance-4 matches of length 258
+             b"".join(b"chr%d\t%d\trs%d\tA\tG\t100\tPASS\tAC=%d;AF=0.%d\tGT\t" % (i % 22, 1000 + 7 * i, i, i % 9, i) +
+                      b"\t".join(rng.choice([b"0|0", b"0|0", b"0|0", b"0|1", b"1|1", b".|."]) for _ in range(300)) + b"\n"
+                      for i in range(400)),
+             bytes(rng.choice(b"ACGT") for _ in range(100000)),                    # four symbols: short codes
+             b"x", b""]
+    data = b"".join(parts)
+    if kind == "dynamic":
+        comp = bgzf.compress(data, level=6)
+    elif kind == "fixed":
+        comp = bgzf.compress(data, level=6, strategy=zlib.Z_FIXED)
+    elif kind == "stored":
+        comp = bgzf.compress(data, level=0)
+    else:
+        comp = b"".join(bgzf.compress(data[i:i + 100001], level=lv, block_text=bt, eof=False)
+                        for i, (lv, bt) in zip(range(0, len(data), 100001), [(1, 1), (9, 65280), (4, 777), (6, 65280), (2, 31000)] * 10)) + bgzf.EOF_BLOCK
+    import gzip
+
+    assert gzip.decompress(comp) == data
+    assert _inflate_on_gpu(comp, len(data)) == data
+
+
+def test_gpu_inflate_rejects_corrupt_blocks():
+    from bystro_vcf_b200 import BvcfError, Transformer, bgzf
+
+    comp = bytearray(bgzf.compress(b"0|0\t1|1\t" * 30000, eof=False))
+    comp[40] ^= 0x55  # inside the first block's DEFLATE payload
+    with Transformer(_cfg()) as tr:
+        tr.set_header(b"#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO")
+        tr.resident_alloc(1 << 20, 4096)
+        with pytest.raises(BvcfError):
+            tr.resident_inflate_bgzf(bytes(comp))
+        with pytest.raises(BvcfError):
+            tr.resident_inflate_bgzf(b"not bgzf at all, just text\n")
+
+
+def test_bgzf_vcf_matches_plain(chr1_fixture):
+    """a .vcf.gz (bgzf) through read_vcf: compressed bytes to the device, inflated there, rows identical to the plain path;
+    groups smaller than the file, so partial lines are carried from group to group"""
+    import io
+
+    from bystro_vcf_b200 import Config, bgzf, host, read_vcf
+
+    vcf = chr1_fixture[:60 << 20].rsplit(b"\n", 1)[0] + b"\nunterminated last line"
+    comp = bgzf.compress(vcf)
+    assert len(comp) < len(vcf) // 10
+    c = Config()
+    c.allowedFilters = {"PASS": True, ".": True}
+    c.keepID = c.keepInfo = True
+    plain = io.BytesIO()
+    st0 = read_vcf(c, io.BytesIO(vcf), plain)
+    for batch in (512 << 20, 7 << 20):
+        out = io.BytesIO()
+        st = host._read_vcf_bgzf(c, comp[:1 << 20], io.BytesIO(comp[1 << 20:]), out, batch_text=batch)
+        assert out.getvalue() == plain.getvalue()
+        assert st["n_rows"] == st0["n_rows"] and st["compressed_bytes"] <= len(comp)
+    out = io.BytesIO()
+    read_vcf(c, io.BytesIO(comp), out)  # auto-detected
+    assert out.getvalue() == plain.getvalue()
