@@ -294,6 +294,55 @@ def run_ours(args):
         parity["e2e_checked"] = bool(k == 0 or e2e_first[:k] == got_rows[:k])
         assert parity["e2e_checked"], "end-to-end rows differ from the device-resident rows"
 
+    # ---- the same end-to-end step with bgzf-COMPRESSED host buffers: only the compressed bytes cross
+    # PCIe, the GPU inflates them into the resident region, runs the transform there, rows come back.  Beside `e2e`,
+    # not instead of it: the north star's e2e is uncompressed input. ----
+    e2e_bgzf = None
+    if rank == 0 and world == 1 and not args.no_bgzf and n_samples > 0:
+        from bystro_vcf_b200 import bgzf
+
+        bz_bytes = int(min(e2e_bytes, args.bgzf_mb << 20))
+        nlb = np.flatnonzero(hview[max(0, bz_bytes - (8 << 20)):bz_bytes] == 10)
+        bz_bytes = max(0, bz_bytes - (8 << 20)) + int(nlb[-1]) + 1
+        text = hview[:bz_bytes].tobytes()
+        t0 = time.perf_counter()
+        comp = bgzf.compress(text, level=6)
+        t_comp = time.perf_counter() - t0
+        cp = C.c_void_p()
+        _lib.check(L.bvcf_host_alloc(C.byref(cp), len(comp)), None, "bvcf_host_alloc")
+        C.memmove(cp.value, comp, len(comp))
+        out_host = C.c_void_p()
+        _lib.check(L.bvcf_host_alloc(C.byref(out_host), int(bz_bytes * 0.2) + (16 << 20)), None, "bvcf_host_alloc")
+        bz_ms = inf_ms = 0.0
+        for it in range(args.warmup + args.steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            got_n = tr.resident_inflate_bgzf((cp.value, len(comp)))
+            t1 = time.perf_counter()
+            st_b, _ = tr.resident_run(got_n, want_times=False)
+            _lib.check(L.bvcf_resident_download(tr._ctx, 0, out_host, st_b["out_bytes"]), tr._ctx, "download")
+            t2 = time.perf_counter()
+            if it >= args.warmup:
+                bz_ms += (t2 - t0) * 1e3
+                inf_ms += (t1 - t0) * 1e3
+        assert got_n == bz_bytes
+        rows_b = C.string_at(out_host, min(st_b["out_bytes"], parity["bytes"])) if parity else b""
+        ok_b = (not parity) or rows_b == got_rows[:len(rows_b)]
+        e2e_bgzf = {"value": st_b["n_lines"] * args.steps / (bz_ms / 1e3), "unit": "variants/s",
+                    "h2d_bytes_per_step": len(comp), "d2h_bytes_per_step": st_b["out_bytes"], "text_bytes_per_step": bz_bytes,
+                    "variants_per_step": st_b["n_lines"], "compression_ratio": bz_bytes / len(comp),
+                    "inflate_gb_per_s": bz_bytes * args.steps / (inf_ms / 1e3) / 1e9,
+                    "text_gb_per_s": bz_bytes * args.steps / (bz_ms / 1e3) / 1e9, "parity_checked": bool(ok_b),
+                    "sample": "first %d variants, bgzf level 6 (%d blocks), pinned host memory; H2D of the compressed bytes + "
+                              "GPU inflate + transform + D2H of the rows, one group, no overlap between the stages"
+                              % (st_b["n_lines"], -(-bz_bytes // bgzf.MAX_TEXT)),
+                    "host_compress_s": t_comp}
+        assert ok_b, "rows from bgzf input differ"
+        L.bvcf_host_free(cp)
+        L.bvcf_host_free(out_host)
+        # the resident region was overwritten: put the workload back for the strong-scaling arm / later use
+        synth.device_lines(seed, n_samples, shape, first_line, n_lines, d_in, need, dev)
+
     # ---- CPU baseline sample (N=1 only), taken while the weak slice is still in host memory ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -399,6 +448,8 @@ def run_ours(args):
             "parity_checked": bool(parity and parity["checked"] and parity.get("e2e_checked", True)), "parity": parity,
             "clocks": clk.summary(),
         }
+        if e2e_bgzf is not None:
+            result["e2e_bgzf"] = e2e_bgzf
         if strong is not None:
             result["strong"] = strong
         if cpu_baseline is not None:
@@ -470,6 +521,8 @@ def main():
     ap.add_argument("--parity-lines", type=int, default=2000, help="lines of the timed output checked against the oracle")
     ap.add_argument("--chunk-mb", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bgzf", action="store_true", help="skip the bgzf-compressed end-to-end line")
+    ap.add_argument("--bgzf-mb", type=int, default=1024, help="text bytes of the bgzf end-to-end sample")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "ours" else args.warmup

@@ -982,7 +982,8 @@ int bvcf_resident_inflate_bgzf(bvcf_ctx *ctx, const void *comp, size_t comp_len,
   InflateParams ip{};
   ip.comp = (const uint8_t *)ctx->r_comp.p; ip.out = (uint8_t *)ctx->r_in.p; ip.blocks = (const InflateBlock *)ctx->r_blocks.p;
   ip.n_blocks = (uint32_t)blocks.size(); ip.n_bad = ctx->r_d_bad;
-  bvcf_inflate_kernel<<<(ip.n_blocks + 63) / 64, 64, 0, ctx->r_stream>>>(ip);
+  cudaFuncSetAttribute(bvcf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM);
+  bvcf_inflate_kernel<<<ip.n_blocks, 32, INF_SMEM, ctx->r_stream>>>(ip);
   ctx->launches++;
   uint32_t bad = 0;
   CK(cudaMemcpyAsync(&bad, ctx->r_d_bad, 4, cudaMemcpyDeviceToHost, ctx->r_stream));
