@@ -111,8 +111,10 @@ struct TileParams {
   DiagSink diag;
 };
 
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
+// staged bytes: no "memory" clobber on purpose -- the arena is only read back after a __syncwarp(), and with the
+// clobber every global byte load of a span() had to complete before the next one could even be issued
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v)); }
 // up to 7 bytes of v (little-endian) to g, widest naturally aligned pieces first where the address allows
 __device__ __forceinline__ void store_head(uint8_t *&g, unsigned long long &v, uint32_t &n, uint32_t &moved) {
   // bytes up to the next 8-byte boundary of g (at most n)
@@ -137,8 +139,10 @@ __device__ __forceinline__ unsigned long long ldg64_unaligned(const uint8_t *s) 
 // n bytes from global memory (a tile's scratch block, a span of the input line: both padded, so whole words may be
 // read) to global memory, any alignments: at most three narrow stores up to the first 8-byte boundary of the
 // destination, aligned 8-byte stores of funnel-shifted source words, at most three narrow stores at the end.
-__device__ __forceinline__ void copy_g2g(uint8_t *g, const uint8_t *s, uint32_t n) {
+__device__ __forceinline__ void copy_g2g(uint8_t *__restrict__ g_, const uint8_t *__restrict__ s_, uint32_t n) {
   if (n == 0) return;
+  uint8_t *g = g_;
+  const uint8_t *s = s_;
   if ((uintptr_t)g & 7u) {
     unsigned long long v = ldg64_unaligned(s);
     if (n < 8 && (((uintptr_t)g & 7u) + n) <= 8u) {  // the whole piece sits inside one 8-byte word of the destination
@@ -151,13 +155,24 @@ __device__ __forceinline__ void copy_g2g(uint8_t *g, const uint8_t *s, uint32_t 
   }
   if (n >= 8) {
     const uint32_t sh = (uint32_t)((uintptr_t)s & 3u) * 8u;
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
+    const uint32_t *__restrict__ wp = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
     uint32_t w0 = wp[0];
-    do {
+    // 32 bytes per round, all eight source words in flight before the first store (the source is an L2 round trip
+    // away: one word pair per round trip made this loop the copy-out kernel's whole run time)
+    while (n >= 32) {
+      const uint32_t w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4], w5 = wp[5], w6 = wp[6], w7 = wp[7], w8 = wp[8];
+      uint2 *gv = reinterpret_cast<uint2 *>(g);
+      gv[0] = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+      gv[1] = make_uint2(__funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+      gv[2] = make_uint2(__funnelshift_r(w4, w5, sh), __funnelshift_r(w5, w6, sh));
+      gv[3] = make_uint2(__funnelshift_r(w6, w7, sh), __funnelshift_r(w7, w8, sh));
+      w0 = w8; wp += 8; g += 32; s += 32; n -= 32;
+    }
+    while (n >= 8) {
       const uint32_t w1 = wp[1], w2 = wp[2];
       *reinterpret_cast<uint2 *>(g) = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
       w0 = w2; wp += 2; g += 8; s += 8; n -= 8;
-    } while (n >= 8);
+    }
   }
   if (n) store_tail(g, ldg64_unaligned(s), n);
 }
