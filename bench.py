@@ -288,6 +288,13 @@ def run_ours(args):
     for _ in range(n_up):
         tr.resident_upload(0, (host_ptr.value, e2e_bytes))
     pcie_gbs = n_up * e2e_bytes / (time.perf_counter() - tp0) / 1e9
+    # the same with every rank copying at once: what the host side (DRAM, root complexes) can feed N GPUs together
+    barrier()
+    tp0 = time.perf_counter()
+    for _ in range(n_up):
+        tr.resident_upload(0, (host_ptr.value, e2e_bytes))
+    barrier()
+    h2d_concurrent_gbs = n_up * e2e_bytes / (time.perf_counter() - tp0) / 1e9  # this rank's share; summed below
     e2e_ms, e2e_lines_per_step, e2e_out_per_step, e2e_dos_per_step, e2e_first = e2e_steps(host_ptr, cuts)
     if rank == 0 and parity is not None:  # the e2e path returns the same rows
         k = min(len(e2e_first), parity["bytes"])
@@ -298,7 +305,7 @@ def run_ours(args):
     # PCIe, the GPU inflates them into the resident region, runs the transform there, rows come back.  Beside `e2e`,
     # not instead of it: the north star's e2e is uncompressed input. ----
     e2e_bgzf = None
-    if rank == 0 and world == 1 and not args.no_bgzf and n_samples > 0:
+    if not args.no_bgzf and n_samples > 0:
         from bystro_vcf_b200 import bgzf
 
         bz_bytes = int(min(e2e_bytes, args.bgzf_mb << 20))
@@ -306,34 +313,44 @@ def run_ours(args):
         bz_bytes = max(0, bz_bytes - (8 << 20)) + int(nlb[-1]) + 1
         text = hview[:bz_bytes].tobytes()
         t0 = time.perf_counter()
-        comp = bgzf.compress(text, level=6)
+        comp = bgzf.compress(text, level=6, threads=max(1, (os.cpu_count() or 1) // world))
         t_comp = time.perf_counter() - t0
         cp = C.c_void_p()
         _lib.check(L.bvcf_host_alloc(C.byref(cp), len(comp)), None, "bvcf_host_alloc")
         C.memmove(cp.value, comp, len(comp))
         out_host = C.c_void_p()
         _lib.check(L.bvcf_host_alloc(C.byref(out_host), int(bz_bytes * 0.2) + (16 << 20)), None, "bvcf_host_alloc")
-        bz_ms = inf_ms = 0.0
+        inf_ms = 0.0
         for it in range(args.warmup + args.steps):
-            torch.cuda.synchronize()
+            if it == args.warmup:
+                barrier()
+                tb0 = time.perf_counter()
             t0 = time.perf_counter()
             got_n = tr.resident_inflate_bgzf((cp.value, len(comp)))
             t1 = time.perf_counter()
             st_b, _ = tr.resident_run(got_n, want_times=False)
             _lib.check(L.bvcf_resident_download(tr._ctx, 0, out_host, st_b["out_bytes"]), tr._ctx, "download")
-            t2 = time.perf_counter()
             if it >= args.warmup:
-                bz_ms += (t2 - t0) * 1e3
                 inf_ms += (t1 - t0) * 1e3
+        barrier()
+        bz_ms = (time.perf_counter() - tb0) * 1e3
         assert got_n == bz_bytes
         rows_b = C.string_at(out_host, min(st_b["out_bytes"], parity["bytes"])) if parity else b""
         ok_b = (not parity) or rows_b == got_rows[:len(rows_b)]
-        e2e_bgzf = {"value": st_b["n_lines"] * args.steps / (bz_ms / 1e3), "unit": "variants/s",
+        bz_lines_all = st_b["n_lines"]
+        if world > 1:
+            tt = torch.tensor([bz_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            bz_ms = float(tt.item())
+            tv = torch.tensor([float(st_b["n_lines"])], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tv, op=dist.ReduceOp.SUM)
+            bz_lines_all = float(tv.item())
+        e2e_bgzf = {"value": bz_lines_all * args.steps / (bz_ms / 1e3), "unit": "variants/s", "n_gpus": world,
                     "h2d_bytes_per_step": len(comp), "d2h_bytes_per_step": st_b["out_bytes"], "text_bytes_per_step": bz_bytes,
                     "variants_per_step": st_b["n_lines"], "compression_ratio": bz_bytes / len(comp),
                     "inflate_gb_per_s": bz_bytes * args.steps / (inf_ms / 1e3) / 1e9,
-                    "text_gb_per_s": bz_bytes * args.steps / (bz_ms / 1e3) / 1e9, "parity_checked": bool(ok_b),
-                    "sample": "first %d variants, bgzf level 6 (%d blocks), pinned host memory; H2D of the compressed bytes + "
+                    "text_gb_per_s": world * bz_bytes * args.steps / (bz_ms / 1e3) / 1e9, "parity_checked": bool(ok_b),
+                    "sample": "first %d variants of each rank's shard, bgzf level 6 (%d blocks), pinned host memory; H2D of the compressed bytes + "
                               "GPU inflate + transform + D2H of the rows, one group, no overlap between the stages"
                               % (st_b["n_lines"], -(-bz_bytes // bgzf.MAX_TEXT)),
                     "host_compress_s": t_comp}
@@ -391,10 +408,14 @@ def run_ours(args):
                   "note": "the same total work as the 1-GPU run split over %d GPUs; no collective (shards never interact)" % world}
 
     # ---- max over ranks ----
+    h2d_all = h2d_concurrent_gbs
     if world > 1:
         t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall_ms, e2e_ms = (float(x) for x in t.tolist())
+        t = torch.tensor([h2d_concurrent_gbs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_all = float(t.item())
 
     result = None
     if rank == 0:
@@ -441,6 +462,11 @@ def run_ours(args):
                     "d2h_bytes_per_step": e2e_out_per_step + e2e_dos_per_step, "variants_per_step": e2e_lines_per_step,
                     "input_gb_per_s": world * e2e_bytes * args.steps / (e2e_ms / 1e3) / 1e9,
                     "pcie_h2d_gbs_measured": pcie_gbs,
+                    "h2d_gbs_all_ranks_at_once": h2d_all,
+                    "frac_of_concurrent_h2d_bound": (world * e2e_bytes * args.steps / (e2e_ms / 1e3) / 1e9) / h2d_all,
+                    "host": {"cpus": len(os.sched_getaffinity(0)), "numa_nodes": len([d for d in os.listdir("/sys/devices/system/node")
+                                                                                       if d.startswith("node")])
+                             if os.path.isdir("/sys/devices/system/node") else None},
                     "frac_of_pcie_h2d_bound": (e2e_bytes * args.steps / (e2e_ms / 1e3) / 1e9) / pcie_gbs,
                     "sample": "first %d variants of each rank's shard, pinned host memory, %d MiB chunks, 3 slots"
                               % (e2e_lines_per_step, args.chunk_mb)},

@@ -93,7 +93,7 @@ def build_host(force: bool = False) -> str:
         else:
             extra = ["-DBVCF_NO_ARROW"]
         cmd = (["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", out, src] + objs +
-               ["-L", LIBDIR, "-lbvcf", "-Wl,-rpath,$ORIGIN/../lib"] + extra)
+               ["-L", LIBDIR, "-lbvcf", "-lz", "-Wl,-rpath,$ORIGIN/../lib"] + extra)
         print("[build]", " ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
     return out

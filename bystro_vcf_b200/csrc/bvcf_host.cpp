@@ -26,6 +26,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <zlib.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -256,6 +257,189 @@ struct Turnstile {
   void done() { std::lock_guard<std::mutex> l(m); next++; cv.notify_all(); }
 };
 
+// ---- bgzf input (.vcf.gz as bgzip / htslib write it): the compressed bytes go to the GPU, which inflates them ----
+// Replaces the `pigz -d -c in.vcf.gz |` in front of the reference (README.md:10,46).  Groups of whole blocks are
+// uploaded and inflated straight into the resident input region (bvcf_resident_inflate_bgzf), the transform runs
+// there, only rows come back.  One GPU, rows only (no --dosageOutput, no diagnostics on this path yet).
+bool looks_bgzf(const uint8_t *p, size_t n) {
+  return n >= 18 && p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 4) && p[12] == 'B' && p[13] == 'C';
+}
+size_t bgzf_block_size(const uint8_t *p, size_t n) {  // 0: header incomplete
+  if (n < 18) return 0;
+  const size_t xlen = (size_t)p[10] | ((size_t)p[11] << 8);
+  if (n < 12 + xlen) return 0;
+  for (size_t q = 12; q + 4 <= 12 + xlen;) {
+    const size_t slen = (size_t)p[q + 2] | ((size_t)p[q + 3] << 8);
+    if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2) return ((size_t)p[q + 4] | ((size_t)p[q + 5] << 8)) + 1;
+    q += 4 + slen;
+  }
+  fatal("gzip input without the bgzf BC subfield: decompress it first (gzip -dc | ...)");
+}
+// the first text bytes of a bgzf buffer, inflated on the host: only to read the VCF preamble
+std::string bgzf_inflate_host(const uint8_t *p, size_t n, size_t want) {
+  std::string out;
+  size_t off = 0;
+  while (off < n && out.size() < want) {
+    const size_t bs = bgzf_block_size(p + off, n - off);
+    if (!bs || off + bs > n) break;
+    const size_t xlen = (size_t)p[off + 10] | ((size_t)p[off + 11] << 8);
+    const uint32_t isize = (uint32_t)p[off + bs - 4] | ((uint32_t)p[off + bs - 3] << 8) | ((uint32_t)p[off + bs - 2] << 16) | ((uint32_t)p[off + bs - 1] << 24);
+    std::string text(isize, '\0');
+    z_stream z{};
+    if (inflateInit2(&z, -15) != Z_OK) fatal("zlib: inflateInit2 failed");
+    z.next_in = const_cast<Bytef *>(p + off + 12 + xlen); z.avail_in = (uInt)(bs - 12 - xlen - 8);
+    z.next_out = (Bytef *)text.data(); z.avail_out = isize;
+    const int zr = inflate(&z, Z_FINISH);
+    inflateEnd(&z);
+    if (zr != Z_STREAM_END && isize) fatal("corrupt bgzf block in the VCF preamble");
+    out += text;
+    off += bs;
+  }
+  return out;
+}
+
+int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len, std::vector<uint8_t> &head, int out_fd) {
+  if (!config.dosageMatrixOutPath.empty()) fatal("--dosageOutput with bgzf input is not supported: decompress first (bgzip -dc | ...)");
+  // compressed bytes: the mapping, or a growing buffer read from the pipe
+  std::vector<uint8_t> &buf = head;
+  size_t consumed = 0;  // bytes of the compressed stream already handed to the GPU
+  bool eof = map != nullptr;
+  auto avail = [&]() { return map ? map_len - consumed : buf.size() - consumed; };
+  auto at = [&](size_t off) { return map ? map + consumed + off : buf.data() + consumed + off; };
+  auto fill = [&](size_t want) {
+    while (!eof && avail() < want) {
+      const size_t old = buf.size();
+      buf.resize(old + (8u << 20));
+      const ssize_t r = read(in_fd, buf.data() + old, 8u << 20);
+      if (r < 0) { if (errno == EINTR) { buf.resize(old); continue; } fatal(std::string("read: ") + strerror(errno)); }
+      buf.resize(old + (size_t)r);
+      if (r == 0) eof = true;
+    }
+  };
+  // ---- preamble (main.go:250-294) from the first blocks ----
+  std::string chrom_line;
+  size_t data_off = 0;
+  int eol_width = 1;
+  for (size_t want = 1u << 20;; want *= 4) {
+    fill(want);
+    const std::string t = bgzf_inflate_host(at(0), avail(), want * 4);
+    const char *nl = (const char *)memchr(t.data(), '\n', t.size());
+    if (!nl) { if (eof) fatal("Not a VCF file"); continue; }
+    size_t first_end = nl - t.data();
+    if (first_end > 0 && t[first_end - 1] == '\r') { eol_width = 2; first_end--; }
+    if (!memmem(t.data(), first_end, "##fileformat=VCFv4", 18)) fatal("Not a VCF file");
+    bool found = false;
+    for (size_t q = (nl - t.data()) + 1; q < t.size();) {
+      const char *e = (const char *)memchr(t.data() + q, '\n', t.size() - q);
+      if (!e) break;
+      size_t cl = (e - t.data()) - q;
+      cl = cl + 1 >= (size_t)eol_width ? cl + 1 - eol_width : 0;
+      if (cl >= 6 && memcmp(t.data() + q, "#CHROM", 6) == 0 && (cl == 6 || t[q + 6] == '\t')) {
+        chrom_line.assign(t.data() + q, cl);
+        data_off = (e - t.data()) + 1;
+        found = true;
+        break;
+      }
+      q = (e - t.data()) + 1;
+    }
+    if (found) break;
+    if (eof) fatal("No header found");
+  }
+  if (!config.sampleListPath.empty() && !config.noOut) {
+    FILE *f = fopen(config.sampleListPath.c_str(), "w");
+    if (!f) fatal("Couldn't write sample list file");
+    int field = 0;
+    size_t s0 = 0;
+    for (size_t i = 0; i <= chrom_line.size(); i++)
+      if (i == chrom_line.size() || chrom_line[i] == '\t') {
+        if (field >= 9) { std::string nm = chrom_line.substr(s0, i - s0); for (auto &ch : nm) if (ch == '.') ch = '_'; fprintf(f, "%s\n", nm.c_str()); }
+        field++; s0 = i + 1;
+      }
+    fclose(f);
+  }
+  std::vector<const char *> allow_c, excl_c;
+  for (auto &s : config.allowed) allow_c.push_back(s.c_str());
+  for (auto &s : config.excluded) excl_c.push_back(s.c_str());
+  bvcf_config bc{};
+  bc.empty_field = config.emptyField.c_str(); bc.field_delim = config.fieldDelimiter.c_str();
+  bc.keep_id = config.keepID; bc.keep_info = config.keepInfo; bc.keep_pos = config.keepPos;
+  bc.want_tsv = !config.noOut; bc.want_dosage = 0;
+  bc.allow = allow_c.data(); bc.n_allow = config.allowAll ? -1 : (int)allow_c.size();
+  bc.exclude = excl_c.data(); bc.n_exclude = (int)excl_c.size();
+  bc.eol_width = eol_width; bc.normalize_dots = 1;
+  bvcf_ctx *ctx = nullptr;
+  int rc = bvcf_create(&ctx, config.devices.empty() ? 0 : config.devices[0], &bc);
+  if (rc) fatal(std::string("bvcf_create: ") + bvcf_strerror(rc) + " -- a CUDA device is required, there is no CPU fallback");
+  if ((rc = bvcf_set_header(ctx, chrom_line.data(), chrom_line.size()))) fatal(std::string("bvcf_set_header: ") + bvcf_strerror(rc));
+  const size_t batch_text = std::max<size_t>(config.chunkBytes * 8, 64u << 20), max_line = 8u << 20;
+  void *d_in, *d_out;
+  if ((rc = bvcf_resident_alloc(ctx, batch_text + max_line + (1u << 20), batch_text / 4 + (64u << 20), &d_in, &d_out)))
+    fatal(std::string("bvcf_resident_alloc: ") + bvcf_strerror(rc));
+  uint8_t *pin = nullptr, *out_host = nullptr;   // pinned: compressed group in, rows out
+  size_t pin_cap = 0, out_cap = 0;
+  std::vector<uint8_t> carry, tail;
+  size_t begin = data_off;
+  for (;;) {
+    // ---- a group of whole blocks worth about batch_text bytes of text ----
+    size_t p = 0, text = 0;
+    while (text < batch_text) {
+      fill(p + (1u << 16) + 18);
+      const size_t bs = bgzf_block_size(at(p), avail() - p);
+      if (!bs || p + bs > avail()) {
+        if (!eof) { fill(p + std::max<size_t>(bs, 1u << 16) + 18); continue; }
+        break;
+      }
+      const uint8_t *e = at(p + bs - 4);
+      text += (size_t)e[0] | ((size_t)e[1] << 8) | ((size_t)e[2] << 16) | ((size_t)e[3] << 24);
+      p += bs;
+    }
+    if (p == 0) break;
+    if (p > pin_cap) {
+      if (pin) bvcf_host_free(pin);
+      pin_cap = p + p / 4;
+      if (bvcf_host_alloc((void **)&pin, pin_cap)) fatal("bvcf_host_alloc failed");
+    }
+    memcpy(pin, at(0), p);
+    consumed += p;
+    if (!map && consumed > (64u << 20)) { buf.erase(buf.begin(), buf.begin() + consumed); consumed = 0; }
+    if (!carry.empty() && (rc = bvcf_resident_upload(ctx, 0, carry.data(), carry.size()))) fatal(std::string("upload: ") + bvcf_strerror(rc));
+    size_t n_text = 0;
+    if ((rc = bvcf_resident_inflate_bgzf(ctx, pin, p, carry.size(), &n_text)))
+      fatal(std::string("bgzf: ") + bvcf_strerror(rc) + " " + bvcf_last_error(ctx));
+    const size_t total = carry.size() + n_text;
+    // ---- the longest newline-terminated prefix; the rest is carried into the next group ----
+    const size_t tail_n = std::min(total - begin, max_line);
+    tail.resize(tail_n);
+    if (tail_n && (rc = bvcf_resident_peek(ctx, total - tail_n, tail.data(), tail_n))) fatal(std::string("peek: ") + bvcf_strerror(rc));
+    const uint8_t *last_nl = tail_n ? (const uint8_t *)memrchr(tail.data(), '\n', tail_n) : nullptr;
+    if (!last_nl) {
+      if (tail_n < total - begin) fatal("a single line exceeds 8 MiB");
+      carry.assign(tail.begin(), tail.end());  // no complete line yet: everything is carried
+      begin = 0;
+      continue;
+    }
+    const size_t end = total - tail_n + (size_t)(last_nl - tail.data()) + 1;
+    bvcf_chunk_stats st{};
+    if ((rc = bvcf_resident_run_at(ctx, begin, end, &st, nullptr))) fatal(std::string("bvcf_resident_run: ") + bvcf_strerror(rc) + " " + bvcf_last_error(ctx));
+    if (!config.noOut && st.out_bytes) {
+      if (st.out_bytes > out_cap) {
+        if (out_host) bvcf_host_free(out_host);
+        out_cap = st.out_bytes + st.out_bytes / 4;
+        if (bvcf_host_alloc((void **)&out_host, out_cap)) fatal("bvcf_host_alloc failed");
+      }
+      if ((rc = bvcf_resident_download(ctx, 0, out_host, st.out_bytes))) fatal(std::string("download: ") + bvcf_strerror(rc));
+      write_all(out_fd, out_host, st.out_bytes);
+    }
+    carry.assign(last_nl + 1, (const uint8_t *)tail.data() + tail_n);
+    begin = 0;
+  }
+  // an unterminated last line (the carry) is dropped (main.go:354-357)
+  if (pin) bvcf_host_free(pin);
+  if (out_host) bvcf_host_free(out_host);
+  bvcf_destroy(ctx);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -296,8 +480,30 @@ int main(int argc, char **argv) {
     }
   }
 
-  // ---- preamble (main.go:250-294): EOL, ##fileformat check, #CHROM line ----
   std::vector<uint8_t> head;  // pipe input: what has been read so far
+  {  // .vcf.gz (bgzf): another path altogether
+    bool bz = false;
+    if (map) bz = looks_bgzf(map, map_len);
+    else {
+      head.resize(1 << 16);
+      size_t got = 0;
+      while (got < 18) {
+        const ssize_t r = read(in_fd, head.data() + got, head.size() - got);
+        if (r < 0) { if (errno == EINTR) continue; fatal(std::string("read: ") + strerror(errno)); }
+        if (r == 0) break;
+        got += (size_t)r;
+      }
+      head.resize(got);
+      bz = looks_bgzf(head.data(), head.size());
+    }
+    if (bz) {
+      const int rc = run_bgzf(config, in_fd, map, map_len, head, out_fd);
+      if (map) munmap((void *)map, map_len);
+      if (out_fd != 1) close(out_fd);
+      return rc;
+    }
+  }
+  // ---- preamble (main.go:250-294): EOL, ##fileformat check, #CHROM line ----
   size_t data_off = 0;
   int eol_width = 1;
   std::string chrom_line;
@@ -316,6 +522,7 @@ int main(int argc, char **argv) {
       if (r == 0) eof = true;
       p = head.data(); n = head.size();
     }
+    if (n == 0 && eof) fatal("Not a VCF file");
     const uint8_t *nl = (const uint8_t *)memchr(p, '\n', n);
     if (!nl) { if (eof) fatal("Not a VCF file"); continue; }
     size_t first_end = nl - p;

@@ -215,3 +215,23 @@ def test_file_to_file_wall_clock(chr1_fixture, tmp_path):
         for p in (inp, outp):
             if os.path.exists(p):
                 os.remove(p)
+
+
+@pytest.mark.parametrize("how", ["cpp-file", "cpp-pipe", "python"])
+def test_cli_bgzf_input(chr1_fixture, tmp_path, how):
+    """`--in x.vcf.gz` / a bgzf pipe: the compressed bytes go to the GPU, rows equal the plain path's"""
+    from bystro_vcf_b200 import bgzf
+
+    vcf = chr1_fixture[:50 << 20].rsplit(b"\n", 1)[0] + b"\n"
+    comp = bgzf.compress(vcf)
+    flags = ["--keepId", "--keepInfo"]
+    plain, _ = _run([BIN] + flags, vcf)
+    if how == "cpp-file":
+        p = tmp_path / "in.vcf.gz"
+        p.write_bytes(comp)
+        got, _ = _run([BIN, "--in", str(p), "--chunkBytes", str(2 << 20)] + flags, b"")
+    elif how == "cpp-pipe":
+        got, _ = _run([BIN] + flags, comp)
+    else:
+        got, _ = _run([sys.executable, "-m", "bystro_vcf_b200"] + flags, comp)
+    assert got == plain
