@@ -229,6 +229,15 @@ __device__ __forceinline__ void w_dec(W &w, long long v) {  // strconv.Itoa
   }
 }
 
+// counts below 10,000 (ac, an of most cohorts) without the digit loop of itoa_pack
+template <class W>
+__device__ __forceinline__ void w_dec_small(W &w, uint32_t v) {
+  if (v >= 10000u) { w_dec(w, (long long)v); return; }
+  const uint32_t d3 = v / 1000u, r3 = v - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
+  const uint32_t txt = (0x30u + d3) | ((0x30u + d2) << 8) | ((0x30u + d1) << 16) | ((0x30u + d0) << 24);
+  const int len = v >= 1000u ? 4 : (v >= 100u ? 3 : (v >= 10u ? 2 : 1));
+  w.packed((unsigned long long)(txt >> (8 * (4 - len))), len);
+}
 // what one record contributes to its tile
 struct RecOut {
   unsigned long long bytes;   // TSV bytes of all its rows
@@ -468,8 +477,8 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
         }
         w.byte('\t');
       }
-      w_dec(w, gs.ac); w.byte('\t');
-      w_dec(w, gs.an); w.byte('\t');
+      w_dec_small(w, gs.ac); w.byte('\t');
+      w_dec_small(w, gs.an); w.byte('\t');
       if (gs.ac == 0) w.byte('0');
       else { int fl; const uint64_t ft = format_ratio_g3(gs.ac, gs.an, fl); w.packed(ft, fl); }
     }
@@ -620,7 +629,9 @@ __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, co
   g.s = 0; g.alt_idx = 0; g.mnp_i = -1; g.ta = alt; g.tn = 0; g.last = false;
   g.done = !(pass && ref_n > 0 && alt_n > 0);
   g.ipos = 0;
-  g.pos_ok = g.done ? false : atoi_go(lc.pos, lc.pos_n, g.ipos);
+  // strconv.Atoi(POS) is only ever consulted when REF is longer than one base (main.go:752,822): SNPs and plain
+  // insertions copy the POS text verbatim
+  g.pos_ok = (g.done || ref_n <= 1) ? false : atoi_go(lc.pos, lc.pos_n, g.ipos);
   const unsigned long long line_no = p.ctr->chunk_line_base + rec.ord;
   if (!g.done) gen_begin(g, lc, p.diag, line_no, diag);
   GtStats gs;
