@@ -99,8 +99,8 @@ class ClockSampler:
 
 def scan_traffic_ratio():
     """DRAM bytes (read+write) per algorithmic byte of the scan kernel, from the committed ncu --set full
-    capture (profiles/r01_scan_traffic.json); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r01_scan_traffic.json")
+    capture (profiles/r02_scan_traffic.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_scan_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
