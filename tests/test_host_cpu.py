@@ -142,3 +142,37 @@ def test_synth_shapes_through_the_oracle():
         body = synth.host_lines(7, ns, shape, 0, n)
         r = O.read_vcf(O.OracleConfig(**kw), synth.header(7, ns) + body, threads=4)
         assert r.n_lines == n and r.n_rows > n * 0.8
+
+
+def test_bgzf_helpers_round_trip():
+    """bystro_vcf_b200.bgzf (host side of the GPU inflate path): blocks gzip can read, header walking, preamble inflate"""
+    import gzip
+
+    from bystro_vcf_b200 import bgzf
+
+    data = b"##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n" + b"1\t5\t.\tA\tG\t.\tPASS\t.\n" * 20000
+    comp = bgzf.compress(data, level=6, block_text=5000)
+    assert gzip.decompress(comp) == data
+    assert bgzf.is_bgzf(comp) and not bgzf.is_bgzf(data)
+    p = n = 0
+    while p < len(comp):
+        bs = bgzf.block_size(comp, p)
+        assert bs > 0
+        p += bs
+        n += 1
+    assert p == len(comp) and n == -(-len(data) // 5000) + 1  # + the EOF block
+    assert bgzf.block_size(comp[:10], 0) == 0  # header not complete yet
+    assert bgzf.inflate_host(comp, 12000) == data[:15000]  # whole blocks until at least 12,000 bytes
+
+
+def test_read_vcf_multi_is_chunk_round_robin():
+    """shard.chunk_ranges cuts on newlines and covers the region; chunk k goes to device k mod N (pure host logic)"""
+    from bystro_vcf_b200.shard import chunk_ranges
+
+    data = b"".join(b"line%d\tx\n" % i for i in range(5000))
+    ch = chunk_ranges(data, 0, len(data), 700)
+    assert ch[0][0] == 0 and ch[-1][1] == len(data)
+    assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+    assert all(data[hi - 1:hi] == b"\n" and hi - lo <= 700 for lo, hi in ch)
+    one_long = b"x" * 5000 + b"\n" + b"y\n"
+    assert chunk_ranges(one_long, 0, len(one_long), 100)[0] == (0, 5001)  # a line longer than a chunk stays whole
