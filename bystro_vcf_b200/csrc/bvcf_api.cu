@@ -26,6 +26,7 @@
 #include "bvcf_names.cuh"
 #include "bvcf_scan.cuh"
 #include "bvcf_inflate.cuh"
+#include "bvcf_deflate.cuh"
 
 using namespace bvcf;
 
@@ -87,7 +88,7 @@ struct bvcf_ctx {
   DevBuf d_filt_blob, d_filt_off, d_names, d_name_off, d_name8, d_name16;
   std::vector<Slot> slots;
   // resident path
-  DevBuf r_in, r_out, r_dosage, r_loci, r_loci_off, r_comp, r_blocks;
+  DevBuf r_in, r_out, r_dosage, r_loci, r_loci_off, r_comp, r_blocks, r_def_slots, r_def_sizes, r_def_offs, r_def_out;
   uint32_t *r_d_bad = nullptr;
   size_t r_in_bytes = 0;
   Scratch r_sc;
@@ -559,7 +560,8 @@ void bvcf_destroy(bvcf_ctx *ctx) {
     if (s.h_loci_off) cudaFreeHost(s.h_loci_off);
   }
   for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->d_name8, &ctx->d_name16, &ctx->r_in, &ctx->r_out,
-                    &ctx->r_dosage, &ctx->r_loci, &ctx->r_loci_off, &ctx->r_comp, &ctx->r_blocks})
+                    &ctx->r_dosage, &ctx->r_loci, &ctx->r_loci_off, &ctx->r_comp, &ctx->r_blocks, &ctx->r_def_slots,
+                    &ctx->r_def_sizes, &ctx->r_def_offs, &ctx->r_def_out})
     dev_free(*b);
   scratch_free(ctx->r_sc);
   if (ctx->r_stream) cudaStreamDestroy(ctx->r_stream);
@@ -989,6 +991,54 @@ int bvcf_resident_inflate_bgzf(bvcf_ctx *ctx, const void *comp, size_t comp_len,
   CK(cudaMemcpyAsync(&bad, ctx->r_d_bad, 4, cudaMemcpyDeviceToHost, ctx->r_stream));
   CK(cudaStreamSynchronize(ctx->r_stream));
   if (bad) { ctx->last_error = std::to_string(bad) + " bgzf block(s) did not inflate to their ISIZE"; return BVCF_E_ARG; }
+  return BVCF_OK;
+}
+
+// ---- bgzf output -----------------------------------------------------------------------------
+int bvcf_resident_download_bgzf(bvcf_ctx *ctx, size_t offset, size_t len, void *host, size_t host_cap, size_t *comp_len) {
+  if (!ctx || !host || !comp_len) return BVCF_E_ARG;
+  if (offset + len > ctx->r_out.cap) return BVCF_E_ARG;
+  *comp_len = 0;
+  if (len == 0) return BVCF_OK;
+  cudaSetDevice(ctx->device);
+  const uint64_t nb64 = (len + DEF_SLICE - 1) / DEF_SLICE;
+  if (nb64 >= (1ull << 31)) return BVCF_E_TOO_LARGE;
+  const uint32_t nb = (uint32_t)nb64;
+  int rc;
+  if ((rc = dev_reserve(ctx, ctx->r_def_slots, (size_t)nb * DEF_SLOT))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->r_def_sizes, (size_t)nb * 4))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->r_def_offs, (size_t)nb * 8))) return rc;
+  cudaStream_t st = ctx->r_stream;
+  CK(cudaMemsetAsync(ctx->r_def_slots.p, 0, (size_t)nb * DEF_SLOT, st));  // the token bits are OR-ed in
+  DeflateParams dp{};
+  dp.text = (const uint8_t *)ctx->r_out.p + offset; dp.text_len = len; dp.slots = (uint8_t *)ctx->r_def_slots.p;
+  dp.sizes = (uint32_t *)ctx->r_def_sizes.p; dp.n_blocks = nb;
+  bvcf_deflate_kernel<<<nb, 32, 0, st>>>(dp);
+  std::vector<uint32_t> sizes(nb);
+  CK(cudaMemcpyAsync(sizes.data(), dp.sizes, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<unsigned long long> offs(nb);
+  unsigned long long total = 0;
+  for (uint32_t i = 0; i < nb; i++) { offs[i] = total; total += sizes[i]; }
+  if (total > host_cap) { *comp_len = (size_t)total; return BVCF_E_TOO_LARGE; }  // comp_len says how much room it takes
+  if ((rc = dev_reserve(ctx, ctx->r_def_out, (size_t)total + 16))) return rc;
+  CK(cudaMemcpyAsync(ctx->r_def_offs.p, offs.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+  DeflatePackParams pp{};
+  pp.slots = dp.slots; pp.sizes = dp.sizes; pp.offs = (const unsigned long long *)ctx->r_def_offs.p;
+  pp.out = (uint8_t *)ctx->r_def_out.p; pp.n_blocks = nb;
+  bvcf_deflate_pack_kernel<<<nb, 128, 0, st>>>(pp);
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(host, ctx->r_def_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));  // the compressed rows cross PCIe
+  CK(cudaStreamSynchronize(st));
+  *comp_len = (size_t)total;
+  return BVCF_OK;
+}
+
+int bvcf_resident_write_output(bvcf_ctx *ctx, size_t offset, const void *host, size_t len) {
+  if (!ctx || !host) return BVCF_E_ARG;
+  if (offset + len > ctx->r_out.cap) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaMemcpy((uint8_t *)ctx->r_out.p + offset, host, len, cudaMemcpyHostToDevice));
   return BVCF_OK;
 }
 

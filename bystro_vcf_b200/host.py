@@ -319,6 +319,19 @@ class Transformer:
         times = {k: getattr(kt, k) for k, _ in CKernelTimes._fields_}
         return stats, times
 
+    def resident_write_output(self, offset: int, data: bytes) -> None:
+        check(self._L.bvcf_resident_write_output(self._ctx, offset, data, len(data)), self._ctx, "bvcf_resident_write_output")
+
+    def resident_download_bgzf(self, offset: int, length: int) -> bytes:
+        """rows [offset, offset + length) of the resident output, deflated on the GPU: whole bgzf blocks (append
+        bgzf.EOF_BLOCK at the end of a file)"""
+        cap = length + length // 4 + (1 << 16)
+        buf = C.create_string_buffer(cap)
+        n = C.c_size_t()
+        check(self._L.bvcf_resident_download_bgzf(self._ctx, offset, length, buf, cap, C.byref(n)), self._ctx,
+              "bvcf_resident_download_bgzf")
+        return buf.raw[:n.value]
+
     def resident_download(self, offset: int, length: int) -> bytes:
         buf = C.create_string_buffer(max(length, 1))
         check(self._L.bvcf_resident_download(self._ctx, offset, buf, length), self._ctx, "bvcf_resident_download")

@@ -163,6 +163,17 @@ int bvcf_resident_inflate_bgzf(bvcf_ctx *ctx, const void *comp, size_t comp_len,
 /* Host only: the uncompressed size (sum of ISIZE) and block count of a bgzf buffer of whole blocks. */
 int bvcf_bgzf_text_bytes(const void *comp, size_t comp_len, uint64_t *text_bytes, uint64_t *n_blocks);
 
+/* bgzf-compressed output (downstream of the reference stands `| pigz -c`, README.md:10,71): the rows in
+ * [offset, offset + len) of the resident output region are deflated on the GPU (48 KiB slices, LZ77 + fixed Huffman
+ * codes, CRC-32) and only the compressed blocks cross PCIe.  The bytes are whole bgzf blocks: concatenate the
+ * pieces of a file and end it with the 28-byte bgzf EOF block.  BVCF_E_TOO_LARGE: host_cap is too small, *comp_len
+ * says what is needed. */
+int bvcf_resident_download_bgzf(bvcf_ctx *ctx, size_t offset, size_t len, void *host, size_t host_cap, size_t *comp_len);
+
+/* Put host bytes into the resident output region (a host that wants its own text -- the TSV header line, say --
+ * to leave through bvcf_resident_download_bgzf with the rows). */
+int bvcf_resident_write_output(bvcf_ctx *ctx, size_t offset, const void *host, size_t len);
+
 /* Copy `len` output bytes starting at `offset` back to the host. */
 int bvcf_resident_download(bvcf_ctx *ctx, size_t offset, void *host, size_t len);
 /* Copy `len` bytes of the resident INPUT region back to the host (device-generated workloads). */

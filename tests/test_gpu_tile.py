@@ -220,3 +220,54 @@ def test_bgzf_vcf_matches_plain(chr1_fixture):
     out = io.BytesIO()
     read_vcf(c, io.BytesIO(comp), out)  # auto-detected
     assert out.getvalue() == plain.getvalue()
+
+
+# ---- bgzf output: rows deflated on the GPU ------------------------------------------------------
+def test_gpu_deflate_output_is_valid_bgzf(chr1_fixture):
+    """The rows of a resident run leave as bgzf blocks made on the GPU (LZ77 + fixed Huffman + CRC-32): gzip on the host
+    -- which verifies every member's CRC-32 and ISIZE -- gives the uncompressed rows back, block headers are bgzf's."""
+    import gzip
+
+    from bystro_vcf_b200 import Config, Transformer, bgzf, parse_preamble
+
+    vcf = chr1_fixture[:40 << 20].rsplit(b"\n", 1)[0] + b"\n"
+    w, chrom, off = parse_preamble(vcf)
+    body = vcf[off:]
+    c = Config()
+    c.allowedFilters = {"PASS": True, ".": True}
+    c.keepID = c.keepInfo = True
+    with Transformer(c, eol_width=w) as tr:
+        tr.set_header(chrom)
+        tr.resident_alloc(len(body), len(body) // 4 + (1 << 20))
+        tr.resident_upload(0, body)
+        stats, _ = tr.resident_run(len(body))
+        n = stats["out_bytes"]
+        rows = tr.resident_download(0, n)
+        comp = tr.resident_download_bgzf(0, n)
+        assert gzip.decompress(comp + bgzf.EOF_BLOCK) == rows
+        assert len(comp) < n * 0.6  # sample-name lists and repeated columns do compress
+        p = k = 0
+        while p < len(comp):  # whole bgzf blocks of at most 48 KiB of text
+            bs = bgzf.block_size(comp, p)
+            assert bs > 0 and int.from_bytes(comp[p + bs - 4:p + bs], "little") <= 49152
+            p += bs
+            k += 1
+        assert p == len(comp) and k == -(-n // 49152)
+        # odd sizes and offsets: one byte, a slice boundary +- 1, an unaligned start
+        for o, ln in ((0, 1), (3, 49151), (5, 49152), (7, 49153), (12345, 200001)):
+            assert gzip.decompress(tr.resident_download_bgzf(o, ln) + bgzf.EOF_BLOCK) == rows[o:o + ln]
+
+
+def test_gpu_deflate_incompressible_and_repetitive():
+    """random bytes (every literal, 9-bit codes: the block grows) and one byte repeated (distance-1 matches of 258)"""
+    import gzip
+
+    from bystro_vcf_b200 import Transformer, bgzf
+
+    rng = random.Random(41)
+    for data in (bytes(rng.randrange(256) for _ in range(120000)), b"A" * 150000, b"0|0\t1|1\t" * 20000 + b"\n"):
+        with Transformer(_cfg()) as tr:
+            tr.set_header(b"#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO")
+            tr.resident_alloc(1 << 20, len(data) + 4096)
+            tr.resident_write_output(0, data)
+            assert gzip.decompress(tr.resident_download_bgzf(0, len(data)) + bgzf.EOF_BLOCK) == data
