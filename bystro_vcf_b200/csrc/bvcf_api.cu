@@ -220,11 +220,8 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
   const uint64_t total_ranges = (len - a0 + sc.range_bytes - 1) / sc.range_bytes;
   int smem = SCAN_WARPS * RING;
   if (const char *e = getenv("BVCF_SCAN_SMEM_KB")) smem = std::max(smem, atoi(e) * 1024);  // experiments: cap CTAs/SM
-  static const bool scan_bulk = getenv("BVCF_SCAN_BULK") != nullptr;  // experiments: cp.async.bulk + mbarrier ring
-  smem += SCAN_WARPS * 32;  // the BULK variant's mbarriers live behind the rings
-  cudaFuncSetAttribute(bvcf_scan_genotype_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(bvcf_scan_genotype_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(bvcf_scan_genotype_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(bvcf_scan_genotype_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(bvcf_scan_genotype_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
   for (uint64_t r0 = 0; r0 < total_ranges; r0 += sc.n_ranges) {
@@ -255,10 +252,9 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
     sp.ctr = d_ctr; sp.H = dc.H; sp.eol_width = dc.eol_width;
     const unsigned grid = (nr + SCAN_WARPS - 1) / SCAN_WARPS;
     if (dc.n_samples > 0)
-      if (scan_bulk) bvcf_scan_genotype_kernel<true, true><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);
-      else bvcf_scan_genotype_kernel<true, false><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);
+      bvcf_scan_genotype_kernel<true><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);
     else
-      bvcf_scan_genotype_kernel<false, false><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);
+      bvcf_scan_genotype_kernel<false><<<grid, SCAN_WARPS * 32, smem, st>>>(sp);
     ctx->launches++;
     if (se) CK(cudaEventRecord(se->e[1], st));
     // 2. per-range counts -> bases

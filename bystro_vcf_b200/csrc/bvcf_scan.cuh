@@ -487,10 +487,7 @@ __device__ __forceinline__ void scan_window_general(const ScanParams &p, WarpSta
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-// BULK: the ring is filled by ONE lane with cp.async.bulk (the TMA bulk-copy engine; SASS UBLKCP) completing on an
-// mbarrier per ring slot, instead of 2 x 32 cp.async (LDGSTS) + commit / wait_group.  Measured side by side
-// (DESIGN.md 5): the experiment VERDICT r1 asked for.  The default stays LDGSTS.
-template <bool HAS_SAMPLES, bool BULK>
+template <bool HAS_SAMPLES>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(const ScanParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -524,51 +521,14 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
     const uint32_t seek_limit = (uint32_t)((rend - rstart + WIN - 1) / WIN);  // no owned line can start later
     const uint8_t *gsrc = p.in + rstart + lane * 16;
     uint32_t issue_off = 0;  // ring offset of the next pair of windows
-    // BULK: an mbarrier per ring slot (four 1 KiB pairs), behind the rings in shared memory; pair k uses slot k & 3 and
-    // completes that barrier's phase k >> 2
-    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(smem + SCAN_WARPS * RING) + warp * 32;
-    uint32_t pairs_issued = 0, pairs_landed = 0;
-    if (BULK) {
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_s + 8 * k));
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
-      }
-      __syncwarp();
-    }
     // one commit group per 1 KiB pair; the buffer carries 8 KiB of slack, so the prefetch needs no bounds test
     auto issue_pair = [&]() {
-      if (BULK) {
-        if (lane == 0) {
-          const uint32_t bar = bar_s + 8 * (pairs_issued & 3u);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2 * WIN) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(ring_base_s + issue_off),
-                       "l"(gsrc), "r"(2 * WIN), "r"(bar)
-                       : "memory");
-        }
-        pairs_issued++;
-      } else {
-        const uint32_t d = ring_lane_s + issue_off;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + WIN), "l"(gsrc + WIN));
-        asm volatile("cp.async.commit_group;\n" ::);
-      }
+      const uint32_t d = ring_lane_s + issue_off;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + WIN), "l"(gsrc + WIN));
+      asm volatile("cp.async.commit_group;\n" ::);
       gsrc += 2 * WIN;
       issue_off = (issue_off + 2 * WIN) & (RING - 1);
-    };
-    // pairs 0 .. k of this range have landed (LDGSTS: all but the PF_PAIRS - 1 youngest groups)
-    auto wait_landed = [&](uint32_t k) {
-      if (BULK) {
-        for (; pairs_landed <= k; pairs_landed++) {
-          const uint32_t bar = bar_s + 8 * (pairs_landed & 3u), parity = (pairs_landed >> 2) & 1u;
-          uint32_t ok;
-          do {
-            asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-          } while (!ok);
-        }
-      } else {
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(PF_PAIRS - 1));
-      }
     };
 #pragma unroll
     for (int k = 0; k < PF_PAIRS; k++) issue_pair();
@@ -581,7 +541,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
     bool fast = HAS_SAMPLES && st.mode == 1 && st.col >= 9 && (uint32_t)st.fsr < 4u;
     for (uint32_t it = 0; it + 2 < n_avail && !done; it += 2, stage_off = (stage_off + 2 * WIN) & (RING - 1)) {
       issue_pair();
-      wait_landed((it >> 1) + 1);  // windows it .. it+3 have landed
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(PF_PAIRS - 1));  // windows it .. it+3 have landed
       __syncwarp();
       int hint = 0;  // 1: window A was regular and is done, B is known not to be; 2: A is known not to be regular
       if (fast) {
@@ -608,7 +568,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
           if (!(it + 4 < n_avail)) break;  // the next pair would be the last the loop takes: leave it to the loop
           it += 2; stage_off = (stage_off + 2 * WIN) & (RING - 1);
           issue_pair();
-          wait_landed((it >> 1) + 1);
+          asm volatile("cp.async.wait_group %0;\n" ::"n"(PF_PAIRS - 1));
           __syncwarp();
         }
         if (allref) continue;
@@ -689,7 +649,6 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) bvcf_scan_genotype_kernel(con
       }
       __syncwarp();  // everyone is done with these stages before they are refilled
     }
-    if (BULK && pairs_issued) wait_landed(pairs_issued - 1);  // shared memory must outlive the copies still in flight
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
   if (lane == 0) {
