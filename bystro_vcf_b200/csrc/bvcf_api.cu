@@ -156,7 +156,11 @@ int scratch_reserve(bvcf_ctx *ctx, Scratch &sc, uint64_t total_bytes, uint64_t s
     const uint64_t min_r = round_up(5ull * (uint64_t)std::max(ctx->dcfg.n_samples, 0), 512);
     if (min_r > sc.range_bytes) sc.range_bytes = (uint32_t)std::min<uint64_t>(min_r, 64ull << 20);
   }
-  uint64_t sub = std::min<uint64_t>(round_up(total_bytes + 512, sc.range_bytes), round_up(sub_limit, sc.range_bytes));
+  // sub-chunks of equal size (63 GB under a 24 GiB limit: three of 19.6 GiB, not two of 24 and a short one: the last
+  // sub-chunk's kernels would run half empty)
+  const uint64_t whole = round_up(total_bytes + 512, sc.range_bytes);
+  const uint64_t n_sub = std::max<uint64_t>(1, (whole + sub_limit - 1) / std::max<uint64_t>(sub_limit, 1));
+  uint64_t sub = std::min<uint64_t>(whole, round_up((whole + n_sub - 1) / n_sub, sc.range_bytes));
   sc.sub_bytes = sub;
   sc.n_ranges = (uint32_t)(sub / sc.range_bytes);
   // a record needs at least H bytes (H - 1 tabs + the newline); with H < 16 the first guess is 16 and slot_overflow
@@ -499,7 +503,7 @@ int bvcf_create(bvcf_ctx **out, int cuda_device, const bvcf_config *cfg) {
   if (const char *e = getenv("BVCF_DIAG_CAP")) ctx->diag_cap = (uint32_t)std::max(1, atoi(e));  // tests: force the grow-and-retry path
   if (ctx->cfg.n_slots <= 0) ctx->cfg.n_slots = 3;
   if (ctx->cfg.max_chunk_bytes == 0) ctx->cfg.max_chunk_bytes = 256ull << 20;
-  if (ctx->cfg.resident_subchunk_bytes == 0) ctx->cfg.resident_subchunk_bytes = 16ull << 30;
+  if (ctx->cfg.resident_subchunk_bytes == 0) ctx->cfg.resident_subchunk_bytes = 24ull << 30;
   ctx->cfg.allow = nullptr; ctx->cfg.exclude = nullptr; ctx->cfg.empty_field = nullptr; ctx->cfg.field_delim = nullptr;
 
   auto fail = [&](int rc) { *out = ctx; bvcf_destroy(ctx); *out = nullptr; return rc; };

@@ -47,7 +47,7 @@ typedef struct {
   /* tuning; 0 = library default */
   int n_slots;                 /* host chunks in flight (streams), default 3 */
   size_t max_chunk_bytes;      /* largest host chunk bvcf_submit will be given, default 256 MiB */
-  size_t resident_subchunk_bytes; /* device-resident runs are cut into pieces of this size, default 16 GiB */
+  size_t resident_subchunk_bytes; /* device-resident runs are cut into equal pieces of at most this size, default 24 GiB */
 } bvcf_config;
 
 /* error codes */
