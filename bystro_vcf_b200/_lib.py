@@ -36,7 +36,7 @@ class CConfig(C.Structure):
 
 
 class CDiag(C.Structure):
-    _fields_ = [("line_no", C.c_uint64), ("alt_no", C.c_int32), ("code", C.c_int32)]
+    _fields_ = [("line_no", C.c_uint64), ("alt_no", C.c_int32), ("code", C.c_int32), ("line_start", C.c_uint64)]
 
 
 class CDosageBatch(C.Structure):
@@ -80,7 +80,7 @@ SYMBOLS = [
     "bvcf_submit", "bvcf_collect", "bvcf_release", "bvcf_resident_alloc", "bvcf_resident_upload",
     "bvcf_resident_run", "bvcf_resident_download", "bvcf_resident_peek", "bvcf_resident_line_index", "bvcf_strerror",
     "bvcf_last_error", "bvcf_abi_version", "bvcf_launch_count", "bvcf_resident_run_at", "bvcf_resident_inflate_bgzf",
-    "bvcf_bgzf_text_bytes", "bvcf_resident_download_bgzf", "bvcf_resident_write_output",
+    "bvcf_bgzf_text_bytes", "bvcf_resident_download_bgzf", "bvcf_resident_write_output", "bvcf_resident_results",
 ]
 
 _lib = None
@@ -128,6 +128,8 @@ def lib():
     L.bvcf_resident_inflate_bgzf.argtypes = [vp, vp, sz, sz, C.POINTER(sz)]
     L.bvcf_bgzf_text_bytes.restype = C.c_int
     L.bvcf_bgzf_text_bytes.argtypes = [vp, sz, C.POINTER(u64), C.POINTER(u64)]
+    L.bvcf_resident_results.restype = C.c_int
+    L.bvcf_resident_results.argtypes = [vp, C.POINTER(CDosageBatch), C.POINTER(C.POINTER(CDiag)), C.POINTER(sz)]
     L.bvcf_resident_write_output.restype = C.c_int
     L.bvcf_resident_write_output.argtypes = [vp, sz, vp, sz]
     L.bvcf_resident_download_bgzf.restype = C.c_int

@@ -88,7 +88,11 @@ struct bvcf_ctx {
   DevBuf d_filt_blob, d_filt_off, d_names, d_name_off, d_name8, d_name16;
   std::vector<Slot> slots;
   // resident path
-  DevBuf r_in, r_out, r_dosage, r_loci, r_loci_off, r_comp, r_blocks, r_def_slots, r_def_sizes, r_def_offs, r_def_out;
+  DevBuf r_in, r_out, r_dosage, r_loci, r_loci_off, r_comp, r_blocks, r_def_slots, r_def_sizes, r_def_offs, r_def_out, r_diags;
+  std::vector<bvcf_diag> r_h_diags;
+  std::vector<int8_t> r_h_dosage;
+  std::vector<uint8_t> r_h_loci;
+  std::vector<uint64_t> r_h_loci_off;
   uint32_t *r_d_bad = nullptr;
   size_t r_in_bytes = 0;
   Scratch r_sc;
@@ -435,7 +439,7 @@ int slot_enqueue(bvcf_ctx *ctx, Slot &s, bool upload) {
       dos_rows = est;
     }
   }
-  if ((rc = dev_reserve(ctx, s.d_diags, (size_t)ctx->diag_cap * 16))) return rc;
+  if ((rc = dev_reserve(ctx, s.d_diags, (size_t)ctx->diag_cap * DIAG_WORDS * 4))) return rc;
   if (upload) CK(cudaMemcpyAsync(s.d_in.p, s.h_src, len, cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemsetAsync((uint8_t *)s.d_in.p + len, '\n', buf_len - len, s.stream));
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(RunCounters), s.stream));
@@ -565,7 +569,7 @@ void bvcf_destroy(bvcf_ctx *ctx) {
   }
   for (DevBuf *b : {&ctx->d_filt_blob, &ctx->d_filt_off, &ctx->d_names, &ctx->d_name_off, &ctx->d_name8, &ctx->d_name16, &ctx->r_in, &ctx->r_out,
                     &ctx->r_dosage, &ctx->r_loci, &ctx->r_loci_off, &ctx->r_comp, &ctx->r_blocks, &ctx->r_def_slots,
-                    &ctx->r_def_sizes, &ctx->r_def_offs, &ctx->r_def_out})
+                    &ctx->r_def_sizes, &ctx->r_def_offs, &ctx->r_def_out, &ctx->r_diags})
     dev_free(*b);
   scratch_free(ctx->r_sc);
   if (ctx->r_stream) cudaStreamDestroy(ctx->r_stream);
@@ -765,8 +769,8 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
   }
   const uint32_t nd = c.n_diags;  // <= diag_cap: larger counts re-ran the chunk above
   if (nd) {
-    s->h_diag_raw.resize((size_t)nd * 4);
-    CK(cudaMemcpyAsync(s->h_diag_raw.data(), s->d_diags.p, (size_t)nd * 16, cudaMemcpyDeviceToHost, s->stream));
+    s->h_diag_raw.resize((size_t)nd * DIAG_WORDS);
+    CK(cudaMemcpyAsync(s->h_diag_raw.data(), s->d_diags.p, (size_t)nd * DIAG_WORDS * 4, cudaMemcpyDeviceToHost, s->stream));
   }
   CK(cudaStreamSynchronize(s->stream));
   if (tsv) *tsv = s->h_out;
@@ -785,9 +789,11 @@ int bvcf_collect(bvcf_ctx *ctx, uint64_t seq, const uint8_t **tsv, size_t *tsv_l
   s->h_diags.clear();
   for (uint32_t i = 0; i < nd; i++) {
     bvcf_diag d;
-    d.line_no = (uint64_t)s->h_diag_raw[4 * i] | ((uint64_t)s->h_diag_raw[4 * i + 1] << 32);
-    d.alt_no = (int32_t)s->h_diag_raw[4 * i + 2];
-    d.code = (int32_t)s->h_diag_raw[4 * i + 3];
+    const uint32_t *w = &s->h_diag_raw[(size_t)DIAG_WORDS * i];
+    d.line_no = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+    d.alt_no = (int32_t)w[2];
+    d.code = (int32_t)w[3];
+    d.line_start = (uint64_t)w[4] | ((uint64_t)w[5] << 32);
     s->h_diags.push_back(d);
   }
   std::sort(s->h_diags.begin(), s->h_diags.end(), [](const bvcf_diag &a, const bvcf_diag &b) {
@@ -851,6 +857,7 @@ int bvcf_resident_run_at(bvcf_ctx *ctx, size_t begin, size_t len, bvcf_chunk_sta
   for (;;) {
     int rc;
     if ((rc = scratch_reserve(ctx, ctx->r_sc, len - (begin & ~511ull), ctx->cfg.resident_subchunk_bytes))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->r_diags, (size_t)ctx->diag_cap * DIAG_WORDS * 4))) return rc;
     // the bytes after `len` must not look like data: pad (idempotent)
     const uint64_t buf_len = std::min<uint64_t>((ctx->r_in.cap - IN_SLACK) / 1024 * 1024, round_up(len, 1024) + 2048);
     CK(cudaMemsetAsync(ctx->r_d_ctr, 0, sizeof(RunCounters), ctx->r_stream));
@@ -863,8 +870,8 @@ int bvcf_resident_run_at(bvcf_ctx *ctx, size_t begin, size_t len, bvcf_chunk_sta
     launches0 = ctx->launches;
     rc = enqueue_pipeline(ctx, ctx->r_sc, ctx->r_stream, (const uint8_t *)ctx->r_in.p, begin, len, buf_len,
                           (uint8_t *)ctx->r_out.p, ctx->r_out.cap, ctx->r_d_ctr, (int8_t *)ctx->r_dosage.p, dos_rows,
-                          (uint8_t *)ctx->r_loci.p, ctx->r_loci.cap, (unsigned long long *)ctx->r_loci_off.p, nullptr,
-                          times ? &timing : nullptr);
+                          (uint8_t *)ctx->r_loci.p, ctx->r_loci.cap, (unsigned long long *)ctx->r_loci_off.p,
+                          (uint32_t *)ctx->r_diags.p, times ? &timing : nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->r_h_ctr, ctx->r_d_ctr, sizeof(RunCounters), cudaMemcpyDeviceToHost, ctx->r_stream));
     CK(cudaStreamSynchronize(ctx->r_stream));
@@ -883,6 +890,7 @@ int bvcf_resident_run_at(bvcf_ctx *ctx, size_t begin, size_t len, bvcf_chunk_sta
     }
     if (c.row_overflow) { ctx->r_sc.row_cap = ctx->r_sc.row_cap * 4 + c.row_cursor; again = true; }
     if (c.scratch_overflow) { ctx->r_sc.scratch_cap = c.scratch_cursor + c.scratch_cursor / 4 + (1ull << 20); again = true; }
+    if (c.n_diags > ctx->diag_cap) { ctx->diag_cap = c.n_diags + c.n_diags / 4; again = true; }
     if (c.slow_overflow) { ctx->r_sc.slow_cap = c.n_slow + c.n_slow / 4 + 1024; again = true; }
     if (c.out_overflow) {
       if ((rc = dev_reserve(ctx, ctx->r_out, (size_t)(c.out_cursor + c.out_cursor / 8 + 4096)))) return rc;
@@ -1035,6 +1043,50 @@ int bvcf_resident_download_bgzf(bvcf_ctx *ctx, size_t offset, size_t len, void *
   CK(cudaMemcpyAsync(host, ctx->r_def_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));  // the compressed rows cross PCIe
   CK(cudaStreamSynchronize(st));
   *comp_len = (size_t)total;
+  return BVCF_OK;
+}
+
+int bvcf_resident_results(bvcf_ctx *ctx, bvcf_dosage_batch *dosage, const bvcf_diag **diags, size_t *n_diags) {
+  if (!ctx) return BVCF_E_ARG;
+  cudaSetDevice(ctx->device);
+  const RunCounters &c = *ctx->r_h_ctr;
+  const DevCfg &dc = ctx->dcfg;
+  if (dosage) {
+    memset(dosage, 0, sizeof(*dosage));
+    dosage->n_samples = (uint32_t)dc.n_samples;
+    if (dc.want_dosage && dc.n_samples > 0 && c.row_cursor) {
+      ctx->r_h_dosage.resize((size_t)c.row_cursor * dc.n_samples);
+      ctx->r_h_loci.resize((size_t)c.loci_cursor);
+      ctx->r_h_loci_off.resize((size_t)c.row_cursor + 1);
+      CK(cudaMemcpy(ctx->r_h_dosage.data(), ctx->r_dosage.p, ctx->r_h_dosage.size(), cudaMemcpyDeviceToHost));
+      if (c.loci_cursor) CK(cudaMemcpy(ctx->r_h_loci.data(), ctx->r_loci.p, (size_t)c.loci_cursor, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(ctx->r_h_loci_off.data(), ctx->r_loci_off.p, (size_t)c.row_cursor * 8, cudaMemcpyDeviceToHost));
+      ctx->r_h_loci_off[c.row_cursor] = c.loci_cursor;
+      dosage->n_rows = c.row_cursor;
+      dosage->dosage = ctx->r_h_dosage.data();
+      dosage->loci = ctx->r_h_loci.data();
+      dosage->loci_off = ctx->r_h_loci_off.data();
+    }
+  }
+  ctx->r_h_diags.clear();
+  const uint32_t nd = std::min<uint32_t>(c.n_diags, ctx->diag_cap);
+  if (nd && ctx->r_diags.p) {
+    std::vector<uint32_t> raw((size_t)nd * DIAG_WORDS);
+    CK(cudaMemcpy(raw.data(), ctx->r_diags.p, raw.size() * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < nd; i++) {
+      const uint32_t *w = &raw[(size_t)DIAG_WORDS * i];
+      bvcf_diag d;
+      d.line_no = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+      d.alt_no = (int32_t)w[2]; d.code = (int32_t)w[3];
+      d.line_start = (uint64_t)w[4] | ((uint64_t)w[5] << 32);
+      ctx->r_h_diags.push_back(d);
+    }
+    std::sort(ctx->r_h_diags.begin(), ctx->r_h_diags.end(), [](const bvcf_diag &a, const bvcf_diag &b) {
+      return a.line_no != b.line_no ? a.line_no < b.line_no : a.alt_no < b.alt_no;
+    });
+  }
+  if (diags) *diags = ctx->r_h_diags.data();
+  if (n_diags) *n_diags = ctx->r_h_diags.size();
   return BVCF_OK;
 }
 

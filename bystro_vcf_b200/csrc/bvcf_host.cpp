@@ -161,30 +161,27 @@ const char *diag_text(int code) {  // main.go:41-51
   return "?";
 }
 
-// the reference's log.Printf lines (main.go:730-986); chrom:pos are looked up in the chunk that is still pinned
-void log_diags(const uint8_t *chunk, size_t len, const bvcf_diag *d, size_t n) {
-  if (!n) return;
-  std::vector<size_t> starts{0};
-  for (size_t i = 0; i < len; i++)
-    if (chunk[i] == '\n') starts.push_back(i + 1);
-  for (size_t k = 0; k < n; k++) {
-    if (d[k].line_no >= starts.size()) continue;
-    const char *l = (const char *)chunk + starts[d[k].line_no];
-    const char *end = (const char *)chunk + len;
-    const char *t0 = (const char *)memchr(l, '\t', end - l);
-    if (!t0) continue;
-    const char *t1 = (const char *)memchr(t0 + 1, '\t', end - t0 - 1);
-    if (!t1) continue;
-    const std::string chrom(l, t0), pos(t0 + 1, t1);
-    const char *msg = diag_text(d[k].code);
-    switch (d[k].code) {
-      case BVCF_DIAG_SAME: fprintf(stderr, "%s:%s : %s\n", chrom.c_str(), pos.c_str(), msg); break;
-      case BVCF_DIAG_MIXED: case BVCF_DIAG_DEL1_LIST:
-        fprintf(stderr, "%s:%s ALT#%d %s\n", chrom.c_str(), pos.c_str(), d[k].alt_no, msg); break;
-      case BVCF_DIAG_POS_LIST: fprintf(stderr, "%s:%s %s\n", chrom.c_str(), pos.c_str(), msg); break;
-      default: fprintf(stderr, "%s:%s ALT #%d %s\n", chrom.c_str(), pos.c_str(), d[k].alt_no, msg);
-    }
+// one of the reference's log.Printf lines (main.go:730-986); `line` points at the diagnosed line (CHROM \t POS \t ...)
+void log_one_diag(const char *line, size_t avail, const bvcf_diag &d) {
+  const char *end = line + avail;
+  const char *t0 = (const char *)memchr(line, '\t', avail);
+  if (!t0) return;
+  const char *t1 = (const char *)memchr(t0 + 1, '\t', end - t0 - 1);
+  if (!t1) return;
+  const std::string chrom(line, t0), pos(t0 + 1, t1);
+  const char *msg = diag_text(d.code);
+  switch (d.code) {
+    case BVCF_DIAG_SAME: fprintf(stderr, "%s:%s : %s\n", chrom.c_str(), pos.c_str(), msg); break;
+    case BVCF_DIAG_MIXED: case BVCF_DIAG_DEL1_LIST:
+      fprintf(stderr, "%s:%s ALT#%d %s\n", chrom.c_str(), pos.c_str(), d.alt_no, msg); break;
+    case BVCF_DIAG_POS_LIST: fprintf(stderr, "%s:%s %s\n", chrom.c_str(), pos.c_str(), msg); break;
+    default: fprintf(stderr, "%s:%s ALT #%d %s\n", chrom.c_str(), pos.c_str(), d.alt_no, msg);
   }
+}
+// the diagnostics of a chunk that is still pinned: every entry carries its line's offset
+void log_diags(const uint8_t *chunk, size_t len, const bvcf_diag *d, size_t n) {
+  for (size_t k = 0; k < n; k++)
+    if (d[k].line_start < len) log_one_diag((const char *)chunk + d[k].line_start, len - d[k].line_start, d[k]);
 }
 
 struct Chunk {
@@ -260,7 +257,7 @@ struct Turnstile {
 // ---- bgzf input (.vcf.gz as bgzip / htslib write it): the compressed bytes go to the GPU, which inflates them ----
 // Replaces the `pigz -d -c in.vcf.gz |` in front of the reference (README.md:10,46).  Groups of whole blocks are
 // uploaded and inflated straight into the resident input region (bvcf_resident_inflate_bgzf), the transform runs
-// there, only rows come back.  One GPU, rows only (no --dosageOutput, no diagnostics on this path yet).
+// there; rows, dosage batches and diagnostics come back.  One GPU, one group at a time.
 bool looks_bgzf(const uint8_t *p, size_t n) {
   return n >= 18 && p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 4) && p[12] == 'B' && p[13] == 'C';
 }
@@ -299,7 +296,6 @@ std::string bgzf_inflate_host(const uint8_t *p, size_t n, size_t want) {
 }
 
 int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len, std::vector<uint8_t> &head, int out_fd) {
-  if (!config.dosageMatrixOutPath.empty()) fatal("--dosageOutput with bgzf input is not supported: decompress first (bgzip -dc | ...)");
   // compressed bytes: the mapping, or a growing buffer read from the pipe
   std::vector<uint8_t> &buf = head;
   size_t consumed = 0;  // bytes of the compressed stream already handed to the GPU
@@ -363,7 +359,36 @@ int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len
   bvcf_config bc{};
   bc.empty_field = config.emptyField.c_str(); bc.field_delim = config.fieldDelimiter.c_str();
   bc.keep_id = config.keepID; bc.keep_info = config.keepInfo; bc.keep_pos = config.keepPos;
-  bc.want_tsv = !config.noOut; bc.want_dosage = 0;
+  std::vector<std::string> sample_names;
+  {
+    int field = 0;
+    size_t s0 = 0;
+    for (size_t i = 0; i <= chrom_line.size(); i++)
+      if (i == chrom_line.size() || chrom_line[i] == '\t') {
+        if (field >= 9) { std::string nm = chrom_line.substr(s0, i - s0); for (auto &ch : nm) if (ch == '.') ch = '_'; sample_names.push_back(nm); }
+        field++; s0 = i + 1;
+      }
+  }
+  bool want_dosage = !config.dosageMatrixOutPath.empty();
+#ifndef BVCF_NO_ARROW
+  bvcf_arrow_writer *arrow = nullptr;
+  if (want_dosage) {
+    if (sample_names.empty()) {  // main.go:308-318
+      fprintf(stderr, "No samples found in VCF file; writing empty dosage matrix file\n");
+      FILE *f = fopen(config.dosageMatrixOutPath.c_str(), "w");
+      if (!f) fatal(config.dosageMatrixOutPath + ": " + strerror(errno));
+      fclose(f);
+      want_dosage = false;
+    } else {
+      std::vector<const char *> nm;
+      for (auto &s : sample_names) nm.push_back(s.c_str());
+      char err[512];
+      arrow = bvcf_arrow_open(config.dosageMatrixOutPath.c_str(), nm.data(), (uint32_t)nm.size(), err, sizeof err);
+      if (!arrow) fatal(std::string("dosage output: ") + err);
+    }
+  }
+#endif
+  bc.want_tsv = !config.noOut; bc.want_dosage = want_dosage;
   bc.allow = allow_c.data(); bc.n_allow = config.allowAll ? -1 : (int)allow_c.size();
   bc.exclude = excl_c.data(); bc.n_exclude = (int)excl_c.size();
   bc.eol_width = eol_width; bc.normalize_dots = 1;
@@ -430,14 +455,33 @@ int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len
       if ((rc = bvcf_resident_download(ctx, 0, out_host, st.out_bytes))) fatal(std::string("download: ") + bvcf_strerror(rc));
       write_all(out_fd, out_host, st.out_bytes);
     }
+    {  // dosage batch and diagnostics of this group
+      bvcf_dosage_batch dos;
+      const bvcf_diag *dg = nullptr;
+      size_t nd = 0;
+      if ((rc = bvcf_resident_results(ctx, want_dosage ? &dos : nullptr, &dg, &nd))) fatal(std::string("results: ") + bvcf_strerror(rc));
+#ifndef BVCF_NO_ARROW
+      if (arrow && want_dosage && dos.n_rows && bvcf_arrow_write(arrow, dos.n_rows, dos.dosage, dos.loci, dos.loci_off))
+        fatal(std::string("dosage output: ") + bvcf_arrow_error(arrow));
+#endif
+      char line[4096];
+      for (size_t k = 0; k < nd; k++) {
+        const size_t n = std::min<size_t>(sizeof line, end - dg[k].line_start);
+        if (dg[k].line_start < end && !bvcf_resident_peek(ctx, dg[k].line_start, line, n)) log_one_diag(line, n, dg[k]);
+      }
+    }
     carry.assign(last_nl + 1, (const uint8_t *)tail.data() + tail_n);
     begin = 0;
   }
   // an unterminated last line (the carry) is dropped (main.go:354-357)
   if (pin) bvcf_host_free(pin);
   if (out_host) bvcf_host_free(out_host);
+  int rc_exit = 0;
+#ifndef BVCF_NO_ARROW
+  if (arrow && bvcf_arrow_close(arrow)) rc_exit = 1;
+#endif
   bvcf_destroy(ctx);
-  return 0;
+  return rc_exit;
 }
 
 }  // namespace

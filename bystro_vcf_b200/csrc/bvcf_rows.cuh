@@ -45,11 +45,14 @@ struct __align__(16) RowDesc {
   uint32_t row;                                   // row number within the sub-chunk (its dosage row)
 };
 
-// diagnostics (main.go:730-986 log.Printf sites): 4 words each -- line_lo, line_hi, alt_no, code
+// diagnostics (main.go:730-986 log.Printf sites): DIAG_WORDS words each -- line_lo, line_hi, alt_no, code, and the
+// byte offset of the line in the input region (the host reads CHROM and POS there for the log text)
+constexpr uint32_t DIAG_WORDS = 6;
 struct DiagSink {
   uint32_t *diags;
   uint32_t cap;
   RunCounters *ctr;
+  unsigned long long line_start;   // set per record by the caller
 };
 
 // site types (bystro-utils parse.Snp/Ins/Del/Mnp/Multi)
@@ -376,10 +379,10 @@ __device__ __forceinline__ void push_diag(const DiagSink &p, unsigned long long 
   if (!p.diags) return;
   const uint32_t i = atomicAdd(&p.ctr->n_diags, 1u);
   if (i < p.cap) {
-    p.diags[4 * i] = (uint32_t)line_no;
-    p.diags[4 * i + 1] = (uint32_t)(line_no >> 32);
-    p.diags[4 * i + 2] = (uint32_t)alt_no;
-    p.diags[4 * i + 3] = (uint32_t)code;
+    uint32_t *d = p.diags + (size_t)DIAG_WORDS * i;
+    d[0] = (uint32_t)line_no; d[1] = (uint32_t)(line_no >> 32);
+    d[2] = (uint32_t)alt_no; d[3] = (uint32_t)code;
+    d[4] = (uint32_t)p.line_start; d[5] = (uint32_t)(p.line_start >> 32);
   }
 }
 

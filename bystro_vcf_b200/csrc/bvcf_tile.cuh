@@ -633,13 +633,15 @@ __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, co
   // insertions copy the POS text verbatim
   g.pos_ok = (g.done || ref_n <= 1) ? false : atoi_go(lc.pos, lc.pos_n, g.ipos);
   const unsigned long long line_no = p.ctr->chunk_line_base + rec.ord;
-  if (!g.done) gen_begin(g, lc, p.diag, line_no, diag);
+  DiagSink ds = p.diag;
+  ds.line_start = rec.start;
+  if (!g.done) gen_begin(g, lc, ds, line_no, diag);
   GtStats gs;
   gs.n_het = gs.n_hom = gs.n_miss = gs.ac = gs.an = gs.het_bytes = gs.hom_bytes = gs.miss_bytes = 0;
   int gs_idx = -1;
   OutAllele oa;
   oa.ins_p = nullptr; oa.ins_n = 0; oa.del_n = 0; oa.pos_val = 0;
-  while (gen_next(g, oa, p.diag, line_no, diag)) tile_emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, ro, sh, so);
+  while (gen_next(g, oa, ds, line_no, diag)) tile_emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, ro, sh, so);
 }
 
 // inclusive scan of v over the warp; the total in `total`

@@ -162,10 +162,33 @@ class ChunkResult:
     n_lines: int
     n_records: int
     n_rows: int
-    diags: List[tuple] = field(default_factory=list)
+    diags: List[tuple] = field(default_factory=list)          # (line_no, alt_no, code)
+    diag_starts: List[int] = field(default_factory=list)      # byte offset of each diagnostic's line in the chunk
     loci: List[bytes] = field(default_factory=list)
     dosage: Optional[object] = None  # numpy int8 [rows, samples]
     retries: int = 0
+
+
+def _unpack_dosage(dos):
+    """bvcf_dosage_batch -> (list of locus strings, numpy int8 [rows, samples]) copies"""
+    import numpy as np
+
+    if not dos.n_rows:
+        return [], None
+    nr, ns = dos.n_rows, dos.n_samples
+    dosage = np.frombuffer(C.string_at(dos.dosage, nr * ns), dtype=np.int8).reshape(nr, ns).copy()
+    offs = np.ctypeslib.as_array(dos.loci_off, shape=(nr + 1,)).tolist()
+    blob = C.string_at(dos.loci, offs[-1])
+    return [blob[offs[i]:offs[i + 1]] for i in range(nr)], dosage
+
+
+def locus_at(block, start: int):
+    """CHROM and POS text of the line that starts at block[start]: what the reference's log lines start with
+    (main.go:730-986 "%s:%s ...")."""
+    f = bytes(block[start:start + 4096]).split(b"\t", 2)
+    if len(f) < 3:
+        return "?", "?"
+    return f[0].decode("latin-1"), f[1].decode("latin-1")
 
 
 class Transformer:
@@ -264,12 +287,8 @@ class Transformer:
         out = ChunkResult(tsv=C.string_at(tsv, n.value) if n.value else b"", n_lines=st.n_lines,
                           n_records=st.n_records, n_rows=st.n_rows, retries=st.retries)
         out.diags = [(dg[i].line_no, dg[i].alt_no, dg[i].code) for i in range(nd.value)]
-        if dos.n_rows:
-            nr, ns = dos.n_rows, dos.n_samples
-            out.dosage = np.frombuffer(C.string_at(dos.dosage, nr * ns), dtype=np.int8).reshape(nr, ns).copy()
-            offs = [dos.loci_off[i] for i in range(nr + 1)]
-            blob = C.string_at(dos.loci, offs[-1])
-            out.loci = [blob[offs[i]:offs[i + 1]] for i in range(nr)]
+        out.diag_starts = [dg[i].line_start for i in range(nd.value)]
+        out.loci, out.dosage = _unpack_dosage(dos)
         check(self._L.bvcf_release(self._ctx, seq), self._ctx, "bvcf_release")
         if hasattr(self, "_keep_chunk"):
             self._keep_chunk.pop(seq, None)
@@ -318,6 +337,15 @@ class Transformer:
         stats = {k: getattr(st, k) for k, _ in CChunkStats._fields_}
         times = {k: getattr(kt, k) for k, _ in CKernelTimes._fields_}
         return stats, times
+
+    def resident_results(self):
+        """(loci, dosage, [(line_no, alt_no, code, line_start)]) of the last resident run"""
+        dos = CDosageBatch()
+        dg = C.POINTER(CDiag)()
+        nd = C.c_size_t()
+        check(self._L.bvcf_resident_results(self._ctx, C.byref(dos), C.byref(dg), C.byref(nd)), self._ctx, "bvcf_resident_results")
+        loci, dosage = _unpack_dosage(dos)
+        return loci, dosage, [(dg[i].line_no, dg[i].alt_no, dg[i].code, dg[i].line_start) for i in range(nd.value)]
 
     def resident_write_output(self, offset: int, data: bytes) -> None:
         check(self._L.bvcf_resident_write_output(self._ctx, offset, data, len(data)), self._ctx, "bvcf_resident_write_output")
@@ -402,20 +430,6 @@ def parse_preamble(data: bytes):
         p = e + 1
 
 
-def chunk_line_locus(block, line_no: int):
-    """CHROM and POS text of data line `line_no` (0-based) of a chunk: what the reference's log lines start with
-    (main.go:730-986 "%s:%s ...")."""
-    p = 0
-    for _ in range(line_no):
-        p = block.find(b"\n", p) + 1
-        if p <= 0:
-            return "?", "?"
-    f = bytes(block[p:block.find(b"\n", p)]).split(b"\t", 2)
-    if len(f) < 2:
-        return "?", "?"
-    return f[0].decode("latin-1"), f[1].decode("latin-1")
-
-
 class PinnedRing:
     """n pinned host buffers (bvcf_host_alloc) with writable views: chunks are read or copied into them so that
     bvcf_submit's H2D copy is a true asynchronous DMA."""
@@ -461,15 +475,13 @@ def write_sample_list(config: Config, chrom_line: bytes, normalize: bool = True)
                 fh.write((s.replace(b".", b"_") if normalize else s) + b"\n")
 
 
-def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Optional[BinaryIO], batch_text: int = 512 << 20) -> dict:
+def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Optional[BinaryIO], batch_text: int = 512 << 20,
+                   diag_sink=None) -> dict:
     """readVcf (main.go:241-396) for bgzf input: groups of whole blocks are uploaded COMPRESSED and inflated on the GPU
-    straight into the resident input region; the transform runs there; only rows come back.  Replaces the `pigz -d -c |`
-    in front of the reference (README.md:10).  Rows only: the dosage matrix and the diagnostics of skipped alleles are
-    not produced on this path yet."""
+    straight into the resident input region; the transform runs there; rows, dosage batches and diagnostics come
+    back.  Replaces the `pigz -d -c |` in front of the reference (README.md:10)."""
     from . import bgzf
 
-    if config.dosageMatrixOutPath:
-        raise BvcfError("--dosageOutput with bgzf input is not supported: decompress first (bgzip -dc | ...)")
     buf = bytearray(head)
     eof = False
 
@@ -498,6 +510,15 @@ def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Option
     if not config.noOut:
         write_sample_list(config, chrom_line, config.normalizeHeader)
     max_line = 8 << 20  # room for the carried partial line
+    arrow = None
+    n_samples_hdr = max(len(chrom_line.split(b"\t")) - 9, 0)
+    if config.dosageMatrixOutPath and n_samples_hdr == 0:
+        open(config.dosageMatrixOutPath, "wb").close()  # main.go:308-318
+    elif config.dosageMatrixOutPath:
+        from .dosage import DosageWriter
+
+        names = [s.replace(b".", b"_") if config.normalizeHeader else s for s in chrom_line.split(b"\t")[9:]]
+        arrow = DosageWriter(config.dosageMatrixOutPath, names)
     with Transformer(config, eol_width=width) as tr:
         tr.set_header(chrom_line)
         tr.resident_alloc(batch_text + max_line + (1 << 20), batch_text // 4 + (64 << 20))
@@ -539,12 +560,22 @@ def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Option
             stats, _ = tr.resident_run(end, want_times=False, begin=begin)
             if writer is not None and not config.noOut and stats["out_bytes"]:
                 writer.write(tr.resident_download(0, stats["out_bytes"]))
+            if arrow is not None or diag_sink is not None:
+                loci, dosage, diags = tr.resident_results()
+                if arrow is not None and dosage is not None:
+                    arrow.write(loci, dosage)
+                if diag_sink is not None:
+                    for ln, alt_no, code, st in diags:
+                        chrom, pos = locus_at(tr.resident_peek(st, min(4096, end - st)), 0)
+                        diag_sink(format_diag(chrom, pos, alt_no, code), totals["n_lines"] + ln, alt_no, code)
             for key in ("n_lines", "n_records", "n_rows", "out_bytes"):
                 totals[key] += stats[key]
             totals["in_bytes"] += end - begin
             carry = tail[k + 1:]
             begin = 0
         # an unterminated last line (carry) is dropped (main.go:354-357)
+    if arrow is not None:
+        arrow.close()
     return totals
 
 
@@ -562,7 +593,7 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
     if bgzf.is_bgzf(head):  # .vcf.gz: the compressed bytes go to the GPU, which inflates them
         if transformer is not None:
             raise BvcfError("read_vcf: pass no transformer for bgzf input")
-        return _read_vcf_bgzf(config, head, reader, writer)
+        return _read_vcf_bgzf(config, head, reader, writer, diag_sink=diag_sink)
     while True:  # make sure the whole preamble (meta lines + #CHROM line) is in `head`
         try:
             width, chrom_line, off = parse_preamble(head)
@@ -609,9 +640,8 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
                 if arrow is not None and res.dosage is not None:
                     arrow.write(res.loci, res.dosage)
                 if diag_sink is not None and res.diags:
-                    block_of_seq = C.string_at(addr, blen)
-                    for ln, alt_no, code in res.diags:
-                        chrom, pos = chunk_line_locus(block_of_seq, ln)
+                    for (ln, alt_no, code), st in zip(res.diags, res.diag_starts):
+                        chrom, pos = locus_at(C.string_at(addr + st, min(4096, blen - st)), 0)
                         diag_sink(format_diag(chrom, pos, alt_no, code), totals["n_lines"] + ln, alt_no, code)
                 totals["n_lines"] += res.n_lines
                 totals["n_records"] += res.n_records

@@ -22,7 +22,7 @@ import queue
 import threading
 from typing import BinaryIO, List, Optional, Sequence, Tuple
 
-from .host import Config, PinnedRing, Transformer, chunk_line_locus, format_diag, parse_preamble, write_sample_list
+from .host import Config, PinnedRing, Transformer, format_diag, locus_at, parse_preamble, write_sample_list
 
 
 def partition(data, begin: int, end: int, n: int) -> List[Tuple[int, int]]:
@@ -155,9 +155,8 @@ def read_vcf_multi(config: Config, data, writer: Optional[BinaryIO], devices: Se
                 arrow.write(res.loci, res.dosage)
             if diag_sink is not None and res.diags:
                 lo, hi = chunks[k]
-                block = data[lo:hi]
-                for ln, alt_no, code in res.diags:
-                    chrom, pos = chunk_line_locus(block, ln)
+                for (ln, alt_no, code), st in zip(res.diags, res.diag_starts):
+                    chrom, pos = locus_at(data, lo + st)
                     diag_sink(format_diag(chrom, pos, alt_no, code), totals["n_lines"] + ln, alt_no, code)
             totals["n_lines"] += res.n_lines
             totals["n_records"] += res.n_records

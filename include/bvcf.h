@@ -73,9 +73,10 @@ enum {
   BVCF_DIAG_POS_LIST = 8   /* POS inside the ALT list:  "%s:%s %s"                    main.go:827 */
 };
 typedef struct {
-  uint64_t line_no; /* 0-based data-line index within the chunk */
-  int32_t alt_no;   /* 1-based ALT number; 0 if the message carries none */
-  int32_t code;     /* BVCF_DIAG_* */
+  uint64_t line_no;    /* 0-based data-line index within the chunk */
+  int32_t alt_no;      /* 1-based ALT number; 0 if the message carries none */
+  int32_t code;        /* BVCF_DIAG_* */
+  uint64_t line_start; /* byte offset of that line in the chunk (its CHROM and POS fields start the log text) */
 } bvcf_diag;
 
 /* One chunk's share of the dosage matrix (main.go:576-584): row i is locus i + n_samples int8. */
@@ -173,6 +174,11 @@ int bvcf_resident_download_bgzf(bvcf_ctx *ctx, size_t offset, size_t len, void *
 /* Put host bytes into the resident output region (a host that wants its own text -- the TSV header line, say --
  * to leave through bvcf_resident_download_bgzf with the rows). */
 int bvcf_resident_write_output(bvcf_ctx *ctx, size_t offset, const void *host, size_t len);
+
+/* What the last bvcf_resident_run[_at] produced besides the rows: the dosage batch (when the context was created
+ * with want_dosage) and the diagnostics; line_start offsets are into the resident input region.  Library-owned
+ * memory, valid until the next resident run.  Either pointer may be NULL. */
+int bvcf_resident_results(bvcf_ctx *ctx, bvcf_dosage_batch *dosage, const bvcf_diag **diags, size_t *n_diags);
 
 /* Copy `len` output bytes starting at `offset` back to the host. */
 int bvcf_resident_download(bvcf_ctx *ctx, size_t offset, void *host, size_t len);

@@ -235,3 +235,32 @@ def test_cli_bgzf_input(chr1_fixture, tmp_path, how):
     else:
         got, _ = _run([sys.executable, "-m", "bystro_vcf_b200"] + flags, comp)
     assert got == plain
+
+
+def test_bgzf_input_with_dosage_and_diagnostics(tmp_path):
+    """the bgzf path is the whole transform: rows, the Arrow dosage file and the reference's log lines"""
+    import numpy as np
+    import pyarrow as pa
+
+    from bystro_vcf_b200 import bgzf
+    from oracle import oracle as O
+
+    n = 40
+    hdr = V.HDR8 + ["FORMAT"] + ["SM%05d" % i for i in range(n)]
+    recs = []
+    for i in range(3000):
+        gts = ["0|1" if (i + j) % 17 == 0 else ("1|1" if (i * j) % 29 == 1 else "0|0") for j in range(n)]
+        alt = "<DEL>" if i % 500 == 3 else ("G,T" if i % 7 == 0 else "G")
+        recs.append(["1", str(100 + i), "rs%d" % i, "A", alt, ".", "PASS", "DP=%d" % i, "GT"] + gts)
+    vcf = V._vcf(hdr, recs)
+    ref = O.read_vcf(O.OracleConfig(want_dosage=True), vcf)
+    comp = bgzf.compress(vcf, block_text=20000)
+    for host in ("cpp", "python"):
+        path = tmp_path / ("d_%s.feather" % host)
+        cmd = [BIN] if host == "cpp" else [sys.executable, "-m", "bystro_vcf_b200"]
+        raw, err = _run(cmd + ["--dosageOutput", str(path)], comp)
+        assert raw.partition(b"\n")[2] == ref.tsv
+        tab = pa.ipc.open_file(str(path)).read_all()
+        assert [x.encode() for x in tab.column(0).to_pylist()] == ref.loci
+        assert np.array_equal(np.stack([tab.column(j + 1).to_numpy() for j in range(n)], axis=1), ref.dosage)
+        assert sorted(err.strip().split("\n")) == sorted("1:%d ALT #1 ALT not ACTG" % (100 + i) for i in range(3000) if i % 500 == 3)
