@@ -328,7 +328,10 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       // L2 prefetch of the next tile's lines / scratch block: measured, no gain (compose 0.323 -> 0.329 ms, copy-out
       // 0.116 -> 0.124 ms on 600,000 chr1-shape variants: the waits are dependent L1/L2 hits, not DRAM), so off
       static const int pf = getenv("BVCF_PREFETCH") ? atoi(getenv("BVCF_PREFETCH")) : 0;  // experiments: bit 0 compose, bit 1 copy-out
-      if (dc.n_samples == 0) {
+      static const bool sites_old = getenv("BVCF_SITES_OLD") != nullptr;  // experiments: the thread-per-record composer
+      if (dc.n_samples == 0 && !sites_old) {
+        launch(bvcf_compose_sites_kernel<5, 6144, 128>, 6144, 128, 5);
+      } else if (dc.n_samples == 0) {
         if (pf & 1) launch(bvcf_compose_kernel<4, 8192, 160, true>, 8192, 160, 4);
         else launch(bvcf_compose_kernel<4, 8192, 160, false>, 8192, 160, 4);
       } else {

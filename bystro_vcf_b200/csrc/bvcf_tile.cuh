@@ -65,7 +65,8 @@ struct __align__(16) TileAgg {
   unsigned long long scratch_off;     // byte offset of the block in the scratch buffer
   uint32_t rows, loci, n_big, n_long;
   uint32_t arena_used, n_trows;       // block layout: 32 LaneRec, n_trows TRow, arena_used bytes (16-byte padded)
-  uint32_t n_mid, pad;
+  uint32_t n_mid;
+  uint32_t flags;                     // bit 0: dense block -- nothing but the tile's output bytes, in order (sites-only composer)
 };
 static_assert(sizeof(TileAgg) == 48, "TileAgg layout");
 // exclusive prefix of the totals over the tiles before this one (tile offsets kernels)
@@ -350,6 +351,66 @@ __device__ __forceinline__ void small_dosage(const TileParams &p, const LineRec 
   }
 }
 
+// CountWriter: the length of a text without writing it
+struct CountWriter {
+  static constexpr bool kStage = true;
+  uint32_t a;
+  __device__ __forceinline__ void byte(uint32_t) { a++; }
+  __device__ __forceinline__ void packed(unsigned long long, int len) { a += len; }
+  __device__ __forceinline__ void span(const uint8_t *, int len) { a += len; }
+};
+__device__ __forceinline__ int dec_len(long long v) {  // len(strconv.Itoa(v))
+  const unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+  int d = 1;
+  while (d < 20 && u >= BVCF_P10[d]) d++;
+  return d + (v < 0 ? 1 : 0);
+}
+__device__ __forceinline__ void w_dec(CountWriter &w, long long v) { w.a += (uint32_t)dec_len(v); }
+
+// ---- the text of a row that every cohort shares -----------------------------------------------------------
+// "chrom \t pos \t type \t ref \t alt \t trTv \t" (main.go:570-606)
+template <class W>
+__device__ __forceinline__ void row_text_head(W &w, const LineCtx &lc, const OutAllele &oa) {
+  // chrom (main.go:570-574)
+  if (lc.chrom_n < 4 || lc.chrom[0] != 'c') w.packed(0x726863ull, 3);  // "chr"
+  w.span(lc.chrom, lc.chrom_n);
+  w.byte('\t');
+  if (oa.pos_verbatim) w.span(lc.pos, lc.pos_n); else w_dec(w, oa.pos_val);
+  if (lc.site_type != T_MULTI) {  // "\tSNP\t": the three-letter types as one piece
+    const uint8_t *tt = (const uint8_t *)TYPE_TXT[lc.site_type];
+    w.packed(0x09ull | ((uint64_t)tt[0] << 8) | ((uint64_t)tt[1] << 16) | ((uint64_t)tt[2] << 24) | (0x09ull << 32), 5);
+  } else {
+    w.byte('\t');
+    w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
+    w.byte('\t');
+  }
+  const uint8_t trtv = lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0');  // main.go:602-606
+  if (oa.kind == 0) {  // "R\tA\tt\t" as one piece
+    w.packed((uint64_t)oa.ref | (0x09ull << 8) | ((uint64_t)oa.alt_c << 16) | (0x09ull << 24) | ((uint64_t)trtv << 32) | (0x09ull << 40), 6);
+  } else {
+    w.byte(oa.ref);
+    w.byte('\t');
+    if (oa.kind == 1) { w.byte('+'); w.span(oa.ins_p, oa.ins_n); }
+    else w_dec(w, oa.del_n);
+    w.byte('\t');
+    w.byte(trtv);
+    w.byte('\t');
+  }
+}
+// the --keepPos / --keepId / --keepInfo columns and the end of the row (main.go:671-692); INFO: the ALT index here,
+// the span itself only when the writer goes straight to the output (staged rows get it at copy-out)
+template <class W, bool INFO_SPAN>
+__device__ __forceinline__ void row_text_keep(W &w, const DevCfg &cfg, const LineCtx &lc, const OutAllele &oa) {
+  if (cfg.keep_pos) { w.byte('\t'); w.span(lc.pos, lc.pos_n); }
+  if (cfg.keep_id) { w.byte('\t'); w.span(lc.id, lc.id_n); }
+  if (cfg.keep_info) {
+    w.byte('\t'); w_dec(w, oa.alt_idx); w.byte('\t');
+    if constexpr (INFO_SPAN) { w.span(lc.info, lc.info_n); w.byte('\n'); }
+  } else {
+    w.byte('\n');
+  }
+}
+
 // ---- one output row (main.go:555-695) -------------------------------------------------------------------
 // W = StageWriter: pass A (compose into the arena, or size only once the record has failed over to the slow path);
 // W = GlobalWriter: pass C of a slow-path record.
@@ -428,31 +489,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
   unsigned long long dsts[3] = {~0ull, ~0ull, ~0ull};
 
   if (cfg.want_tsv) {
-    // chrom (main.go:570-574)
-    if (lc.chrom_n < 4 || lc.chrom[0] != 'c') w.packed(0x726863ull, 3);  // "chr"
-    w.span(lc.chrom, lc.chrom_n);
-    w.byte('\t');
-    if (oa.pos_verbatim) w.span(lc.pos, lc.pos_n); else w_dec(w, oa.pos_val);
-    if (lc.site_type != T_MULTI) {  // "\tSNP\t": the three-letter types as one piece
-      const uint8_t *tt = (const uint8_t *)TYPE_TXT[lc.site_type];
-      w.packed(0x09ull | ((uint64_t)tt[0] << 8) | ((uint64_t)tt[1] << 16) | ((uint64_t)tt[2] << 24) | (0x09ull << 32), 5);
-    } else {
-      w.byte('\t');
-      w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
-      w.byte('\t');
-    }
-    const uint8_t trtv = lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0');  // main.go:602-606
-    if (oa.kind == 0) {  // "R\tA\tt\t" as one piece
-      w.packed((uint64_t)oa.ref | (0x09ull << 8) | ((uint64_t)oa.alt_c << 16) | (0x09ull << 24) | ((uint64_t)trtv << 32) | (0x09ull << 40), 6);
-    } else {
-      w.byte(oa.ref);
-      w.byte('\t');
-      if (oa.kind == 1) { w.byte('+'); w.span(oa.ins_p, oa.ins_n); }
-      else w_dec(w, oa.del_n);
-      w.byte('\t');
-      w.byte(trtv);
-      w.byte('\t');
-    }
+    row_text_head(w, lc, oa);
     if (!has_samples) {  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0"
       w.span(cfg.tail0, cfg.tail0_len);  // composed once by the host
     } else {
@@ -482,14 +519,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
       if (gs.ac == 0) w.byte('0');
       else { int fl; const uint64_t ft = format_ratio_g3(gs.ac, gs.an, fl); w.packed(ft, fl); }
     }
-    if (cfg.keep_pos) { w.byte('\t'); w.span(lc.pos, lc.pos_n); }
-    if (cfg.keep_id) { w.byte('\t'); w.span(lc.id, lc.id_n); }
-    if (cfg.keep_info) {
-      w.byte('\t'); w_dec(w, oa.alt_idx); w.byte('\t');
-      if constexpr (!W::kStage) { w.span(lc.info, lc.info_n); w.byte('\n'); }  // staged rows: appended at copy-out
-    } else {
-      w.byte('\n');
-    }
+    row_text_keep<W, !W::kStage>(w, cfg, lc, oa);
   }
 
   uint32_t slen = 0, loc_len = 0;
@@ -567,18 +597,17 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
   }
 }
 
-// ---- one record: field index, linePasses, getAlleles, one tile_emit_row per output allele ----------------
-template <class W>
-__device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, const LineRec &rec, W &w, RecOut &ro,
-                                            const TileShared &sh, SlowOut &so, const uint8_t *s_filt, const uint32_t *s_filt_off,
-                                            bool diag, const uint8_t *&info_p, uint32_t &info_n) {
+// ---- one record: field index, linePasses (main.go:447-454), the start of getAlleles ---------------------------
+// Leaves the generator ready for gen_next (or done: filtered out / nothing to emit).
+__device__ __forceinline__ void record_open(const TileParams &p, uint32_t li, const LineRec &rec, const uint8_t *s_filt,
+                                            const uint32_t *s_filt_off, bool diag, LineCtx &lc, AlleleGen &g, DiagSink &ds,
+                                            unsigned long long &line_no, uint32_t t[9]) {
   const DevCfg &cfg = p.cfg;
   const int n_filt = cfg.n_allow + cfg.n_excl;
   const uint8_t *L = p.in + rec.start;
   const uint32_t n = rec.len >= (uint32_t)cfg.eol_width ? rec.len - (uint32_t)cfg.eol_width : 0;  // main.go:535
   // ---- first eight/nine tabs (strings.Split, main.go:535) ----
   const int need = cfg.H - 1 < 9 ? cfg.H - 1 : 9;
-  uint32_t t[9];
   int found = need;
   bool far = false;  // a tab beyond 64 KiB from the line start: the scan kernel could not record it
 #pragma unroll
@@ -598,7 +627,6 @@ __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, co
   bool pass = found >= need;  // always true for scan-kernel records; defensive
 #pragma unroll
   for (int k = 0; k < 9; k++) if (k >= found) t[k] = n;
-  LineCtx lc;
   lc.L = L; lc.content_len = n; lc.li = li;
   lc.chrom = L; lc.chrom_n = (int)t[0];
   lc.pos = L + t[0] + 1; lc.pos_n = (int)(t[1] - t[0] - 1);
@@ -608,7 +636,6 @@ __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, co
   const uint8_t *filt = L + t[5] + 1; const int filt_n = (int)(t[6] - t[5] - 1);
   lc.info = L + t[6] + 1; lc.info_n = (int)(t[7] - t[6] - 1);
   lc.multi = false; lc.site_type = T_SNP;
-  info_p = lc.info; info_n = (uint32_t)lc.info_n;
 
   // ---- linePasses (main.go:447-454): exact whole-field match against the shared-memory table ----
   if (pass && (!cfg.allow_all || cfg.n_excl > 0)) {
@@ -623,8 +650,7 @@ __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, co
     if (in_excl) pass = false;
   }
 
-  // ---- getAlleles (main.go:723-1038) as a resumable generator: one converged tile_emit_row call site ----
-  AlleleGen g;
+  // ---- getAlleles (main.go:723-1038) as a resumable generator ----
   g.ref = ref; g.alt = alt; g.ref_n = ref_n; g.alt_n = alt_n;
   g.s = 0; g.alt_idx = 0; g.mnp_i = -1; g.ta = alt; g.tn = 0; g.last = false;
   g.done = !(pass && ref_n > 0 && alt_n > 0);
@@ -632,10 +658,24 @@ __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, co
   // strconv.Atoi(POS) is only ever consulted when REF is longer than one base (main.go:752,822): SNPs and plain
   // insertions copy the POS text verbatim
   g.pos_ok = (g.done || ref_n <= 1) ? false : atoi_go(lc.pos, lc.pos_n, g.ipos);
-  const unsigned long long line_no = p.ctr->chunk_line_base + rec.ord;
-  DiagSink ds = p.diag;
+  line_no = p.ctr->chunk_line_base + rec.ord;
+  ds = p.diag;
   ds.line_start = rec.start;
   if (!g.done) gen_begin(g, lc, ds, line_no, diag);
+}
+
+// ---- one record, one thread: one converged tile_emit_row call site per output allele -------------------------
+template <class W>
+__device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, const LineRec &rec, W &w, RecOut &ro,
+                                            const TileShared &sh, SlowOut &so, const uint8_t *s_filt, const uint32_t *s_filt_off,
+                                            bool diag, const uint8_t *&info_p, uint32_t &info_n) {
+  LineCtx lc;
+  AlleleGen g;
+  DiagSink ds;
+  unsigned long long line_no;
+  uint32_t t[9];
+  record_open(p, li, rec, s_filt, s_filt_off, diag, lc, g, ds, line_no, t);
+  info_p = lc.info; info_n = (uint32_t)lc.info_n;
   GtStats gs;
   gs.n_het = gs.n_hom = gs.n_miss = gs.ac = gs.an = gs.het_bytes = gs.hom_bytes = gs.miss_bytes = 0;
   int gs_idx = -1;
@@ -772,7 +812,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
     if (lane == 0) {
       TileAgg ag;
       ag.bytes = tot_b; ag.scratch_off = soff; ag.rows = tot_rows; ag.loci = tot_loci; ag.n_big = tot_big; ag.n_long = tot_long;
-      ag.arena_used = arena_used; ag.n_trows = n_trows; ag.n_mid = tot_mid; ag.pad = 0;
+      ag.arena_used = arena_used; ag.n_trows = n_trows; ag.n_mid = tot_mid; ag.flags = 0;
       p.tile_agg[tile] = ag;
       if (!fits) p.ctr->scratch_overflow = 1;
     }
@@ -793,6 +833,210 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
       for (uint32_t i = lane; i < nav; i += 32) dst[i] = asrc[i];
     }
     __syncwarp();  // every lane is done with the arena before the next tile's cursor reset
+  }
+}
+
+// ---- compose, sites-only input ---------------------------------------------------------------------------------
+// No samples: a row is its fixed columns, and 30 % of BASELINE's lines give two to eight of them.  With a thread per
+// record a tile ran as long as its widest record (6.8 of 32 lanes active, 10,000 warp instructions per tile).  Here
+// the generator still runs per record (phase B) but only PLANS the rows -- a 32-byte PendRow each, with the length of
+// its text -- and the text is composed by whichever lane is free (phase C, a row per lane).  Because every length is
+// known before a byte is written the rows land in the arena in output order, back to back: the tile's block is its
+// output, and the copy-out kernel moves it with one coalesced warp copy (TileAgg::flags bit 0) -- unless --keepInfo
+// interleaves INFO spans or a record overflowed to the slow path, which fall back to the row table.
+struct __align__(16) PendRow {
+  long long pos_val;
+  uint32_t ins_off;       // kind 1: the inserted bases, offset from the line start
+  int32_t n;              // kind 1: how many; kind 2: the (negative) deletion count
+  uint32_t rel_off;       // text bytes of the record's rows before this one
+  uint16_t len;           // text bytes of this row
+  uint16_t next;          // next row of the record
+  uint16_t alt_idx;
+  uint8_t kind;           // OutAllele::kind, 0xFF: empty slot
+  uint8_t ref, alt_c, verbatim, owner, pad;
+};
+static_assert(sizeof(PendRow) == sizeof(TRow), "a PendRow becomes a TRow in place");
+
+template <class W>
+__device__ __forceinline__ void sites_row_text(W &w, const DevCfg &cfg, const LineCtx &lc, const OutAllele &oa) {
+  row_text_head(w, lc, oa);
+  w.span(cfg.tail0, cfg.tail0_len);  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0", composed once by the host
+  row_text_keep<W, false>(w, cfg, lc, oa);
+}
+
+template <int MINB, uint32_t ARENA, uint32_t ROWS>
+__global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_sites_kernel(const __grid_constant__ TileParams p) {
+  constexpr uint32_t TILE_SMEM_WARP = tile_smem_warp(ARENA, ROWS);
+  static_assert(ROWS <= TILE_ROWS_MAX && ROWS >= TILE_THREADS && ARENA < 65536u, "row table / arena size");
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ uint8_t s_filt[FILT_SMEM];
+  __shared__ uint32_t s_filt_off[65];
+  __shared__ uint32_t s_next[TILE_WARPS];   // per warp: next free row slot
+  const DevCfg &cfg = p.cfg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_filt = cfg.n_allow + cfg.n_excl;
+  for (int i = threadIdx.x; i < cfg.filt_bytes && i < FILT_SMEM; i += blockDim.x) s_filt[i] = cfg.filt_blob[i];
+  for (int i = threadIdx.x; i <= n_filt && i < 65; i += blockDim.x) s_filt_off[i] = cfg.filt_off[i];
+  __syncthreads();
+  if (p.ctr->ev_overflow | p.ctr->slot_overflow) return;
+  const uint32_t n_rec = p.ctr->chunk_records;
+  const uint32_t n_tiles = (n_rec + TILE_THREADS - 1) / TILE_THREADS;
+  uint8_t *const my_smem = s_dyn + (size_t)warp * TILE_SMEM_WARP;
+  TRow *const s_rows = reinterpret_cast<TRow *>(my_smem + ARENA + 16);
+  PendRow *const s_pend = reinterpret_cast<PendRow *>(s_rows);
+  const uint32_t arena_s = (uint32_t)__cvta_generic_to_shared(my_smem);
+  const uint32_t tail = (cfg.want_tsv && cfg.keep_info) ? 1u : 0u;  // INFO span + EOL appended at copy-out
+
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) { tile = atomicAdd(&p.ctr->tile_ticket, 1u); s_next[warp] = TILE_THREADS; }
+    tile = __shfl_sync(FULL, tile, 0);
+    __syncwarp();  // the cursor reset before the lanes' allocations
+    if (tile >= n_tiles) break;
+    const uint32_t li = tile * TILE_THREADS + lane;
+    const bool valid = li < n_rec;
+
+    // ---- phase B: a record per lane plans its rows ----
+    s_pend[lane].kind = 0xFF;
+    uint32_t n_rows = 0, last = ROW_NONE, first = ROW_NONE, info_n = 0, info_off = 0;
+    unsigned long long staged = 0, start = 0;
+    uint32_t t0 = 0, t1 = 0, t2 = 0, misc = 0;
+    bool failed = false;
+    if (valid) {
+      const LineRec rec = p.lines[li];
+      LineCtx lc;
+      AlleleGen g;
+      DiagSink ds;
+      unsigned long long line_no;
+      uint32_t t[9];
+      record_open(p, li, rec, s_filt, s_filt_off, true, lc, g, ds, line_no, t);
+      start = rec.start; t0 = t[0]; t1 = t[1]; t2 = t[2];
+      info_n = (uint32_t)lc.info_n; info_off = t[6] + 1;
+      OutAllele oa;
+      oa.ins_p = lc.L; oa.ins_n = 0; oa.del_n = 0; oa.pos_val = 0;
+      while (gen_next(g, oa, ds, line_no, true)) {
+        CountWriter cw;
+        cw.a = 0;
+        if (cfg.want_tsv) sites_row_text(cw, cfg, lc, oa);
+        if (!failed) {
+          const uint32_t slot = n_rows == 0 ? (uint32_t)lane : atomicAdd(&s_next[warp], 1u);
+          if (slot >= ROWS) {
+            failed = true;  // slow path; the sizes stay exact
+          } else if (cw.a > 0xFFFFu || staged > 0xFFFFFFFFull || oa.alt_idx > 0xFFFF) {
+            failed = true;
+            s_pend[slot].kind = 0xFF;
+          } else {
+            PendRow pr;
+            pr.pos_val = oa.pos_val;
+            pr.ins_off = oa.kind == 1 ? (uint32_t)(oa.ins_p - lc.L) : 0u;
+            pr.n = oa.kind == 1 ? (int32_t)oa.ins_n : (int32_t)oa.del_n;
+            pr.rel_off = (uint32_t)staged; pr.len = (uint16_t)cw.a; pr.next = (uint16_t)ROW_NONE;
+            pr.alt_idx = (uint16_t)oa.alt_idx; pr.kind = (uint8_t)oa.kind; pr.ref = oa.ref; pr.alt_c = oa.alt_c;
+            pr.verbatim = oa.pos_verbatim ? 1 : 0; pr.owner = (uint8_t)lane; pr.pad = 0;
+            s_pend[slot] = pr;
+            if (n_rows) s_pend[last].next = (uint16_t)slot; else first = slot;
+            last = slot;
+          }
+        }
+        staged += cw.a;
+        n_rows++;
+      }
+      misc = (uint32_t)lc.site_type | (lc.multi ? 0x100u : 0u);
+    }
+    __syncwarp();
+
+    // ---- the arena in output order: records one after the other, a record's rows back to back ----
+    failed = failed || staged > ARENA;
+    const uint32_t mine = failed ? 0u : (uint32_t)staged;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (!failed && incl > ARENA) failed = true;  // the tail of an overfull tile
+    const uint32_t base = incl - mine;
+    const uint32_t fmask = __ballot_sync(FULL, failed && n_rows > 0);
+    uint32_t arena_used = __reduce_max_sync(FULL, failed ? 0u : incl);
+    uint32_t n_slots = s_next[warp];
+    if (n_slots > ROWS) n_slots = ROWS;
+    const bool dense = fmask == 0u && tail == 0u;
+
+    // ---- phase C: a row per lane composes its text ----
+    for (uint32_t r0 = 0; r0 < n_slots; r0 += 32) {
+      const uint32_t r = r0 + lane;
+      PendRow pr;
+      pr.kind = 0xFF; pr.owner = (uint8_t)lane;
+      if (r < n_slots) pr = s_pend[r];
+      const int owner = pr.kind == 0xFF ? lane : (int)pr.owner;
+      const unsigned long long o_start = __shfl_sync(FULL, start, owner);
+      const uint32_t o_t0 = __shfl_sync(FULL, t0, owner), o_t1 = __shfl_sync(FULL, t1, owner), o_t2 = __shfl_sync(FULL, t2, owner);
+      const uint32_t o_misc = __shfl_sync(FULL, misc, owner), o_base = __shfl_sync(FULL, base, owner);
+      if (pr.kind != 0xFF && !((fmask >> owner) & 1u)) {
+        LineCtx lc;
+        lc.L = p.in + o_start; lc.content_len = 0; lc.li = 0;
+        lc.chrom = lc.L; lc.chrom_n = (int)o_t0;
+        lc.pos = lc.L + o_t0 + 1; lc.pos_n = (int)(o_t1 - o_t0 - 1);
+        lc.id = lc.L + o_t1 + 1; lc.id_n = (int)(o_t2 - o_t1 - 1);
+        lc.info = lc.L; lc.info_n = 0;
+        lc.site_type = (int)(o_misc & 0xFFu); lc.multi = (o_misc & 0x100u) != 0;
+        OutAllele oa;
+        oa.pos_val = pr.pos_val; oa.ins_p = lc.L + pr.ins_off; oa.ins_n = pr.kind == 1 ? pr.n : 0;
+        oa.del_n = pr.kind == 2 ? (long long)pr.n : 0; oa.alt_idx = pr.alt_idx; oa.kind = pr.kind;
+        oa.ref = pr.ref; oa.alt_c = pr.alt_c; oa.pos_verbatim = pr.verbatim != 0;
+        StageWriter w;
+        w.stg = true; w.a = arena_s + o_base + pr.rel_off;
+        if (cfg.want_tsv) sites_row_text(w, cfg, lc, oa);
+        if (!dense) {
+          TRow tr;
+          tr.hole_len[0] = tr.hole_len[1] = tr.hole_len[2] = 0;
+          tr.hole_pos[0] = tr.hole_pos[1] = tr.hole_pos[2] = 0;
+          tr.soff = (uint16_t)(o_base + pr.rel_off); tr.slen = pr.len; tr.loc_len = 0;
+          tr.next = pr.next; tr.allele = (uint16_t)(pr.alt_idx + 1u); tr.flags = (uint16_t)tail; tr.pad = 0;
+          s_rows[r] = tr;
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- the tile's totals and its scratch block ----
+    const unsigned long long bytes = staged + (tail ? (unsigned long long)n_rows * (info_n + 1ull) : 0ull);
+    const unsigned long long tot_b = warp_sum64(bytes);
+    const uint32_t tot_rows = __reduce_add_sync(FULL, n_rows);
+    arena_used = (arena_used + 15u) & ~15u;
+    const uint32_t n_trows = dense ? 0u : n_slots;
+    const uint32_t block_bytes = dense ? arena_used : TILE_BLOCK_HDR + n_trows * (uint32_t)sizeof(TRow) + arena_used;
+    unsigned long long soff = 0;
+    if (lane == 0) soff = atomicAdd(reinterpret_cast<unsigned long long *>(&p.ctr->scratch_cursor), (unsigned long long)block_bytes);
+    soff = __shfl_sync(FULL, soff, 0);
+    const bool fits = soff + block_bytes <= p.scratch_cap;
+    if (lane == 0) {
+      TileAgg ag;
+      ag.bytes = tot_b; ag.scratch_off = soff; ag.rows = tot_rows; ag.loci = 0; ag.n_big = 0; ag.n_long = 0;
+      ag.arena_used = arena_used; ag.n_trows = n_trows; ag.n_mid = 0; ag.flags = dense ? 1u : 0u;
+      p.tile_agg[tile] = ag;
+      if (!fits) p.ctr->scratch_overflow = 1;
+    }
+    if (fits) {
+      uint8_t *blk = p.scratch + soff;
+      uint4 *dst = reinterpret_cast<uint4 *>(blk);
+      if (!dense) {
+        LaneRec lr;
+        lr.bytes = bytes; lr.rows = n_rows; lr.loci = 0; lr.n_desc = 0;
+        lr.first = (uint16_t)(failed ? ROW_NONE : first); lr.flags = (uint16_t)((failed ? 1u : 0u) | (1u << 1));
+        lr.info_off = info_off; lr.info_n = info_n;
+        reinterpret_cast<LaneRec *>(blk)[lane] = lr;
+        dst = reinterpret_cast<uint4 *>(blk + TILE_BLOCK_HDR);
+        const uint4 *rsrc = reinterpret_cast<const uint4 *>(s_rows);
+        const uint32_t nrv = n_trows * (uint32_t)(sizeof(TRow) / 16);
+        for (uint32_t i = lane; i < nrv; i += 32) dst[i] = rsrc[i];
+        dst += nrv;
+      }
+      const uint4 *asrc = reinterpret_cast<const uint4 *>(my_smem);
+      const uint32_t nav = arena_used >> 4;
+      for (uint32_t i = lane; i < nav; i += 32) dst[i] = asrc[i];
+    }
+    __syncwarp();  // every lane is done with the arena and the row table before the next tile
   }
 }
 
@@ -920,6 +1164,24 @@ __device__ __forceinline__ TRow ld_trow(const uint8_t *p) {
   t.flags = (uint16_t)b.w; t.pad = 0;
   return t;
 }
+// n bytes of a tile's scratch block (16-byte aligned, padded) to any address, the whole warp: aligned 16-byte stores
+__device__ __forceinline__ void warp_copy_out(uint8_t *d, const uint8_t *s, uint32_t n, int lane) {
+  uint32_t head = (uint32_t)((0u - (uintptr_t)d) & 15u);
+  if (head > n) head = n;
+  if ((uint32_t)lane < head) d[lane] = s[lane];
+  d += head; s += head; n -= head;
+  const uint32_t nv = n >> 4;
+  const uint32_t sh = (uint32_t)((uintptr_t)s & 3u) * 8u;
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
+  uint4 *dv = reinterpret_cast<uint4 *>(d);
+  for (uint32_t v = lane; v < nv; v += 32) {
+    const uint32_t *q = wp + 4 * v;
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+    dv[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+  }
+  const uint32_t done = nv << 4, rest = n - done;
+  if ((uint32_t)lane < rest) d[done + lane] = s[done + lane];
+}
 template <bool PREFETCH>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const __grid_constant__ TileParams p) {
   const DevCfg &cfg = p.cfg;
@@ -944,7 +1206,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
   uint32_t tile = ticket(), tile_n1 = ticket();
   TileAgg ag_next;
   ag_next.bytes = 0; ag_next.scratch_off = 0; ag_next.rows = ag_next.loci = ag_next.n_big = ag_next.n_long = 0;
-  ag_next.arena_used = ag_next.n_trows = 0;
+  ag_next.arena_used = ag_next.n_trows = 0; ag_next.n_mid = 0; ag_next.flags = 0;
   if (tile < n_tiles) ag_next = p.tile_agg[tile];
   for (; tile < n_tiles; tile = tile_n1, tile_n1 = ticket()) {
     const TileAgg ag = ag_next;
@@ -955,6 +1217,10 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
     }
     const TileBase tb = p.tile_base[tile];
     const uint8_t *blk = p.scratch + ag.scratch_off;
+    if (ag.flags & 1u) {  // a dense block: the tile's output bytes, in order
+      warp_copy_out(p.out + out_base + tb.bytes, blk, (uint32_t)ag.bytes, lane);
+      continue;
+    }
     const LaneRec lr = reinterpret_cast<const LaneRec *>(blk)[lane];
     const uint8_t *rows_g = blk + TILE_BLOCK_HDR;
     const uint8_t *arena_g = rows_g + (size_t)ag.n_trows * sizeof(TRow);

@@ -85,6 +85,90 @@ def test_slow_path_records(with_samples):
         assert gpu_rows(vcf, **kw) == oracle_rows(vcf, **kw)
 
 
+def _sites_recs(rng, n, heavy=0.3):
+    """sites-only records at BASELINE's mix: SNPs, multi-allelic sites, MNPs, padded indels, rejected alleles"""
+    seq = lambda k: "".join(rng.choice("ACGT") for _ in range(k))
+    recs = []
+    for i in range(n):
+        pos = str(10_000 + 13 * i)
+        u = rng.random()
+        if u > heavy:
+            recs.append([rng.choice(["1", "chr2", "X", "chrM"]), pos, "rs%d" % i, rng.choice("ACGT"), rng.choice("ACGT"), ".", "PASS", "AC=%d" % i])
+            continue
+        k = rng.randrange(7)
+        if k == 0:    # multi-allelic, 2..8 ALTs of mixed shapes
+            ref = seq(rng.choice([1, 1, 2, 4]))
+            alts = [rng.choice([seq(1), seq(2), ref[0] + seq(3), ref[:1], "<DEL>", "*", ref + seq(2)]) for _ in range(rng.randrange(2, 9))]
+            recs.append(["3", pos, ".", ref, ",".join(alts), ".", "PASS", "M=%d" % i])
+        elif k == 1:  # MNP
+            r = seq(rng.randrange(2, 9))
+            recs.append(["4", pos, ".", r, "".join(rng.choice("ACGT") for _ in r), ".", "PASS", "."])
+        elif k == 2:  # deletion, padded
+            r = seq(rng.randrange(2, 30))
+            recs.append(["5", pos, "", r, r[:rng.randrange(1, len(r))], ".", "PASS", ""])
+        elif k == 3:  # insertion, padded on both sides
+            r = seq(rng.randrange(1, 6))
+            recs.append(["chr6", pos, ".", r, r[:1] + seq(rng.randrange(1, 40)) + r[1:], ".", "PASS", "I"])
+        elif k == 4:  # POS that is not a number / negative / huge, REF longer than one base
+            recs.append(["7", rng.choice(["abc", "-5", "99999999999", "1e3", "007"]), ".", "AC", rng.choice(["A", "ACG", "GT", "A,ACT"]), ".", "PASS", "P"])
+        elif k == 5:  # FILTER variety
+            recs.append(["8", pos, ".", "A", "G", ".", rng.choice(["q10", ".", "PASS", "LowQual"]), "F"])
+        else:         # REF == ALT, empty fields
+            recs.append(["9", pos, ".", rng.choice(["A", ""]), rng.choice(["A", "", "."]), ".", "PASS", "E"])
+    return recs
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(keep_info=True), dict(keep_id=True, keep_pos=True), dict(keep_id=True, keep_info=True, keep_pos=True)])
+def test_sites_only_rows_spread_over_lanes(kw):
+    """bvcf_compose_sites_kernel: rows planned per record and composed a row per lane, dense blocks copied out whole;
+    --keepInfo takes the row-table path.  20,000 records, 30 % with two to eight candidate rows (main.go:723-1038)."""
+    rng = random.Random(2024)
+    vcf = V._vcf(V.HDR8, _sites_recs(rng, 20_000))
+    assert gpu_rows(vcf, **kw) == oracle_rows(vcf, **kw)
+
+
+def test_sites_only_overfull_tiles():
+    """tiles whose rows exceed the row table (128) or the arena (6 KiB): the tail records take the slow path, the
+    others stay staged; tiles where every record fails; a 70-row MNP next to SNPs"""
+    rng = random.Random(77)
+    seq = lambda k: "".join(rng.choice("ACGT") for _ in range(k))
+    recs = []
+    for i in range(3000):
+        pos = str(500 + 3 * i)
+        blk = (i // 32) % 6
+        if blk == 0:    # 32 records x 8 rows = 256 rows in one tile
+            recs.append(["1", pos, ".", "A", ",".join(rng.choice("CGT") for _ in range(8)), ".", "PASS", "."])
+        elif blk == 1:  # 32 records x ~400 text bytes
+            recs.append(["2", pos, ".", "A", "A" + seq(350), ".", "PASS", "."])
+        elif blk == 2:  # a record on its own too large for the arena, SNPs around it
+            recs.append(["3", pos, ".", "A", "A" + seq(7000), ".", "PASS", "."] if i % 32 == 7 else ["3", pos, ".", "C", "T", ".", "PASS", "."])
+        elif blk == 3:  # 70-row MNP
+            r = seq(70)
+            a = "".join({"A": "C", "C": "G", "G": "T", "T": "A"}[ch] for ch in r)
+            recs.append(["4", pos, ".", r, a, ".", "PASS", "."] if i % 32 in (0, 31) else ["4", pos, ".", "G", "A", ".", "PASS", "."])
+        elif blk == 4:  # nothing comes out of the whole tile
+            recs.append(["5", pos, ".", "A", "A", ".", "PASS", "."])
+        else:
+            recs.append(["6", pos, "rs%d" % i, "T", "C", ".", "PASS", "DP=%d" % i])
+    vcf = V._vcf(V.HDR8, recs)
+    for kw in (dict(), dict(keep_info=True, keep_id=True)):
+        assert gpu_rows(vcf, **kw) == oracle_rows(vcf, **kw)
+
+
+def test_sites_only_matches_thread_per_record_composer(monkeypatch):
+    """the two sites-only composers (BVCF_SITES_OLD selects round 2's first one) give the same bytes and diagnostics"""
+    from oracle import oracle as O
+
+    rng = random.Random(4)
+    vcf = V._vcf(V.HDR8, _sites_recs(rng, 6000, heavy=0.6))
+    ref = O.read_vcf(O.OracleConfig(keep_info=True), vcf)
+    a = _process(vcf, _cfg(keep_info=True))
+    monkeypatch.setenv("BVCF_SITES_OLD", "1")
+    b = _process(vcf, _cfg(keep_info=True))
+    assert a.tsv == b.tsv == ref.tsv
+    assert sorted(a.diags) == sorted(b.diags) == sorted(ref.diags)
+
+
 def test_long_info_spans_appended_at_copy_out():
     """--keepInfo with INFO fields from 0 to 9,000 bytes: the span is copied from the input line after the staged row"""
     rng = random.Random(3)
