@@ -330,7 +330,11 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       static const int pf = getenv("BVCF_PREFETCH") ? atoi(getenv("BVCF_PREFETCH")) : 0;  // experiments: bit 0 compose, bit 1 copy-out
       static const bool sites_old = getenv("BVCF_SITES_OLD") != nullptr;  // experiments: the thread-per-record composer
       if (dc.n_samples == 0 && !sites_old) {
-        launch(bvcf_compose_sites_kernel<5, 6144, 128>, 6144, 128, 5);
+        static const int sv = getenv("BVCF_SITES_VAR") ? atoi(getenv("BVCF_SITES_VAR")) : 0;  // experiments
+        // 8 resident CTAs (64 registers, 3.5 KiB arena + 96 rows per warp) against 5 (80 registers, 6 KiB + 128 rows):
+        // 20.9 against 25.9 ms on 50 M lines -- the kernel waits on dependent loads and taken branches, warps hide both
+        if (sv == 5) launch(bvcf_compose_sites_kernel<5, 6144, 128>, 6144, 128, 5);
+        else launch(bvcf_compose_sites_kernel<8, 3584, 96>, 3584, 96, 8);
       } else if (dc.n_samples == 0) {
         if (pf & 1) launch(bvcf_compose_kernel<4, 8192, 160, true>, 8192, 160, 4);
         else launch(bvcf_compose_kernel<4, 8192, 160, false>, 8192, 160, 4);

@@ -375,7 +375,7 @@ struct LineCtx {
 };
 
 
-__device__ __forceinline__ void push_diag(const DiagSink &p, unsigned long long line_no, int alt_no, int code) {
+__device__ __noinline__ void push_diag(const DiagSink &p, unsigned long long line_no, int alt_no, int code) {
   if (!p.diags) return;
   const uint32_t i = atomicAdd(&p.ctr->n_diags, 1u);
   if (i < p.cap) {
@@ -402,6 +402,7 @@ struct AlleleGen {
 __device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const DiagSink &p, unsigned long long line_no,
                                           bool diag) {
   bool same = g.alt_n == g.ref_n;
+#pragma unroll 1
   for (int i = 0; same && i < g.alt_n; i++) same = g.alt[i] == g.ref[i];
   if (same) {                                                         // :729
     if (diag) push_diag(p, line_no, 0, 1);
@@ -409,6 +410,7 @@ __device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const DiagS
     return;
   }
   bool multi = false;                                                 // :777-779, 1012: ALT holds a comma
+#pragma unroll 1
   for (int i = 0; i < g.alt_n; i++) multi = multi || g.alt[i] == ',';
   lc.multi = multi;
   lc.site_type = T_MULTI;
@@ -418,6 +420,7 @@ __device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const DiagS
     else if (g.alt_n < g.ref_n) lc.site_type = T_DEL;
     else {
       int nd = 0;
+#pragma unroll 1
       for (int i = 0; i < g.ref_n; i++) nd += g.ref[i] != g.alt[i];
       lc.site_type = nd > 1 ? T_MNP : T_SNP;
     }
@@ -431,6 +434,7 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Diag
   for (;;) {
     if (g.done) return false;
     if (g.mnp_i >= 0) {                                               // :855-873 one row per differing base
+#pragma unroll 1
       for (int i = g.mnp_i; i < ref_n; i++) {
         if (ref[i] != g.ta[i]) {
           oa.kind = 0; oa.ref = ref[i]; oa.alt_c = g.ta[i]; oa.pos_verbatim = false; oa.pos_val = g.ipos + i;
@@ -459,6 +463,7 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Diag
     }
     // next comma-separated allele                                    // :774
     int e = g.s;
+#pragma unroll 1
     while (e < g.alt_n && g.alt[e] != ',') e++;
     const uint8_t *ta = g.alt + g.s;
     const int tn = e - g.s;
@@ -470,6 +475,7 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Diag
     if (last) g.done = true;  // cleared again below when an MNP still has bases to yield
     oa.alt_idx = alt_idx;
     bool valid = tn > 0;                                              // altIsValid :456-474
+#pragma unroll 1
     for (int i = 0; valid && i < tn; i++) valid = is_acgt(ta[i]);
     if (!valid) { if (diag) push_diag(p, line_no, alt_idx + 1, 2); continue; }
     if (ref_n == 1) {                                                 // :786
@@ -498,9 +504,11 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Diag
     }
     if (tn > ref_n) {                                                 // :899 insertion with padding
       int r = 0;
+#pragma unroll 1
       while (tn + r > 0 && ref_n + r > 1 && ta[tn + r - 1] == ref[ref_n + r - 1]) r--;
       const int off = ref_n + r;                                      // :932
       bool pre = true;
+#pragma unroll 1
       for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
       if (!pre) { if (diag) push_diag(p, line_no, alt_idx + 1, 6); continue; }
       oa.kind = 1; oa.ref = ref[off - 1]; oa.ins_p = ta + off; oa.ins_n = tn + r - off;
@@ -509,9 +517,11 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Diag
     }
     {                                                                 // :971 deletion with padding
       int r = 0;
+#pragma unroll 1
       while (tn + r > 1 && ref_n + r > 0 && ta[tn + r - 1] == ref[ref_n + r - 1]) r--;
       const int off = tn + r;                                         // :984
       bool pre = true;
+#pragma unroll 1
       for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
       if (!pre) { if (diag) push_diag(p, line_no, alt_idx + 1, 6); continue; }
       oa.kind = 2; oa.ref = ref[off]; oa.del_n = -((long long)ref_n + r - off);

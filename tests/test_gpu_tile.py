@@ -128,7 +128,7 @@ def test_sites_only_rows_spread_over_lanes(kw):
 
 
 def test_sites_only_overfull_tiles():
-    """tiles whose rows exceed the row table (128) or the arena (6 KiB): the tail records take the slow path, the
+    """tiles whose rows exceed the row table (96) or the arena (3.5 KiB): the tail records take the slow path, the
     others stay staged; tiles where every record fails; a 70-row MNP next to SNPs"""
     rng = random.Random(77)
     seq = lambda k: "".join(rng.choice("ACGT") for _ in range(k))
