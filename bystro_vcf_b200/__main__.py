@@ -2,7 +2,9 @@
 
 Same flags, same stdin/stdout behaviour: header line first (main.go:199), then rows in input order; the
 reference's log.Printf lines ("chrom:pos ALT #k message", main.go:730-986) on stderr, or appended to --err.
-`--gpus N` (extension) shards the input over N GPUs of the box (shard.read_vcf_multi)."""
+`--gpus N` (extension) shards the input over N GPUs of the box (shard.read_vcf_multi); `--bgzfOut` (extension) writes
+the rows as bgzf blocks deflated on the GPU -- with a .vcf.gz input the command stands for the whole
+`pigz -d -c in.vcf.gz | bystro-vcf ... | pigz -c > out.gz` of README.md:10."""
 from __future__ import annotations
 
 import os
@@ -48,12 +50,20 @@ def main(argv=None) -> int:
             out = os.fdopen(os.open(cfg.outPath, os.O_WRONLY | os.O_CREAT, 0o644), "wb")
         else:
             out = sys.stdout.buffer
-        out.write(string_header(cfg).encode() + b"\n")  # main.go:199
+        hdr = string_header(cfg).encode() + b"\n"  # main.go:199
+        if cfg.bgzfOut:
+            from . import bgzf
+
+            hdr = bgzf.compress(hdr, eof=False)
+        out.write(hdr)
 
     def log(text, line_no, alt_no, code):  # the reference's log.Printf sites (main.go:730-986)
         print(text, file=err)
 
     try:
+        if gpus > 1 and cfg.bgzfOut:
+            print("--bgzfOut runs on one GPU", file=err)
+            return 1
         if gpus > 1:
             import mmap
 
@@ -66,6 +76,10 @@ def main(argv=None) -> int:
             read_vcf_multi(cfg, data, out, list(range(gpus)), diag_sink=log)
         else:
             read_vcf(cfg, inp, out, diag_sink=log)
+        if out is not None and cfg.bgzfOut:
+            from . import bgzf
+
+            out.write(bgzf.EOF_BLOCK)
     except NotAVcfError as e:
         print(str(e), file=err)  # log.Fatal main.go:263,293
         return 1

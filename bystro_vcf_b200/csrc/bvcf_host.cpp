@@ -48,6 +48,7 @@ struct Config {  // main.go:63-80
   int gpus = 1;
   std::vector<int> devices;  // --devices a,b,...: CUDA device of each worker (a device may be listed twice); default 0..gpus-1
   size_t chunkBytes = 64u << 20;
+  bool bgzfOut = false;  // --bgzfOut: the rows leave as bgzf blocks deflated on the GPU (the `| pigz -c` of README.md:10,71)
 };
 
 std::string trim(const std::string &s) {  // strings.TrimSpace
@@ -84,7 +85,7 @@ Config setup(int argc, char **argv) {  // main.go:82-126
                    {"allowFilter", &allow}, {"excludeFilter", &exclude}};
   struct BF { const char *name; bool *dst; };
   const BF bf[] = {{"noOut", &c.noOut}, {"keepId", &c.keepID}, {"keepQual", &c.keepQual}, {"keepPos", &c.keepPos},
-                   {"keepInfo", &c.keepInfo}};
+                   {"keepInfo", &c.keepInfo}, {"bgzfOut", &c.bgzfOut}};
   std::string gpus, chunk, devices;
   for (int i = 1; i < argc; i++) {
     std::string s = argv[i];
@@ -295,7 +296,31 @@ std::string bgzf_inflate_host(const uint8_t *p, size_t n, size_t want) {
   return out;
 }
 
-int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len, std::vector<uint8_t> &head, int out_fd) {
+// one bgzf block (SAM spec 4.1) around `text` (< 64 KiB), deflated on the host: the TSV header line
+std::vector<uint8_t> bgzf_block_host(const uint8_t *text, size_t n) {
+  std::vector<uint8_t> out(18 + compressBound(n) + 8);
+  z_stream z{};
+  if (deflateInit2(&z, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) fatal("deflateInit2 failed");
+  z.next_in = const_cast<Bytef *>(text); z.avail_in = (uInt)n;
+  z.next_out = out.data() + 18; z.avail_out = (uInt)(out.size() - 18 - 8);
+  if (deflate(&z, Z_FINISH) != Z_STREAM_END) fatal("deflate failed");
+  const size_t payload = z.total_out;
+  deflateEnd(&z);
+  const size_t bsize = 18 + payload + 8;
+  static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+  memcpy(out.data(), hdr, 16);
+  out[16] = (uint8_t)((bsize - 1) & 0xFF); out[17] = (uint8_t)((bsize - 1) >> 8);
+  const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), text, (uInt)n), isize = (uint32_t)n;
+  for (int k = 0; k < 4; k++) { out[18 + payload + k] = (uint8_t)(crc >> (8 * k)); out[22 + payload + k] = (uint8_t)(isize >> (8 * k)); }
+  out.resize(bsize);
+  return out;
+}
+const uint8_t BGZF_EOF[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+// readVcf over the resident regions, for compressed streams on either side: bgzf input is inflated on the GPU
+// (compressed_in), --bgzfOut rows are deflated there
+int run_resident(const Config &config, int in_fd, const uint8_t *map, size_t map_len, std::vector<uint8_t> &head, int out_fd,
+                 bool compressed_in) {
   // compressed bytes: the mapping, or a growing buffer read from the pipe
   std::vector<uint8_t> &buf = head;
   size_t consumed = 0;  // bytes of the compressed stream already handed to the GPU
@@ -318,7 +343,7 @@ int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len
   int eol_width = 1;
   for (size_t want = 1u << 20;; want *= 4) {
     fill(want);
-    const std::string t = bgzf_inflate_host(at(0), avail(), want * 4);
+    const std::string t = compressed_in ? bgzf_inflate_host(at(0), avail(), want * 4) : std::string((const char *)at(0), std::min(avail(), want * 4));
     const char *nl = (const char *)memchr(t.data(), '\n', t.size());
     if (!nl) { if (eof) fatal("Not a VCF file"); continue; }
     size_t first_end = nl - t.data();
@@ -407,7 +432,11 @@ int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len
   for (;;) {
     // ---- a group of whole blocks worth about batch_text bytes of text ----
     size_t p = 0, text = 0;
-    while (text < batch_text) {
+    if (!compressed_in) {
+      fill(batch_text);
+      p = std::min(avail(), batch_text);
+    }
+    while (compressed_in && text < batch_text) {
       fill(p + (1u << 16) + 18);
       const size_t bs = bgzf_block_size(at(p), avail() - p);
       if (!bs || p + bs > avail()) {
@@ -429,8 +458,13 @@ int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len
     if (!map && consumed > (64u << 20)) { buf.erase(buf.begin(), buf.begin() + consumed); consumed = 0; }
     if (!carry.empty() && (rc = bvcf_resident_upload(ctx, 0, carry.data(), carry.size()))) fatal(std::string("upload: ") + bvcf_strerror(rc));
     size_t n_text = 0;
-    if ((rc = bvcf_resident_inflate_bgzf(ctx, pin, p, carry.size(), &n_text)))
-      fatal(std::string("bgzf: ") + bvcf_strerror(rc) + " " + bvcf_last_error(ctx));
+    if (compressed_in) {
+      if ((rc = bvcf_resident_inflate_bgzf(ctx, pin, p, carry.size(), &n_text)))
+        fatal(std::string("bgzf: ") + bvcf_strerror(rc) + " " + bvcf_last_error(ctx));
+    } else {
+      if ((rc = bvcf_resident_upload(ctx, carry.size(), pin, p))) fatal(std::string("upload: ") + bvcf_strerror(rc));
+      n_text = p;
+    }
     const size_t total = carry.size() + n_text;
     // ---- the longest newline-terminated prefix; the rest is carried into the next group ----
     const size_t tail_n = std::min(total - begin, max_line);
@@ -452,8 +486,21 @@ int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len
         out_cap = st.out_bytes + st.out_bytes / 4;
         if (bvcf_host_alloc((void **)&out_host, out_cap)) fatal("bvcf_host_alloc failed");
       }
-      if ((rc = bvcf_resident_download(ctx, 0, out_host, st.out_bytes))) fatal(std::string("download: ") + bvcf_strerror(rc));
-      write_all(out_fd, out_host, st.out_bytes);
+      if (config.bgzfOut) {
+        size_t comp = 0;
+        rc = bvcf_resident_download_bgzf(ctx, 0, st.out_bytes, out_host, out_cap, &comp);
+        if (rc == BVCF_E_TOO_LARGE) {  // comp: the bytes needed
+          bvcf_host_free(out_host);
+          out_cap = comp + comp / 8;
+          if (bvcf_host_alloc((void **)&out_host, out_cap)) fatal("bvcf_host_alloc failed");
+          rc = bvcf_resident_download_bgzf(ctx, 0, st.out_bytes, out_host, out_cap, &comp);
+        }
+        if (rc) fatal(std::string("download: ") + bvcf_strerror(rc) + " " + bvcf_last_error(ctx));
+        write_all(out_fd, out_host, comp);
+      } else {
+        if ((rc = bvcf_resident_download(ctx, 0, out_host, st.out_bytes))) fatal(std::string("download: ") + bvcf_strerror(rc));
+        write_all(out_fd, out_host, st.out_bytes);
+      }
     }
     {  // dosage batch and diagnostics of this group
       bvcf_dosage_batch dos;
@@ -474,6 +521,7 @@ int run_bgzf(const Config &config, int in_fd, const uint8_t *map, size_t map_len
     begin = 0;
   }
   // an unterminated last line (the carry) is dropped (main.go:354-357)
+  if (config.bgzfOut && !config.noOut) write_all(out_fd, BGZF_EOF, sizeof BGZF_EOF);
   if (pin) bvcf_host_free(pin);
   if (out_host) bvcf_host_free(out_host);
   int rc_exit = 0;
@@ -506,7 +554,12 @@ int main(int argc, char **argv) {
     fatal(config.outPath + ": " + strerror(errno));
   if (!config.noOut) {
     const std::string h = string_header(config) + "\n";  // main.go:199: before any input is read
-    write_all(out_fd, (const uint8_t *)h.data(), h.size());
+    if (config.bgzfOut) {
+      const std::vector<uint8_t> b = bgzf_block_host((const uint8_t *)h.data(), h.size());
+      write_all(out_fd, b.data(), b.size());
+    } else {
+      write_all(out_fd, (const uint8_t *)h.data(), h.size());
+    }
   }
 
   // ---- input: a regular file is memory-mapped, anything else (pipes) is read ----
@@ -540,8 +593,9 @@ int main(int argc, char **argv) {
       head.resize(got);
       bz = looks_bgzf(head.data(), head.size());
     }
-    if (bz) {
-      const int rc = run_bgzf(config, in_fd, map, map_len, head, out_fd);
+    if (bz || config.bgzfOut) {
+      if (config.bgzfOut && config.gpus > 1) fatal("--bgzfOut runs on one GPU");
+      const int rc = run_resident(config, in_fd, map, map_len, head, out_fd, bz);
       if (map) munmap((void *)map, map_len);
       if (out_fd != 1) close(out_fd);
       return rc;

@@ -76,12 +76,16 @@ class Config:
     device: int = 0
     chunkBytes: int = 64 << 20
     normalizeHeader: bool = True
+    # not in the reference: the rows leave as bgzf blocks deflated on the GPU (stands in for the `| pigz -c` behind the
+    # reference, README.md:10,71); --bgzfOut
+    bgzfOut: bool = False
 
 
 _STRING_FLAGS = {"in": "inPath", "fam": "famPath", "err": "errPath", "out": "outPath", "dosageOutput": "dosageMatrixOutPath",
                  "sample": "sampleListPath", "emptyField": "emptyField", "fieldDelimiter": "fieldDelimiter",
                  "cpuProfile": "cpuProfile", "allowFilter": None, "excludeFilter": None}
-_BOOL_FLAGS = {"noOut": "noOut", "keepId": "keepID", "keepQual": "keepQual", "keepPos": "keepPos", "keepInfo": "keepInfo"}
+_BOOL_FLAGS = {"noOut": "noOut", "keepId": "keepID", "keepQual": "keepQual", "keepPos": "keepPos", "keepInfo": "keepInfo",
+               "bgzfOut": "bgzfOut"}
 
 
 def setup(args: Optional[Sequence[str]] = None) -> Config:
@@ -475,11 +479,13 @@ def write_sample_list(config: Config, chrom_line: bytes, normalize: bool = True)
                 fh.write((s.replace(b".", b"_") if normalize else s) + b"\n")
 
 
-def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Optional[BinaryIO], batch_text: int = 512 << 20,
-                   diag_sink=None) -> dict:
-    """readVcf (main.go:241-396) for bgzf input: groups of whole blocks are uploaded COMPRESSED and inflated on the GPU
-    straight into the resident input region; the transform runs there; rows, dosage batches and diagnostics come
-    back.  Replaces the `pigz -d -c |` in front of the reference (README.md:10)."""
+def _read_vcf_resident(config: Config, head: bytes, reader: BinaryIO, writer: Optional[BinaryIO], batch_text: int = 512 << 20,
+                       diag_sink=None, compressed_in: bool = True) -> dict:
+    """readVcf (main.go:241-396) over the resident regions, for compressed streams on either side.
+    compressed_in: groups of whole bgzf blocks are uploaded COMPRESSED and inflated on the GPU straight into the
+    resident input region (replaces the `pigz -d -c |` in front of the reference, README.md:10); otherwise groups
+    of plain text are uploaded.  The transform runs there; rows, dosage batches and diagnostics come back -- the
+    rows as bgzf blocks deflated on the GPU when config.bgzfOut (replaces the `| pigz -c` behind it)."""
     from . import bgzf
 
     buf = bytearray(head)
@@ -498,7 +504,7 @@ def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Option
     want = 1 << 20
     while True:
         fill(want)
-        text0 = bgzf.inflate_host(buf, want * 4)
+        text0 = bgzf.inflate_host(buf, want * 4) if compressed_in else bytes(buf)
         try:
             width, chrom_line, data_off = parse_preamble(text0)
             break
@@ -527,7 +533,10 @@ def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Option
         while True:
             # ---- a group of whole blocks worth about batch_text bytes of text ----
             p = text = 0
-            while text < batch_text:
+            if not compressed_in:
+                fill(batch_text)
+                p = min(len(buf), batch_text)
+            while compressed_in and text < batch_text:
                 fill(p + (1 << 16) + 18)
                 bs = bgzf.block_size(buf, p)
                 if bs == 0 or p + bs > len(buf):
@@ -543,7 +552,11 @@ def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Option
             del buf[:p]
             if carry:
                 tr.resident_upload(0, carry)
-            n_text = tr.resident_inflate_bgzf(group, len(carry))
+            if compressed_in:
+                n_text = tr.resident_inflate_bgzf(group, len(carry))
+            else:
+                tr.resident_upload(len(carry), group)
+                n_text = len(group)
             total = len(carry) + n_text
             totals["compressed_bytes"] += len(group)
             # ---- the longest newline-terminated prefix; what follows it is carried into the next group ----
@@ -559,7 +572,10 @@ def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Option
             end = total - tail_n + k + 1
             stats, _ = tr.resident_run(end, want_times=False, begin=begin)
             if writer is not None and not config.noOut and stats["out_bytes"]:
-                writer.write(tr.resident_download(0, stats["out_bytes"]))
+                if config.bgzfOut:
+                    writer.write(tr.resident_download_bgzf(0, stats["out_bytes"]))
+                else:
+                    writer.write(tr.resident_download(0, stats["out_bytes"]))
             if arrow is not None or diag_sink is not None:
                 loci, dosage, diags = tr.resident_results()
                 if arrow is not None and dosage is not None:
@@ -579,6 +595,9 @@ def _read_vcf_bgzf(config: Config, head: bytes, reader: BinaryIO, writer: Option
     return totals
 
 
+_read_vcf_bgzf = _read_vcf_resident  # the name round 2 first gave it
+
+
 def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], transformer: Optional[Transformer] = None,
              diag_sink=None) -> dict:
     """readVcf (main.go:241-396) on the GPU: header discovery on the host, every data line on the device.
@@ -593,7 +612,11 @@ def read_vcf(config: Config, reader: BinaryIO, writer: Optional[BinaryIO], trans
     if bgzf.is_bgzf(head):  # .vcf.gz: the compressed bytes go to the GPU, which inflates them
         if transformer is not None:
             raise BvcfError("read_vcf: pass no transformer for bgzf input")
-        return _read_vcf_bgzf(config, head, reader, writer, diag_sink=diag_sink)
+        return _read_vcf_resident(config, head, reader, writer, diag_sink=diag_sink)
+    if config.bgzfOut:  # the rows are deflated where they are: on the device
+        if transformer is not None:
+            raise BvcfError("read_vcf: pass no transformer with bgzfOut")
+        return _read_vcf_resident(config, head, reader, writer, diag_sink=diag_sink, compressed_in=False)
     while True:  # make sure the whole preamble (meta lines + #CHROM line) is in `head`
         try:
             width, chrom_line, off = parse_preamble(head)

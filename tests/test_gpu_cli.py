@@ -264,3 +264,40 @@ def test_bgzf_input_with_dosage_and_diagnostics(tmp_path):
         assert [x.encode() for x in tab.column(0).to_pylist()] == ref.loci
         assert np.array_equal(np.stack([tab.column(j + 1).to_numpy() for j in range(n)], axis=1), ref.dosage)
         assert sorted(err.strip().split("\n")) == sorted("1:%d ALT #1 ALT not ACTG" % (100 + i) for i in range(3000) if i % 500 == 3)
+
+
+@pytest.mark.parametrize("host", ["cpp", "python"])
+@pytest.mark.parametrize("compressed_in", [False, True])
+def test_bgzf_out_is_the_whole_pipeline(chr1_fixture, tmp_path, host, compressed_in):
+    """--bgzfOut: header + rows leave as bgzf blocks deflated on the GPU; with .vcf.gz input the one command stands for
+    `pigz -d -c in.vcf.gz | bystro-vcf ... | pigz -c` (README.md:10).  gzip reads the file back to the plain rows."""
+    import gzip
+
+    from bystro_vcf_b200 import bgzf
+
+    vcf = chr1_fixture[:30 << 20].rsplit(b"\n", 1)[0] + b"\n"
+    flags = ["--keepId"]
+    plain, _ = _run([BIN] + flags, vcf)
+    cmd = [BIN] if host == "cpp" else [sys.executable, "-m", "bystro_vcf_b200"]
+    out = tmp_path / "rows.tsv.gz"
+    data = bgzf.compress(vcf) if compressed_in else vcf
+    got, _ = _run(cmd + flags + ["--bgzfOut", "--out", str(out)], data)
+    assert got == b""
+    raw = out.read_bytes()
+    assert raw.endswith(bgzf.EOF_BLOCK) and bgzf.is_bgzf(raw)
+    assert gzip.decompress(raw) == plain
+    assert len(raw) < len(plain) * 0.9
+    # every member is a bgzf block of at most 64 KiB
+    p = n = 0
+    while p < len(raw):
+        bs = bgzf.block_size(raw, p)
+        assert 0 < bs <= 65536
+        p += bs
+        n += 1
+    assert p == len(raw) and n > 10
+
+
+def test_bgzf_out_refuses_several_gpus(tmp_path):
+    for cmd in ([BIN], [sys.executable, "-m", "bystro_vcf_b200"]):
+        r = subprocess.run(cmd + ["--bgzfOut", "--gpus", "2"], input=b"##fileformat=VCFv4.1\n", capture_output=True, cwd=ROOT)
+        assert r.returncode == 1 and b"--bgzfOut runs on one GPU" in r.stderr

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bystro_vcf_b200 import Config, Transformer, synth
 N = int(os.environ.get("LINES", "3000000"))
-for sub_gib in (16, 20, 24):
+for sub_gib in [int(x) for x in os.environ.get("SUB_GIB", "16,20,24").split(",")]:
     c = Config(); c.allowedFilters = {"PASS": True, ".": True}
     tr = Transformer(c, resident_subchunk_bytes=sub_gib << 30)
     tr.set_header(synth.chrom_line(20130502, 2504))
