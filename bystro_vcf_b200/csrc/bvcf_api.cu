@@ -332,9 +332,11 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       if (dc.n_samples == 0 && !sites_old) {
         static const int sv = getenv("BVCF_SITES_VAR") ? atoi(getenv("BVCF_SITES_VAR")) : 0;  // experiments
         // 8 resident CTAs (64 registers, 3.5 KiB arena + 96 rows per warp) against 5 (80 registers, 6 KiB + 128 rows):
-        // 20.9 against 25.9 ms on 50 M lines -- the kernel waits on dependent loads and taken branches, warps hide both
-        if (sv == 5) launch(bvcf_compose_sites_kernel<5, 6144, 128>, 6144, 128, 5);
-        else launch(bvcf_compose_sites_kernel<8, 3584, 96>, 3584, 96, 8);
+        // 19.5 against 23.3 ms on 50 M lines -- the kernel waits on dependent loads and taken branches, warps hide both
+        // (REF / ALT held in registers, which pays at 128 registers, spills at 64: 20.3 ms; 7 CTAs x 72 registers with
+        // them: 20.9 ms; 8 CTAs without: 19.5 ms)
+        if (sv == 5) launch(bvcf_compose_sites_kernel<5, 6144, 128, true>, 6144, 128, 5);
+        else launch(bvcf_compose_sites_kernel<8, 3584, 96, false>, 3584, 96, 8);
       } else if (dc.n_samples == 0) {
         if (pf & 1) launch(bvcf_compose_kernel<4, 8192, 160, true>, 8192, 160, 4);
         else launch(bvcf_compose_kernel<4, 8192, 160, false>, 8192, 160, 4);

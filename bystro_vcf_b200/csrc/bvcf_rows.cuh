@@ -390,20 +390,46 @@ __device__ __noinline__ void push_diag(const DiagSink &p, unsigned long long lin
 // gen_begin does the whole-line checks (REF == ALT, site type); gen_next yields one output allele per call,
 // in the order the reference appends them, so that all lanes of a warp meet at a single emit_row call.
 struct AlleleGen {
-  const uint8_t *ref, *alt, *ta;  // ta/tn: the equal-length allele being decomposed base by base
+  const uint8_t *ref, *alt;
   int ref_n, alt_n, tn;
+  int ta_off;     // the equal-length allele being decomposed base by base: its offset in ALT
   int s;          // cursor in ALT: start of the next comma-separated allele
   int alt_idx;    // its index in the ALT list
   int mnp_i;      // >= 0: resume the MNP decomposition at this base
   long long ipos;
   bool pos_ok, last, done;
+  // REF (up to 8 bases) and ALT (up to 16 characters) held in registers: the loops below walk these fields several
+  // times a byte at a time, and every byte from memory was a dependent load the whole warp waited for
+  bool cached;
+  unsigned long long rw, aw0, aw1;
 };
+__device__ __forceinline__ uint32_t gen_ref(const AlleleGen &g, int i) {
+  return g.cached ? (uint32_t)(g.rw >> (8 * i)) & 0xFFu : (uint32_t)g.ref[i];
+}
+__device__ __forceinline__ uint32_t gen_alt(const AlleleGen &g, int i) {
+  if (!g.cached) return g.alt[i];
+  const unsigned long long w = i < 8 ? g.aw0 : g.aw1;
+  return (uint32_t)(w >> (8 * (i & 7))) & 0xFFu;
+}
+template <bool CACHE>
+__device__ __forceinline__ void gen_cache(AlleleGen &g) {
+  g.cached = CACHE && g.ref_n <= 8 && g.alt_n <= 16;
+  g.rw = g.aw0 = g.aw1 = 0;
+  if (g.cached) {
+    g.rw = ld64_any(g.ref);
+    g.aw0 = ld64_any(g.alt);
+    if (g.alt_n > 8) g.aw1 = ld64_any(g.alt + 8);
+  }
+}
 
+// CACHE false: a kernel built for 64 registers has no room for the three words (it spilled, and ran slower)
+template <bool CACHE = true>
 __device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const DiagSink &p, unsigned long long line_no,
                                           bool diag) {
+  gen_cache<CACHE>(g);
   bool same = g.alt_n == g.ref_n;
 #pragma unroll 1
-  for (int i = 0; same && i < g.alt_n; i++) same = g.alt[i] == g.ref[i];
+  for (int i = 0; same && i < g.alt_n; i++) same = gen_alt(g, i) == gen_ref(g, i);
   if (same) {                                                         // :729
     if (diag) push_diag(p, line_no, 0, 1);
     g.done = true;
@@ -411,7 +437,7 @@ __device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const DiagS
   }
   bool multi = false;                                                 // :777-779, 1012: ALT holds a comma
 #pragma unroll 1
-  for (int i = 0; i < g.alt_n; i++) multi = multi || g.alt[i] == ',';
+  for (int i = 0; i < g.alt_n; i++) multi = multi || gen_alt(g, i) == ',';
   lc.multi = multi;
   lc.site_type = T_MULTI;
   if (!multi) {  // a single allele: type from its shape (main.go:742,764,1018-1037)
@@ -421,7 +447,7 @@ __device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const DiagS
     else {
       int nd = 0;
 #pragma unroll 1
-      for (int i = 0; i < g.ref_n; i++) nd += g.ref[i] != g.alt[i];
+      for (int i = 0; i < g.ref_n; i++) nd += gen_ref(g, i) != gen_alt(g, i);
       lc.site_type = nd > 1 ? T_MNP : T_SNP;
     }
   }
@@ -429,15 +455,15 @@ __device__ __forceinline__ void gen_begin(AlleleGen &g, LineCtx &lc, const DiagS
 
 __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const DiagSink &p, unsigned long long line_no,
                                          bool diag) {
-  const uint8_t *ref = g.ref;
   const int ref_n = g.ref_n;
   for (;;) {
     if (g.done) return false;
     if (g.mnp_i >= 0) {                                               // :855-873 one row per differing base
 #pragma unroll 1
       for (int i = g.mnp_i; i < ref_n; i++) {
-        if (ref[i] != g.ta[i]) {
-          oa.kind = 0; oa.ref = ref[i]; oa.alt_c = g.ta[i]; oa.pos_verbatim = false; oa.pos_val = g.ipos + i;
+        const uint32_t r = gen_ref(g, i), a = gen_alt(g, g.ta_off + i);
+        if (r != a) {
+          oa.kind = 0; oa.ref = (uint8_t)r; oa.alt_c = (uint8_t)a; oa.pos_verbatim = false; oa.pos_val = g.ipos + i;
           g.mnp_i = i + 1;
           return true;
         }
@@ -448,25 +474,25 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Diag
     }
     if (g.alt_n == 1) {                                               // :735 the single one-base ALT
       g.done = true;
-      const uint8_t a0 = g.alt[0];
+      const uint8_t a0 = (uint8_t)gen_alt(g, 0);
       oa.alt_idx = 0;
       if (!is_acgt(a0)) { if (diag) push_diag(p, line_no, 1, 2); return false; }
       if (ref_n == 1) {                                               // :742 SNP, POS text verbatim
-        oa.kind = 0; oa.ref = ref[0]; oa.alt_c = a0; oa.pos_verbatim = true;
+        oa.kind = 0; oa.ref = (uint8_t)gen_ref(g, 0); oa.alt_c = a0; oa.pos_verbatim = true;
         return true;
       }
-      if (a0 != ref[0]) { if (diag) push_diag(p, line_no, 1, 3); return false; }   // :747
+      if (a0 != gen_ref(g, 0)) { if (diag) push_diag(p, line_no, 1, 3); return false; }   // :747
       if (!g.pos_ok) { if (diag) push_diag(p, line_no, 1, 4); return false; }      // :752
-      oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n;               // :764
+      oa.kind = 2; oa.ref = (uint8_t)gen_ref(g, 1); oa.del_n = 1 - (long long)ref_n;               // :764
       oa.pos_verbatim = false; oa.pos_val = g.ipos + 1;
       return true;
     }
     // next comma-separated allele                                    // :774
-    int e = g.s;
+    const int t0 = g.s;  // its offset in ALT
+    int e = t0;
 #pragma unroll 1
-    while (e < g.alt_n && g.alt[e] != ',') e++;
-    const uint8_t *ta = g.alt + g.s;
-    const int tn = e - g.s;
+    while (e < g.alt_n && gen_alt(g, e) != ',') e++;
+    const int tn = e - t0;
     const bool last = e >= g.alt_n;
     const int alt_idx = g.alt_idx;
     g.s = e + 1;
@@ -476,15 +502,16 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Diag
     oa.alt_idx = alt_idx;
     bool valid = tn > 0;                                              // altIsValid :456-474
 #pragma unroll 1
-    for (int i = 0; valid && i < tn; i++) valid = is_acgt(ta[i]);
+    for (int i = 0; valid && i < tn; i++) valid = is_acgt((uint8_t)gen_alt(g, t0 + i));
     if (!valid) { if (diag) push_diag(p, line_no, alt_idx + 1, 2); continue; }
+    const uint32_t ta0 = gen_alt(g, t0), r0 = gen_ref(g, 0);
     if (ref_n == 1) {                                                 // :786
       if (tn == 1) {
-        oa.kind = 0; oa.ref = ref[0]; oa.alt_c = ta[0]; oa.pos_verbatim = true;
+        oa.kind = 0; oa.ref = (uint8_t)r0; oa.alt_c = (uint8_t)ta0; oa.pos_verbatim = true;
         return true;
       }
-      if (ta[0] != ref[0]) { if (diag) push_diag(p, line_no, alt_idx + 1, 5); continue; }   // :797
-      oa.kind = 1; oa.ref = ref[0]; oa.ins_p = ta + 1; oa.ins_n = tn - 1; oa.pos_verbatim = true;  // :803
+      if (ta0 != r0) { if (diag) push_diag(p, line_no, alt_idx + 1, 5); continue; }   // :797
+      oa.kind = 1; oa.ref = (uint8_t)r0; oa.ins_p = g.alt + t0 + 1; oa.ins_n = tn - 1; oa.pos_verbatim = true;  // :803
       return true;
     }
     if (!g.pos_ok) {                                                  // :822-830 stop, keep what we have
@@ -493,38 +520,38 @@ __device__ __forceinline__ bool gen_next(AlleleGen &g, OutAllele &oa, const Diag
       return false;
     }
     if (tn == 1) {                                                    // :832
-      if (ta[0] != ref[0]) { if (diag) push_diag(p, line_no, alt_idx + 1, 7); continue; }
-      oa.kind = 2; oa.ref = ref[1]; oa.del_n = 1 - (long long)ref_n; oa.pos_verbatim = false;
+      if (ta0 != r0) { if (diag) push_diag(p, line_no, alt_idx + 1, 7); continue; }
+      oa.kind = 2; oa.ref = (uint8_t)gen_ref(g, 1); oa.del_n = 1 - (long long)ref_n; oa.pos_verbatim = false;
       oa.pos_val = g.ipos + 1;
       return true;
     }
     if (tn == ref_n) {                                                // :855 MNP / padded SNP
-      g.ta = ta; g.tn = tn; g.mnp_i = 0; g.done = false;
+      g.ta_off = t0; g.tn = tn; g.mnp_i = 0; g.done = false;
       continue;
     }
     if (tn > ref_n) {                                                 // :899 insertion with padding
       int r = 0;
 #pragma unroll 1
-      while (tn + r > 0 && ref_n + r > 1 && ta[tn + r - 1] == ref[ref_n + r - 1]) r--;
+      while (tn + r > 0 && ref_n + r > 1 && gen_alt(g, t0 + tn + r - 1) == gen_ref(g, ref_n + r - 1)) r--;
       const int off = ref_n + r;                                      // :932
       bool pre = true;
 #pragma unroll 1
-      for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
+      for (int i = 0; pre && i < off; i++) pre = gen_ref(g, i) == gen_alt(g, t0 + i);
       if (!pre) { if (diag) push_diag(p, line_no, alt_idx + 1, 6); continue; }
-      oa.kind = 1; oa.ref = ref[off - 1]; oa.ins_p = ta + off; oa.ins_n = tn + r - off;
+      oa.kind = 1; oa.ref = (uint8_t)gen_ref(g, off - 1); oa.ins_p = g.alt + t0 + off; oa.ins_n = tn + r - off;
       oa.pos_verbatim = false; oa.pos_val = g.ipos + off - 1;
       return true;
     }
     {                                                                 // :971 deletion with padding
       int r = 0;
 #pragma unroll 1
-      while (tn + r > 1 && ref_n + r > 0 && ta[tn + r - 1] == ref[ref_n + r - 1]) r--;
+      while (tn + r > 1 && ref_n + r > 0 && gen_alt(g, t0 + tn + r - 1) == gen_ref(g, ref_n + r - 1)) r--;
       const int off = tn + r;                                         // :984
       bool pre = true;
 #pragma unroll 1
-      for (int i = 0; pre && i < off; i++) pre = ref[i] == ta[i];
+      for (int i = 0; pre && i < off; i++) pre = gen_ref(g, i) == gen_alt(g, t0 + i);
       if (!pre) { if (diag) push_diag(p, line_no, alt_idx + 1, 6); continue; }
-      oa.kind = 2; oa.ref = ref[off]; oa.del_n = -((long long)ref_n + r - off);
+      oa.kind = 2; oa.ref = (uint8_t)gen_ref(g, off); oa.del_n = -((long long)ref_n + r - off);
       oa.pos_verbatim = false; oa.pos_val = g.ipos + off;
       return true;
     }

@@ -161,15 +161,30 @@ __device__ __noinline__ int itoa_pack(long long v, unsigned long long &lo, unsig
   return n;
 }
 
+// eight bytes at any alignment (three aligned words, funnel-shifted); reads up to 11 bytes past s -- the input
+// buffers are padded
+__device__ __forceinline__ unsigned long long ld64_any(const uint8_t *s) {
+  const uint32_t sh = (uint32_t)((uintptr_t)s & 3u) * 8u;
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
+  const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+  return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+}
+
 // ---- strconv.Atoi (main.go:752,824): optional sign, >= 1 digits, must fit int64 -----------------
+// p points into the (padded) input: fields of up to 16 characters are read with two word loads, not a byte at a time
 __device__ __forceinline__ bool atoi_go(const uint8_t *p, int n, long long &out) {
   if (n == 0) return false;
+  const bool in_regs = n <= 16;
+  const unsigned long long w0 = in_regs ? ld64_any(p) : 0ull, w1 = (in_regs && n > 8) ? ld64_any(p + 8) : 0ull;
+  auto at = [&](int i) -> unsigned { return in_regs ? (unsigned)((i < 8 ? w0 : w1) >> (8 * (i & 7))) & 0xFFu : (unsigned)p[i]; };
   int i = 0;
   bool neg = false;
-  if (p[0] == '-' || p[0] == '+') { neg = p[0] == '-'; i = 1; if (n == 1) return false; }
+  const unsigned c0 = at(0);
+  if (c0 == '-' || c0 == '+') { neg = c0 == '-'; i = 1; if (n == 1) return false; }
   unsigned long long v = 0;
+#pragma unroll 1
   for (; i < n; i++) {
-    const unsigned d = (unsigned)p[i] - '0';
+    const unsigned d = at(i) - '0';
     if (d > 9) return false;
     if (v > 1844674407370955161ull || (v == 1844674407370955161ull && d > 5)) return false;  // v * 10 + d > 2^64 - 1
     v = v * 10 + d;

@@ -129,13 +129,7 @@ __device__ __forceinline__ void store_tail(uint8_t *g, unsigned long long v, uin
   if (n & 2u) { *reinterpret_cast<uint16_t *>(g) = (uint16_t)v; v >>= 16; g += 2; }
   if (n & 1u) *g = (uint8_t)v;
 }
-// eight bytes from global memory at any alignment (three aligned words, funnel-shifted); reads up to 11 bytes past s
-__device__ __forceinline__ unsigned long long ldg64_unaligned(const uint8_t *s) {
-  const uint32_t sh = (uint32_t)((uintptr_t)s & 3u) * 8u;
-  const uint32_t *wp = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
-  const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-  return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
-}
+__device__ __forceinline__ unsigned long long ldg64_unaligned(const uint8_t *s) { return ld64_any(s); }
 
 // n bytes from global memory (a tile's scratch block, a span of the input line: both padded, so whole words may be
 // read) to global memory, any alignments: at most three narrow stores up to the first 8-byte boundary of the
@@ -195,8 +189,22 @@ struct StageWriter {
     }
     a += len;
   }
+  // a span of the INPUT (padded: whole words may be read): eight bytes per round trip to memory instead of one
   __device__ __forceinline__ void span(const uint8_t *p, int len) {
-    // rolled, like packed(): unrolled by four at some twenty call sites this loop alone was a third of the kernels' code
+    if (stg) {
+#pragma unroll 1
+      for (int i = 0; i < len; i += 8) {
+        const unsigned long long v = ld64_any(p + i);
+        uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        const int m = len - i < 8 ? len - i : 8;
+#pragma unroll 1
+        for (int k = 0; k < m; k++) { sts8(a + i + k, lo & 0xFFu); lo = __funnelshift_r(lo, hi, 8); hi >>= 8; }
+      }
+    }
+    a += len;
+  }
+  // bytes of the configuration (kernel parameters, constant memory)
+  __device__ __forceinline__ void span_const(const uint8_t *p, int len) {
     if (stg) {
 #pragma unroll 1
       for (int i = 0; i < len; i++) sts8(a + i, p[i]);
@@ -225,6 +233,7 @@ struct GlobalWriter {
     }
     g += len;
   }
+  __device__ __forceinline__ void span_const(const uint8_t *p, int len) { span(p, len); }
 };
 template <class W>
 __device__ __noinline__ void w_dec_long(W &w, long long v) {  // more than 16 characters: out of line, it never runs on real data
@@ -373,12 +382,20 @@ struct CountWriter {
   __device__ __forceinline__ void byte(uint32_t) { a++; }
   __device__ __forceinline__ void packed(unsigned long long, int len) { a += len; }
   __device__ __forceinline__ void span(const uint8_t *, int len) { a += len; }
+  __device__ __forceinline__ void span_const(const uint8_t *, int len) { a += len; }
 };
 __device__ __forceinline__ int dec_len(long long v) {  // len(strconv.Itoa(v))
   const unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
-  int d = 1;
+  int d;
+  if (u < 4294967296ull) {  // positions, counts: ten compares against immediates, no table in memory
+    const uint32_t x = (uint32_t)u;
+    d = 1 + (x >= 10u) + (x >= 100u) + (x >= 1000u) + (x >= 10000u) + (x >= 100000u) + (x >= 1000000u) + (x >= 10000000u) +
+        (x >= 100000000u) + (x >= 1000000000u);
+  } else {
+    d = 10;
 #pragma unroll 1
-  while (d < 20 && u >= BVCF_P10[d]) d++;
+    while (d < 20 && u >= BVCF_P10[d]) d++;
+  }
   return d + (v < 0 ? 1 : 0);
 }
 __device__ __forceinline__ void w_dec(CountWriter &w, long long v) { w.a += (uint32_t)dec_len(v); }
@@ -397,7 +414,7 @@ __device__ __forceinline__ void row_text_head(W &w, const LineCtx &lc, const Out
     w.packed(0x09ull | ((uint64_t)tt[0] << 8) | ((uint64_t)tt[1] << 16) | ((uint64_t)tt[2] << 24) | (0x09ull << 32), 5);
   } else {
     w.byte('\t');
-    w.span((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
+    w.span_const((const uint8_t *)TYPE_TXT[lc.site_type], TYPE_LEN[lc.site_type]);
     w.byte('\t');
   }
   const uint8_t trtv = lc.multi ? '0' : (oa.kind == 0 ? trtv_char(oa.ref, oa.alt_c) : '0');  // main.go:602-606
@@ -507,14 +524,14 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
   if (cfg.want_tsv) {
     row_text_head(w, lc, oa);
     if (!has_samples) {  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0"
-      w.span(cfg.tail0, cfg.tail0_len);  // composed once by the host
+      w.span_const(cfg.tail0, cfg.tail0_len);  // composed once by the host
     } else {
       const uint32_t eff = (uint32_t)cfg.n_samples - gs.n_miss;  // main.go:563
       const uint32_t den[3] = {eff, eff, (uint32_t)cfg.n_samples};
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         if (cnts[k] == 0) {
-          w.span(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0');
+          w.span_const(cfg.empty, cfg.empty_len); w.byte('\t'); w.byte('0');
         } else {
           if constexpr (W::kStage) {
             if (inline_lists) { la[k] = w.a; w.a += lb[k]; }      // filled below
@@ -615,6 +632,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
 
 // ---- one record: field index, linePasses (main.go:447-454), the start of getAlleles ---------------------------
 // Leaves the generator ready for gen_next (or done: filtered out / nothing to emit).
+template <bool CACHE = true>
 __device__ __forceinline__ void record_open(const TileParams &p, uint32_t li, const LineRec &rec, const uint8_t *s_filt,
                                             const uint32_t *s_filt_off, bool diag, LineCtx &lc, AlleleGen &g, DiagSink &ds,
                                             unsigned long long &line_no, uint32_t t[9]) {
@@ -656,10 +674,13 @@ __device__ __forceinline__ void record_open(const TileParams &p, uint32_t li, co
   // ---- linePasses (main.go:447-454): exact whole-field match against the shared-memory table ----
   if (pass && (!cfg.allow_all || cfg.n_excl > 0)) {
     bool in_allow = false, in_excl = false;
+    const bool fshort = filt_n <= 8;  // "PASS", ".", "q10": the field in a register, one round trip to memory
+    const unsigned long long fw = (fshort && filt_n > 0) ? ld64_any(filt) : 0ull;
     for (int k = 0; k < n_filt; k++) {
       const uint32_t o = s_filt_off[k], ln = s_filt_off[k + 1] - o;
       bool eq = (int)ln == filt_n;
-      for (int i = 0; eq && i < filt_n; i++) eq = s_filt[o + i] == filt[i];
+#pragma unroll 1
+      for (int i = 0; eq && i < filt_n; i++) eq = s_filt[o + i] == (fshort ? (uint8_t)(fw >> (8 * i)) : filt[i]);
       if (eq) { if (k < cfg.n_allow) in_allow = true; else in_excl = true; }
     }
     if (!cfg.allow_all && !in_allow) pass = false;
@@ -668,7 +689,7 @@ __device__ __forceinline__ void record_open(const TileParams &p, uint32_t li, co
 
   // ---- getAlleles (main.go:723-1038) as a resumable generator ----
   g.ref = ref; g.alt = alt; g.ref_n = ref_n; g.alt_n = alt_n;
-  g.s = 0; g.alt_idx = 0; g.mnp_i = -1; g.ta = alt; g.tn = 0; g.last = false;
+  g.s = 0; g.alt_idx = 0; g.mnp_i = -1; g.ta_off = 0; g.tn = 0; g.last = false;
   g.done = !(pass && ref_n > 0 && alt_n > 0);
   g.ipos = 0;
   // strconv.Atoi(POS) is only ever consulted when REF is longer than one base (main.go:752,822): SNPs and plain
@@ -677,7 +698,8 @@ __device__ __forceinline__ void record_open(const TileParams &p, uint32_t li, co
   line_no = p.ctr->chunk_line_base + rec.ord;
   ds = p.diag;
   ds.line_start = rec.start;
-  if (!g.done) gen_begin(g, lc, ds, line_no, diag);
+  if (!g.done) gen_begin<CACHE>(g, lc, ds, line_no, diag);
+  else g.cached = false;
 }
 
 // ---- one record, one thread: one converged tile_emit_row call site per output allele -------------------------
@@ -876,11 +898,11 @@ static_assert(sizeof(PendRow) == sizeof(TRow), "a PendRow becomes a TRow in plac
 template <class W>
 __device__ __forceinline__ void sites_row_text(W &w, const DevCfg &cfg, const LineCtx &lc, const OutAllele &oa) {
   row_text_head(w, lc, oa);
-  w.span(cfg.tail0, cfg.tail0_len);  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0", composed once by the host
+  w.span_const(cfg.tail0, cfg.tail0_len);  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0", composed once by the host
   row_text_keep<W, false>(w, cfg, lc, oa);
 }
 
-template <int MINB, uint32_t ARENA, uint32_t ROWS>
+template <int MINB, uint32_t ARENA, uint32_t ROWS, bool CACHE>
 __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_sites_kernel(const __grid_constant__ TileParams p) {
   constexpr uint32_t TILE_SMEM_WARP = tile_smem_warp(ARENA, ROWS);
   static_assert(ROWS <= TILE_ROWS_MAX && ROWS >= TILE_THREADS && ARENA < 65536u, "row table / arena size");
@@ -925,7 +947,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_sites_kern
       DiagSink ds;
       unsigned long long line_no;
       uint32_t t[9];
-      record_open(p, li, rec, s_filt, s_filt_off, true, lc, g, ds, line_no, t);
+      record_open<CACHE>(p, li, rec, s_filt, s_filt_off, true, lc, g, ds, line_no, t);
       start = rec.start; t0 = t[0]; t1 = t[1]; t2 = t[2];
       info_n = (uint32_t)lc.info_n; info_off = t[6] + 1;
       OutAllele oa;
