@@ -1,12 +1,9 @@
 mkdir -p gpurun_out
-for v in 0 7 9; do
-BVCF_SITES_VAR=$v python bench.py --config c3 --steps 3 --warmup 3 --no-bgzf --no-cpu-baseline --e2e-lines 100000 > gpurun_out/var_c3_v$v.json 2> gpurun_out/var_c3_v$v.err
-done
+LINES=3000000 BVCF_TRACE=1 timeout 600 python tools/e2e_probe.py 2>&1 | grep -v "^\[bvcf\]" | tail -5
+python bench.py --config c3 --steps 3 --warmup 3 --no-bgzf --no-cpu-baseline > gpurun_out/dg_c3.json 2> gpurun_out/dg_c3.err
 python - <<'P'
 import json
-for f in ("var_c3_v0","var_c3_v7","var_c3_v9"):
-    try:
-        d=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
-        print(f, round(d["ms_per_step"],3), {k:round(v,3) for k,v in d["kernel_ms_per_step"].items()}, d.get("parity_checked"))
-    except Exception as e: print(f, "ERR", e)
+d=json.loads(open("gpurun_out/dg_c3.json").read().strip().splitlines()[-1])
+print(round(d["ms_per_step"],3), d["e2e"])
 P
+timeout 900 python -m pytest tests -x -q -m gpu -k "diag or cli or golden or fuzz" 2>&1 | tail -3
