@@ -7,6 +7,7 @@
 //   bvcf_line_stats_{,big_}kernel  genotype summaries the scan could not finish inline
 //   bvcf_compose_kernel            FILTER + getAlleles + row text + short name lists, staged per tile of 32 records
 //   bvcf_tile_{reduce,spine,offsets}  tile totals -> output offsets, cursors            (north-star kernels 2+4)
+//   bvcf_dosage_zero_kernel        the sub-chunk's dosage rows start as zeros (only with --dosageOutput)
 //   bvcf_copyout_kernel            rows to the output with aligned stores, loci, RowDesc work lists
 //   bvcf_slow_rows_kernel          the few records that do not fit a tile's arena
 //   bvcf_names_{vec,long,big}_     long sample-name lists, their dosage rows  (north-star kernel 4b)
@@ -350,6 +351,10 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
       bvcf_tile_spine_kernel<<<1, 32, 0, st>>>(tp);
       bvcf_tile_offsets_kernel<<<TSCAN_BLOCKS, TSCAN_THREADS, 0, st>>>(tp);
       if (se) CK(cudaEventRecord(se->e[7], st));
+      if (dc.want_dosage && dc.n_samples > 0 && d_dosage) {
+        bvcf_dosage_zero_kernel<<<(unsigned)n_sm * 8, 256, 0, st>>>(tp);
+        ctx->launches += 1;
+      }
       if (pf & 2) bvcf_copyout_kernel<true><<<(unsigned)n_sm * 16, TILE_WARPS * 32, 0, st>>>(tp);
       else bvcf_copyout_kernel<false><<<(unsigned)n_sm * 16, TILE_WARPS * 32, 0, st>>>(tp);
     }

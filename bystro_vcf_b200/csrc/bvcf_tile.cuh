@@ -1188,6 +1188,33 @@ __global__ void __launch_bounds__(TSCAN_THREADS) bvcf_tile_offsets_kernel(const 
   }
 }
 
+// ---- dosage rows start as all-reference (main.go:576-584: a row of zeros, then the non-reference samples) ---------
+// The sub-chunk's rows [chunk_row_base, row_cursor) x n_samples bytes, known once the tile spine has run: plain 16-byte
+// stores at memory speed, 15.5 GB of them at C5.  (Zeroing each tile's rows inside the copy-out kernel, which runs at
+// half occupancy and waits on its loads, was no slower in total: 6.09 against 5.93 ms for the two together.)
+__global__ void __launch_bounds__(256) bvcf_dosage_zero_kernel(const __grid_constant__ TileParams p) {
+  const RunCounters *c = p.ctr;
+  if (c->ev_overflow | c->slot_overflow | c->out_overflow | c->row_overflow | c->scratch_overflow) return;
+  if (!p.dosage || p.cfg.n_samples <= 0) return;
+  unsigned long long r_lo = c->chunk_row_base, r_hi = c->row_cursor;
+  if (r_hi > p.dosage_cap_rows) r_hi = p.dosage_cap_rows;
+  if (r_lo >= r_hi) return;
+  const unsigned long long ns = (unsigned long long)p.cfg.n_samples;
+  uint8_t *const base = reinterpret_cast<uint8_t *>(p.dosage);
+  const unsigned long long b0 = r_lo * ns, b1 = r_hi * ns;
+  const unsigned long long a0 = (b0 + 15ull) & ~15ull, a1 = b1 & ~15ull;  // cudaMalloc'ed: base is 256-byte aligned
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+  if (a0 >= a1) {
+    for (unsigned long long i = b0 + tid; i < b1; i += nth) base[i] = 0;
+    return;
+  }
+  for (unsigned long long i = b0 + tid; i < a0; i += nth) base[i] = 0;
+  uint4 *v = reinterpret_cast<uint4 *>(base + a0);
+  const unsigned long long nv = (a1 - a0) >> 4;
+  for (unsigned long long i = tid; i < nv; i += nth) v[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (unsigned long long i = a1 + tid; i < b1; i += nth) base[i] = 0;
+}
+
 // ---- copy-out -----------------------------------------------------------------------------------------------
 // No shared memory and few registers: the staged bytes are read straight from the tile's scratch block (L2), so the
 // kernel runs at full occupancy and hides those latencies with warps instead.
@@ -1276,28 +1303,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) bvcf_copyout_kernel(const 
       for (uint32_t o = lane * 128u; o < nbytes; o += 32u * 128u) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(nb + o));
     }
 
-    // this tile's dosage rows start as all-reference (0); the small rows' samples are scattered below, the queued
-    // rows' by the names kernels
-    if (want_locus && p.dosage && ag.rows) {
-      const unsigned long long ns = (unsigned long long)cfg.n_samples;
-      unsigned long long r_lo = row0 + tb.rows, r_hi = r_lo + ag.rows;
-      if (r_hi > p.dosage_cap_rows) r_hi = p.dosage_cap_rows;
-      if (r_lo < r_hi) {
-        uint8_t *const base = reinterpret_cast<uint8_t *>(p.dosage);
-        const unsigned long long b0 = r_lo * ns, b1 = r_hi * ns;
-        const unsigned long long a0 = (b0 + 15ull) & ~15ull, a1 = b1 & ~15ull;  // cudaMalloc'ed: base is 256-byte aligned
-        if (a0 >= a1) {
-          for (unsigned long long i = b0 + lane; i < b1; i += 32) base[i] = 0;
-        } else {
-          for (unsigned long long i = b0 + lane; i < a0; i += 32) base[i] = 0;
-          uint4 *v = reinterpret_cast<uint4 *>(base + a0);
-          const unsigned long long nv = (a1 - a0) >> 4;
-          for (unsigned long long i = lane; i < nv; i += 32) v[i] = make_uint4(0u, 0u, 0u, 0u);
-          for (unsigned long long i = a1 + lane; i < b1; i += 32) base[i] = 0;
-        }
-      }
-      __syncwarp();
-    }
+    // (the tile's dosage rows were zeroed by bvcf_dosage_zero_kernel: all-reference; the small rows' samples are
+    // scattered below, the queued rows' by the names kernels)
     if (li < n_rec && lr.rows) {
       unsigned long long off = out_base + tb.bytes + (in_b - lr.bytes);           // first output byte of this record
       unsigned long long r = (unsigned long long)tb.rows + ((uint32_t)in_rl - lr.rows);  // its first row within the sub-chunk

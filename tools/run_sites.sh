@@ -1,9 +1,11 @@
 mkdir -p gpurun_out
-LINES=3000000 BVCF_TRACE=1 timeout 600 python tools/e2e_probe.py 2>&1 | grep -v "^\[bvcf\]" | tail -5
-python bench.py --config c3 --steps 3 --warmup 3 --no-bgzf --no-cpu-baseline > gpurun_out/dg_c3.json 2> gpurun_out/dg_c3.err
+python bench.py --config c5 --steps 3 --warmup 3 --no-bgzf --no-cpu-baseline --e2e-lines 100000 > gpurun_out/dz_c5.json 2> gpurun_out/dz_c5.err
 python - <<'P'
 import json
-d=json.loads(open("gpurun_out/dg_c3.json").read().strip().splitlines()[-1])
-print(round(d["ms_per_step"],3), d["e2e"])
+for f in ("dz_c5",):
+    try:
+        d=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
+        print(f, round(d["ms_per_step"],3), {k:round(v,3) for k,v in d["kernel_ms_per_step"].items()}, d.get("parity_checked"))
+    except Exception as e: print(f, "ERR", e); print(open(f"gpurun_out/{f}.err").read()[-1500:])
 P
-timeout 900 python -m pytest tests -x -q -m gpu -k "diag or cli or golden or fuzz" 2>&1 | tail -3
+timeout 900 python -m pytest tests -x -q -m gpu -k "dosage or locus or slow_path or c5 or arrow or feather" 2>&1 | tail -3
