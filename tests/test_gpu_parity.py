@@ -542,7 +542,7 @@ def _fuzz_alleles_vcf(rng, n_lines, with_samples):
     hdr = V.HDR8 + (["FORMAT", "S1", "S2", "S3"] if with_samples else [])
     recs = []
     for i in range(n_lines):
-        ref = bases(rng.choice([1, 1, 1, 2, 3, 4, 8]))
+        ref = bases(rng.choice([1, 1, 1, 2, 3, 4, 8, 9, 13]))  # 9, 13: beyond the eight REF bases the generator keeps in registers
         alts = ",".join(alt_of(ref) for _ in range(rng.choice([1, 1, 1, 2, 3, 5])))
         odd_pos = [str(rng.randrange(1, 10 ** rng.randrange(1, 10))), "x", "+5", "-3", "007", "9223372036854775807"]
         pos = rng.choice(odd_pos) if rng.random() < 0.1 else str(rng.randrange(1, 250000000))
