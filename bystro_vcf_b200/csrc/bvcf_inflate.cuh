@@ -9,7 +9,7 @@
 // codes of unknown length, matches that copy from the bytes just written), so:
 //   * every lane runs the same bit reader and the same canonical Huffman decode (count / symbol arrays in shared
 //     memory, code length by code length as in zlib's puff.c): uniform control flow, no broadcasts;
-//   * the block's text is built in shared memory (64 KiB per warp), where a match is a PARALLEL copy -- lane i writes
+//   * the block's text is built in shared memory (a 16 KiB ring per warp), where a match is a PARALLEL copy -- lane i writes
 //     byte i, reading byte (i mod distance) of the source, so even the distance-4 runs of genotype text ("0|0\t"
 //     repeated 64 times per match) move 32 bytes per step instead of waiting on a store-to-load round trip per byte;
 //   * the finished block leaves as coalesced 16-byte stores.
@@ -152,10 +152,13 @@ __device__ const short INF_DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49,
 __device__ const short INF_DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __device__ const unsigned char INF_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// The text of a block goes through a 32 KiB ring in shared memory (DEFLATE matches reach back 32 KiB at most): text
-// byte t lives at ring byte t & INF_RING_MASK.  Finished 8 KiB pieces leave for global memory as soon as the decoder
-// is 8 KiB past them -- long before their ring bytes are written again.
-constexpr uint32_t INF_RING = 32768, INF_RING_MASK = INF_RING - 1, INF_PIECE = 8192;
+// The text of a block goes through a 16 KiB ring in shared memory: text byte t lives at ring byte t & INF_RING_MASK.
+// Finished 4 KiB pieces leave for global memory as soon as the decoder is 4 KiB past them -- long before their ring
+// bytes are written again.  DEFLATE matches reach back 32 KiB: a source byte that has left the ring (more than
+// 16 KiB - 258 behind the decoder, so flushed at least 7 KiB ago) is read back from the text in global memory.  Half the
+// ring of the first version: 10 resident warps per SM instead of 7 for a kernel that is one serial chain per warp.
+constexpr uint32_t INF_RING = 16384, INF_RING_MASK = INF_RING - 1, INF_PIECE = 4096;
+static_assert(2 * INF_PIECE + 258 + 1 < INF_RING - 258, "a byte outside the ring has been flushed");
 struct InfOut {
   uint32_t ring_s;     // shared-memory byte address of the ring
   const uint8_t *ring; // the same, generic
@@ -215,10 +218,21 @@ __device__ __forceinline__ int inf_codes(InfBits &b, const InfHuff &lc, const In
       __syncwarp();                       // the literals and matches written so far are visible to every lane
       const uint32_t src = w.o - dist, dst = w.o;
       if (dist >= len) {                  // plain copy
-        for (uint32_t i = lane; i < len; i += 32) {
-          uint32_t c;
-          asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(c) : "r"(w.ring_s + ((src + i) & INF_RING_MASK)) : "memory");
-          asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(w.ring_s + ((dst + i) & INF_RING_MASK)), "r"(c) : "memory");
+        // text bytes below ring_lo are no longer in the ring (or are about to be overwritten by this very match)
+        const uint32_t ring_lo = w.o + len > INF_RING ? w.o + len - INF_RING : 0u;
+        if (src >= ring_lo) {
+          for (uint32_t i = lane; i < len; i += 32) {
+            uint32_t c;
+            asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(c) : "r"(w.ring_s + ((src + i) & INF_RING_MASK)) : "memory");
+            asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(w.ring_s + ((dst + i) & INF_RING_MASK)), "r"(c) : "memory");
+          }
+        } else {                          // a far match: (part of) its source was flushed long ago
+          for (uint32_t i = lane; i < len; i += 32) {
+            uint32_t c;
+            if (src + i >= ring_lo) asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(c) : "r"(w.ring_s + ((src + i) & INF_RING_MASK)) : "memory");
+            else c = __ldcg(w.g + src + i);  // L2: written by this warp's own flush, ordered by the __syncwarp() above
+            asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(w.ring_s + ((dst + i) & INF_RING_MASK)), "r"(c) : "memory");
+          }
         }
       } else {                            // the source runs into the bytes being written: byte i repeats byte i mod dist
         uint32_t m, step;

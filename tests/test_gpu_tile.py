@@ -267,6 +267,43 @@ def test_gpu_inflate_block_types(kind):
     assert _inflate_on_gpu(comp, len(data)) == data
 
 
+@pytest.mark.parametrize("gap", [15000, 16126, 16127, 16384, 20000, 32000, 32768])
+def test_gpu_inflate_far_matches(gap):
+    """matches whose source has left the 16 KiB shared-memory ring (distance up to DEFLATE's 32 KiB) are read back from
+    the flushed text in global memory; sources that straddle the ring's edge; a stored block as the far source"""
+    import gzip
+    import zlib
+
+    from bystro_vcf_b200 import bgzf
+
+    rng = random.Random(gap)
+    motif = bytes(rng.randrange(256) for _ in range(600))          # incompressible, so it can only come back as a match
+    filler = bytes(rng.randrange(256) for _ in range(gap - 600))
+    tail = b"".join(motif[j:j + 37] + bytes([j & 255]) for j in range(0, 560, 7))
+    block = motif + filler + motif + filler[:500] + motif[100:400] + tail   # second motif: distance == gap
+    data = block * 3
+    for level, strategy in ((9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED)):
+        comp = bgzf.compress(data, level=level, block_text=65280, strategy=strategy)
+        assert gzip.decompress(comp) == data
+        assert _inflate_on_gpu(comp, len(data)) == data
+    # one member = stored block(s) holding the first motif and the filler, then compressed blocks whose matches reach
+    # back into the stored text (the compressor gets that text as its preset dictionary)
+    import struct
+
+    text = block[:gap + 600]
+    c2 = zlib.compressobj(9, zlib.DEFLATED, -15, 9, zlib.Z_DEFAULT_STRATEGY, text[-32768:])
+    rest = block[gap + 600:]
+    stored = b"".join(struct.pack("<BHH", 0, len(text[i:i + 65535]), len(text[i:i + 65535]) ^ 0xFFFF) + text[i:i + 65535]
+                      for i in range(0, len(text), 65535))
+    member_payload = stored + c2.compress(rest) + c2.flush()
+    whole = text + rest
+    assert zlib.decompress(member_payload, -15) == whole
+    if len(whole) <= 65280 and len(member_payload) + 26 <= 65536:
+        member = (bgzf.MAGIC + b"\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(member_payload) + 25) +
+                  member_payload + struct.pack("<II", zlib.crc32(whole), len(whole)))
+        assert _inflate_on_gpu(member + bgzf.EOF_BLOCK, len(whole)) == whole
+
+
 def test_gpu_inflate_rejects_corrupt_blocks():
     from bystro_vcf_b200 import BvcfError, Transformer, bgzf
 
