@@ -176,3 +176,26 @@ def test_read_vcf_multi_is_chunk_round_robin():
     assert all(data[hi - 1:hi] == b"\n" and hi - lo <= 700 for lo, hi in ch)
     one_long = b"x" * 5000 + b"\n" + b"y\n"
     assert chunk_ranges(one_long, 0, len(one_long), 100)[0] == (0, 5001)  # a line longer than a chunk stays whole
+
+
+def test_bgzf_out_flag_and_its_refusals():
+    """--bgzfOut (extension): parsed like a Go bool flag by both hosts; several GPUs are refused before any device
+    work, after the (compressed) header line has gone out (main.go:199 writes it before reading input)"""
+    import gzip
+    import subprocess
+    import sys
+
+    from bystro_vcf_b200 import host
+
+    assert host.setup(["--bgzfOut"]).bgzfOut is True
+    assert host.setup(["--bgzfOut=false", "--keepId"]).bgzfOut is False
+    assert host.setup([]).bgzfOut is False
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmds = [[sys.executable, "-m", "bystro_vcf_b200"]]
+    binary = os.path.join(root, "bystro_vcf_b200", "bin", "bystro-vcf-b200")
+    if os.path.exists(binary):
+        cmds.append([binary])
+    for cmd in cmds:
+        r = subprocess.run(cmd + ["--bgzfOut", "--gpus", "2"], input=b"##fileformat=VCFv4.1\n", capture_output=True, cwd=root)
+        assert r.returncode == 1 and b"--bgzfOut runs on one GPU" in r.stderr
+        assert gzip.decompress(r.stdout).decode().split("\t")[:3] == ["chrom", "pos", "type"]
