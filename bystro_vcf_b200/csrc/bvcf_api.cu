@@ -343,7 +343,13 @@ int enqueue_pipeline(bvcf_ctx *ctx, Scratch &sc, cudaStream_t st, const uint8_t 
         if (pf & 1) launch(bvcf_compose_kernel<4, 8192, 160, true>, 8192, 160, 4);
         else launch(bvcf_compose_kernel<4, 8192, 160, false>, 8192, 160, 4);
       } else {
+        // the build for the default flags: TSV rows, no --keepPos/Id/Info, no dosage matrix, 7-character names joined by
+        // one character -- a smaller kernel (see "Code size" in DESIGN.md)
+        static const bool no_spec = getenv("BVCF_NO_SPEC") != nullptr;  // experiments
+        const bool spec = !no_spec && dc.want_tsv && !dc.keep_pos && !dc.keep_id && !dc.keep_info && !dc.want_dosage && dc.name8 &&
+                          dc.delim_len == 1 && dc.name_fixed_w == 7;
         if (pf & 1) launch(bvcf_compose_kernel<4, 10240, 48, true>, 10240, 48, 4);
+        else if (spec) launch(bvcf_compose_kernel<4, 10240, 48, false, true>, 10240, 48, 4);
         else launch(bvcf_compose_kernel<4, 10240, 48, false>, 10240, 48, 4);
       }
       if (se) CK(cudaEventRecord(se->e[6], st));

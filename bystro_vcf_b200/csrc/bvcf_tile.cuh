@@ -300,12 +300,15 @@ __device__ __forceinline__ int row_class(const TileParams &p, uint32_t ev_count)
 
 // the names of a short record's row into the staged lists (main.go:617,639,653 strings.Join): one walk over the
 // record's quad events (at most SMALL_EVENTS / 2), header order
+// SPEC (everywhere below): the kernel is built for the default flags -- TSV rows, no --keepPos/Id/Info, no dosage
+// matrix, 7-character sample names and a one-character delimiter -- and the code of the other cases is not in it
+template <bool SPEC>
 __device__ __forceinline__ void fill_small_lists(const TileParams &p, const LineRec &rec, const LineCtx &lc, uint32_t a,
                                                  uint32_t la0, uint32_t la1, uint32_t la2) {
   const DevCfg &cfg = p.cfg;
   const uint32_t *ev = p.events + rec.ev_start;
   const bool simple = !(rec.flags & 1) && a == 1;
-  const uint32_t dl = (uint32_t)cfg.delim_len;
+  const uint32_t dl = SPEC ? 1u : (uint32_t)cfg.delim_len;
   uint32_t nh = 0, no = 0, nm = 0;
   for (uint32_t q = 0; 2 * q + 1 < rec.ev_count; q++) {
     const uint2 e = *reinterpret_cast<const uint2 *>(ev + 2 * q);
@@ -324,8 +327,8 @@ __device__ __forceinline__ void fill_small_lists(const TileParams &p, const Line
         for (uint32_t i = 0; i < dl; i++) sts8(d + i, cfg.delim[i]);
         d += dl;
       }
-      const uint32_t nl = name_len(cfg, samp);
-      if (cfg.name8) {
+      const uint32_t nl = SPEC ? 7u : name_len(cfg, samp);
+      if (SPEC || cfg.name8) {
         const unsigned long long it = cfg.name8[samp];
 #pragma unroll
         for (int i = 0; i < 7; i++) sts8(d + i, (uint32_t)(it >> (8 * i)) & 0xFFu);
@@ -432,8 +435,9 @@ __device__ __forceinline__ void row_text_head(W &w, const LineCtx &lc, const Out
 }
 // the --keepPos / --keepId / --keepInfo columns and the end of the row (main.go:671-692); INFO: the ALT index here,
 // the span itself only when the writer goes straight to the output (staged rows get it at copy-out)
-template <class W, bool INFO_SPAN>
+template <class W, bool INFO_SPAN, bool SPEC = false>
 __device__ __forceinline__ void row_text_keep(W &w, const DevCfg &cfg, const LineCtx &lc, const OutAllele &oa) {
+  if (SPEC) { w.byte('\n'); return; }
   if (cfg.keep_pos) { w.byte('\t'); w.span(lc.pos, lc.pos_n); }
   if (cfg.keep_id) { w.byte('\t'); w.span(lc.id, lc.id_n); }
   if (cfg.keep_info) {
@@ -447,20 +451,23 @@ __device__ __forceinline__ void row_text_keep(W &w, const DevCfg &cfg, const Lin
 // ---- one output row (main.go:555-695) -------------------------------------------------------------------
 // W = StageWriter: pass A (compose into the arena, or size only once the record has failed over to the slow path);
 // W = GlobalWriter: pass C of a slow-path record.
-template <class W>
+template <class W, bool SPEC = false>
 __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec &rec, const LineCtx &lc, const OutAllele &oa,
                                               GtStats &gs, int &gs_idx, W &w, RecOut &ro, const TileShared &sh, SlowOut &so) {
   const DevCfg &cfg = p.cfg;
+  const bool want_tsv = SPEC ? true : (bool)cfg.want_tsv, keep_pos = SPEC ? false : (bool)cfg.keep_pos,
+             keep_id = SPEC ? false : (bool)cfg.keep_id, keep_info = SPEC ? false : (bool)cfg.keep_info;
+  const uint32_t fixed_w = SPEC ? 7u : (uint32_t)(cfg.name_fixed_w > 0 ? cfg.name_fixed_w : 0);  // name bytes, without the delimiter
   const uint32_t a = (uint32_t)oa.alt_idx + 1;
   const bool has_samples = cfg.n_samples > 0;
   if (has_samples) {
     if (gs_idx != oa.alt_idx) {  // MNP bases share their ALT index: reduce once (main.go:865-868)
-      if (cfg.name_fixed_w > 0 && !(rec.flags & 1)) {
+      if (fixed_w > 0 && !(rec.flags & 1)) {
         // the scan kernel's inline summary is complete: only ALT #1 occurs among the samples
         gs.n_het = a == 1 ? rec.n_het1 : 0; gs.n_hom = a == 1 ? rec.n_hom1 : 0; gs.ac = a == 1 ? rec.ac1 : 0;
         gs.n_miss = rec.n_miss; gs.an = rec.an;
-        gs.het_bytes = gs.n_het * cfg.name_fixed_w; gs.hom_bytes = gs.n_hom * cfg.name_fixed_w;
-        gs.miss_bytes = gs.n_miss * cfg.name_fixed_w;
+        gs.het_bytes = gs.n_het * fixed_w; gs.hom_bytes = gs.n_hom * fixed_w;
+        gs.miss_bytes = gs.n_miss * fixed_w;
       } else if (a <= (uint32_t)STAT_ALLELES) {
         const LineStats &ls = p.stats[lc.li];
         gs.n_het = ls.n_het[a - 1]; gs.n_hom = ls.n_hom[a - 1]; gs.ac = ls.ac[a - 1];
@@ -473,15 +480,15 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
     }
     if (gs.ac == 0) return;  // main.go:558
   }
-  const uint32_t dl = (uint32_t)cfg.delim_len;
+  const uint32_t dl = SPEC ? 1u : (uint32_t)cfg.delim_len;
   const uint32_t cnts[3] = {has_samples ? gs.n_het : 0u, has_samples ? gs.n_hom : 0u, has_samples ? gs.n_miss : 0u};
   const uint32_t nb[3] = {gs.het_bytes, gs.hom_bytes, gs.miss_bytes};
   uint32_t lb[3];  // list bytes
 #pragma unroll
-  for (int k = 0; k < 3; k++) lb[k] = (cfg.want_tsv && cnts[k]) ? nb[k] + (cnts[k] - 1) * dl : 0u;
+  for (int k = 0; k < 3; k++) lb[k] = (want_tsv && cnts[k]) ? nb[k] + (cnts[k] - 1) * dl : 0u;
   const bool big = has_samples && rec.ev_count > SMALL_EVENTS;  // lists and dosages are left to the names kernels
-  const bool want_locus = cfg.want_dosage && has_samples;
-  const uint32_t tail = (cfg.want_tsv && cfg.keep_info) ? (uint32_t)lc.info_n + 1u : 0u;  // INFO span + EOL, never staged
+  const bool want_locus = SPEC ? false : (cfg.want_dosage && has_samples);
+  const uint32_t tail = (want_tsv && keep_info) ? (uint32_t)lc.info_n + 1u : 0u;  // INFO span + EOL, never staged
 
   // ---- where the bytes go ----
   TRow *row = nullptr;
@@ -494,9 +501,9 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
       const uint32_t pos_b = oa.pos_verbatim ? (uint32_t)lc.pos_n : 20u;
       const uint32_t alt_b = oa.kind == 1 ? (uint32_t)oa.ins_n + 1u : 21u;
       uint32_t need = 0;
-      if (cfg.want_tsv) {
+      if (want_tsv) {
         need = 104u + (uint32_t)lc.chrom_n + pos_b + alt_b + (has_samples ? 3u * (uint32_t)cfg.empty_len : (uint32_t)cfg.tail0_len) +
-               (cfg.keep_pos ? (uint32_t)lc.pos_n : 0u) + (cfg.keep_id ? (uint32_t)lc.id_n : 0u);
+               (keep_pos ? (uint32_t)lc.pos_n : 0u) + (keep_id ? (uint32_t)lc.id_n : 0u);
         if (!big) need += lb[0] + lb[1] + lb[2];
       }
       if (want_locus) need += 8u + (uint32_t)lc.chrom_n + pos_b + alt_b;
@@ -508,7 +515,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
       } else {
         row = &sh.rows[ri];
         a0 = sh.arena_s + off;
-        inline_lists = !big && cfg.want_tsv;
+        inline_lists = !big && want_tsv;
       }
     }
     w.stg = row != nullptr;
@@ -521,7 +528,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
   uint32_t hpos[3] = {0, 0, 0}, hlen[3] = {0, 0, 0};
   unsigned long long dsts[3] = {~0ull, ~0ull, ~0ull};
 
-  if (cfg.want_tsv) {
+  if (want_tsv) {
     row_text_head(w, lc, oa);
     if (!has_samples) {  // main.go:612-616,634-637,648-651,667: "! 0 ! 0 ! 0 0 0 0"
       w.span_const(cfg.tail0, cfg.tail0_len);  // composed once by the host
@@ -552,7 +559,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
       if (gs.ac == 0) w.byte('0');
       else { int fl; const uint64_t ft = format_ratio_g3(gs.ac, gs.an, fl); w.packed(ft, fl); }
     }
-    row_text_keep<W, !W::kStage>(w, cfg, lc, oa);
+    row_text_keep<W, !W::kStage, SPEC>(w, cfg, lc, oa);
   }
 
   uint32_t slen = 0, loc_len = 0;
@@ -611,7 +618,7 @@ __device__ __forceinline__ void tile_emit_row(const TileParams &p, const LineRec
       row->flags = (uint16_t)((tail ? 1u : 0u) | (big ? 2u : 0u));
       if (ro.first == ROW_NONE) ro.first = ri; else sh.rows[ro.last].next = (uint16_t)ri;
       ro.last = ri;
-      if (inline_lists && (cnts[0] | cnts[1] | cnts[2])) fill_small_lists(p, rec, lc, a, la[0], la[1], la[2]);
+      if (inline_lists && (cnts[0] | cnts[1] | cnts[2])) fill_small_lists<SPEC>(p, rec, lc, a, la[0], la[1], la[2]);
     }
   } else {
     if (has_samples) {  // every row of a slow-path record is queued for the names kernels
@@ -703,7 +710,7 @@ __device__ __forceinline__ void record_open(const TileParams &p, uint32_t li, co
 }
 
 // ---- one record, one thread: one converged tile_emit_row call site per output allele -------------------------
-template <class W>
+template <class W, bool SPEC = false>
 __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, const LineRec &rec, W &w, RecOut &ro,
                                             const TileShared &sh, SlowOut &so, const uint8_t *s_filt, const uint32_t *s_filt_off,
                                             bool diag, const uint8_t *&info_p, uint32_t &info_n) {
@@ -719,7 +726,7 @@ __device__ __forceinline__ void tile_record(const TileParams &p, uint32_t li, co
   int gs_idx = -1;
   OutAllele oa;
   oa.ins_p = nullptr; oa.ins_n = 0; oa.del_n = 0; oa.pos_val = 0;
-  while (gen_next(g, oa, ds, line_no, diag)) tile_emit_row<W>(p, rec, lc, oa, gs, gs_idx, w, ro, sh, so);
+  while (gen_next(g, oa, ds, line_no, diag)) tile_emit_row<W, SPEC>(p, rec, lc, oa, gs, gs_idx, w, ro, sh, so);
 }
 
 // inclusive scan of v over the warp; the total in `total`
@@ -742,7 +749,7 @@ constexpr uint32_t TILE_BLOCK_HDR = 32u * (uint32_t)sizeof(LaneRec);
 // MINB resident CTAs per SM (sets the register budget), ARENA staging bytes and ROWS row descriptors per warp.
 // Records with samples give about one row each (wide text: 10 KiB, 48 rows); sites-only input gives 1.6 short rows per
 // record at BASELINE's 30 % multi-allelic / MNP mix (8 KiB, 160 rows).
-template <int MINB, uint32_t ARENA, uint32_t ROWS, bool PREFETCH>
+template <int MINB, uint32_t ARENA, uint32_t ROWS, bool PREFETCH, bool SPEC = false>
 __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(const __grid_constant__ TileParams p) {
   constexpr uint32_t TILE_ARENA = ARENA, TILE_ROWS = ROWS, TILE_SMEM_WARP = tile_smem_warp(ARENA, ROWS);
   static_assert(ROWS <= TILE_ROWS_MAX && ROWS >= TILE_THREADS, "row table size");
@@ -826,7 +833,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, MINB) bvcf_compose_kernel(con
       ev_count = rec.ev_count;
       StageWriter w;
       w.a = 0; w.stg = false;
-      tile_record<StageWriter>(p, li, rec, w, ro, sh, so, s_filt, s_filt_off, true, info_p, info_n);
+      tile_record<StageWriter, SPEC>(p, li, rec, w, ro, sh, so, s_filt, s_filt_off, true, info_p, info_n);
       info_off = (uint32_t)(info_p - (p.in + rec.start));
     }
     const int cls = row_class(p, ev_count);
