@@ -199,3 +199,37 @@ def test_bgzf_out_flag_and_its_refusals():
         r = subprocess.run(cmd + ["--bgzfOut", "--gpus", "2"], input=b"##fileformat=VCFv4.1\n", capture_output=True, cwd=root)
         assert r.returncode == 1 and b"--bgzfOut runs on one GPU" in r.stderr
         assert gzip.decompress(r.stdout).decode().split("\t")[:3] == ["chrom", "pos", "type"]
+
+
+@pytest.mark.parametrize("data,msg", [(b"hello\nworld\n", b"Not a VCF file"), (b"##fileformat=VCFv4.2\n##x\n", b"No header found")])
+def test_cli_fatal_paths_like_reference(data, msg):
+    """log.Fatal of readVcf (main.go:263,293) in both hosts: the TSV header line is out already (main.go:199), the
+    message goes to stderr, exit status 1 -- before any device is touched"""
+    import subprocess
+    import sys
+
+    cmds = [[sys.executable, "-m", "bystro_vcf_b200"]]
+    binary = os.path.join(ROOT, "bystro_vcf_b200", "bin", "bystro-vcf-b200")
+    if os.path.exists(binary):
+        cmds.append([binary])
+    for cmd in cmds:
+        r = subprocess.run(cmd, input=data, capture_output=True, cwd=ROOT)
+        assert r.returncode == 1
+        assert msg in r.stderr
+        assert r.stdout.decode().rstrip("\n").split("\t") == V.BASE_HEADER
+
+
+def test_cli_flag_errors_like_reference():
+    """main.go:160,164: --noOut with --out, --noOut without --dosageOutput"""
+    import subprocess
+    import sys
+
+    cmds = [[sys.executable, "-m", "bystro_vcf_b200"]]
+    binary = os.path.join(ROOT, "bystro_vcf_b200", "bin", "bystro-vcf-b200")
+    if os.path.exists(binary):
+        cmds.append([binary])
+    for cmd in cmds:
+        r = subprocess.run(cmd + ["--noOut", "--out", "x.tsv"], input=b"", capture_output=True, cwd=ROOT)
+        assert r.returncode == 1 and b"Cannot specify --noOut and --out" in r.stderr
+        r = subprocess.run(cmd + ["--noOut"], input=b"", capture_output=True, cwd=ROOT)
+        assert r.returncode == 1 and b"When specifying --noOut, must specify --dosageOutput" in r.stderr
